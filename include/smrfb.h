@@ -1,0 +1,124 @@
+/*
+ * smrfb.h -- C-ABI of libsmrfb.so: B200 (sm_100a) spatial distribution for SMRF.
+ *
+ * The drop-in boundary for the reference's per-timestep distribution path
+ * (reference paths relative to USDA-ARS-NWRC/smrf):
+ *
+ *   smrfb_idw_*            replaces smrf/spatial/idw.py:14-144      (IDW.__init__, calculateIDW, detrendedIDW)
+ *   smrfb_dk_*             replaces smrf/spatial/dk/dk.py:20-168    (DK.calculate, calculateWeights, detrend/retrend)
+ *   smrfb_krige_grid       replaces smrf/spatial/dk/dk_header.h:23  (krige_grid(), reached through
+ *                                   detrended_kriging.pyx:32-67 call_grid) -- same arguments, same in-place output
+ *   smrfb_grid_*           replaces smrf/spatial/grid.py:23-231     (GRID.__init__, detrendedInterpolation[Mask],
+ *                                   calculateInterpolation, grid_method='linear')
+ *   vmin/vmax arguments    replace  smrf/utils/utils.py:137-161     (set_min_max, fused into the store)
+ *   smrfb_set_min_max      replaces smrf/utils/utils.py:137-161     (stand-alone form)
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (0 = SMRFB_OK); the message of the
+ *     last failure on the calling thread is smrfb_last_error().  Nothing here calls exit()
+ *     (the reference's C does on a singular kriging matrix, krige.c:161-164).
+ *   - station data are row-major double [T][nsta]; NaN marks a missing station (idw.py:88, dk.py:75).
+ *   - outputs are row-major double [T][ncell], ncell = ny*nx, cell (i,j) at flat index i*nx + j.
+ *   - grid_kind 0: separable mesh as np.meshgrid(x, y) gives (smrf/data/load_topo.py:65):
+ *                  gx[nx], gy[ny]; cell (i,j) sits at (gx[j], gy[i]).
+ *     grid_kind 1: arbitrary cell coordinates gx[ncell], gy[ncell] (GridX.ravel(), GridY.ravel()).
+ *   - a multi-GPU run gives every rank its own handle over its own row slab (pass the slab's
+ *     gy / dem rows); slabs are independent, there is no collective.
+ *   - handles are independent: one device + one internal CUDA stream each; calls on different
+ *     handles may run concurrently from different host threads, calls on one handle must be
+ *     serialised by the caller (true of the reference: one thread per variable,
+ *     smrf/framework/model_framework.py:615-632).
+ *   - *_dev variants take DEVICE pointers and enqueue on the given cudaStream_t (passed as void*;
+ *     NULL = the handle's stream) without synchronising.
+ *   - slope_flag is the reference's detrend_slope: +1 / -1 constrain the sign of the elevation
+ *     trend (both coefficients become 0 when violated, idw.py:124-127), 0 = unconstrained.
+ *   - pv_in (nullable, [T][2] = slope, intercept) bypasses the device regression, e.g. to feed
+ *     np.polyfit's coefficients; pv_out (nullable, [T][2]) returns the coefficients used.
+ *   - vmin / vmax: pass -INFINITY / +INFINITY for "no bound" (image_data.py:148-154).
+ */
+#ifndef SMRFB_H
+#define SMRFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smrfb_handle_s* smrfb_handle_t;
+
+enum {
+    SMRFB_OK = 0,
+    SMRFB_ERR_ARG = 1,       /* bad argument */
+    SMRFB_ERR_CUDA = 2,      /* CUDA runtime failure (message holds the cudaError string) */
+    SMRFB_ERR_SINGULAR = 3,  /* singular kriging system (co-located stations) */
+    SMRFB_ERR_LIMIT = 4,     /* size outside what the kernels support */
+    SMRFB_ERR_NODATA = 5     /* a timestep has no valid station at all (image_data.py:229-231) */
+};
+
+const char* smrfb_last_error(void);
+int smrfb_version(void);
+int smrfb_device_count(int* count);
+int smrfb_destroy(smrfb_handle_t h);
+/* Block until everything enqueued on the handle's own stream has finished. */
+int smrfb_synchronize(smrfb_handle_t h);
+/* Number of kernels this library has launched since load (all handles); bench.py's gpu_launches. */
+int64_t smrfb_launch_count(void);
+
+/* ------------------------------------------------------------------ IDW (idw.py) */
+int smrfb_idw_create(int nsta, const double* mx, const double* my, const double* mz /* nullable */,
+                     int ny, int nx, int grid_kind, const double* gx, const double* gy,
+                     const double* dem /* nullable: required for detrend */,
+                     double power, int device, smrfb_handle_t* out);
+/* detrend = 0: calculateIDW (idw.py:82-94); detrend = 1: detrendedIDW (idw.py:96-110). Host buffers. */
+int smrfb_idw_distribute(smrfb_handle_t h, const double* data, int T, int detrend, int slope_flag,
+                         double vmin, double vmax, const double* pv_in, double* pv_out, double* out);
+int smrfb_idw_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int detrend, int slope_flag,
+                             double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
+                             double* d_out, void* stream);
+
+/* ------------------------------------------------------------------ DK (dk.py, krige.c, lusolv.c) */
+int smrfb_dk_create(int nsta, const double* mx, const double* my, const double* mz,
+                    int ny, int nx, int grid_kind, const double* gx, const double* gy, const double* dem,
+                    int slope_flag, int device, smrfb_handle_t* out);
+/* DK.calculate for T rows; kriging weights are built on first sight of each NaN mask and cached. */
+int smrfb_dk_distribute(smrfb_handle_t h, const double* data, int T, double vmin, double vmax,
+                        const double* pv_in, double* pv_out, double* out);
+int smrfb_dk_distribute_dev(smrfb_handle_t h, const double* d_data, const double* h_data /* same rows, host copy
+                            used to read the NaN masks */, int T, double vmin, double vmax,
+                            const double* d_pv_in, double* d_pv_out, double* d_out, void* stream);
+/* Dense weights [ncell][nvalid] (columns = valid stations in station order) for one NaN mask,
+ * exactly what DK.calculateWeights leaves in wg (dk.py:127-130).  nan_mask[nsta]: 1 = missing. */
+int smrfb_dk_weights(smrfb_handle_t h, const uint8_t* nan_mask, double* weights_out);
+/* Statistics of the weight builder: masks built, cells that needed the exact per-cell fallback, max active set. */
+int smrfb_dk_stats(smrfb_handle_t h, int64_t* masks_built, int64_t* fallback_cells, int* max_active);
+
+/* krige_grid() of dk_header.h:23 on the GPU: same argument order and meaning, weights[ngrid][nsta]
+ * written in place. nthreads is accepted and ignored.  Returns a status instead of exit()ing. */
+int smrfb_krige_grid(int nsta, int ngrid, const double* ad, const double* dgrid, const double* elevations,
+                     int nthreads, double* weights);
+
+/* ------------------------------------------------------------------ GRID linear (grid.py) */
+/* The Delaunay triangulation and the per-cell simplex are built once on the host (scipy, as the
+ * reference does): simplices[nsimp][3], transform[nsimp][3][2] (scipy.spatial.Delaunay.transform),
+ * cell_simplex[ncell] (-1 = outside the hull -> NaN), point_mask[npts] (grid.py:80-94; NULL = all). */
+int smrfb_grid_create(int npts, const double* mx, const double* my, const double* mz /* nullable */,
+                      int ny, int nx, int grid_kind, const double* gx, const double* gy,
+                      const double* dem /* nullable */,
+                      int nsimp, const int32_t* simplices, const double* transform,
+                      const int32_t* cell_simplex, const uint8_t* point_mask, int device, smrfb_handle_t* out);
+/* detrend = 1: detrendedInterpolationMask (grid.py:179-212); 0: calculateInterpolation (grid.py:214-231). */
+int smrfb_grid_distribute(smrfb_handle_t h, const double* data, int T, int detrend, int slope_flag,
+                          double vmin, double vmax, const double* pv_in, double* pv_out, double* out);
+int smrfb_grid_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int detrend, int slope_flag,
+                              double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
+                              double* d_out, void* stream);
+
+/* ------------------------------------------------------------------ clamp (utils.py:137-161) */
+/* In place on a host array: x<=vmin -> vmin, x>=vmax -> vmax, NaN stays NaN. */
+int smrfb_set_min_max(double* data, int64_t n, double vmin, double vmax, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMRFB_H */

@@ -1,0 +1,164 @@
+// common.cuh -- shared host/device plumbing of libsmrfb (handles, errors, step records, PTX helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smrfb.h"
+
+namespace smrfb {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define SMRFB_CUDA(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            smrfb::set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return SMRFB_ERR_CUDA;                                                                \
+        }                                                                                         \
+    } while (0)
+
+#define SMRFB_CHECK(cond, code, ...)       \
+    do {                                   \
+        if (!(cond)) {                     \
+            smrfb::set_error(__VA_ARGS__); \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+#define SMRFB_PROPAGATE(call)          \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != SMRFB_OK) return rc__; \
+    } while (0)
+
+// ---------------------------------------------------------------- geometry (device pointers)
+struct Geom {
+    int ny = 0, nx = 0, kind = 0;
+    long long ncell = 0;
+    double* gx = nullptr;   // kind 0: [nx]; kind 1: [ncell]
+    double* gy = nullptr;   // kind 0: [ny]; kind 1: [ncell]
+    double* dem = nullptr;  // [ncell] or null
+};
+
+__device__ __forceinline__ void cell_xy(const Geom& g, long long c, double& X, double& Y) {
+    if (g.kind == 0) {
+        long long i = c / g.nx;
+        int j = (int)(c - i * g.nx);
+        X = __ldg(g.gx + j);
+        Y = __ldg(g.gy + i);
+    } else {
+        X = __ldg(g.gx + c);
+        Y = __ldg(g.gy + c);
+    }
+}
+
+// ---------------------------------------------------------------- per-timestep station record
+// One record per timestep, written by prep_steps_kernel, consumed by the distribute kernels:
+//   rec[t][0 .. S_pad)            residuals d_s - (mz_s*p0 + p1); 0 for missing stations and padding
+//   rec[t][S_pad + 0]             p0 (slope)            rec[t][S_pad + 1]   p1 (intercept)
+//   rec[t][S_pad + 2]             number of missing stations (as double)
+//   rec[t][S_pad + 3 + j]         index of the j-th missing station (as double), j < min(nmiss, maxm)
+// RS (record stride, doubles) is chosen = 4 or 12 (mod 16) so that DMMA A-fragment loads from a
+// staged record block are shared-memory bank-conflict free.
+// keep_nan: missing stations keep NaN in the residual slot (GRID: NaN propagates like griddata's).
+struct RecLayout {
+    int S = 0, S_pad = 0, RS = 0, maxm = 0, keep_nan = 0;
+    __host__ __device__ int meta() const { return S_pad; }
+};
+RecLayout make_layout(int S, int k_align, int maxm, bool mma_stride);
+
+enum HandleKind { HK_IDW = 0x1d0, HK_DK = 0xd4, HK_GRID = 0x621d };
+
+struct HandleBase {
+    int kind;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    Geom g;
+    int S = 0;
+    double *d_mx = nullptr, *d_my = nullptr, *d_mz = nullptr;
+    uint8_t* d_fitmask = nullptr;  // optional [S]
+    // scratch for prepared step records
+    double* d_rec = nullptr;
+    size_t rec_cap = 0;          // doubles
+    uint8_t* d_valid = nullptr;  // [T][S]
+    size_t valid_cap = 0;
+    double* d_data = nullptr;    // staged station rows (host API)
+    size_t data_cap = 0;
+    double* d_pv = nullptr;      // [T][2]
+    size_t pv_cap = 0;
+    int* d_flags = nullptr;      // [1] device-side status flags (bit0: a step had no valid station)
+    explicit HandleBase(int k) : kind(k) {}
+    virtual ~HandleBase();
+};
+
+int upload_geom(HandleBase* h, int nsta, const double* mx, const double* my, const double* mz, int ny, int nx,
+                int grid_kind, const double* gx, const double* gy, const double* dem);
+int ensure_cap(void** p, size_t* cap, size_t need_bytes);
+
+// Launch the station-prep kernel: regression, residuals, missing lists for T steps.
+//   fit_mode 0: residuals for every non-NaN station (IDW, GRID);   fit over (valid & fitmask)
+//   want_miss: fill the missing-station list
+int launch_prep(cudaStream_t st, const double* d_data, int T, int T_pad, int S, const RecLayout& L, const double* d_mz,
+                const uint8_t* d_fitmask, int detrend, int slope_flag, const double* d_pv_in, double* d_pv_out,
+                double* d_rec, uint8_t* d_valid, int* d_flags);
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// fp64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
+// lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c0/c1 = C[lane>>2][(lane&3)*2 + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double clamp_nan_keep(double v, double vmin, double vmax) {
+    // utils.py:137-161: x<=min -> min, then x>=max -> max; NaN fails both tests and stays NaN
+    if (v <= vmin) v = vmin;
+    if (v >= vmax) v = vmax;
+    return v;
+}
+
+}  // namespace smrfb

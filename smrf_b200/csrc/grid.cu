@@ -1,0 +1,270 @@
+// grid.cu -- GRID linear interpolation (smrf/spatial/grid.py:179-231 over scipy.interpolate.griddata).
+//
+// The Delaunay triangulation and the simplex of every DEM cell are built once on the host with
+// scipy (as the reference does, except that it redoes it on every call) and uploaded at create
+// time.  Per batch of T timesteps one kernel runs:
+//   per cell (once):  barycentric coordinates from the simplex transform
+//                       c0 = T00*(x-r0) + T01*(y-r1);  c1 = T10*(x-r0) + T11*(y-r1);  c2 = (1-c0)-c1
+//   per step:         out = ((0 + c0*v_a) + c1*v_b) + c2*v_c  [+ p0*Z + p1]  -> clamp -> streaming store
+// evaluated with separate multiplies and adds (no FMA contraction), the order that reproduces
+// griddata(method='linear') bit for bit.  Cells outside the hull are NaN.
+//
+// Residual values are read from the transposed block vt[point][T_pad] (written by a small
+// transpose kernel after station prep) so that one thread reads its three vertices' values for
+// four consecutive steps with 2 x 128-bit loads each; neighbouring cells share a simplex, so these
+// are L1 broadcast hits and the kernel is bound by the output stream to HBM.
+#include "common.cuh"
+
+namespace smrfb {
+
+constexpr int GRID_THREADS = 256;
+constexpr int GRID_TU = 4;   // steps per inner iteration
+
+struct GridHandle : HandleBase {
+    int nsimp = 0;
+    int32_t* d_simplices = nullptr;    // [nsimp][3]
+    double* d_transform = nullptr;     // [nsimp][3][2]
+    int32_t* d_cell_simplex = nullptr; // [ncell]
+    RecLayout L;
+    double* d_vt = nullptr;            // [S][T_pad] transposed residuals
+    size_t vt_cap = 0;
+    double* d_pvt = nullptr;           // [T_pad][2]
+    size_t pvt_cap = 0;
+    GridHandle() : HandleBase(HK_GRID) {}
+    ~GridHandle() override {
+        cudaSetDevice(device);
+        cudaFree(d_simplices);
+        cudaFree(d_transform);
+        cudaFree(d_cell_simplex);
+        cudaFree(d_vt);
+        cudaFree(d_pvt);
+    }
+};
+
+// rec[t][s] -> vt[s][t] (+ pv[t] = p0,p1), tiled through shared memory.
+__global__ void grid_transpose_kernel(const double* __restrict__ rec, RecLayout L, int T_pad, double* __restrict__ vt,
+                                      double* __restrict__ pvt) {
+    __shared__ double tile[32][33];
+    int s0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int t = t0 + r, s = s0 + threadIdx.x;
+        tile[r][threadIdx.x] = (t < T_pad && s < L.S) ? rec[(size_t)t * L.RS + s] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int s = s0 + r, t = t0 + threadIdx.x;
+        if (s < L.S && t < T_pad) vt[(size_t)s * T_pad + t] = tile[threadIdx.x][r];
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 0) {
+        int t = t0 + threadIdx.x;
+        if (t < T_pad) {
+            pvt[2 * t] = rec[(size_t)t * L.RS + L.meta()];
+            pvt[2 * t + 1] = rec[(size_t)t * L.RS + L.meta() + 1];
+        }
+    }
+}
+
+struct GridArgs {
+    Geom g;
+    const int32_t* simplices;
+    const double* transform;
+    const int32_t* cell_simplex;
+    const double* vt;
+    const double* pvt;
+    int T, T_pad, detrend;
+    double vmin, vmax;
+    double* out;
+};
+
+__global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs a) {
+    const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (c >= a.g.ncell) return;
+    const int sx = __ldg(a.cell_simplex + c);
+    double* op = a.out + c;
+    const size_t ncell = (size_t)a.g.ncell;
+    if (sx < 0) {
+        const double qnan = nan("");
+        for (int t = 0; t < a.T; t++) __stcs(op + (size_t)t * ncell, qnan);
+        return;
+    }
+    double X, Y;
+    cell_xy(a.g, c, X, Y);
+    const double* Tm = a.transform + (size_t)sx * 6;
+    const double dx = __dsub_rn(X, __ldg(Tm + 4)), dy = __dsub_rn(Y, __ldg(Tm + 5));
+    const double c0 = __dadd_rn(__dmul_rn(__ldg(Tm + 0), dx), __dmul_rn(__ldg(Tm + 1), dy));
+    const double c1 = __dadd_rn(__dmul_rn(__ldg(Tm + 2), dx), __dmul_rn(__ldg(Tm + 3), dy));
+    const double c2 = __dsub_rn(__dsub_rn(1.0, c0), c1);
+    const double* va = a.vt + (size_t)__ldg(a.simplices + 3 * sx + 0) * a.T_pad;
+    const double* vb = a.vt + (size_t)__ldg(a.simplices + 3 * sx + 1) * a.T_pad;
+    const double* vc = a.vt + (size_t)__ldg(a.simplices + 3 * sx + 2) * a.T_pad;
+    const double Z = (a.detrend && a.g.dem) ? __ldg(a.g.dem + c) : 0.0;
+
+    for (int t0 = 0; t0 < a.T; t0 += GRID_TU) {   // T_pad is a multiple of GRID_TU: vector loads stay in bounds
+        double xa[GRID_TU], xb[GRID_TU], xc[GRID_TU], pv[2 * GRID_TU];
+#pragma unroll
+        for (int u = 0; u < GRID_TU; u += 2) {
+            double2 ta = __ldg(reinterpret_cast<const double2*>(va + t0 + u));
+            double2 tb = __ldg(reinterpret_cast<const double2*>(vb + t0 + u));
+            double2 tc = __ldg(reinterpret_cast<const double2*>(vc + t0 + u));
+            xa[u] = ta.x; xa[u + 1] = ta.y;
+            xb[u] = tb.x; xb[u + 1] = tb.y;
+            xc[u] = tc.x; xc[u + 1] = tc.y;
+        }
+#pragma unroll
+        for (int u = 0; u < GRID_TU; u++) {
+            double2 p = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * (t0 + u)));
+            pv[2 * u] = p.x;
+            pv[2 * u + 1] = p.y;
+        }
+#pragma unroll
+        for (int u = 0; u < GRID_TU; u++) {
+            if (t0 + u < a.T) {
+                double v = __dadd_rn(0.0, __dmul_rn(c0, xa[u]));
+                v = __dadd_rn(v, __dmul_rn(c1, xb[u]));
+                v = __dadd_rn(v, __dmul_rn(c2, xc[u]));
+                if (a.detrend) v = __dadd_rn(__dadd_rn(v, __dmul_rn(pv[2 * u], Z)), pv[2 * u + 1]);  // grid.py:210
+                __stcs(op + (size_t)(t0 + u) * ncell, clamp_nan_keep(v, a.vmin, a.vmax));
+            }
+        }
+    }
+}
+
+static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int slope_flag, double vmin, double vmax,
+                    const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
+    SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    SMRFB_CHECK(!detrend || (h->g.dem && h->d_mz), SMRFB_ERR_ARG, "detrended GRID needs mz and GridZ");
+    const int T_pad = (T + 31) / 32 * 32;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_rec, &h->rec_cap, (size_t)T_pad * h->L.RS * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_vt, &h->vt_cap, (size_t)T_pad * h->S * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pvt, &h->pvt_cap, (size_t)T_pad * 2 * sizeof(double)));
+    SMRFB_PROPAGATE(launch_prep(st, d_data, T, T_pad, h->S, h->L, h->d_mz, h->d_fitmask, detrend, slope_flag, d_pv_in,
+                                d_pv_out, h->d_rec, nullptr, h->d_flags));
+    dim3 tb(32, 8), tg((h->S + 31) / 32, T_pad / 32);
+    grid_transpose_kernel<<<tg, tb, 0, st>>>(h->d_rec, h->L, T_pad, h->d_vt, h->d_pvt);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    GridArgs a;
+    a.g = h->g;
+    a.simplices = h->d_simplices;
+    a.transform = h->d_transform;
+    a.cell_simplex = h->d_cell_simplex;
+    a.vt = h->d_vt;
+    a.pvt = h->d_pvt;
+    a.T = T;
+    a.T_pad = T_pad;
+    a.detrend = detrend;
+    a.vmin = vmin;
+    a.vmax = vmax;
+    a.out = d_out;
+    long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
+    SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+    grid_distribute_kernel<<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+}  // namespace smrfb
+
+using namespace smrfb;
+
+extern "C" {
+
+int smrfb_grid_create(int npts, const double* mx, const double* my, const double* mz, int ny, int nx, int grid_kind,
+                      const double* gx, const double* gy, const double* dem, int nsimp, const int32_t* simplices,
+                      const double* transform, const int32_t* cell_simplex, const uint8_t* point_mask, int device,
+                      smrfb_handle_t* out) {
+    SMRFB_CHECK(out, SMRFB_ERR_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    SMRFB_CHECK(nsimp > 0 && simplices && transform && cell_simplex, SMRFB_ERR_ARG, "triangulation arrays are required");
+    for (int i = 0; i < 3 * nsimp; i++)
+        SMRFB_CHECK(simplices[i] >= 0 && simplices[i] < npts, SMRFB_ERR_ARG, "simplex vertex %d out of range", simplices[i]);
+    GridHandle* h = new GridHandle();
+    h->device = device;
+    int rc = upload_geom(h, npts, mx, my, mz, ny, nx, grid_kind, gx, gy, dem);
+    auto up = [&](void** dst, const void* src, size_t bytes) {
+        if (rc != SMRFB_OK) return;
+        if (cudaMalloc(dst, bytes) != cudaSuccess || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("GRID: upload of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+            rc = SMRFB_ERR_CUDA;
+        }
+    };
+    if (rc == SMRFB_OK) {
+        const size_t ncell = (size_t)ny * nx;
+        for (size_t c = 0; c < ncell && rc == SMRFB_OK; c++)
+            if (cell_simplex[c] < -1 || cell_simplex[c] >= nsimp) {
+                set_error("cell_simplex[%zu] = %d out of range", c, cell_simplex[c]);
+                rc = SMRFB_ERR_ARG;
+            }
+        h->nsimp = nsimp;
+        up((void**)&h->d_simplices, simplices, (size_t)nsimp * 3 * sizeof(int32_t));
+        up((void**)&h->d_transform, transform, (size_t)nsimp * 6 * sizeof(double));
+        up((void**)&h->d_cell_simplex, cell_simplex, ncell * sizeof(int32_t));
+        if (point_mask) up((void**)&h->d_fitmask, point_mask, (size_t)npts);
+        h->L = make_layout(npts, 2, 0, false);
+        h->L.keep_nan = 1;
+    }
+    if (rc != SMRFB_OK) {
+        delete h;
+        return rc;
+    }
+    *out = reinterpret_cast<smrfb_handle_t>(h);
+    return SMRFB_OK;
+}
+
+int smrfb_grid_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, int detrend, int slope_flag, double vmin,
+                              double vmax, const double* d_pv_in, double* d_pv_out, double* d_out, void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CHECK(d_data && d_out, SMRFB_ERR_ARG, "NULL data/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return grid_run(h, d_data, T, detrend, slope_flag, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+}
+
+int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detrend, int slope_flag, double vmin,
+                          double vmax, const double* pv_in, double* pv_out, double* out) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CHECK(data && out && T > 0, SMRFB_ERR_ARG, "NULL data/out or T <= 0");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    const size_t ncell = (size_t)h->g.ncell, S = (size_t)h->S;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_data, &h->data_cap, (size_t)T * S * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pv, &h->pv_cap, (size_t)T * 4 * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpyAsync(h->d_data, data, (size_t)T * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double* d_pvin = nullptr;
+    if (pv_in) {
+        d_pvin = h->d_pv + (size_t)2 * T;
+        SMRFB_CUDA(cudaMemcpyAsync(d_pvin, pv_in, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    const size_t budget = (size_t)1 << 30;
+    int tb = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / (ncell * sizeof(double))));
+    double* d_out = nullptr;
+    SMRFB_CUDA(cudaMalloc((void**)&d_out, (size_t)tb * ncell * sizeof(double)));
+    int rc = SMRFB_OK;
+    for (int t0 = 0; t0 < T && rc == SMRFB_OK; t0 += tb) {
+        const int tn = std::min(tb, T - t0);
+        rc = grid_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, vmin, vmax,
+                      d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, d_out, h->stream);
+        if (rc != SMRFB_OK) break;
+        if (cudaMemcpyAsync(out + (size_t)t0 * ncell, d_out, (size_t)tn * ncell * sizeof(double), cudaMemcpyDeviceToHost,
+                            h->stream) != cudaSuccess) {
+            set_error("GRID D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SMRFB_ERR_CUDA;
+        }
+    }
+    if (rc == SMRFB_OK && pv_out &&
+        cudaMemcpyAsync(pv_out, h->d_pv, (size_t)T * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+        rc = SMRFB_ERR_CUDA;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (rc == SMRFB_OK && e != cudaSuccess) {
+        set_error("GRID distribute failed on the device: %s", cudaGetErrorString(e));
+        rc = SMRFB_ERR_CUDA;
+    }
+    return rc;
+}
+
+}  // extern "C"

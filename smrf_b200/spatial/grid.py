@@ -1,0 +1,108 @@
+"""Drop-in for smrf.spatial.grid.GRID (linear method) running on libsmrfb (CUDA, sm_100a).
+
+Same constructor and methods as the reference class (smrf/spatial/grid.py:23-231) as used by
+smrf/distribute/image_data.py:189-195 and :245-255.  The reference re-triangulates and re-walks
+every cell on every call (scipy.interpolate.griddata); here the Delaunay triangulation and the
+simplex of every cell are built ONCE on the host with scipy -- the same qhull call the reference
+makes -- and the per-timestep work (barycentric interpolation, retrend, clamp) is one CUDA kernel.
+
+Covered: grid_method='linear', grid_local=False (detrendedInterpolationMask, calculateInterpolation).
+'cubic' / 'nearest' / grid_local raise NotImplementedError (SURVEY.md section 8f row N-b).
+"""
+import numpy as np
+
+from .. import _lib
+
+
+class GRID:
+    def __init__(self, config, mx, my, GridX, GridY, mz=None, GridZ=None, mask=None, metadata=None, device=None):
+        from scipy.spatial import Delaunay
+
+        self.config = config
+        self.mx = _lib.as_f64(mx)
+        self.my = _lib.as_f64(my)
+        self.mz = None if mz is None else _lib.as_f64(mz)
+        self.npoints = len(self.mx)
+        self.GridX, self.GridY, self.GridZ = GridX, GridY, GridZ
+        self.shape = tuple(np.shape(GridX))
+        self.metadata = metadata
+        self.pv = None
+        if config.get("grid_local", False):
+            raise NotImplementedError("grid_local=True is not on the B200 path yet (SURVEY.md 8f N-b)")
+
+        # point mask, grid.py:80-94 (first minimum wins, like np.argmin)
+        if config.get("grid_mask", False):
+            assert mask.shape == self.shape
+            m = np.asarray(mask).astype(bool)
+            x = np.asarray(GridX)[0, :]
+            y = np.asarray(GridY)[:, 0]
+            xi = np.argmin(np.abs(x[None, :] - self.mx[:, None]), axis=1)
+            yi = np.argmin(np.abs(y[None, :] - self.my[:, None]), axis=1)
+            self.mask = m[yi, xi]
+        else:
+            self.mask = np.ones(self.npoints, dtype=bool)
+
+        # triangulation + per-cell simplex, once (scipy.spatial.Delaunay default options, as griddata)
+        self.tri = Delaunay(np.column_stack([self.mx, self.my]))
+        kind, gx, gy = _lib.mesh_or_points(GridX, GridY)
+        xi = np.column_stack([np.asarray(GridX, dtype=np.float64).ravel(), np.asarray(GridY, dtype=np.float64).ravel()])
+        self.cell_simplex = np.ascontiguousarray(self.tri.find_simplex(xi).astype(np.int32))
+        simplices = np.ascontiguousarray(self.tri.simplices.astype(np.int32))
+        transform = np.ascontiguousarray(self.tri.transform, dtype=np.float64)
+        pm = np.ascontiguousarray(self.mask.astype(np.uint8))
+        dem = None if GridZ is None else _lib.as_f64(GridZ).reshape(-1)
+        self.device = _lib.default_device() if device is None else int(device)
+        self._h = _lib.handle_t()
+        _lib.check(_lib.lib().smrfb_grid_create(
+            self.npoints, _lib.dptr(self.mx), _lib.dptr(self.my), _lib.dptr(self.mz),
+            self.shape[0], self.shape[1], kind, _lib.dptr(gx), _lib.dptr(gy), _lib.dptr(dem),
+            simplices.shape[0], simplices.ctypes.data_as(_lib.c_i32_p), _lib.dptr(transform.reshape(-1)),
+            self.cell_simplex.ctypes.data_as(_lib.c_i32_p), pm.ctypes.data_as(_lib.c_u8_p), self.device, self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().smrfb_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @staticmethod
+    def _check_method(grid_method):
+        if grid_method != "linear":
+            raise NotImplementedError("grid_method=%r: only 'linear' is on the B200 path (SURVEY.md 8f N-b)" % grid_method)
+
+    def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None):
+        """[T, npoints] -> float64 [T, ny, nx] in one launch; NaN outside the convex hull."""
+        data = _lib.as_f64(data)
+        if data.ndim == 1:
+            data = data[None, :]
+        T, S = data.shape
+        if S != self.npoints:
+            raise ValueError("data has %d points, GRID was built for %d" % (S, self.npoints))
+        if out is None:
+            out = np.empty((T,) + self.shape, dtype=np.float64)
+        pv_in = None if pv is None else _lib.as_f64(pv).reshape(T, 2)
+        pv_out = np.empty((T, 2), dtype=np.float64)
+        lo = -np.inf if vmin is None else float(vmin)
+        hi = np.inf if vmax is None else float(vmax)
+        _lib.check(_lib.lib().smrfb_grid_distribute(
+            self._h, _lib.dptr(data), T, int(bool(detrend)), int(flag), lo, hi,
+            _lib.dptr(pv_in), _lib.dptr(pv_out), _lib.dptr(out)))
+        self.pv_block = pv_out
+        return out
+
+    def detrendedInterpolation(self, data, flag=0, grid_method="linear"):
+        """grid.py:96-113 -> detrendedInterpolationMask (grid.py:179-212). ``data`` may be a pandas Series."""
+        self._check_method(grid_method)
+        v = self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=True, flag=flag)[0]
+        self.pv = self.pv_block[0].copy()
+        return v
+
+    detrendedInterpolationMask = detrendedInterpolation
+
+    def calculateInterpolation(self, data, grid_method="linear"):
+        """grid.py:214-231."""
+        self._check_method(grid_method)
+        return self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=False)[0]
