@@ -30,7 +30,12 @@ def test_idw_rme_golden(sp, golden):
         for t in range(len(data)):
             assert parity(out[t], g["out_" + name][t], step_scale(data[t])) <= TOL
         if name == "air_temp":
-            np.testing.assert_allclose(idw.pv_block, g["pv_air_temp"], rtol=1e-9, atol=1e-9)
+            # coefficients agree wherever the fit is not degenerate (equal station values give a slope of
+            # +-1e-19 in np.polyfit and exactly 0 here; the sign constraint may then zero one and not the
+            # other -- the distributed field is the same either way, which the loop above checked)
+            ref_pv = g["pv_air_temp"]
+            generic = np.abs(data[:, 0] - data[:, 1]) > 1e-9
+            np.testing.assert_allclose(idw.pv_block[generic], ref_pv[generic], rtol=1e-9, atol=1e-9)
     # the per-step reference API gives the same thing, and leaves the caller's row untouched
     row = g["air_temp"][3].copy()
     v = idw.detrendedIDW(row, -1)

@@ -24,7 +24,9 @@ def main():
                                   _lib.dptr(dem.reshape(-1)), 2.0, 0, h))
     d_data = torch.from_numpy(data).cuda()
     d_out = torch.empty((T, ny * nx), dtype=torch.float64, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
     for det in (1, 0):
         for _ in range(2):
             _lib.check(L.smrfb_idw_distribute_dev(h, d_data.data_ptr(), T, det, -1, -73.0, 47.0, None, None, d_out.data_ptr(), st))
