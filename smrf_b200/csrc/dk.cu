@@ -1,12 +1,1085 @@
-// dk.cu -- placeholder while the kriging builder is written (replaced in the next commit).
+// dk.cu -- detrended kriging (smrf/spatial/dk/dk.py + krige.c + lusolv.c) on sm_100a.
+//
+// Per NaN mask (set V of n valid stations) the reference solves, per cell, the ordinary-kriging
+// system  [[ad,1],[1',0]] [w;mu] = [d;1]  over and over, each time dropping the highest-elevation
+// station that got a negative weight (krige.c:134-198): up to n-1 full LU solves per cell, O(n^4).
+//
+// Here (validated against the reference on CPU):
+//   1. host: B0 = inverse of the full (n+1)x(n+1) system, stations ordered by (elevation desc,
+//      index asc) so that "highest-elevation negative weight" == "first negative weight".
+//   2. dk_build_kernel -- one persistent CTA per SM, B (packed symmetric, <=162 KB) lives in shared
+//      memory.  A tile of 32 neighbouring cells (one warp each) walks the elimination tree depth
+//      first: cells that agree on the station to drop share ONE rank-1 downdate of B
+//      (B -= b b'/beta, w -= (w_k/beta) b); where they disagree the tile forks, and on the way
+//      back every downdate is undone with the saved column (B += b b'/beta), so B returns to B0
+//      without ever being re-read.  Output: the final active set of every cell (bit mask).
+//   3. dk_final_kernel -- one thread per cell: a fresh solve on the final active set in station
+//      order with the reference's exact arithmetic (Crout LU, implicit scaling, >= pivot rule,
+//      no FMA), which is precisely what the reference's last loop iteration computes; if a negative
+//      weight shows up the reference loop simply continues here.  Weights go to an ELL table
+//      [K][ncell] (station index uint8 + fp64 weight), K = largest final active set.
+//   4. dk_distribute_kernel -- per timestep: sum_k w_k * residual[station_k] + p0*Z + p1, clamp,
+//      streaming stores; HBM-write bound.
+#include <algorithm>
+#include <list>
+#include <map>
+
 #include "common.cuh"
-using namespace smrfb;
-extern "C" {
-int smrfb_dk_create(int, const double*, const double*, const double*, int, int, int, const double*, const double*,
-                    const double*, int, int, smrfb_handle_t* out) { if (out) *out = nullptr; set_error("DK: not built yet"); return SMRFB_ERR_LIMIT; }
-int smrfb_dk_distribute(smrfb_handle_t, const double*, int, double, double, const double*, double*, double*) { set_error("DK: not built yet"); return SMRFB_ERR_LIMIT; }
-int smrfb_dk_distribute_dev(smrfb_handle_t, const double*, const double*, int, double, double, const double*, double*, double*, void*) { set_error("DK: not built yet"); return SMRFB_ERR_LIMIT; }
-int smrfb_dk_weights(smrfb_handle_t, const uint8_t*, double*) { set_error("DK: not built yet"); return SMRFB_ERR_LIMIT; }
-int smrfb_dk_stats(smrfb_handle_t, int64_t*, int64_t*, int*) { set_error("DK: not built yet"); return SMRFB_ERR_LIMIT; }
-int smrfb_krige_grid(int, int, const double*, const double*, const double*, int, double*) { set_error("DK: not built yet"); return SMRFB_ERR_LIMIT; }
+
+namespace smrfb {
+
+constexpr int DK_TILE = 32;
+constexpr int DK_THREADS = 1024;
+constexpr int DK_MAXN = 200;          // packed B for n+1 = 201 is 162 KB of shared memory
+constexpr int DK_WORDS = 8;           // 256 active-set bits per cell
+constexpr int DK_NSMAX = 31;          // largest final active set solved in thread-local memory
+constexpr int DK_KREG = 16;           // ELL entries kept in registers by the distribute kernel
+constexpr int DK_QMAX = (DK_MAXN + 1 + 31) / 32;  // 7 column slots per lane
+
+struct DkPending {
+    int k;
+    unsigned mask;
+    int depth;
+    int pad;
+};
+
+struct DkBuildArgs {
+    int n, NN, NNP, nsel;
+    long long ncell;
+    Geom g;
+    const double* sx;      // [n] station x in RANK order (coordinate mode)
+    const double* sy;
+    const double* dgrid;   // optional [ncell][n], COMPRESSED station order (krige_grid mode)
+    const int* perm;       // [n] rank -> compressed station index
+    const double* B0p;     // packed upper triangle of the inverse, rank order, NN*(NN+1)/2
+    double* undo;          // [gridDim.x][n][NNP]
+    uint32_t* final_act;   // [ncell][DK_WORDS], bits over RANK index
+    unsigned long long* tile_counter;
+    int* maxcount;
+};
+
+__device__ __forceinline__ double dist_rn(double X, double Y, double sx, double sy) {
+    // dk.py:122  np.sqrt((Xa - mx[i])**2 + (Ya - my[i])**2), separate roundings
+    double dx = __dsub_rn(X, sx), dy = __dsub_rn(Y, sy);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
+
+__global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, NN = a.NN, NNP = a.NNP;
+    const int npk = NN * (NN + 1) / 2;
+    double* Bp = reinterpret_cast<double*>(smem_raw);           // [npk]
+    double* w = Bp + npk;                                       // [32][NN]
+    double* bcol = w + DK_TILE * NN;                            // [NNP]
+    double* betastack = bcol + NNP;                             // [NN]
+    int* rowoff = reinterpret_cast<int*>(betastack + NN);       // [NNP]
+    int* kstack = rowoff + NNP;                                 // [NN]
+    int* kc = kstack + NN;                                      // [32]
+    int* ctrl = kc + DK_TILE;                                   // [8]
+    DkPending* pend = reinterpret_cast<DkPending*>(ctrl + 8);   // [64]
+    unsigned char* act = reinterpret_cast<unsigned char*>(pend + 64);  // [NNP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* undo_g = a.undo + (size_t)blockIdx.x * n * NNP;
+    const long long ntiles = (a.ncell + DK_TILE - 1) / DK_TILE;
+
+    for (int i = tid; i < NNP; i += DK_THREADS) rowoff[i] = i * NN - (i * (i + 1)) / 2;   // idx(i,j>=i) = rowoff[i] + j
+    for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];
+    int since_refresh = 0;
+    __syncthreads();
+
+    // rank-1 update of the packed upper triangle with the column in bcol (zeros = skip):
+    //   B[i][j] += sgn * (bcol[i]/beta) * bcol[j]   for j >= i
+    auto rank1 = [&](double beta, double sgn) {
+        double bj[DK_QMAX];
+#pragma unroll
+        for (int q = 0; q < DK_QMAX; q++) {
+            int j = lane + 32 * q;
+            bj[q] = (j < NN) ? bcol[j] : 0.0;
+        }
+        for (int i = warp; i < NN; i += 32) {
+            const double bi = bcol[i];
+            if (bi == 0.0) continue;
+            const double bs = sgn * (bi / beta);
+            double* row = Bp + rowoff[i];
+            const int q0 = i >> 5;
+#pragma unroll
+            for (int q = 0; q < DK_QMAX; q++) {
+                int j = lane + 32 * q;
+                if (q >= q0 && j >= i && j < NN) row[j] = fma(bs, bj[q], row[j]);
+            }
+        }
+    };
+
+    for (;;) {
+        if (tid == 0) ctrl[0] = (int)atomicAdd(a.tile_counter, 1ULL);
+        __syncthreads();
+        const long long tile = (unsigned)ctrl[0];
+        if (tile >= ntiles) break;
+        if (++since_refresh == 64) {   // bound the do/undo rounding drift: re-read the pristine inverse
+            since_refresh = 0;
+            for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];
+        }
+        const long long cell = tile * DK_TILE + warp;
+        const bool live = cell < a.ncell;
+        double* wc = w + warp * NN;
+        {   // right-hand side [dist to every station ; 1] in rank order
+            double X = 0.0, Y = 0.0;
+            if (live && !a.dgrid) cell_xy(a.g, cell, X, Y);
+            for (int j = lane; j < NN; j += 32) {
+                double v = 0.0;
+                if (live) {
+                    if (j == n) v = 1.0;
+                    else if (a.dgrid) v = a.dgrid[(size_t)cell * n + a.perm[j]];
+                    else v = dist_rn(X, Y, a.sx[j], a.sy[j]);
+                }
+                wc[j] = v;
+            }
+        }
+        for (int i = tid; i < NNP; i += DK_THREADS) act[i] = (i < NN) ? 1 : 0;
+        __syncthreads();
+        if (live) {   // w = B0 * rhs (B symmetric, packed)
+            double acc[DK_QMAX];
+#pragma unroll
+            for (int q = 0; q < DK_QMAX; q++) acc[q] = 0.0;
+            for (int i = 0; i < NN; i++) {
+                const double r = wc[i];
+                const int ro = rowoff[i];
+#pragma unroll
+                for (int q = 0; q < DK_QMAX; q++) {
+                    int j = lane + 32 * q;
+                    if (j < NN) {
+                        double b = (j >= i) ? Bp[ro + j] : Bp[rowoff[j] + i];
+                        acc[q] = fma(b, r, acc[q]);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < DK_QMAX; q++) {
+                int j = lane + 32 * q;
+                if (j < NN) wc[j] = acc[q];
+            }
+        }
+        const long long rem = a.ncell - tile * DK_TILE;
+        unsigned cur_mask = rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
+        int depth = 0, npend = 0;
+        __syncthreads();
+
+        for (;;) {   // ---- depth-first walk of the tile's elimination tree
+            // SELECT: first (= highest elevation) active station with a negative weight
+            if ((cur_mask >> warp) & 1u) {
+                int k = -1;
+                for (int q = 0; q < DK_QMAX; q++) {
+                    int j = lane + 32 * q;
+                    bool c = (j < a.nsel) && act[j] && (wc[j] < 0.0);
+                    unsigned b = __ballot_sync(0xffffffffu, c);
+                    if (b) {
+                        k = 32 * q + __ffs(b) - 1;
+                        break;
+                    }
+                }
+                if (k < 0) {   // this cell is done: publish its active set
+                    unsigned myword = 0;
+                    int cnt = 0;
+                    for (int q = 0; q < DK_WORDS; q++) {
+                        int j = lane + 32 * q;
+                        unsigned b = __ballot_sync(0xffffffffu, (j < n) && act[j]);
+                        cnt += __popc(b);
+                        if (lane == q) myword = b;
+                    }
+                    if (lane < DK_WORDS) a.final_act[(size_t)cell * DK_WORDS + lane] = myword;
+                    if (lane == 0) atomicMax(a.maxcount, cnt);
+                }
+                if (lane == 0) kc[warp] = k;
+            } else if (lane == 0) {
+                kc[warp] = -2;
+            }
+            __syncthreads();
+            if (warp == 0) {   // partition the group by chosen station
+                const int k = kc[lane];
+                const unsigned livem = __ballot_sync(0xffffffffu, k >= 0);
+                const unsigned grp = __match_any_sync(0xffffffffu, k);
+                const bool leader = (k >= 0) && (lane == __ffs(grp) - 1);
+                const unsigned lead = __ballot_sync(0xffffffffu, leader);
+                const int p = __popc(lead);
+                if (p == 1) {
+                    if (leader) {
+                        ctrl[1] = 1;   // APPLY directly
+                        ctrl[2] = k;
+                        ctrl[3] = (int)livem;
+                    }
+                } else {
+                    if (leader) {
+                        int slot = npend + __popc(lead & ((1u << lane) - 1u));
+                        pend[slot].k = k;
+                        pend[slot].mask = grp;
+                        pend[slot].depth = depth;
+                    }
+                    if (lane == 0) {
+                        ctrl[1] = 0;   // POP (or finish)
+                        ctrl[4] = p;
+                    }
+                }
+            }
+            __syncthreads();
+            int k;
+            unsigned mask;
+            if (ctrl[1] == 1) {
+                k = ctrl[2];
+                mask = (unsigned)ctrl[3];
+            } else {
+                npend += ctrl[4];
+                const int target = npend > 0 ? pend[npend - 1].depth : 0;
+                while (depth > target) {   // undo back to the fork point
+                    depth--;
+                    const int ku = kstack[depth];
+                    const double beta = betastack[depth];
+                    for (int i = tid; i < NNP; i += DK_THREADS) bcol[i] = undo_g[(size_t)depth * NNP + i];
+                    __syncthreads();
+                    rank1(beta, 1.0);
+                    if (tid == 0) act[ku] = 1;
+                    __syncthreads();
+                }
+                if (npend == 0) break;   // tile finished, B is back at B0
+                npend--;
+                k = pend[npend].k;
+                mask = pend[npend].mask;
+                __syncthreads();         // everyone has read pend[npend] before warp 0 may overwrite it
+            }
+            // APPLY: drop station k for the cells in mask
+            const double beta = Bp[rowoff[k] + k];
+            for (int i = tid; i < NNP; i += DK_THREADS) {
+                double v = 0.0;
+                if (i < NN && i != k && act[i]) v = (i < k) ? Bp[rowoff[i] + k] : Bp[rowoff[k] + i];
+                bcol[i] = v;
+                undo_g[(size_t)depth * NNP + i] = v;
+            }
+            if (tid == 0) {
+                kstack[depth] = k;
+                betastack[depth] = beta;
+            }
+            __syncthreads();
+            if ((mask >> warp) & 1u) {
+                const double f = wc[k] / beta;
+                for (int j = lane; j < NN; j += 32) wc[j] = fma(-f, bcol[j], wc[j]);
+                __syncwarp();
+                if (lane == 0) wc[k] = 0.0;
+            }
+            rank1(beta, -1.0);
+            if (tid == 0) {
+                act[k] = 0;
+                ctrl[4] = 0;
+            }
+            depth++;
+            cur_mask = mask;
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact reference solve on the final active set (krige.c:140-197 + lusolv.c), one thread per cell.
+// ------------------------------------------------------------------------------------------
+struct DkFinalArgs {
+    int n, K;
+    long long ncell;
+    Geom g;
+    const double* cx;        // [n] station x, COMPRESSED (station) order
+    const double* cy;
+    const double* elev;      // [n]
+    const double* ad;        // [n][n]
+    const double* dgrid;     // optional [ncell][n]
+    const int* perm;         // rank -> compressed
+    const int* orig;         // compressed -> original station index (column of the data rows)
+    const uint32_t* final_act;
+    uint8_t* widx;           // [K][ncell]
+    double* wval;            // [K][ncell]
+    int* status;             // bit0 singular, bit1 active set larger than DK_NSMAX
+    unsigned long long* fallback_cells;
+    int* maxcount_final;
+};
+
+// Crout LU with implicit scaling on a[(ns1) x (ns1+1)] (row stride lda), solving in place; no FMA.
+__device__ int crout_solve_exact(double* a, int nn, int lda, int* indx, double* vv) {
+    int imax = 0;
+    for (int i = 0; i < nn; i++) {
+        double big = 0.0;
+        for (int j = 0; j < nn; j++) {
+            double t = fabs(a[i * lda + j]);
+            if (t > big) big = t;
+        }
+        if (big == 0.0) return 1;
+        vv[i] = __ddiv_rn(1.0, big);
+    }
+    for (int j = 0; j < nn; j++) {
+        for (int i = 0; i < j; i++) {
+            double sum = a[i * lda + j];
+            for (int k = 0; k < i; k++) sum = __dsub_rn(sum, __dmul_rn(a[i * lda + k], a[k * lda + j]));
+            a[i * lda + j] = sum;
+        }
+        double big = 0.0;
+        for (int i = j; i < nn; i++) {
+            double sum = a[i * lda + j];
+            for (int k = 0; k < j; k++) sum = __dsub_rn(sum, __dmul_rn(a[i * lda + k], a[k * lda + j]));
+            a[i * lda + j] = sum;
+            double dum = __dmul_rn(vv[i], fabs(sum));
+            if (dum >= big) {
+                big = dum;
+                imax = i;
+            }
+        }
+        if (j != imax) {
+            for (int k = 0; k < nn; k++) {
+                double t = a[imax * lda + k];
+                a[imax * lda + k] = a[j * lda + k];
+                a[j * lda + k] = t;
+            }
+            vv[imax] = vv[j];
+        }
+        indx[j] = imax;
+        if (a[j * lda + j] == 0.0) return 1;
+        if (j != nn - 1) {
+            double inv = __ddiv_rn(1.0, a[j * lda + j]);
+            for (int i = j + 1; i < nn; i++) a[i * lda + j] = __dmul_rn(a[i * lda + j], inv);
+        }
+    }
+    int ii = -1;
+    for (int i = 0; i < nn; i++) {
+        int ip = indx[i];
+        double sum = a[ip * lda + nn];
+        a[ip * lda + nn] = a[i * lda + nn];
+        if (ii >= 0) {
+            for (int j = ii; j < i; j++) sum = __dsub_rn(sum, __dmul_rn(a[i * lda + j], a[j * lda + nn]));
+        } else if (sum > 0.0) {
+            ii = i;
+        }
+        a[i * lda + nn] = sum;
+    }
+    for (int i = nn - 1; i >= 0; i--) {
+        double sum = a[i * lda + nn];
+        for (int j = i + 1; j < nn; j++) sum = __dsub_rn(sum, __dmul_rn(a[i * lda + j], a[j * lda + nn]));
+        a[i * lda + nn] = __ddiv_rn(sum, a[i * lda + i]);
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.ncell) return;
+    constexpr int LDA = DK_NSMAX + 2;
+    double A[(DK_NSMAX + 1) * LDA];
+    double vv[DK_NSMAX + 1];
+    int indx[DK_NSMAX + 1];
+    int ids[DK_NSMAX + 1];
+    int ns = 0;
+    bool over = false;
+    for (int q = 0; q < DK_WORDS; q++) {
+        unsigned b = a.final_act[(size_t)cell * DK_WORDS + q];
+        while (b) {
+            int bit = __ffs(b) - 1;
+            b &= b - 1;
+            if (ns < DK_NSMAX) ids[ns] = a.perm[32 * q + bit];
+            else over = true;
+            ns++;
+        }
+    }
+    if (over) {
+        atomicOr(a.status, 2);
+        return;
+    }
+    for (int i = 1; i < ns; i++) {   // station (compressed index) order, as the reference loops m = 0..nsta-1
+        int v = ids[i], j = i - 1;
+        while (j >= 0 && ids[j] > v) {
+            ids[j + 1] = ids[j];
+            j--;
+        }
+        ids[j + 1] = v;
+    }
+    double X = 0.0, Y = 0.0;
+    if (!a.dgrid) cell_xy(a.g, cell, X, Y);
+    bool fell_back = false;
+    for (;;) {
+        for (int m = 0; m < ns; m++) {
+            const int sm = ids[m];
+            for (int q = 0; q < ns; q++) A[m * LDA + q] = a.ad[(size_t)sm * a.n + ids[q]];
+            A[m * LDA + ns] = 1.0;
+            A[ns * LDA + m] = 1.0;
+            A[m * LDA + ns + 1] = a.dgrid ? a.dgrid[(size_t)cell * a.n + sm] : dist_rn(X, Y, a.cx[sm], a.cy[sm]);
+        }
+        A[ns * LDA + ns] = 0.0;
+        A[ns * LDA + ns + 1] = 1.0;
+        if (crout_solve_exact(A, ns + 1, LDA, indx, vv)) {
+            atomicOr(a.status, 1);
+            return;
+        }
+        double esave = 0.0;   // krige.c:169-185
+        int msave = -1;
+        for (int m = 0; m < ns; m++) {
+            if (A[m * LDA + ns + 1] < 0.0 && a.elev[ids[m]] > esave) {
+                msave = m;
+                esave = a.elev[ids[m]];
+            }
+        }
+        if (msave < 0) break;
+        fell_back = true;      // the downdated path stopped one step early: continue the reference loop exactly
+        for (int m = msave; m + 1 < ns; m++) ids[m] = ids[m + 1];
+        ns--;
+    }
+    if (fell_back) atomicAdd(a.fallback_cells, 1ULL);
+    atomicMax(a.maxcount_final, ns);
+    for (int j = 0; j < a.K; j++) {
+        const bool on = j < ns;
+        a.widx[(size_t)j * a.ncell + cell] = on ? (uint8_t)a.orig[ids[j]] : 0;
+        a.wval[(size_t)j * a.ncell + cell] = on ? A[j * LDA + ns + 1] : 0.0;
+    }
+}
+
+// dense expansion for smrfb_dk_weights / smrfb_krige_grid: out[cell][col], col = compressed index
+__global__ void dk_expand_kernel(int K, long long ncell, int n, const uint8_t* widx, const double* wval,
+                                 const int* orig2comp, double* out) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    for (int j = 0; j < K; j++) {
+        double v = wval[(size_t)j * ncell + cell];
+        if (v != 0.0) out[(size_t)cell * n + orig2comp[widx[(size_t)j * ncell + cell]]] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Steady state (dk.py:86-96): out = sum_k w_k * r[station_k] + p0*Z + p1
+// ------------------------------------------------------------------------------------------
+// rec[steps[tl]][s] -> vt[s][tl], pvt[tl] = (p0, p1) for the steps of one mask group.
+__global__ void dk_gather_kernel(const double* __restrict__ rec, RecLayout L, const int* __restrict__ steps, int Tm,
+                                 int Tm_pad, double* __restrict__ vt, double* __restrict__ pvt) {
+    __shared__ double tile[32][33];
+    const int s0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int tl = t0 + r, s = s0 + threadIdx.x;
+        tile[r][threadIdx.x] = (tl < Tm && s < L.S) ? rec[(size_t)steps[tl] * L.RS + s] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int s = s0 + r, tl = t0 + threadIdx.x;
+        if (s < L.S && tl < Tm_pad) vt[(size_t)s * Tm_pad + tl] = tile[threadIdx.x][r];
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 0) {
+        int tl = t0 + threadIdx.x;
+        if (tl < Tm_pad) {
+            pvt[2 * tl] = tl < Tm ? rec[(size_t)steps[tl] * L.RS + L.meta()] : 0.0;
+            pvt[2 * tl + 1] = tl < Tm ? rec[(size_t)steps[tl] * L.RS + L.meta() + 1] : 0.0;
+        }
+    }
+}
+
+struct DkDistArgs {
+    long long ncell;
+    const double* dem;
+    int K;
+    const uint8_t* widx;
+    const double* wval;
+    const double* vt;    // [S][Tm_pad]
+    const double* pvt;   // [Tm_pad][2]
+    const int* steps;    // [Tm] output step index
+    int Tm, Tm_pad;
+    double vmin, vmax;
+    double* out;         // [T][ncell]
+};
+
+template <int KR>
+__global__ void __launch_bounds__(256) dk_distribute_kernel(DkDistArgs a) {
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.ncell) return;
+    double wv[KR];
+    const double* vp[KR];
+#pragma unroll
+    for (int j = 0; j < KR; j++) {
+        const bool on = j < a.K;
+        wv[j] = on ? __ldg(a.wval + (size_t)j * a.ncell + c) : 0.0;
+        vp[j] = a.vt + (size_t)(on ? __ldg(a.widx + (size_t)j * a.ncell + c) : 0) * a.Tm_pad;
+    }
+    const double Z = __ldg(a.dem + c);
+    for (int t0 = 0; t0 < a.Tm; t0 += 2) {
+        double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < KR; j++) {
+            if (j < a.K) {
+                double2 x = __ldg(reinterpret_cast<const double2*>(vp[j] + t0));
+                r0 = fma(wv[j], x.x, r0);
+                r1 = fma(wv[j], x.y, r1);
+            }
+        }
+        const double2 pa = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0));
+        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
+        const double4 p = make_double4(pa.x, pa.y, pb.x, pb.y);
+        double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(p.x, Z)), p.y);   // dk.py:168, left to right
+        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncell + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+        if (t0 + 1 < a.Tm) {
+            double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(p.z, Z)), p.w);
+            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncell + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+        }
+    }
+}
+
+// generic K (> DK_KREG): weights re-read per step pair (L2)
+__global__ void __launch_bounds__(256) dk_distribute_generic_kernel(DkDistArgs a) {
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.ncell) return;
+    const double Z = __ldg(a.dem + c);
+    for (int t0 = 0; t0 < a.Tm; t0 += 2) {
+        double r0 = 0.0, r1 = 0.0;
+        for (int j = 0; j < a.K; j++) {
+            double wj = __ldg(a.wval + (size_t)j * a.ncell + c);
+            const double* v = a.vt + (size_t)__ldg(a.widx + (size_t)j * a.ncell + c) * a.Tm_pad;
+            double2 x = __ldg(reinterpret_cast<const double2*>(v + t0));
+            r0 = fma(wj, x.x, r0);
+            r1 = fma(wj, x.y, r1);
+        }
+        const double2 pa = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0));
+        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
+        const double4 p = make_double4(pa.x, pa.y, pb.x, pb.y);
+        double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(p.x, Z)), p.y);
+        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncell + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+        if (t0 + 1 < a.Tm) {
+            double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(p.z, Z)), p.w);
+            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncell + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct DkWeights {   // cached per NaN mask
+    int n = 0, K = 0;
+    uint8_t* widx = nullptr;
+    double* wval = nullptr;
+    std::vector<int> orig;   // compressed -> original station index
+    size_t bytes = 0;
+    ~DkWeights() {
+        cudaFree(widx);
+        cudaFree(wval);
+    }
+};
+
+struct DkHandle : HandleBase {
+    int slope_flag = 0;
+    std::vector<double> h_mx, h_my, h_mz;
+    RecLayout L;
+    std::list<std::pair<std::vector<uint8_t>, DkWeights*>> cache;   // LRU, front = most recent
+    size_t cache_bytes = 0, cache_budget = (size_t)48 << 30;
+    long long masks_built = 0, fallback_cells = 0;
+    int max_active = 0;
+    double* d_vt = nullptr;
+    size_t vt_cap = 0;
+    double* d_pvt = nullptr;
+    size_t pvt_cap = 0;
+    int* d_steps = nullptr;
+    size_t steps_cap = 0;
+    DkHandle() : HandleBase(HK_DK) {}
+    ~DkHandle() override {
+        cudaSetDevice(device);
+        for (auto& e : cache) delete e.second;
+        cudaFree(d_vt);
+        cudaFree(d_pvt);
+        cudaFree(d_steps);
+    }
+};
+
+// Inverse of [[ad,1],[1',0]] (n+1 x n+1) by Gauss-Jordan with partial pivoting in long double on the
+// equilibrated system (distances / dmax), returned in the ORIGINAL scaling.  false = singular.
+static bool invert_kriging_system(int n, const std::vector<double>& ad, std::vector<double>& inv) {
+    const int NN = n + 1;
+    double dmax = 0.0;
+    for (double v : ad) dmax = std::max(dmax, std::fabs(v));
+    if (dmax == 0.0) dmax = 1.0;
+    std::vector<long double> M((size_t)NN * 2 * NN, 0.0L);
+    auto at = [&](int i, int j) -> long double& { return M[(size_t)i * 2 * NN + j]; };
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) at(i, j) = (long double)ad[(size_t)i * n + j] / dmax;
+        at(i, n) = 1.0L;
+        at(n, i) = 1.0L;
+    }
+    for (int i = 0; i < NN; i++) at(i, NN + i) = 1.0L;
+    for (int c = 0; c < NN; c++) {
+        int piv = c;
+        long double best = fabsl(at(c, c));
+        for (int r = c + 1; r < NN; r++)
+            if (fabsl(at(r, c)) > best) {
+                best = fabsl(at(r, c));
+                piv = r;
+            }
+        if (best < 1e-14L) return false;
+        if (piv != c)
+            for (int j = 0; j < 2 * NN; j++) std::swap(at(c, j), at(piv, j));
+        long double ip = 1.0L / at(c, c);
+        for (int j = 0; j < 2 * NN; j++) at(c, j) *= ip;
+        for (int r = 0; r < NN; r++) {
+            if (r == c) continue;
+            long double f = at(r, c);
+            if (f == 0.0L) continue;
+            for (int j = 0; j < 2 * NN; j++) at(r, j) -= f * at(c, j);
+        }
+    }
+    // A = D A' D with D = diag(sqrt(dmax) x n, 1/sqrt(dmax))  =>  A^-1 = D^-1 A'^-1 D^-1
+    inv.assign((size_t)NN * NN, 0.0);
+    for (int i = 0; i < NN; i++)
+        for (int j = 0; j < NN; j++) {
+            long double v = at(i, NN + j);
+            if (i < n && j < n) v /= dmax;
+            else if (i == n && j == n) v *= dmax;
+            inv[(size_t)i * NN + j] = (double)v;
+        }
+    return true;
+}
+
+struct DkBuildInput {
+    int n;                         // valid stations
+    const double* cx;              // [n] compressed-order coordinates (may be null in dgrid mode)
+    const double* cy;
+    const double* elev;            // [n]
+    const double* ad;              // [n][n] or null (computed from cx, cy like dk.py:108-114)
+    const double* d_dgrid;         // device [ncell][n] or null
+    const int* orig;               // [n] compressed -> original column
+    long long ncell;
+    Geom g;
+};
+
+template <typename T>
+static int dev_upload(T** dst, const T* src, size_t n) {
+    SMRFB_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) SMRFB_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return SMRFB_OK;
+}
+
+// Build the ELL weights for one station set. Synchronous.
+static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long long* fallback_cells) {
+    const int n = in.n, NN = n + 1, NNP = (NN + 31) / 32 * 32;
+    SMRFB_CHECK(n >= 1, SMRFB_ERR_NODATA, "DK: no valid station");
+    SMRFB_CHECK(n <= DK_MAXN, SMRFB_ERR_LIMIT, "DK supports at most %d valid stations (got %d)", DK_MAXN, n);
+    std::vector<double> ad((size_t)n * n, 0.0);
+    if (in.ad) {
+        std::copy(in.ad, in.ad + (size_t)n * n, ad.begin());
+    } else {
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++) {
+                double dx = in.cx[i] - in.cx[j], dy = in.cy[i] - in.cy[j];
+                double d = std::sqrt(dx * dx + dy * dy);   // dk.py:113 (separate roundings; host code is built without FMA contraction)
+                ad[(size_t)i * n + j] = ad[(size_t)j * n + i] = d;
+            }
+    }
+    std::vector<double> inv;
+    SMRFB_CHECK(invert_kriging_system(n, ad, inv), SMRFB_ERR_SINGULAR,
+                "DK: singular kriging system (co-located stations?)");
+    // rank order: elevation descending, index ascending (krige.c:169-185 picks the first such station)
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return in.elev[x] > in.elev[y]; });
+    int nsel = 0;
+    for (int r = 0; r < n; r++)
+        if (in.elev[perm[r]] > 0.0) nsel = r + 1;   // elevations <= 0 sort last and can never be dropped
+    std::vector<int> pfull(NN);
+    for (int r = 0; r < n; r++) pfull[r] = perm[r];
+    pfull[n] = n;
+    const int npk = NN * (NN + 1) / 2;
+    std::vector<double> B0p(npk);
+    for (int i = 0; i < NN; i++)
+        for (int j = i; j < NN; j++) {
+            // symmetrise: the exact inverse is symmetric
+            double v = 0.5 * (inv[(size_t)pfull[i] * NN + pfull[j]] + inv[(size_t)pfull[j] * NN + pfull[i]]);
+            B0p[(size_t)i * NN - (size_t)i * (i + 1) / 2 + j] = v;
+        }
+    std::vector<double> sx(n), sy(n);
+    if (in.cx)
+        for (int r = 0; r < n; r++) {
+            sx[r] = in.cx[perm[r]];
+            sy[r] = in.cy[perm[r]];
+        }
+    int dev = 0, nsm = 0, smem_max = 0;
+    SMRFB_CUDA(cudaGetDevice(&dev));
+    SMRFB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const long long ntiles = (in.ncell + DK_TILE - 1) / DK_TILE;
+    const int grid = (int)std::min<long long>(ntiles, nsm);
+    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + NNP + NN) * sizeof(double) +
+                  ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
+    SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
+
+    double *d_sx = nullptr, *d_sy = nullptr, *d_cx = nullptr, *d_cy = nullptr, *d_elev = nullptr, *d_ad = nullptr,
+           *d_B0p = nullptr, *d_undo = nullptr;
+    int *d_perm = nullptr, *d_orig = nullptr, *d_small = nullptr;
+    uint32_t* d_final = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    int rc = SMRFB_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_sx); cudaFree(d_sy); cudaFree(d_cx); cudaFree(d_cy); cudaFree(d_elev); cudaFree(d_ad);
+        cudaFree(d_B0p); cudaFree(d_undo); cudaFree(d_perm); cudaFree(d_orig); cudaFree(d_small); cudaFree(d_final);
+        cudaFree(d_cnt);
+    };
+#define DK_TRY(x)                 \
+    do {                          \
+        rc = (x);                 \
+        if (rc != SMRFB_OK) {     \
+            cleanup();            \
+            return rc;            \
+        }                         \
+    } while (0)
+#define DK_CUDA(x)                                                                   \
+    do {                                                                             \
+        cudaError_t e__ = (x);                                                       \
+        if (e__ != cudaSuccess) {                                                    \
+            set_error("%s: %s (%s:%d)", #x, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cleanup();                                                               \
+            return SMRFB_ERR_CUDA;                                                   \
+        }                                                                            \
+    } while (0)
+    DK_TRY(dev_upload(&d_sx, sx.data(), n));
+    DK_TRY(dev_upload(&d_sy, sy.data(), n));
+    if (in.cx) {
+        DK_TRY(dev_upload(&d_cx, in.cx, n));
+        DK_TRY(dev_upload(&d_cy, in.cy, n));
+    }
+    DK_TRY(dev_upload(&d_elev, in.elev, n));
+    DK_TRY(dev_upload(&d_ad, ad.data(), (size_t)n * n));
+    DK_TRY(dev_upload(&d_B0p, B0p.data(), npk));
+    DK_TRY(dev_upload(&d_perm, perm.data(), n));
+    DK_TRY(dev_upload(&d_orig, in.orig, n));
+    DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * n * NNP * sizeof(double)));
+    DK_CUDA(cudaMalloc((void**)&d_final, (size_t)in.ncell * DK_WORDS * sizeof(uint32_t)));
+    DK_CUDA(cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)));
+    DK_CUDA(cudaMalloc((void**)&d_small, 4 * sizeof(int)));
+    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+    DK_CUDA(cudaMemsetAsync(d_small, 0, 4 * sizeof(int), st));
+
+    DkBuildArgs ba;
+    ba.n = n; ba.NN = NN; ba.NNP = NNP; ba.nsel = nsel;
+    ba.ncell = in.ncell; ba.g = in.g;
+    ba.sx = d_sx; ba.sy = d_sy; ba.dgrid = in.d_dgrid; ba.perm = d_perm; ba.B0p = d_B0p; ba.undo = d_undo;
+    ba.final_act = d_final; ba.tile_counter = d_cnt; ba.maxcount = d_small;
+    DK_CUDA(cudaFuncSetAttribute(dk_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dk_build_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+    count_launch();
+    DK_CUDA(cudaGetLastError());
+    int h_small[4] = {0, 0, 0, 0};
+    DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    DK_CUDA(cudaStreamSynchronize(st));
+    const int K = std::max(1, std::min(h_small[0], DK_NSMAX));
+    if (h_small[0] > DK_NSMAX) {
+        set_error("DK: a cell ends with %d active stations; this build solves final sets up to %d", h_small[0], DK_NSMAX);
+        cleanup();
+        return SMRFB_ERR_LIMIT;
+    }
+    W->n = n;
+    W->K = K;
+    W->orig.assign(in.orig, in.orig + n);
+    W->bytes = (size_t)K * in.ncell * (sizeof(double) + 1);
+    DK_CUDA(cudaMalloc((void**)&W->widx, (size_t)K * in.ncell));
+    DK_CUDA(cudaMalloc((void**)&W->wval, (size_t)K * in.ncell * sizeof(double)));
+    DkFinalArgs fa;
+    fa.n = n; fa.K = K; fa.ncell = in.ncell; fa.g = in.g;
+    fa.cx = d_cx; fa.cy = d_cy; fa.elev = d_elev; fa.ad = d_ad; fa.dgrid = in.d_dgrid; fa.perm = d_perm; fa.orig = d_orig;
+    fa.final_act = d_final; fa.widx = W->widx; fa.wval = W->wval; fa.status = d_small + 1;
+    fa.fallback_cells = d_cnt + 1; fa.maxcount_final = d_small + 2;
+    dk_final_kernel<<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
+    count_launch();
+    DK_CUDA(cudaGetLastError());
+    unsigned long long h_cnt[2] = {0, 0};
+    DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    DK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    DK_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+#undef DK_TRY
+#undef DK_CUDA
+    SMRFB_CHECK(!(h_small[1] & 1), SMRFB_ERR_SINGULAR, "DK: singular kriging system in the final solve");
+    if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
+    return SMRFB_OK;
+}
+
+static int dk_get_weights(DkHandle* h, const std::vector<uint8_t>& nanmask, DkWeights** out) {
+    for (auto it = h->cache.begin(); it != h->cache.end(); ++it)
+        if (it->first == nanmask) {
+            h->cache.splice(h->cache.begin(), h->cache, it);
+            *out = h->cache.front().second;
+            return SMRFB_OK;
+        }
+    std::vector<double> cx, cy, cz;
+    std::vector<int> orig;
+    for (int s = 0; s < h->S; s++)
+        if (!nanmask[s]) {
+            cx.push_back(h->h_mx[s]);
+            cy.push_back(h->h_my[s]);
+            cz.push_back(h->h_mz[s]);
+            orig.push_back(s);
+        }
+    DkBuildInput in;
+    in.n = (int)cx.size();
+    in.cx = cx.data(); in.cy = cy.data(); in.elev = cz.data(); in.ad = nullptr; in.d_dgrid = nullptr;
+    in.orig = orig.data(); in.ncell = h->g.ncell; in.g = h->g;
+    DkWeights* W = new DkWeights();
+    int rc = dk_build(in, h->stream, W, &h->fallback_cells);
+    if (rc != SMRFB_OK) {
+        delete W;
+        return rc;
+    }
+    h->masks_built++;
+    h->max_active = std::max(h->max_active, W->K);
+    while (!h->cache.empty() && h->cache_bytes + W->bytes > h->cache_budget) {
+        h->cache_bytes -= h->cache.back().second->bytes;
+        delete h->cache.back().second;
+        h->cache.pop_back();
+    }
+    h->cache.emplace_front(nanmask, W);
+    h->cache_bytes += W->bytes;
+    *out = W;
+    return SMRFB_OK;
+}
+
+static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T, double vmin, double vmax,
+                  const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
+    SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    const int S = h->S;
+    // group the steps by NaN mask, in order of first appearance (dk.py:75-85 recomputes on every change)
+    std::vector<std::vector<uint8_t>> masks;
+    std::vector<std::vector<int>> groups;
+    {
+        std::map<std::vector<uint8_t>, int> idx;
+        std::vector<uint8_t> m(S);
+        for (int t = 0; t < T; t++) {
+            int nv = 0;
+            for (int s = 0; s < S; s++) {
+                m[s] = std::isnan(h_data[(size_t)t * S + s]) ? 1 : 0;
+                nv += !m[s];
+            }
+            SMRFB_CHECK(nv > 0, SMRFB_ERR_NODATA, "timestep %d has no valid station (all values NaN)", t);
+            auto it = idx.find(m);
+            if (it == idx.end()) {
+                idx[m] = (int)masks.size();
+                masks.push_back(m);
+                groups.emplace_back(1, t);
+            } else {
+                groups[it->second].push_back(t);
+            }
+        }
+    }
+    const int T_pad = T;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_rec, &h->rec_cap, (size_t)T_pad * h->L.RS * sizeof(double)));
+    SMRFB_PROPAGATE(launch_prep(st, d_data, T, T_pad, S, h->L, h->d_mz, nullptr, 1, h->slope_flag, d_pv_in, d_pv_out,
+                                h->d_rec, nullptr, h->d_flags));
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        DkWeights* W = nullptr;
+        SMRFB_PROPAGATE(dk_get_weights(h, masks[gi], &W));
+        const int Tm = (int)groups[gi].size();
+        const int Tm_pad = (Tm + 31) / 32 * 32;
+        // the staging buffers are reused by the next group: wait for the previous group's kernel
+        SMRFB_CUDA(cudaStreamSynchronize(st));
+        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_vt, &h->vt_cap, (size_t)S * Tm_pad * sizeof(double)));
+        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pvt, &h->pvt_cap, (size_t)Tm_pad * 2 * sizeof(double)));
+        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_steps, &h->steps_cap, (size_t)Tm_pad * sizeof(int)));
+        SMRFB_CUDA(cudaMemcpyAsync(h->d_steps, groups[gi].data(), (size_t)Tm * sizeof(int), cudaMemcpyHostToDevice, st));
+        dim3 tb(32, 8), tg((S + 31) / 32, Tm_pad / 32);
+        dk_gather_kernel<<<tg, tb, 0, st>>>(h->d_rec, h->L, h->d_steps, Tm, Tm_pad, h->d_vt, h->d_pvt);
+        count_launch();
+        SMRFB_CUDA(cudaGetLastError());
+        DkDistArgs a;
+        a.ncell = h->g.ncell; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
+        a.vt = h->d_vt; a.pvt = h->d_pvt; a.steps = h->d_steps; a.Tm = Tm; a.Tm_pad = Tm_pad;
+        a.vmin = vmin; a.vmax = vmax; a.out = d_out;
+        const unsigned nblk = (unsigned)((h->g.ncell + 255) / 256);
+        if (W->K <= 8) dk_distribute_kernel<8><<<nblk, 256, 0, st>>>(a);
+        else if (W->K <= DK_KREG) dk_distribute_kernel<DK_KREG><<<nblk, 256, 0, st>>>(a);
+        else dk_distribute_generic_kernel<<<nblk, 256, 0, st>>>(a);
+        count_launch();
+        SMRFB_CUDA(cudaGetLastError());
+    }
+    return SMRFB_OK;
+}
+
+}  // namespace smrfb
+
+using namespace smrfb;
+
+extern "C" {
+
+int smrfb_dk_create(int nsta, const double* mx, const double* my, const double* mz, int ny, int nx, int grid_kind,
+                    const double* gx, const double* gy, const double* dem, int slope_flag, int device,
+                    smrfb_handle_t* out) {
+    SMRFB_CHECK(out, SMRFB_ERR_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    SMRFB_CHECK(mz && dem, SMRFB_ERR_ARG, "DK needs station elevations and the DEM");
+    SMRFB_CHECK(nsta <= 255, SMRFB_ERR_LIMIT, "DK supports at most 255 stations per handle (got %d)", nsta);
+    DkHandle* h = new DkHandle();
+    h->device = device;
+    h->slope_flag = slope_flag;
+    int rc = upload_geom(h, nsta, mx, my, mz, ny, nx, grid_kind, gx, gy, dem);
+    if (rc != SMRFB_OK) {
+        delete h;
+        return rc;
+    }
+    h->h_mx.assign(mx, mx + nsta);
+    h->h_my.assign(my, my + nsta);
+    h->h_mz.assign(mz, mz + nsta);
+    h->L = make_layout(nsta, 2, 0, false);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->cache_budget = free_b / 2;
+    *out = reinterpret_cast<smrfb_handle_t>(h);
+    return SMRFB_OK;
+}
+
+int smrfb_dk_distribute_dev(smrfb_handle_t hh, const double* d_data, const double* h_data, int T, double vmin,
+                            double vmax, const double* d_pv_in, double* d_pv_out, double* d_out, void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    DkHandle* h = reinterpret_cast<DkHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_DK, SMRFB_ERR_ARG, "not a DK handle");
+    SMRFB_CHECK(d_data && h_data && d_out, SMRFB_ERR_ARG, "NULL data/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return dk_run(h, d_data, h_data, T, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+}
+
+int smrfb_dk_distribute(smrfb_handle_t hh, const double* data, int T, double vmin, double vmax, const double* pv_in,
+                        double* pv_out, double* out) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    DkHandle* h = reinterpret_cast<DkHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_DK, SMRFB_ERR_ARG, "not a DK handle");
+    SMRFB_CHECK(data && out && T > 0, SMRFB_ERR_ARG, "NULL data/out or T <= 0");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    const size_t ncell = (size_t)h->g.ncell, S = (size_t)h->S;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_data, &h->data_cap, (size_t)T * S * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pv, &h->pv_cap, (size_t)T * 4 * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpyAsync(h->d_data, data, (size_t)T * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double* d_pvin = nullptr;
+    if (pv_in) {
+        d_pvin = h->d_pv + (size_t)2 * T;
+        SMRFB_CUDA(cudaMemcpyAsync(d_pvin, pv_in, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    const size_t budget = (size_t)1 << 30;
+    const int tb = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / (ncell * sizeof(double))));
+    double* d_out = nullptr;
+    SMRFB_CUDA(cudaMalloc((void**)&d_out, (size_t)tb * ncell * sizeof(double)));
+    int rc = SMRFB_OK;
+    for (int t0 = 0; t0 < T && rc == SMRFB_OK; t0 += tb) {
+        const int tn = std::min(tb, T - t0);
+        rc = dk_run(h, h->d_data + (size_t)t0 * S, data + (size_t)t0 * S, tn, vmin, vmax,
+                    d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, d_out, h->stream);
+        if (rc != SMRFB_OK) break;
+        if (cudaMemcpyAsync(out + (size_t)t0 * ncell, d_out, (size_t)tn * ncell * sizeof(double), cudaMemcpyDeviceToHost,
+                            h->stream) != cudaSuccess) {
+            set_error("DK D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SMRFB_ERR_CUDA;
+        }
+    }
+    if (rc == SMRFB_OK && pv_out &&
+        cudaMemcpyAsync(pv_out, h->d_pv, (size_t)T * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+        rc = SMRFB_ERR_CUDA;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (rc == SMRFB_OK && e != cudaSuccess) {
+        set_error("DK distribute failed on the device: %s", cudaGetErrorString(e));
+        rc = SMRFB_ERR_CUDA;
+    }
+    return rc;
+}
+
+int smrfb_dk_weights(smrfb_handle_t hh, const uint8_t* nan_mask, double* weights_out) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    DkHandle* h = reinterpret_cast<DkHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_DK, SMRFB_ERR_ARG, "not a DK handle");
+    SMRFB_CHECK(nan_mask && weights_out, SMRFB_ERR_ARG, "NULL mask/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    std::vector<uint8_t> m(nan_mask, nan_mask + h->S);
+    for (auto& v : m) v = v ? 1 : 0;
+    DkWeights* W = nullptr;
+    SMRFB_PROPAGATE(dk_get_weights(h, m, &W));
+    const size_t ncell = (size_t)h->g.ncell;
+    std::vector<int> o2c(256, 0);
+    for (int i = 0; i < W->n; i++) o2c[W->orig[i]] = i;
+    int* d_o2c = nullptr;
+    double* d_dense = nullptr;
+    SMRFB_CUDA(cudaMalloc((void**)&d_o2c, 256 * sizeof(int)));
+    cudaError_t e = cudaMalloc((void**)&d_dense, ncell * W->n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_o2c, o2c.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_dense, 0, ncell * W->n * sizeof(double), h->stream);
+    if (e == cudaSuccess) {
+        dk_expand_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(W->K, (long long)ncell, W->n, W->widx,
+                                                                                  W->wval, d_o2c, d_dense);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(weights_out, d_dense, ncell * W->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_o2c);
+    cudaFree(d_dense);
+    if (e != cudaSuccess) {
+        set_error("smrfb_dk_weights: %s", cudaGetErrorString(e));
+        return SMRFB_ERR_CUDA;
+    }
+    return SMRFB_OK;
+}
+
+int smrfb_dk_stats(smrfb_handle_t hh, int64_t* masks_built, int64_t* fallback_cells, int* max_active) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    DkHandle* h = reinterpret_cast<DkHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_DK, SMRFB_ERR_ARG, "not a DK handle");
+    if (masks_built) *masks_built = h->masks_built;
+    if (fallback_cells) *fallback_cells = h->fallback_cells;
+    if (max_active) *max_active = h->max_active;
+    return SMRFB_OK;
+}
+
+int smrfb_krige_grid(int nsta, int ngrid, const double* ad, const double* dgrid, const double* elevations, int nthreads,
+                     double* weights) {
+    (void)nthreads;
+    SMRFB_CHECK(nsta > 0 && ngrid > 0 && ad && dgrid && elevations && weights, SMRFB_ERR_ARG, "bad krige_grid arguments");
+    SMRFB_CHECK(nsta <= DK_MAXN, SMRFB_ERR_LIMIT, "krige_grid supports at most %d stations (got %d)", DK_MAXN, nsta);
+    int dev = 0;
+    if (const char* e = getenv("SMRFB_DEVICE")) dev = atoi(e);
+    SMRFB_CUDA(cudaSetDevice(dev));
+    cudaStream_t st;
+    SMRFB_CUDA(cudaStreamCreate(&st));
+    double *d_dgrid = nullptr, *d_dense = nullptr;
+    int* d_o2c = nullptr;
+    DkWeights W;
+    std::vector<int> orig(nsta);
+    for (int i = 0; i < nsta; i++) orig[i] = i;
+    int rc = SMRFB_OK;
+    cudaError_t e = cudaMalloc((void**)&d_dgrid, (size_t)ngrid * nsta * sizeof(double));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_dgrid, dgrid, (size_t)ngrid * nsta * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        DkBuildInput in;
+        in.n = nsta; in.cx = nullptr; in.cy = nullptr; in.elev = elevations; in.ad = ad; in.d_dgrid = d_dgrid;
+        in.orig = orig.data(); in.ncell = ngrid;
+        in.g = Geom();
+        in.g.ncell = ngrid;
+        long long fb = 0;
+        rc = dk_build(in, st, &W, &fb);
+    }
+    if (e == cudaSuccess && rc == SMRFB_OK) {
+        e = cudaMalloc((void**)&d_dense, (size_t)ngrid * nsta * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_o2c, 256 * sizeof(int));
+        std::vector<int> o2c(256, 0);
+        for (int i = 0; i < nsta; i++) o2c[i] = i;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_o2c, o2c.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_dense, 0, (size_t)ngrid * nsta * sizeof(double), st);
+        if (e == cudaSuccess) {
+            dk_expand_kernel<<<(unsigned)((ngrid + 255) / 256), 256, 0, st>>>(W.K, ngrid, nsta, W.widx, W.wval, d_o2c, d_dense);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(weights, d_dense, (size_t)ngrid * nsta * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_dgrid);
+    cudaFree(d_dense);
+    cudaFree(d_o2c);
+    cudaStreamDestroy(st);
+    if (rc == SMRFB_OK && e != cudaSuccess) {
+        set_error("smrfb_krige_grid: %s", cudaGetErrorString(e));
+        rc = SMRFB_ERR_CUDA;
+    }
+    return rc;
+}
+
+}  // extern "C"
