@@ -33,6 +33,7 @@ HandleBase::~HandleBase() {
     cudaFree(d_data);
     cudaFree(d_pv);
     cudaFree(d_flags);
+    cudaFree(d_ring);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -99,6 +100,8 @@ struct HandleBase {
     double* d_pv = nullptr;      // [T][2]
     size_t pv_cap = 0;
     int* d_flags = nullptr;      // [1] device-side status flags (bit0: a step had no valid station)
+    double* d_ring = nullptr;    // host-API output ring (up to 2 slots), kept across calls
+    size_t ring_cap = 0;
     explicit HandleBase(int k) : kind(k) {}
     virtual ~HandleBase();
 };
@@ -113,6 +116,70 @@ int ensure_cap(void** p, size_t* cap, size_t need_bytes);
 int launch_prep(cudaStream_t st, const double* d_data, int T, int T_pad, int S, const RecLayout& L, const double* d_mz,
                 const uint8_t* d_fitmask, int detrend, int slope_flag, const double* d_pv_in, double* d_pv_out,
                 double* d_rec, uint8_t* d_valid, int* d_flags);
+
+// Host-buffer driver shared by the three methods: the T steps are cut into sub-batches whose output
+// fits one slot of a 2-slot device ring (SMRFB_RING_BYTES per slot, default 8 GiB); the D2H copy of
+// one sub-batch (copy_stream) overlaps the kernels of the next (stream).  run(t0, tn, d_out, stream)
+// enqueues the kernels for steps [t0, t0+tn).  Synchronises before returning.
+template <class RunFn>
+int run_host_batches(HandleBase* h, int T, int step_align, double* out, RunFn run) {
+    const size_t ncell = (size_t)h->g.ncell;
+    size_t budget = (size_t)8 << 30;
+    {   // at least one full staged block of steps per slot when memory allows (large grids)
+        size_t free_b = 0, total_b = 0;
+        const size_t want = ncell * sizeof(double) * (size_t)step_align;
+        if (want > budget && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && want <= (free_b + h->ring_cap) / 3)
+            budget = want;
+    }
+    if (const char* e = getenv("SMRFB_RING_BYTES")) budget = (size_t)strtoull(e, nullptr, 10);
+    int tb = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / (ncell * sizeof(double))));
+    if (tb > step_align) tb = tb / step_align * step_align;
+    const int nslots = tb >= T ? 1 : 2;
+    const size_t slot_bytes = (size_t)tb * ncell * sizeof(double);
+    if (h->ring_cap < slot_bytes * nslots) {
+        if (h->d_ring) cudaFree(h->d_ring);
+        h->d_ring = nullptr;
+        h->ring_cap = 0;
+        if (cudaMalloc((void**)&h->d_ring, slot_bytes * nslots) != cudaSuccess) {
+            set_error("cudaMalloc of the %zu-byte output ring failed", slot_bytes * nslots);
+            return SMRFB_ERR_CUDA;
+        }
+        h->ring_cap = slot_bytes * nslots;
+    }
+    double* ring[2] = {h->d_ring, nslots > 1 ? h->d_ring + (size_t)tb * ncell : nullptr};
+    cudaEvent_t done[2], copied[2];
+    for (int i = 0; i < 2; i++) {
+        SMRFB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        SMRFB_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    }
+    int rc = SMRFB_OK, slot = 0;
+    for (int t0 = 0; t0 < T && rc == SMRFB_OK; t0 += tb, slot ^= 1) {
+        const int tn = std::min(tb, T - t0);
+        if (t0 >= 2 * tb) cudaStreamWaitEvent(h->stream, copied[slot], 0);   // ring slot free again
+        rc = run(t0, tn, ring[slot], h->stream);
+        if (rc != SMRFB_OK) break;
+        cudaEventRecord(done[slot], h->stream);
+        cudaStreamWaitEvent(h->copy_stream, done[slot], 0);
+        if (cudaMemcpyAsync(out + (size_t)t0 * ncell, ring[slot], (size_t)tn * ncell * sizeof(double),
+                            cudaMemcpyDeviceToHost, h->copy_stream) != cudaSuccess) {
+            set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SMRFB_ERR_CUDA;
+            break;
+        }
+        cudaEventRecord(copied[slot], h->copy_stream);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(done[i]);
+        cudaEventDestroy(copied[i]);
+    }
+    if (rc == SMRFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        set_error("distribute failed on the device: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        rc = SMRFB_ERR_CUDA;
+    }
+    return rc;
+}
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

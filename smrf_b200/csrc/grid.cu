@@ -230,7 +230,7 @@ int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detr
     SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
     SMRFB_CHECK(data && out && T > 0, SMRFB_ERR_ARG, "NULL data/out or T <= 0");
     SMRFB_CUDA(cudaSetDevice(h->device));
-    const size_t ncell = (size_t)h->g.ncell, S = (size_t)h->S;
+    const size_t S = (size_t)h->S;
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_data, &h->data_cap, (size_t)T * S * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pv, &h->pv_cap, (size_t)T * 4 * sizeof(double)));
     SMRFB_CUDA(cudaMemcpyAsync(h->d_data, data, (size_t)T * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -239,29 +239,13 @@ int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detr
         d_pvin = h->d_pv + (size_t)2 * T;
         SMRFB_CUDA(cudaMemcpyAsync(d_pvin, pv_in, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
-    const size_t budget = (size_t)1 << 30;
-    int tb = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / (ncell * sizeof(double))));
-    double* d_out = nullptr;
-    SMRFB_CUDA(cudaMalloc((void**)&d_out, (size_t)tb * ncell * sizeof(double)));
-    int rc = SMRFB_OK;
-    for (int t0 = 0; t0 < T && rc == SMRFB_OK; t0 += tb) {
-        const int tn = std::min(tb, T - t0);
-        rc = grid_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, vmin, vmax,
-                      d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, d_out, h->stream);
-        if (rc != SMRFB_OK) break;
-        if (cudaMemcpyAsync(out + (size_t)t0 * ncell, d_out, (size_t)tn * ncell * sizeof(double), cudaMemcpyDeviceToHost,
-                            h->stream) != cudaSuccess) {
-            set_error("GRID D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = SMRFB_ERR_CUDA;
-        }
-    }
+    int rc = run_host_batches(h, T, 32, out, [&](int t0, int tn, double* d_out, cudaStream_t st) {
+        return grid_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, vmin, vmax,
+                        d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, d_out, st);
+    });
     if (rc == SMRFB_OK && pv_out &&
-        cudaMemcpyAsync(pv_out, h->d_pv, (size_t)T * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
-        rc = SMRFB_ERR_CUDA;
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_out);
-    if (rc == SMRFB_OK && e != cudaSuccess) {
-        set_error("GRID distribute failed on the device: %s", cudaGetErrorString(e));
+        cudaMemcpy(pv_out, h->d_pv, (size_t)T * 2 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("GRID: reading back coefficients failed");
         rc = SMRFB_ERR_CUDA;
     }
     return rc;

@@ -345,63 +345,19 @@ int smrfb_idw_distribute(smrfb_handle_t hh, const double* data, int T, int detre
         d_pvin = h->d_pv + (size_t)2 * T;
         SMRFB_CUDA(cudaMemcpyAsync(d_pvin, pv_in, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
-    const size_t budget = (size_t)1 << 30;  // bytes per ring slot
-    int tb = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / (ncell * sizeof(double))));
-    if (tb > IDW_TC) tb = tb / IDW_TC * IDW_TC;
-    double* ring[2] = {nullptr, nullptr};
-    cudaEvent_t done[2], copied[2];
-    int rc = SMRFB_OK;
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; i++) {
-            if (ring[i]) cudaFree(ring[i]);
-        }
-    };
-    for (int i = 0; i < 2; i++) {
-        SMRFB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        SMRFB_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
-    }
-    for (int i = 0; i < 2 && rc == SMRFB_OK; i++) {
-        if (i == 1 && tb >= T) break;
-        if (cudaMalloc((void**)&ring[i], (size_t)tb * ncell * sizeof(double)) != cudaSuccess) {
-            set_error("cudaMalloc of the output ring failed");
-            rc = SMRFB_ERR_CUDA;
-        }
-    }
-    int slot = 0;
-    for (int t0 = 0; t0 < T && rc == SMRFB_OK; t0 += tb, slot ^= 1) {
-        const int tn = std::min(tb, T - t0);
-        if (t0 >= 2 * tb) cudaStreamWaitEvent(h->stream, copied[slot], 0);  // ring slot free again
-        rc = idw_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, vmin, vmax,
-                     d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, ring[slot], h->stream);
-        if (rc != SMRFB_OK) break;
-        cudaEventRecord(done[slot], h->stream);
-        cudaStreamWaitEvent(h->copy_stream, done[slot], 0);
-        if (cudaMemcpyAsync(out + (size_t)t0 * ncell, ring[slot], (size_t)tn * ncell * sizeof(double),
-                            cudaMemcpyDeviceToHost, h->copy_stream) != cudaSuccess) {
-            set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = SMRFB_ERR_CUDA;
-            break;
-        }
-        cudaEventRecord(copied[slot], h->copy_stream);
-        // the prep scratch (d_rec/d_valid) is reused by the next sub-batch: stream order keeps it safe
-    }
+    int rc = run_host_batches(h, T, IDW_TC, out, [&](int t0, int tn, double* d_out, cudaStream_t st) {
+        return idw_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, vmin, vmax,
+                       d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, d_out, st);
+    });
     int flags = 0;
     if (rc == SMRFB_OK) {
-        if (pv_out && cudaMemcpyAsync(pv_out, h->d_pv, (size_t)T * 2 * sizeof(double), cudaMemcpyDeviceToHost,
-                                      h->stream) != cudaSuccess)
+        cudaError_t e = cudaSuccess;
+        if (pv_out) e = cudaMemcpy(pv_out, h->d_pv, (size_t)T * 2 * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&flags, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("IDW: reading back coefficients failed: %s", cudaGetErrorString(e));
             rc = SMRFB_ERR_CUDA;
-        cudaMemcpyAsync(&flags, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    }
-    cudaError_t e1 = cudaStreamSynchronize(h->stream);
-    cudaError_t e2 = cudaStreamSynchronize(h->copy_stream);
-    for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(done[i]);
-        cudaEventDestroy(copied[i]);
-    }
-    cleanup();
-    if (rc == SMRFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
-        set_error("IDW distribute failed on the device: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-        rc = SMRFB_ERR_CUDA;
+        }
     }
     if (rc == SMRFB_OK && (flags & 1)) {
         set_error("a timestep has no valid station (all values NaN)");
