@@ -88,7 +88,7 @@ RecLayout make_layout(int S, int k_align, int maxm, bool mma_stride) {
     L.S = S;
     L.S_pad = (S + k_align - 1) / k_align * k_align;
     L.maxm = maxm;
-    int rs = L.S_pad + 3 + maxm;
+    int rs = L.S_pad + 2 + (maxm + 1 + 1) / 2;
     if (rs & 1) rs++;
     if (mma_stride)
         while ((rs & 15) != 4 && (rs & 15) != 12) rs += 2;
@@ -205,20 +205,22 @@ prep_steps_kernel(const double* __restrict__ data, int T, int S, RecLayout L, co
             pv_out[2 * t] = p0;
             pv_out[2 * t + 1] = p1;
         }
+        int* mi = reinterpret_cast<int*>(r + L.meta() + 2);
+        const int nints = 2 * (L.RS - L.meta() - 2);
         int nm = 0;
         if (L.maxm > 0) {
             for (int s = 0; s < S; s++) {
                 if (isnan(row[s])) {
-                    if (nm < L.maxm) r[L.meta() + 3 + nm] = (double)s;
+                    if (nm < L.maxm) mi[1 + nm] = s;
                     nm++;
                 }
             }
-            for (int j = nm; j < L.maxm; j++) r[L.meta() + 3 + j] = 0.0;
+            for (int j = (nm < L.maxm ? nm : L.maxm) + 1; j < nints; j++) mi[j] = 0;
         } else {
             nm = S - (int)cnt_valid;
+            for (int j = 1; j < nints; j++) mi[j] = 0;
         }
-        r[L.meta() + 2] = (double)nm;
-        for (int j = L.meta() + 3 + L.maxm; j < L.RS; j++) r[j] = 0.0;
+        mi[0] = nm;
     }
 }
 

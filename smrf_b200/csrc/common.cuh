@@ -68,8 +68,9 @@ __device__ __forceinline__ void cell_xy(const Geom& g, long long c, double& X, d
 // One record per timestep, written by prep_steps_kernel, consumed by the distribute kernels:
 //   rec[t][0 .. S_pad)            residuals d_s - (mz_s*p0 + p1); 0 for missing stations and padding
 //   rec[t][S_pad + 0]             p0 (slope)            rec[t][S_pad + 1]   p1 (intercept)
-//   rec[t][S_pad + 2]             number of missing stations (as double)
-//   rec[t][S_pad + 3 + j]         index of the j-th missing station (as double), j < min(nmiss, maxm)
+//   rec[t][S_pad + 2 ...]         int32 array: [0] = number of missing stations, [1 + j] = index of the
+//                                 j-th missing station, j < min(nmiss, maxm); maxm + 1 is a multiple of 4
+//                                 so a consumer reads 4 entries per 128-bit shared-memory load
 // RS (record stride, doubles) is chosen = 4 or 12 (mod 16) so that DMMA A-fragment loads from a
 // staged record block are shared-memory bank-conflict free.
 // keep_nan: missing stations keep NaN in the residual slot (GRID: NaN propagates like griddata's).
@@ -216,7 +217,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // fp64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
 // lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c0/c1 = C[lane>>2][(lane&3)*2 + {0,1}].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }

@@ -7,23 +7,30 @@
 // One CTA owns CT=64 consecutive cells for the whole batch of T timesteps:
 //   * the [S x 64] weight tile is generated ONCE from the cell / station coordinates into shared
 //     memory (the reference's [ny,nx,S] cube, 160 GB at 1e8 x 200, is never materialised),
-//     together with a double-double sum D[c] of all S weights;
-//   * step records (residuals + p0, p1, missing-station list) stream in blocks of TC=32 steps
-//     through a 2-deep shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier);
-//   * the numerator is an fp64 tensor-core contraction  C[32 steps x 64 cells] += R[32 x S] * W[S x 64]
-//     on DMMA m8n8k4 (8 warps, each 16 steps x 16 cells = 2x2 MMA tiles);
-//   * the masked denominator is D[c] minus the weights of that step's missing stations, carried in
-//     double-double so no digits are lost when a missing station dominates D;
-//   * epilogue: divide, retrend against the DEM, NaN-preserving clamp, 128-bit streaming stores.
+//     together with the sum D[c] of all S weights;
+//   * step records (residuals + p0, p1, missing-station list) stream in blocks of TC=16 steps
+//     through a 4-deep shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier);
+//   * the numerator is an fp64 tensor-core contraction  C[16 steps x 64 cells] += R[16 x S] * W[S x 64]
+//     on DMMA m8n8k4; a warp owns 16 steps x 16 cells = 2x2 MMA tiles;
+//   * the CTA's 8 warps form two groups of 4 that alternate step blocks: while one group issues
+//     DMMAs (tensor pipe) the other runs its epilogue (fp64 pipe + LSU), handing the tensor pipe
+//     over through named barriers, so the tensor pipe never waits for an epilogue;
+//   * the masked denominator is D[c] (sum of all S weights) minus the weights of that step's missing
+//     stations; if that subtraction cancels more than 5 digits (a missing station dominates D,
+//     SURVEY.md H3) the valid weights are re-summed directly, so the result keeps >= 10 digits;
+//   * epilogue: reciprocal (rcp.approx + 2 Newton steps), retrend against the DEM, NaN-preserving
+//     clamp, 128-bit streaming stores.
 #include "common.cuh"
 
 namespace smrfb {
 
 constexpr int IDW_CT = 64;             // cells per CTA
-constexpr int IDW_TC = 32;             // timesteps per staged block
+constexpr int IDW_TC = 16;             // timesteps per staged block
+constexpr int IDW_NBUF = 4;            // record ring depth (2 per warp group)
 constexpr int IDW_WSTR = IDW_CT + 4;   // weight-tile row stride (doubles), = 4 (mod 16): conflict-free B frags
 constexpr int IDW_THREADS = 256;
-constexpr int IDW_MAXM = 13;           // missing-station list length carried in a record
+constexpr int IDW_MAXM = 15;           // missing-station list length carried in a record (16 int32 with the count)
+constexpr int IDW_WU = 5;              // independent weight chains per thread and iteration
 
 struct IdwHandle : HandleBase {
     double power = 2.0;
@@ -46,104 +53,122 @@ struct IdwArgs {
     double* out;
 };
 
-__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
-    s = __dadd_rn(a, b);
-    double bb = __dsub_rn(s, a);
-    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+// 1/x to ~1 ulp for positive normal x: MUFU.RCP64H seed (2^-23) + two Newton steps; no special cases.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
 }
 
 __device__ __forceinline__ double idw_weight(double q, double power) {
-    if (power == 2.0) return 1.0 / q;
+    if (power == 2.0) return fast_rcp(q);     // 1/(sqrt(q))^2 of idw.py:77 up to ~1 ulp
     return 1.0 / pow(sqrt(q), power);          // idw.py:77 as written
 }
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.L.S, S_pad = a.L.S_pad, RS = a.L.RS;
     double* Wt = reinterpret_cast<double*>(smem_raw);                  // [S_pad][WSTR]
-    double* recbuf = Wt + (size_t)S_pad * IDW_WSTR;                    // [2][TC][RS]
-    double* Dhi = recbuf + (size_t)2 * IDW_TC * RS;                    // [CT]
-    double* Dlo = Dhi + IDW_CT;                                        // [CT]
-    double* Zc = Dlo + IDW_CT;                                         // [CT]
-    double* part = Zc + IDW_CT;                                        // [4][CT][2] partial dd sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 4 * IDW_CT * 2);  // [2]
-    int* zflag = reinterpret_cast<int*>(bars + 2);                     // [CT]
+    double* recbuf = Wt + (size_t)S_pad * IDW_WSTR;                    // [NBUF][TC][RS]
+    double* Dall = recbuf + (size_t)IDW_NBUF * IDW_TC * RS;            // [CT] sum of all S weights per cell
+    double* Zc = Dall + IDW_CT;                                        // [CT]
+    double* scratch = Zc + IDW_CT;                                     // [2*S_pad] station coordinates
+    double* scratch2 = scratch + 2 * S_pad;                            // [4*CT] partial weight sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch2 + 4 * IDW_CT);  // [NBUF]
+    int* zflag = reinterpret_cast<int*>(bars + IDW_NBUF);              // [CT]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long cell0 = (long long)blockIdx.x * IDW_CT;
     const int nchunk = a.T_pad / IDW_TC;
     const uint32_t chunk_bytes = (uint32_t)(IDW_TC * RS * sizeof(double));
+    const size_t chunk_elems = (size_t)IDW_TC * RS;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int b = 0; b < IDW_NBUF; b++) mbar_init(&bars[b], 1);
         fence_mbar_init();
     }
     if (tid < IDW_CT) zflag[tid] = 0;
+    for (int s = tid; s < S_pad; s += IDW_THREADS) {   // station coordinates -> shared memory
+        scratch[s] = s < S ? __ldg(a.mx + s) : 0.0;
+        scratch[S_pad + s] = s < S ? __ldg(a.my + s) : 0.0;
+    }
     __syncthreads();
-    if (tid == 0) {  // prefetch the first two record blocks while the weight tile is generated
-        mbar_arrive_expect_tx(&bars[0], chunk_bytes);
-        bulk_g2s(recbuf, a.rec, chunk_bytes, &bars[0]);
-        if (nchunk > 1) {
-            mbar_arrive_expect_tx(&bars[1], chunk_bytes);
-            bulk_g2s(recbuf + (size_t)IDW_TC * RS, a.rec + (size_t)IDW_TC * RS, chunk_bytes, &bars[1]);
+    if (tid == 0) {  // prefetch the first record blocks while the weight tile is generated
+        for (int b = 0; b < IDW_NBUF && b < nchunk; b++) {
+            mbar_arrive_expect_tx(&bars[b], chunk_bytes);
+            bulk_g2s(recbuf + b * chunk_elems, a.rec + b * chunk_elems, chunk_bytes, &bars[b]);
         }
     }
 
-    // ---- weight tile: thread (cell = tid&63, station group = tid>>6) ------------------------------
+    // ---- weight tile: thread (cell = tid&63, station group = tid>>6); branch-free so that the
+    //      IDW_WU independent chains of one iteration interleave (the loop is latency-bound otherwise)
     {
         const int cl = tid & (IDW_CT - 1), sg = tid >> 6;
         const long long c = cell0 + cl;
         const bool live = c < a.g.ncell;
         double X = 0.0, Y = 0.0;
         if (live) cell_xy(a.g, c, X, Y);
-        double hi = 0.0, lo = 0.0;
-        for (int s = sg; s < S_pad; s += IDW_THREADS / IDW_CT) {
-            double w = 0.0;
-            if (live && s < S) {
-                double dx = __dsub_rn(X, __ldg(a.mx + s)), dy = __dsub_rn(Y, __ldg(a.my + s));
-                double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (q == 0.0) {
-                    zflag[cl] = 1;  // coincident station: reference weight is inf; handled in the epilogue
-                } else {
-                    w = idw_weight(q, a.power);
-                    double s1, e1;
-                    two_sum(hi, w, s1, e1);
-                    hi = s1;
-                    lo += e1;
-                }
+        const double* smx = scratch;
+        const double* smy = scratch + S_pad;
+        double dsum[IDW_WU];
+#pragma unroll
+        for (int u = 0; u < IDW_WU; u++) dsum[u] = 0.0;
+        bool coincident = false;
+        const bool p2 = (a.power == 2.0);
+        for (int s0 = sg; s0 < S_pad; s0 += 4 * IDW_WU) {
+#pragma unroll
+            for (int u = 0; u < IDW_WU; u++) {
+                const int s = min(s0 + 4 * u, S_pad - 1);
+                const bool in = (s0 + 4 * u < S_pad);
+                const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
+                const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                const bool ok = live && in && (s < S);
+                const bool zero = (q == 0.0);
+                coincident |= (ok && zero);   // reference weight is inf; handled in the epilogue
+                double w = p2 ? fast_rcp(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
+                w = (ok && !zero) ? w : 0.0;
+                dsum[u] += w;
+                if (in) Wt[s * IDW_WSTR + cl] = w;
             }
-            Wt[s * IDW_WSTR + cl] = w;
         }
-        part[(sg * IDW_CT + cl) * 2] = hi;
-        part[(sg * IDW_CT + cl) * 2 + 1] = lo;
+        if (coincident) zflag[cl] = 1;
+        double d = 0.0;
+#pragma unroll
+        for (int u = 0; u < IDW_WU; u++) d += dsum[u];
+        scratch2[sg * IDW_CT + cl] = d;
         if (sg == 0) Zc[cl] = (live && a.g.dem) ? __ldg(a.g.dem + c) : 0.0;
     }
     __syncthreads();
-    if (tid < IDW_CT) {
-        double hi = part[tid * 2], lo = part[tid * 2 + 1];
-        for (int g2 = 1; g2 < 4; g2++) {
-            double s1, e1;
-            two_sum(hi, part[(g2 * IDW_CT + tid) * 2], s1, e1);
-            hi = s1;
-            lo += e1 + part[(g2 * IDW_CT + tid) * 2 + 1];
-        }
-        double s1, e1;
-        two_sum(hi, lo, s1, e1);
-        Dhi[tid] = s1;
-        Dlo[tid] = e1;
-    }
+    if (tid < IDW_CT) Dall[tid] = (scratch2[tid] + scratch2[IDW_CT + tid]) + (scratch2[2 * IDW_CT + tid] + scratch2[3 * IDW_CT + tid]);
     __syncthreads();
 
-    // ---- main loop over staged step blocks -------------------------------------------------------
-    const int wm = warp >> 2, wn = warp & 3;          // 2 (time) x 4 (cells) warps
+    // ---- main loop: two warp groups alternate step blocks ----------------------------------------
+    const int grp = warp >> 2, wn = warp & 3;         // group (0/1), cell quarter
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / col
     const bool even_pairs = ((a.g.ncell & 1) == 0);
+    // this thread's 4 cells: wn*16 + nt*8 + fc*2 + e
+    double dall[2][2], zc[2][2];
+    bool anyz = false;
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int c1 = wn * 16 + nt * 8 + fc * 2 + e;
+            dall[nt][e] = Dall[c1];
+            zc[nt][e] = Zc[c1];
+            anyz |= (zflag[c1] != 0);
+        }
 
-    for (int ch = 0; ch < nchunk; ch++) {
-        const int buf = ch & 1;
-        const double* rb = recbuf + (size_t)buf * IDW_TC * RS;
-        mbar_wait(&bars[buf], (ch >> 1) & 1);
+    for (int ch = grp; ch < nchunk; ch += 2) {
+        const int buf = ch & (IDW_NBUF - 1);
+        const double* rb = recbuf + buf * chunk_elems;
+        mbar_wait(&bars[buf], (ch >> 2) & 1);
+        if (ch > 0) named_bar_sync(1 + grp, IDW_THREADS);    // my turn on the tensor pipe
 
         double acc[2][2][2];
 #pragma unroll
@@ -151,55 +176,113 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
 #pragma unroll
             for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        const double* ap = rb + (size_t)(wm * 16 + fr) * RS + fc;
+        const double* ap = rb + (size_t)fr * RS + fc;
         const double* bp = Wt + (size_t)fc * IDW_WSTR + wn * 16 + fr;
-#pragma unroll 2
-        for (int k0 = 0; k0 < S_pad; k0 += 4) {
-            double a0 = ap[k0], a1 = ap[k0 + 8 * RS];
-            double b0 = bp[k0 * IDW_WSTR], b1 = bp[k0 * IDW_WSTR + 8];
+        double a0 = ap[0], a1 = ap[8 * RS], b0 = bp[0], b1 = bp[8];
+        for (int k0 = 4; k0 < S_pad; k0 += 4) {   // software pipelined: fragments of the next k-step load under the DMMAs
+            const double na0 = ap[k0], na1 = ap[k0 + 8 * RS];
+            const double nb0 = bp[k0 * IDW_WSTR], nb1 = bp[k0 * IDW_WSTR + 8];
             dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
             dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
             dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
             dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+            a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
         }
+        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+        if (ch + 1 < nchunk) named_bar_arrive(2 - grp, IDW_THREADS);   // hand the tensor pipe to the other group
 
-        // ---- epilogue: thread holds steps {wm*16 + mt*8 + fr} x cells {wn*16 + nt*8 + fc*2 + {0,1}}
+        // ---- epilogue: thread holds steps {mt*8 + fr} x cells {wn*16 + nt*8 + fc*2 + {0,1}}
+        // masked denominator = (sum of all weights) - (weights of this step's missing stations); when that
+        // subtraction cancels more than 5 digits (a missing station almost on the cell) or the
+        // list overflowed, the valid weights are summed directly instead.
+        const double* wcol = Wt + wn * 16 + fc * 2;
+        double den[2][2][2];
+        int nmiss2[2];
+        double2 pp[2];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
-            const int tl = wm * 16 + mt * 8 + fr;
+            const double* meta = rb + (size_t)(mt * 8 + fr) * RS + S_pad;
+            pp[mt] = *reinterpret_cast<const double2*>(meta);
+            const int4* mi = reinterpret_cast<const int4*>(meta + 2);
+            int4 q4 = mi[0];
+            const int nmiss = q4.x;
+            nmiss2[mt] = nmiss;
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                den[mt][nt][0] = dall[nt][0];
+                den[mt][nt][1] = dall[nt][1];
+            }
+            const int nlist = min(nmiss, a.L.maxm);
+            // entries 1..3 of the first quad, then whole quads
+            int idx[4] = {q4.y, q4.z, q4.w, 0};
+            int base = 0, cnt = 3;
+            for (;;) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j < cnt && base + j < nlist) {
+                        const double* wr = wcol + (size_t)idx[j] * IDW_WSTR;
+                        const double2 w0 = *reinterpret_cast<const double2*>(wr);
+                        const double2 w1 = *reinterpret_cast<const double2*>(wr + 8);
+                        den[mt][0][0] -= w0.x;
+                        den[mt][0][1] -= w0.y;
+                        den[mt][1][0] -= w1.x;
+                        den[mt][1][1] -= w1.y;
+                    }
+                }
+                base += cnt;
+                if (base >= nlist) break;
+                q4 = mi[(base + 1) >> 2];
+                idx[0] = q4.x; idx[1] = q4.y; idx[2] = q4.z; idx[3] = q4.w;
+                cnt = 4;
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            const int tl = mt * 8 + fr;
             const int t = ch * IDW_TC + tl;
             if (t >= a.T) continue;
-            const double* meta = rb + (size_t)tl * RS + S_pad;
-            const double p0 = meta[0], p1 = meta[1];
-            const int nmiss = (int)meta[2];
+            const double p0 = pp[mt].x, p1 = pp[mt].y;
+            // per-cell decision, so a cell's value never depends on which other cells share its thread / tile
+            bool need[2][2], redo = false;
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    need[nt][e] = (nmiss2[mt] > a.L.maxm) || !(den[mt][nt][e] > 1e-5 * dall[nt][e]);
+                    redo |= need[nt][e];
+                }
+            if (redo) {   // rare: exact masked sum over the valid stations
+                const uint8_t* vt = a.valid + (size_t)t * S;
+                double ds[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                for (int s = 0; s < S; s++)
+                    if (vt[s]) {
+                        const double* wr = wcol + (size_t)s * IDW_WSTR;
+#pragma unroll
+                        for (int nt = 0; nt < 2; nt++) {
+                            ds[nt][0] += wr[nt * 8];
+                            ds[nt][1] += wr[nt * 8 + 1];
+                        }
+                    }
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                        if (need[nt][e]) den[mt][nt][e] = ds[nt][e];
+            }
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) {
                 const int cl = wn * 16 + nt * 8 + fc * 2;
                 double v[2];
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const int c1 = cl + e;
-                    double num = acc[mt][nt][e];
-                    double den;
-                    if (nmiss <= a.L.maxm) {
-                        double s = Dhi[c1], er = Dlo[c1];
-                        for (int j = 0; j < nmiss; j++) {
-                            int m = (int)meta[3 + j];
-                            double w = Wt[m * IDW_WSTR + c1];
-                            double ns = __dsub_rn(s, w);
-                            er = __dadd_rn(er, __dsub_rn(__dsub_rn(s, ns), w));   // fast two-sum error (s >= w)
-                            s = ns;
-                        }
-                        den = __dadd_rn(s, er);
-                    } else {  // many stations missing: sum the valid weights directly
-                        const uint8_t* vt = a.valid + (size_t)t * S;
-                        den = 0.0;
-                        for (int s = 0; s < S; s++)
-                            if (vt[s]) den += Wt[s * IDW_WSTR + c1];
-                    }
-                    double val = num / den;
-                    if (zflag[c1]) {  // rare: a station sits exactly on this cell
-                        const long long c = cell0 + c1;
+                    const double d = den[mt][nt][e];
+                    // fast reciprocal for ordinary positive denominators, IEEE divide otherwise (0, inf, NaN, subnormal)
+                    double val = (d > 1e-290 && d < 1e290) ? acc[mt][nt][e] * fast_rcp(d) : acc[mt][nt][e] / d;
+                    if (anyz && zflag[cl + e]) {  // rare: a station sits exactly on this cell
+                        const long long c = cell0 + cl + e;
                         if (c < a.g.ncell) {
                             double X, Y;
                             cell_xy(a.g, c, X, Y);
@@ -215,7 +298,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                             if (hit) val = bad ? nan("") : 0.0;                      // inf * 0 dropped by nansum: finite / inf
                         }
                     }
-                    if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(p0, Zc[c1])), p1);   // idw.py:144, left to right
+                    if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(p0, zc[nt][e])), p1);   // idw.py:144, left to right
                     v[e] = clamp_nan_keep(val, a.vmin, a.vmax);
                 }
                 const long long c = cell0 + cl;
@@ -229,17 +312,18 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             }
         }
 
-        __syncthreads();  // every warp is done with rb before the TMA engine overwrites it
-        if (tid == 0 && ch + 2 < nchunk) {
+        named_bar_sync(3 + grp, IDW_THREADS / 2);  // the whole group is done with rb before the TMA engine overwrites it
+        if ((tid & 127) == 0 && ch + IDW_NBUF < nchunk) {
             mbar_arrive_expect_tx(&bars[buf], chunk_bytes);
-            bulk_g2s(recbuf + (size_t)buf * IDW_TC * RS, a.rec + (size_t)(ch + 2) * IDW_TC * RS, chunk_bytes, &bars[buf]);
+            bulk_g2s(recbuf + buf * chunk_elems, a.rec + (size_t)(ch + IDW_NBUF) * chunk_elems, chunk_bytes, &bars[buf]);
         }
     }
 }
 
 static size_t idw_smem_bytes(const RecLayout& L) {
-    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)2 * IDW_TC * L.RS + 3 * IDW_CT + 4 * IDW_CT * 2;
-    return d * sizeof(double) + 2 * sizeof(uint64_t) + IDW_CT * sizeof(int);
+    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * (size_t)L.S_pad +
+               4 * IDW_CT;
+    return d * sizeof(double) + IDW_NBUF * sizeof(uint64_t) + IDW_CT * sizeof(int);
 }
 
 static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int slope_flag, double vmin, double vmax,
