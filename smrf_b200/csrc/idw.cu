@@ -4,20 +4,23 @@
 //   w[c][s] = 1 / dist(c, s)^power                                   (idw.py:53-77)
 //   r[t][s] = d[t][s] - (mz[s]*p0[t] + p1[t])  (0 for missing)       (idw.py:112-136, from prep_steps_kernel)
 //
-// One CTA owns CT=64 consecutive cells for the whole batch of T timesteps:
+// One CTA (512 threads) owns CT=64 consecutive cells for the whole batch of T timesteps:
 //   * the [S x 64] weight tile is generated ONCE from the cell / station coordinates into shared
 //     memory (the reference's [ny,nx,S] cube, 160 GB at 1e8 x 200, is never materialised),
 //     together with the sum D[c] of all S weights;
 //   * step records (residuals + p0, p1, missing-station list) stream in blocks of TC=16 steps
-//     through a 4-deep shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier);
+//     through a 3-deep shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier);
 //   * the numerator is an fp64 tensor-core contraction  C[16 steps x 64 cells] += R[16 x S] * W[S x 64]
-//     on DMMA m8n8k4; a warp owns 16 steps x 16 cells = 2x2 MMA tiles;
-//   * the CTA's 8 warps form two groups of 4 that alternate step blocks: while one group issues
-//     DMMAs (tensor pipe) the other runs its epilogue (fp64 pipe + LSU), handing the tensor pipe
-//     over through named barriers, so the tensor pipe never waits for an epilogue;
-//   * the masked denominator is D[c] (sum of all S weights) minus the weights of that step's missing
-//     stations; if that subtraction cancels more than 5 digits (a missing station dominates D,
-//     SURVEY.md H3) the valid weights are re-summed directly, so the result keeps >= 10 digits;
+//     on DMMA m8n8k4.  A warp owns a 16 x 16 output tile (2x2 MMA tiles) over HALF of the stations;
+//     the two K-halves of a tile swap one 8 x 16 half through shared memory, so each of them
+//     finishes 8 steps x 16 cells;
+//   * the CTA's 16 warps form two groups of 8 that alternate step blocks: while one group issues
+//     DMMAs (tensor pipe, two warps per scheduler -- one warp alone reaches only ~55 % of the DMMA
+//     rate) the other runs its epilogue (fp64 pipe + LSU); the tensor pipe is handed over through
+//     named barriers, so it never waits for an epilogue;
+//   * the masked denominator is D[c] minus the weights of that step's missing stations; if that
+//     subtraction cancels more than 5 digits (a missing station dominates D) the
+//     valid weights are re-summed directly, so the result keeps >= 10 digits;
 //   * epilogue: reciprocal (rcp.approx + 2 Newton steps), retrend against the DEM, NaN-preserving
 //     clamp, 128-bit streaming stores.
 #include "common.cuh"
@@ -26,11 +29,13 @@ namespace smrfb {
 
 constexpr int IDW_CT = 64;             // cells per CTA
 constexpr int IDW_TC = 16;             // timesteps per staged block
-constexpr int IDW_NBUF = 4;            // record ring depth (2 per warp group)
+constexpr int IDW_NBUF = 3;            // record ring depth
 constexpr int IDW_WSTR = IDW_CT + 4;   // weight-tile row stride (doubles), = 4 (mod 16): conflict-free B frags
-constexpr int IDW_THREADS = 256;
+constexpr int IDW_THREADS = 512;
+constexpr int IDW_GROUP = IDW_THREADS / 2;
 constexpr int IDW_MAXM = 15;           // missing-station list length carried in a record (16 int32 with the count)
 constexpr int IDW_WU = 5;              // independent weight chains per thread and iteration
+constexpr int IDW_XSTR = 18;           // exchange tile row stride (doubles)
 
 struct IdwHandle : HandleBase {
     double power = 2.0;
@@ -62,11 +67,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
-__device__ __forceinline__ double idw_weight(double q, double power) {
-    if (power == 2.0) return fast_rcp(q);     // 1/(sqrt(q))^2 of idw.py:77 up to ~1 ulp
-    return 1.0 / pow(sqrt(q), power);          // idw.py:77 as written
-}
-
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -77,10 +77,11 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     double* recbuf = Wt + (size_t)S_pad * IDW_WSTR;                    // [NBUF][TC][RS]
     double* Dall = recbuf + (size_t)IDW_NBUF * IDW_TC * RS;            // [CT] sum of all S weights per cell
     double* Zc = Dall + IDW_CT;                                        // [CT]
-    double* scratch = Zc + IDW_CT;                                     // [2*S_pad] station coordinates
-    double* scratch2 = scratch + 2 * S_pad;                            // [4*CT] partial weight sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch2 + 4 * IDW_CT);  // [NBUF]
-    int* zflag = reinterpret_cast<int*>(bars + IDW_NBUF);              // [CT]
+    double* xbuf = Zc + IDW_CT;                                        // [2 groups][4 quarters][2 halves][8][XSTR]
+    double* scratch = xbuf + 2 * 4 * 2 * 8 * IDW_XSTR;                 // [2*S_pad] station coordinates
+    double* scratch2 = scratch + 2 * S_pad;                            // [8*CT] partial weight sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch2 + 8 * IDW_CT);  // [NBUF]
+    int* zflag = reinterpret_cast<int*>(bars + IDW_NBUF + 1);          // [CT]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long cell0 = (long long)blockIdx.x * IDW_CT;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     // ---- weight tile: thread (cell = tid&63, station group = tid>>6); branch-free so that the
     //      IDW_WU independent chains of one iteration interleave (the loop is latency-bound otherwise)
     {
-        const int cl = tid & (IDW_CT - 1), sg = tid >> 6;
+        const int cl = tid & (IDW_CT - 1), sg = tid >> 6;   // 8 station groups
         const long long c = cell0 + cl;
         const bool live = c < a.g.ncell;
         double X = 0.0, Y = 0.0;
@@ -120,11 +121,11 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
         for (int u = 0; u < IDW_WU; u++) dsum[u] = 0.0;
         bool coincident = false;
         const bool p2 = (a.power == 2.0);
-        for (int s0 = sg; s0 < S_pad; s0 += 4 * IDW_WU) {
+        for (int s0 = sg; s0 < S_pad; s0 += 8 * IDW_WU) {
 #pragma unroll
             for (int u = 0; u < IDW_WU; u++) {
-                const int s = min(s0 + 4 * u, S_pad - 1);
-                const bool in = (s0 + 4 * u < S_pad);
+                const int s = min(s0 + 8 * u, S_pad - 1);
+                const bool in = (s0 + 8 * u < S_pad);
                 const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
                 const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                 const bool ok = live && in && (s < S);
@@ -144,14 +145,22 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
         if (sg == 0) Zc[cl] = (live && a.g.dem) ? __ldg(a.g.dem + c) : 0.0;
     }
     __syncthreads();
-    if (tid < IDW_CT) Dall[tid] = (scratch2[tid] + scratch2[IDW_CT + tid]) + (scratch2[2 * IDW_CT + tid] + scratch2[3 * IDW_CT + tid]);
+    if (tid < IDW_CT) {
+        double d = 0.0;
+#pragma unroll
+        for (int g2 = 0; g2 < 8; g2++) d += scratch2[g2 * IDW_CT + tid];
+        Dall[tid] = d;
+    }
     __syncthreads();
 
     // ---- main loop: two warp groups alternate step blocks ----------------------------------------
-    const int grp = warp >> 2, wn = warp & 3;         // group (0/1), cell quarter
+    const int grp = warp >> 3;                        // group 0/1
+    const int kh = (warp >> 2) & 1;                   // K half: stations [kh*S_pad/2, (kh+1)*S_pad/2)
+    const int wn = warp & 3;                          // cell quarter
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / col
     const bool even_pairs = ((a.g.ncell & 1) == 0);
-    // this thread's 4 cells: wn*16 + nt*8 + fc*2 + e
+    const int khalf = S_pad >> 1;
+    // after the exchange this thread finishes step (kh*8 + fr) for cells wn*16 + nt*8 + fc*2 + e
     double dall[2][2], zc[2][2];
     bool anyz = false;
 #pragma unroll
@@ -163,95 +172,109 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             zc[nt][e] = Zc[c1];
             anyz |= (zflag[c1] != 0);
         }
+    double* xmine = xbuf + (size_t)((grp * 4 + wn) * 2) * 8 * IDW_XSTR;   // [half][8][XSTR] of my warp pair
+    const double* wcol = Wt + wn * 16 + fc * 2;
 
     for (int ch = grp; ch < nchunk; ch += 2) {
-        const int buf = ch & (IDW_NBUF - 1);
+        const int buf = ch % IDW_NBUF;
         const double* rb = recbuf + buf * chunk_elems;
-        mbar_wait(&bars[buf], (ch >> 2) & 1);
-        if (ch > 0) named_bar_sync(1 + grp, IDW_THREADS);    // my turn on the tensor pipe
+        mbar_wait(&bars[buf], (ch / IDW_NBUF) & 1);
+        if (ch > 0) named_bar_sync(1 + grp, IDW_THREADS);    // my group's turn on the tensor pipe
 
         double acc[2][2][2];
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        const double* ap = rb + (size_t)fr * RS + fc;
-        const double* bp = Wt + (size_t)fc * IDW_WSTR + wn * 16 + fr;
-        double a0 = ap[0], a1 = ap[8 * RS], b0 = bp[0], b1 = bp[8];
-        for (int k0 = 4; k0 < S_pad; k0 += 4) {   // software pipelined: fragments of the next k-step load under the DMMAs
-            const double na0 = ap[k0], na1 = ap[k0 + 8 * RS];
-            const double nb0 = bp[k0 * IDW_WSTR], nb1 = bp[k0 * IDW_WSTR + 8];
+        {
+            const double* ap = rb + (size_t)fr * RS + fc + kh * khalf;
+            const double* bp = Wt + (size_t)(fc + kh * khalf) * IDW_WSTR + wn * 16 + fr;
+            double a0 = ap[0], a1 = ap[8 * RS], b0 = bp[0], b1 = bp[8];
+            for (int k0 = 4; k0 < khalf; k0 += 4) {   // software pipelined: next fragments load under the DMMAs
+                const double na0 = ap[k0], na1 = ap[k0 + 8 * RS];
+                const double nb0 = bp[k0 * IDW_WSTR], nb1 = bp[k0 * IDW_WSTR + 8];
+                dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+                dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+                dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+                dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+                a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+            }
             dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
             dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
             dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
             dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
-            a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
         }
-        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
-        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
-        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
-        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
         if (ch + 1 < nchunk) named_bar_arrive(2 - grp, IDW_THREADS);   // hand the tensor pipe to the other group
 
-        // ---- epilogue: thread holds steps {mt*8 + fr} x cells {wn*16 + nt*8 + fc*2 + {0,1}}
+        // ---- swap halves with the other K-half warp of this tile: I keep m-tile kh, give away m-tile 1-kh
+        {
+            double* xo = xmine + (size_t)(1 - kh) * 8 * IDW_XSTR + fr * IDW_XSTR + fc * 2;   // slot read by my partner
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+                *reinterpret_cast<double2*>(xo + nt * 8) = make_double2(kh == 0 ? acc[1][nt][0] : acc[0][nt][0],
+                                                                        kh == 0 ? acc[1][nt][1] : acc[0][nt][1]);
+        }
+        named_bar_sync(3 + grp, IDW_GROUP);
+        double num[2][2];
+        {
+            const double* xi = xmine + (size_t)kh * 8 * IDW_XSTR + fr * IDW_XSTR + fc * 2;
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                const double2 o = *reinterpret_cast<const double2*>(xi + nt * 8);
+                num[nt][0] = (kh == 0 ? acc[0][nt][0] : acc[1][nt][0]) + o.x;
+                num[nt][1] = (kh == 0 ? acc[0][nt][1] : acc[1][nt][1]) + o.y;
+            }
+        }
+
+        // ---- epilogue: step tl = kh*8 + fr, cells wn*16 + nt*8 + fc*2 + {0,1}
         // masked denominator = (sum of all weights) - (weights of this step's missing stations); when that
         // subtraction cancels more than 5 digits (a missing station almost on the cell) or the
         // list overflowed, the valid weights are summed directly instead.
-        const double* wcol = Wt + wn * 16 + fc * 2;
-        double den[2][2][2];
-        int nmiss2[2];
-        double2 pp[2];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-            const double* meta = rb + (size_t)(mt * 8 + fr) * RS + S_pad;
-            pp[mt] = *reinterpret_cast<const double2*>(meta);
+        const int tl = kh * 8 + fr;
+        const int t = ch * IDW_TC + tl;
+        if (t < a.T) {
+            const double* meta = rb + (size_t)tl * RS + S_pad;
+            const double2 pp = *reinterpret_cast<const double2*>(meta);
             const int4* mi = reinterpret_cast<const int4*>(meta + 2);
             int4 q4 = mi[0];
             const int nmiss = q4.x;
-            nmiss2[mt] = nmiss;
+            double den[2][2];
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) {
-                den[mt][nt][0] = dall[nt][0];
-                den[mt][nt][1] = dall[nt][1];
+                den[nt][0] = dall[nt][0];
+                den[nt][1] = dall[nt][1];
             }
-            const int nlist = min(nmiss, a.L.maxm);
-            // entries 1..3 of the first quad, then whole quads
-            int idx[4] = {q4.y, q4.z, q4.w, 0};
-            int base = 0, cnt = 3;
-            for (;;) {
+            {
+                const int nlist = min(nmiss, a.L.maxm);
+                int idx[4] = {q4.y, q4.z, q4.w, 0};   // entries 0..2 ride in the first quad, then whole quads
+                int base = 0, cnt = 3;
+                for (;;) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (j < cnt && base + j < nlist) {
-                        const double* wr = wcol + (size_t)idx[j] * IDW_WSTR;
-                        const double2 w0 = *reinterpret_cast<const double2*>(wr);
-                        const double2 w1 = *reinterpret_cast<const double2*>(wr + 8);
-                        den[mt][0][0] -= w0.x;
-                        den[mt][0][1] -= w0.y;
-                        den[mt][1][0] -= w1.x;
-                        den[mt][1][1] -= w1.y;
+                    for (int j = 0; j < 4; j++) {
+                        if (j < cnt && base + j < nlist) {
+                            const double* wr = wcol + (size_t)idx[j] * IDW_WSTR;
+                            const double2 w0 = *reinterpret_cast<const double2*>(wr);
+                            const double2 w1 = *reinterpret_cast<const double2*>(wr + 8);
+                            den[0][0] -= w0.x;
+                            den[0][1] -= w0.y;
+                            den[1][0] -= w1.x;
+                            den[1][1] -= w1.y;
+                        }
                     }
+                    base += cnt;
+                    if (base >= nlist) break;
+                    q4 = mi[(base + 1) >> 2];
+                    idx[0] = q4.x; idx[1] = q4.y; idx[2] = q4.z; idx[3] = q4.w;
+                    cnt = 4;
                 }
-                base += cnt;
-                if (base >= nlist) break;
-                q4 = mi[(base + 1) >> 2];
-                idx[0] = q4.x; idx[1] = q4.y; idx[2] = q4.z; idx[3] = q4.w;
-                cnt = 4;
             }
-        }
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-            const int tl = mt * 8 + fr;
-            const int t = ch * IDW_TC + tl;
-            if (t >= a.T) continue;
-            const double p0 = pp[mt].x, p1 = pp[mt].y;
             // per-cell decision, so a cell's value never depends on which other cells share its thread / tile
             bool need[2][2], redo = false;
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    need[nt][e] = (nmiss2[mt] > a.L.maxm) || !(den[mt][nt][e] > 1e-5 * dall[nt][e]);
+                    need[nt][e] = (nmiss > a.L.maxm) || !(den[nt][e] > 1e-5 * dall[nt][e]);
                     redo |= need[nt][e];
                 }
             if (redo) {   // rare: exact masked sum over the valid stations
@@ -270,7 +293,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                 for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                     for (int e = 0; e < 2; e++)
-                        if (need[nt][e]) den[mt][nt][e] = ds[nt][e];
+                        if (need[nt][e]) den[nt][e] = ds[nt][e];
             }
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) {
@@ -278,9 +301,9 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                 double v[2];
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const double d = den[mt][nt][e];
+                    const double d = den[nt][e];
                     // fast reciprocal for ordinary positive denominators, IEEE divide otherwise (0, inf, NaN, subnormal)
-                    double val = (d > 1e-290 && d < 1e290) ? acc[mt][nt][e] * fast_rcp(d) : acc[mt][nt][e] / d;
+                    double val = (d > 1e-290 && d < 1e290) ? num[nt][e] * fast_rcp(d) : num[nt][e] / d;
                     if (anyz && zflag[cl + e]) {  // rare: a station sits exactly on this cell
                         const long long c = cell0 + cl + e;
                         if (c < a.g.ncell) {
@@ -298,7 +321,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                             if (hit) val = bad ? nan("") : 0.0;                      // inf * 0 dropped by nansum: finite / inf
                         }
                     }
-                    if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(p0, zc[nt][e])), p1);   // idw.py:144, left to right
+                    if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, zc[nt][e])), pp.y);   // idw.py:144, left to right
                     v[e] = clamp_nan_keep(val, a.vmin, a.vmax);
                 }
                 const long long c = cell0 + cl;
@@ -312,8 +335,8 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             }
         }
 
-        named_bar_sync(3 + grp, IDW_THREADS / 2);  // the whole group is done with rb before the TMA engine overwrites it
-        if ((tid & 127) == 0 && ch + IDW_NBUF < nchunk) {
+        named_bar_sync(3 + grp, IDW_GROUP);  // the whole group is done with rb (and xbuf) before the TMA engine overwrites it
+        if ((tid & (IDW_GROUP - 1)) == 0 && ch + IDW_NBUF < nchunk) {
             mbar_arrive_expect_tx(&bars[buf], chunk_bytes);
             bulk_g2s(recbuf + buf * chunk_elems, a.rec + (size_t)(ch + IDW_NBUF) * chunk_elems, chunk_bytes, &bars[buf]);
         }
@@ -321,9 +344,9 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
 }
 
 static size_t idw_smem_bytes(const RecLayout& L) {
-    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * (size_t)L.S_pad +
-               4 * IDW_CT;
-    return d * sizeof(double) + IDW_NBUF * sizeof(uint64_t) + IDW_CT * sizeof(int);
+    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * 4 * 2 * 8 * IDW_XSTR +
+               2 * (size_t)L.S_pad + 8 * IDW_CT;
+    return d * sizeof(double) + (IDW_NBUF + 1) * sizeof(uint64_t) + IDW_CT * sizeof(int);
 }
 
 static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int slope_flag, double vmin, double vmax,
@@ -373,7 +396,7 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
     h->power = power;
     int rc = upload_geom(h, nsta, mx, my, mz, ny, nx, grid_kind, gx, gy, dem);
     if (rc == SMRFB_OK) {
-        h->L = make_layout(nsta, 4, IDW_MAXM, true);
+        h->L = make_layout(nsta, 8, IDW_MAXM, true);
         h->smem_bytes = idw_smem_bytes(h->L);
         int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
