@@ -77,6 +77,13 @@ int smrfb_idw_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int 
                              double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
                              double* d_out, void* stream);
 
+/* Same, restricted to the cell window [cell_begin, cell_begin + cell_count) of the handle's grid;
+ * d_out is [T][cell_count].  Lets a caller walk a large grid slab by slab with long time blocks
+ * (the per-tile weight generation amortises over T) while the device-resident output stays bounded. */
+int smrfb_idw_distribute_window_dev(smrfb_handle_t h, const double* d_data, int T, int detrend, int slope_flag,
+                                    double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
+                                    int64_t cell_begin, int64_t cell_count, double* d_out, void* stream);
+
 /* ------------------------------------------------------------------ DK (dk.py, krige.c, lusolv.c) */
 int smrfb_dk_create(int nsta, const double* mx, const double* my, const double* mz,
                     int ny, int nx, int grid_kind, const double* gx, const double* gy, const double* dem,
@@ -87,6 +94,9 @@ int smrfb_dk_distribute(smrfb_handle_t h, const double* data, int T, double vmin
 int smrfb_dk_distribute_dev(smrfb_handle_t h, const double* d_data, const double* h_data /* same rows, host copy
                             used to read the NaN masks */, int T, double vmin, double vmax,
                             const double* d_pv_in, double* d_pv_out, double* d_out, void* stream);
+int smrfb_dk_distribute_window_dev(smrfb_handle_t h, const double* d_data, const double* h_data, int T, double vmin,
+                                   double vmax, const double* d_pv_in, double* d_pv_out, int64_t cell_begin,
+                                   int64_t cell_count, double* d_out, void* stream);
 /* Dense weights [ncell][nvalid] (columns = valid stations in station order) for one NaN mask,
  * exactly what DK.calculateWeights leaves in wg (dk.py:127-130).  nan_mask[nsta]: 1 = missing. */
 int smrfb_dk_weights(smrfb_handle_t h, const uint8_t* nan_mask, double* weights_out);

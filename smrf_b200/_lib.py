@@ -37,6 +37,12 @@ _SIGS = {
     "smrfb_idw_distribute_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_idw_distribute_window_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                       ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                       ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_dk_distribute_window_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, c_double_p, ctypes.c_int, ctypes.c_double,
+                                                      ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_dk_create": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                        ctypes.POINTER(handle_t)]),

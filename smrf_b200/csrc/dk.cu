@@ -8,7 +8,7 @@
 //   1. host: B0 = inverse of the full (n+1)x(n+1) system, stations ordered by (elevation desc,
 //      index asc) so that "highest-elevation negative weight" == "first negative weight".
 //   2. dk_build_kernel -- one persistent CTA per SM, B (packed symmetric, <=162 KB) lives in shared
-//      memory.  A tile of 32 neighbouring cells (one warp each) walks the elimination tree depth
+//      memory.  A tile of 32 neighbouring cells (one per warp) walks the elimination tree depth
 //      first: cells that agree on the station to drop share ONE rank-1 downdate of B
 //      (B -= b b'/beta, w -= (w_k/beta) b); where they disagree the tile forks, and on the way
 //      back every downdate is undone with the saved column (B += b b'/beta), so B returns to B0
@@ -30,6 +30,8 @@ namespace smrfb {
 
 constexpr int DK_TILE = 32;
 constexpr int DK_THREADS = 1024;
+constexpr int DK_WARPS = DK_THREADS / 32;
+constexpr int DK_CPW = DK_TILE / DK_WARPS;   // cells per warp
 constexpr int DK_MAXN = 200;          // packed B for n+1 = 201 is 162 KB of shared memory
 constexpr int DK_WORDS = 8;           // 256 active-set bits per cell
 constexpr int DK_NSMAX = 31;          // largest final active set solved in thread-local memory
@@ -45,6 +47,7 @@ struct DkPending {
 
 struct DkBuildArgs {
     int n, NN, NNP, nsel;
+    int handoff;           // active-station count at which cells leave the shared walk for the exact per-cell solver
     long long ncell;
     Geom g;
     const double* sx;      // [n] station x in RANK order (coordinate mode)
@@ -64,14 +67,25 @@ __device__ __forceinline__ double dist_rn(double X, double Y, double sx, double 
     return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
+// 1/x to ~1 ulp for any normal x (MUFU.RCP64H seed + two Newton steps): the IEEE divide's
+// ~35-instruction sequence sat on the critical path of every elimination step.
+__device__ __forceinline__ double dk_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
 __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, NN = a.NN, NNP = a.NNP;
     const int npk = NN * (NN + 1) / 2;
     double* Bp = reinterpret_cast<double*>(smem_raw);           // [npk]
     double* w = Bp + npk;                                       // [32][NN]
-    double* bcol = w + DK_TILE * NN;                            // [NNP]
-    double* betastack = bcol + NNP;                             // [NN]
+    double* bcol = w + DK_TILE * NN;                            // [NNP] column k of B (zeros = inactive)
+    double* bsm = bcol + NNP;                                   // [NNP] bcol / beta
+    double* betastack = bsm + NNP;                              // [NN]
     int* rowoff = reinterpret_cast<int*>(betastack + NN);       // [NNP]
     int* kstack = rowoff + NNP;                                 // [NN]
     int* kc = kstack + NN;                                      // [32]
@@ -89,23 +103,26 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
     __syncthreads();
 
     // rank-1 update of the packed upper triangle with the column in bcol (zeros = skip):
-    //   B[i][j] += sgn * (bcol[i]/beta) * bcol[j]   for j >= i
-    auto rank1 = [&](double beta, double sgn) {
+    //   B[i][j] += sgn * bsm[i] * bcol[j]   for j >= i,   bsm[i] = bcol[i]/beta
+    // Rows are dealt round-robin to the warps.  (Measured on B200, 1e6 cells x 200 stations: 1024 threads with
+    // this plain loop 1.19 s; 512 threads with loads staged ahead of the stores 1.40 s -- the walk is bound by
+    // the barrier / dependent-latency chain of each elimination step, not by the update arithmetic.)
+    auto rank1 = [&](double sgn) {
         double bj[DK_QMAX];
 #pragma unroll
         for (int q = 0; q < DK_QMAX; q++) {
-            int j = lane + 32 * q;
+            const int j = lane + 32 * q;
             bj[q] = (j < NN) ? bcol[j] : 0.0;
         }
-        for (int i = warp; i < NN; i += 32) {
-            const double bi = bcol[i];
+        for (int i = warp; i < NN; i += DK_WARPS) {
+            const double bi = bsm[i];
             if (bi == 0.0) continue;
-            const double bs = sgn * (bi / beta);
+            const double bs = sgn * bi;
             double* row = Bp + rowoff[i];
             const int q0 = i >> 5;
 #pragma unroll
             for (int q = 0; q < DK_QMAX; q++) {
-                int j = lane + 32 * q;
+                const int j = lane + 32 * q;
                 if (q >= q0 && j >= i && j < NN) row[j] = fma(bs, bj[q], row[j]);
             }
         }
@@ -120,80 +137,99 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
             since_refresh = 0;
             for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];
         }
-        const long long cell = tile * DK_TILE + warp;
-        const bool live = cell < a.ncell;
-        double* wc = w + warp * NN;
+        // this warp's cells: warp and warp + DK_WARPS
         {   // right-hand side [dist to every station ; 1] in rank order
-            double X = 0.0, Y = 0.0;
-            if (live && !a.dgrid) cell_xy(a.g, cell, X, Y);
-            for (int j = lane; j < NN; j += 32) {
-                double v = 0.0;
-                if (live) {
-                    if (j == n) v = 1.0;
-                    else if (a.dgrid) v = a.dgrid[(size_t)cell * n + a.perm[j]];
-                    else v = dist_rn(X, Y, a.sx[j], a.sy[j]);
+#pragma unroll
+            for (int h = 0; h < DK_CPW; h++) {
+                const int ci = warp + DK_WARPS * h;
+                const long long cell = tile * DK_TILE + ci;
+                const bool live = cell < a.ncell;
+                double* wc = w + ci * NN;
+                double X = 0.0, Y = 0.0;
+                if (live && !a.dgrid) cell_xy(a.g, cell, X, Y);
+                for (int j = lane; j < NN; j += 32) {
+                    double v = 0.0;
+                    if (live) {
+                        if (j == n) v = 1.0;
+                        else if (a.dgrid) v = a.dgrid[(size_t)cell * n + a.perm[j]];
+                        else v = dist_rn(X, Y, a.sx[j], a.sy[j]);
+                    }
+                    wc[j] = v;
                 }
-                wc[j] = v;
             }
         }
         for (int i = tid; i < NNP; i += DK_THREADS) act[i] = (i < NN) ? 1 : 0;
         __syncthreads();
-        if (live) {   // w = B0 * rhs (B symmetric, packed)
-            double acc[DK_QMAX];
+        {   // w = B0 * rhs (B symmetric, packed); each B element is loaded once for the warp's two cells
+            double acc[DK_CPW][DK_QMAX];
 #pragma unroll
-            for (int q = 0; q < DK_QMAX; q++) acc[q] = 0.0;
+            for (int h = 0; h < DK_CPW; h++)
+#pragma unroll
+                for (int q = 0; q < DK_QMAX; q++) acc[h][q] = 0.0;
             for (int i = 0; i < NN; i++) {
-                const double r = wc[i];
+                double r[DK_CPW];
+#pragma unroll
+                for (int h = 0; h < DK_CPW; h++) r[h] = w[(warp + DK_WARPS * h) * NN + i];
                 const int ro = rowoff[i];
 #pragma unroll
                 for (int q = 0; q < DK_QMAX; q++) {
-                    int j = lane + 32 * q;
+                    const int j = lane + 32 * q;
                     if (j < NN) {
-                        double b = (j >= i) ? Bp[ro + j] : Bp[rowoff[j] + i];
-                        acc[q] = fma(b, r, acc[q]);
+                        const double bv = (j >= i) ? Bp[ro + j] : Bp[rowoff[j] + i];
+#pragma unroll
+                        for (int h = 0; h < DK_CPW; h++) acc[h][q] = fma(bv, r[h], acc[h][q]);
                     }
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < DK_QMAX; q++) {
-                int j = lane + 32 * q;
-                if (j < NN) wc[j] = acc[q];
-            }
+            for (int h = 0; h < DK_CPW; h++)
+#pragma unroll
+                for (int q = 0; q < DK_QMAX; q++) {
+                    const int j = lane + 32 * q;
+                    if (j < NN) w[(warp + DK_WARPS * h) * NN + j] = acc[h][q];
+                }
         }
         const long long rem = a.ncell - tile * DK_TILE;
         unsigned cur_mask = rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
         int depth = 0, npend = 0;
+        unsigned n_apply = 0, n_undo = 0, n_fork = 0;
         __syncthreads();
 
         for (;;) {   // ---- depth-first walk of the tile's elimination tree
             // SELECT: first (= highest elevation) active station with a negative weight
-            if ((cur_mask >> warp) & 1u) {
-                int k = -1;
-                for (int q = 0; q < DK_QMAX; q++) {
-                    int j = lane + 32 * q;
-                    bool c = (j < a.nsel) && act[j] && (wc[j] < 0.0);
-                    unsigned b = __ballot_sync(0xffffffffu, c);
-                    if (b) {
-                        k = 32 * q + __ffs(b) - 1;
-                        break;
+#pragma unroll
+            for (int h = 0; h < DK_CPW; h++) {
+                const int ci = warp + DK_WARPS * h;
+                if ((cur_mask >> ci) & 1u) {
+                    const double* wc = w + ci * NN;
+                    int k = -1;
+                    for (int q = 0; q < DK_QMAX; q++) {
+                        const int j = lane + 32 * q;
+                        const bool c = (j < a.nsel) && act[j] && (wc[j] < 0.0);
+                        const unsigned bb = __ballot_sync(0xffffffffu, c);
+                        if (bb) {
+                            k = 32 * q + __ffs(bb) - 1;
+                            break;
+                        }
                     }
-                }
-                if (k < 0) {   // this cell is done: publish its active set
-                    unsigned myword = 0;
-                    int cnt = 0;
-                    for (int q = 0; q < DK_WORDS; q++) {
-                        int j = lane + 32 * q;
-                        unsigned b = __ballot_sync(0xffffffffu, (j < n) && act[j]);
-                        cnt += __popc(b);
-                        if (lane == q) myword = b;
+                    const bool hand = (k >= 0) && (n - depth <= a.handoff);
+                    if (k < 0 || hand) {   // this cell leaves the shared walk: publish its active set
+                        const long long cell = tile * DK_TILE + ci;
+                        unsigned myword = 0;
+                        for (int q = 0; q < DK_WORDS; q++) {
+                            const int j = lane + 32 * q;
+                            const unsigned bb = __ballot_sync(0xffffffffu, (j < n) && act[j]);
+                            if (lane == q) myword = bb;
+                        }
+                        if (hand && lane == DK_WORDS - 1) myword |= 0x80000000u;   // bit 255: handed off undecided
+                        if (lane < DK_WORDS) a.final_act[(size_t)cell * DK_WORDS + lane] = myword;
+                        k = -1;
                     }
-                    if (lane < DK_WORDS) a.final_act[(size_t)cell * DK_WORDS + lane] = myword;
-                    if (lane == 0) atomicMax(a.maxcount, cnt);
+                    if (lane == 0) kc[ci] = k;
+                } else if (lane == 0) {
+                    kc[ci] = -2;
                 }
-                if (lane == 0) kc[warp] = k;
-            } else if (lane == 0) {
-                kc[warp] = -2;
             }
             __syncthreads();
             if (warp == 0) {   // partition the group by chosen station
@@ -211,7 +247,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     }
                 } else {
                     if (leader) {
-                        int slot = npend + __popc(lead & ((1u << lane) - 1u));
+                        const int slot = npend + __popc(lead & ((1u << lane) - 1u));
                         pend[slot].k = k;
                         pend[slot].mask = grp;
                         pend[slot].depth = depth;
@@ -230,29 +266,45 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                 mask = (unsigned)ctrl[3];
             } else {
                 npend += ctrl[4];
+                n_fork += ctrl[4] > 1;
                 const int target = npend > 0 ? pend[npend - 1].depth : 0;
                 while (depth > target) {   // undo back to the fork point
                     depth--;
+                    n_undo++;
                     const int ku = kstack[depth];
-                    const double beta = betastack[depth];
-                    for (int i = tid; i < NNP; i += DK_THREADS) bcol[i] = undo_g[(size_t)depth * NNP + i];
+                    const double rbeta = dk_rcp(betastack[depth]);
+                    for (int i = tid; i < NNP; i += DK_THREADS) {
+                        const double v = undo_g[(size_t)depth * NNP + i];
+                        bcol[i] = v;
+                        bsm[i] = v * rbeta;
+                    }
                     __syncthreads();
-                    rank1(beta, 1.0);
+                    rank1(1.0);
                     if (tid == 0) act[ku] = 1;
                     __syncthreads();
                 }
-                if (npend == 0) break;   // tile finished, B is back at B0
+                if (npend == 0) {        // tile finished, B is back at B0
+                    if (tid == 0) {
+                        atomicAdd(a.tile_counter + 2, (unsigned long long)n_apply);
+                        atomicAdd(a.tile_counter + 3, (unsigned long long)n_undo);
+                        atomicAdd(a.tile_counter + 4, (unsigned long long)n_fork);
+                    }
+                    break;
+                }
                 npend--;
                 k = pend[npend].k;
                 mask = pend[npend].mask;
                 __syncthreads();         // everyone has read pend[npend] before warp 0 may overwrite it
             }
             // APPLY: drop station k for the cells in mask
+            n_apply++;
             const double beta = Bp[rowoff[k] + k];
+            const double rbeta = dk_rcp(beta);
             for (int i = tid; i < NNP; i += DK_THREADS) {
                 double v = 0.0;
                 if (i < NN && i != k && act[i]) v = (i < k) ? Bp[rowoff[i] + k] : Bp[rowoff[k] + i];
                 bcol[i] = v;
+                bsm[i] = v * rbeta;
                 undo_g[(size_t)depth * NNP + i] = v;
             }
             if (tid == 0) {
@@ -260,13 +312,18 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                 betastack[depth] = beta;
             }
             __syncthreads();
-            if ((mask >> warp) & 1u) {
-                const double f = wc[k] / beta;
-                for (int j = lane; j < NN; j += 32) wc[j] = fma(-f, bcol[j], wc[j]);
-                __syncwarp();
-                if (lane == 0) wc[k] = 0.0;
+#pragma unroll
+            for (int h = 0; h < DK_CPW; h++) {
+                const int ci = warp + DK_WARPS * h;
+                if ((mask >> ci) & 1u) {
+                    double* wc = w + ci * NN;
+                    const double f = wc[k] * rbeta;
+                    for (int j = lane; j < NN; j += 32) wc[j] = fma(-f, bcol[j], wc[j]);
+                    __syncwarp();
+                    if (lane == 0) wc[k] = 0.0;
+                }
             }
-            rank1(beta, -1.0);
+            rank1(-1.0);
             if (tid == 0) {
                 act[k] = 0;
                 ctrl[4] = 0;
@@ -291,8 +348,10 @@ struct DkFinalArgs {
     const double* ad;        // [n][n]
     const double* dgrid;     // optional [ncell][n]
     const int* perm;         // rank -> compressed
+    const int* rankof;       // compressed -> rank
     const int* orig;         // compressed -> original station index (column of the data rows)
-    const uint32_t* final_act;
+    int mode;                // 0: finish the elimination exactly, write the final set back; 1: solve + write the ELL table
+    uint32_t* final_act;
     uint8_t* widx;           // [K][ncell]
     double* wval;            // [K][ncell]
     int* status;             // bit0 singular, bit1 active set larger than DK_NSMAX
@@ -374,8 +433,13 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
     int ids[DK_NSMAX + 1];
     int ns = 0;
     bool over = false;
+    bool handed = false;
     for (int q = 0; q < DK_WORDS; q++) {
         unsigned b = a.final_act[(size_t)cell * DK_WORDS + q];
+        if (q == DK_WORDS - 1) {
+            handed = (b & 0x80000000u) != 0;
+            b &= 0x7fffffffu;
+        }
         while (b) {
             int bit = __ffs(b) - 1;
             b &= b - 1;
@@ -426,13 +490,35 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
         for (int m = msave; m + 1 < ns; m++) ids[m] = ids[m + 1];
         ns--;
     }
-    if (fell_back) atomicAdd(a.fallback_cells, 1ULL);
-    atomicMax(a.maxcount_final, ns);
+    if (a.mode == 0) {   // write the final active set back (rank-indexed bits) for the second pass
+        if (fell_back && !handed) atomicAdd(a.fallback_cells, 1ULL);
+        atomicMax(a.maxcount_final, ns);
+        unsigned words[DK_WORDS];
+        for (int q = 0; q < DK_WORDS; q++) words[q] = 0u;
+        for (int j = 0; j < ns; j++) {
+            const int r = a.rankof[ids[j]];
+            words[r >> 5] |= 1u << (r & 31);
+        }
+        for (int q = 0; q < DK_WORDS; q++) a.final_act[(size_t)cell * DK_WORDS + q] = words[q];
+        return;
+    }
     for (int j = 0; j < a.K; j++) {
         const bool on = j < ns;
         a.widx[(size_t)j * a.ncell + cell] = on ? (uint8_t)a.orig[ids[j]] : 0;
         a.wval[(size_t)j * a.ncell + cell] = on ? A[j * LDA + ns + 1] : 0.0;
     }
+}
+
+// n <= DK_NSMAX: no shared walk at all, every cell starts the exact solver from the full station set
+__global__ void dk_fill_all_kernel(long long ncell, int n, uint32_t* final_act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell * DK_WORDS) return;
+    const int q = (int)(i % DK_WORDS);
+    const int lo = 32 * q;
+    unsigned w = 0u;
+    if (n > lo) w = (n - lo >= 32) ? 0xffffffffu : ((1u << (n - lo)) - 1u);
+    if (q == DK_WORDS - 1) w |= 0x80000000u;
+    final_act[i] = w;
 }
 
 // dense expansion for smrfb_dk_weights / smrfb_krige_grid: out[cell][col], col = compressed index
@@ -473,7 +559,9 @@ __global__ void dk_gather_kernel(const double* __restrict__ rec, RecLayout L, co
 }
 
 struct DkDistArgs {
-    long long ncell;
+    long long ncell;     // cells of the whole grid (ELL plane stride)
+    long long cbase;     // first cell of the window
+    long long ncw;       // cells in the window (out row stride)
     const double* dem;
     int K;
     const uint8_t* widx;
@@ -488,17 +576,18 @@ struct DkDistArgs {
 
 template <int KR>
 __global__ void __launch_bounds__(256) dk_distribute_kernel(DkDistArgs a) {
-    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (c >= a.ncell) return;
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;   // cell within the window
+    if (c >= a.ncw) return;
+    const size_t gc = (size_t)(a.cbase + c);                          // cell within the grid
     double wv[KR];
     const double* vp[KR];
 #pragma unroll
     for (int j = 0; j < KR; j++) {
         const bool on = j < a.K;
-        wv[j] = on ? __ldg(a.wval + (size_t)j * a.ncell + c) : 0.0;
-        vp[j] = a.vt + (size_t)(on ? __ldg(a.widx + (size_t)j * a.ncell + c) : 0) * a.Tm_pad;
+        wv[j] = on ? __ldg(a.wval + (size_t)j * a.ncell + gc) : 0.0;
+        vp[j] = a.vt + (size_t)(on ? __ldg(a.widx + (size_t)j * a.ncell + gc) : 0) * a.Tm_pad;
     }
-    const double Z = __ldg(a.dem + c);
+    const double Z = __ldg(a.dem + gc);
     for (int t0 = 0; t0 < a.Tm; t0 += 2) {
         double r0 = 0.0, r1 = 0.0;
 #pragma unroll
@@ -513,10 +602,10 @@ __global__ void __launch_bounds__(256) dk_distribute_kernel(DkDistArgs a) {
         const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
         const double4 p = make_double4(pa.x, pa.y, pb.x, pb.y);
         double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(p.x, Z)), p.y);   // dk.py:168, left to right
-        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncell + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
         if (t0 + 1 < a.Tm) {
             double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(p.z, Z)), p.w);
-            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncell + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
         }
     }
 }
@@ -524,13 +613,14 @@ __global__ void __launch_bounds__(256) dk_distribute_kernel(DkDistArgs a) {
 // generic K (> DK_KREG): weights re-read per step pair (L2)
 __global__ void __launch_bounds__(256) dk_distribute_generic_kernel(DkDistArgs a) {
     const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (c >= a.ncell) return;
-    const double Z = __ldg(a.dem + c);
+    if (c >= a.ncw) return;
+    const size_t gc = (size_t)(a.cbase + c);
+    const double Z = __ldg(a.dem + gc);
     for (int t0 = 0; t0 < a.Tm; t0 += 2) {
         double r0 = 0.0, r1 = 0.0;
         for (int j = 0; j < a.K; j++) {
-            double wj = __ldg(a.wval + (size_t)j * a.ncell + c);
-            const double* v = a.vt + (size_t)__ldg(a.widx + (size_t)j * a.ncell + c) * a.Tm_pad;
+            double wj = __ldg(a.wval + (size_t)j * a.ncell + gc);
+            const double* v = a.vt + (size_t)__ldg(a.widx + (size_t)j * a.ncell + gc) * a.Tm_pad;
             double2 x = __ldg(reinterpret_cast<const double2*>(v + t0));
             r0 = fma(wj, x.x, r0);
             r1 = fma(wj, x.y, r1);
@@ -539,10 +629,10 @@ __global__ void __launch_bounds__(256) dk_distribute_generic_kernel(DkDistArgs a
         const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
         const double4 p = make_double4(pa.x, pa.y, pb.x, pb.y);
         double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(p.x, Z)), p.y);
-        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncell + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
         if (t0 + 1 < a.Tm) {
             double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(p.z, Z)), p.w);
-            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncell + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
         }
     }
 }
@@ -701,19 +791,19 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const long long ntiles = (in.ncell + DK_TILE - 1) / DK_TILE;
     const int grid = (int)std::min<long long>(ntiles, nsm);
-    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + NNP + NN) * sizeof(double) +
+    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + 2 * NNP + NN) * sizeof(double) +
                   ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
 
     double *d_sx = nullptr, *d_sy = nullptr, *d_cx = nullptr, *d_cy = nullptr, *d_elev = nullptr, *d_ad = nullptr,
            *d_B0p = nullptr, *d_undo = nullptr;
-    int *d_perm = nullptr, *d_orig = nullptr, *d_small = nullptr;
+    int *d_perm = nullptr, *d_orig = nullptr, *d_small = nullptr, *d_rankof = nullptr;
     uint32_t* d_final = nullptr;
     unsigned long long* d_cnt = nullptr;
     int rc = SMRFB_OK;
     auto cleanup = [&]() {
         cudaFree(d_sx); cudaFree(d_sy); cudaFree(d_cx); cudaFree(d_cy); cudaFree(d_elev); cudaFree(d_ad);
-        cudaFree(d_B0p); cudaFree(d_undo); cudaFree(d_perm); cudaFree(d_orig); cudaFree(d_small); cudaFree(d_final);
+        cudaFree(d_B0p); cudaFree(d_undo); cudaFree(d_perm); cudaFree(d_rankof); cudaFree(d_orig); cudaFree(d_small); cudaFree(d_final);
         cudaFree(d_cnt);
     };
 #define DK_TRY(x)                 \
@@ -743,12 +833,17 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     DK_TRY(dev_upload(&d_ad, ad.data(), (size_t)n * n));
     DK_TRY(dev_upload(&d_B0p, B0p.data(), npk));
     DK_TRY(dev_upload(&d_perm, perm.data(), n));
+    {
+        std::vector<int> rankof(n);
+        for (int r = 0; r < n; r++) rankof[perm[r]] = r;
+        DK_TRY(dev_upload(&d_rankof, rankof.data(), n));
+    }
     DK_TRY(dev_upload(&d_orig, in.orig, n));
     DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * n * NNP * sizeof(double)));
     DK_CUDA(cudaMalloc((void**)&d_final, (size_t)in.ncell * DK_WORDS * sizeof(uint32_t)));
-    DK_CUDA(cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)));
+    DK_CUDA(cudaMalloc((void**)&d_cnt, 8 * sizeof(unsigned long long)));
     DK_CUDA(cudaMalloc((void**)&d_small, 4 * sizeof(int)));
-    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
     DK_CUDA(cudaMemsetAsync(d_small, 0, 4 * sizeof(int), st));
 
     DkBuildArgs ba;
@@ -756,34 +851,65 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     ba.ncell = in.ncell; ba.g = in.g;
     ba.sx = d_sx; ba.sy = d_sy; ba.dgrid = in.d_dgrid; ba.perm = d_perm; ba.B0p = d_B0p; ba.undo = d_undo;
     ba.final_act = d_final; ba.tile_counter = d_cnt; ba.maxcount = d_small;
-    DK_CUDA(cudaFuncSetAttribute(dk_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dk_build_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    const bool verbose = getenv("SMRFB_DK_VERBOSE") != nullptr;
+    if (verbose) {
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2);
+        cudaEventRecord(ev0, st);
+    }
+    ba.handoff = 10;   // below ~10 active stations a per-thread exact solve is cheaper than a CTA-wide rank-1 step
+    if (n > DK_NSMAX) {
+        DK_CUDA(cudaFuncSetAttribute(dk_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dk_build_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+    } else {   // small station sets: the exact per-cell solver does the whole elimination (pure reference arithmetic)
+        const long long nw = in.ncell * DK_WORDS;
+        dk_fill_all_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(in.ncell, n, d_final);
+    }
     count_launch();
     DK_CUDA(cudaGetLastError());
+    if (verbose) cudaEventRecord(ev1, st);
+    DkFinalArgs fa;
+    fa.n = n; fa.K = 0; fa.ncell = in.ncell; fa.g = in.g;
+    fa.cx = d_cx; fa.cy = d_cy; fa.elev = d_elev; fa.ad = d_ad; fa.dgrid = in.d_dgrid; fa.perm = d_perm; fa.rankof = d_rankof;
+    fa.orig = d_orig; fa.final_act = d_final; fa.widx = nullptr; fa.wval = nullptr; fa.status = d_small + 1;
+    fa.fallback_cells = d_cnt + 1; fa.maxcount_final = d_small + 2;
+    fa.mode = 0;
+    dk_final_kernel<<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
+    count_launch();
+    DK_CUDA(cudaGetLastError());
+    if (verbose) cudaEventRecord(ev2, st);
     int h_small[4] = {0, 0, 0, 0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaStreamSynchronize(st));
-    const int K = std::max(1, std::min(h_small[0], DK_NSMAX));
-    if (h_small[0] > DK_NSMAX) {
-        set_error("DK: a cell ends with %d active stations; this build solves final sets up to %d", h_small[0], DK_NSMAX);
+    float ms_walk = 0.f, ms_final = 0.f;
+    if (verbose) {
+        cudaEventElapsedTime(&ms_walk, ev0, ev1);
+        cudaEventElapsedTime(&ms_final, ev1, ev2);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    }
+    if (h_small[1] & 2) {
+        set_error("DK: a cell ends the shared walk with more than %d active stations", DK_NSMAX);
         cleanup();
         return SMRFB_ERR_LIMIT;
     }
+    if (h_small[1] & 1) {
+        set_error("DK: singular kriging system (co-located stations?)");
+        cleanup();
+        return SMRFB_ERR_SINGULAR;
+    }
+    const int K = std::max(1, h_small[2]);
     W->n = n;
     W->K = K;
     W->orig.assign(in.orig, in.orig + n);
     W->bytes = (size_t)K * in.ncell * (sizeof(double) + 1);
     DK_CUDA(cudaMalloc((void**)&W->widx, (size_t)K * in.ncell));
     DK_CUDA(cudaMalloc((void**)&W->wval, (size_t)K * in.ncell * sizeof(double)));
-    DkFinalArgs fa;
-    fa.n = n; fa.K = K; fa.ncell = in.ncell; fa.g = in.g;
-    fa.cx = d_cx; fa.cy = d_cy; fa.elev = d_elev; fa.ad = d_ad; fa.dgrid = in.d_dgrid; fa.perm = d_perm; fa.orig = d_orig;
-    fa.final_act = d_final; fa.widx = W->widx; fa.wval = W->wval; fa.status = d_small + 1;
-    fa.fallback_cells = d_cnt + 1; fa.maxcount_final = d_small + 2;
+    fa.K = K; fa.widx = W->widx; fa.wval = W->wval;
+    fa.mode = 1;
     dk_final_kernel<<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
     count_launch();
     DK_CUDA(cudaGetLastError());
-    unsigned long long h_cnt[2] = {0, 0};
+    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaStreamSynchronize(st));
@@ -792,6 +918,9 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
 #undef DK_CUDA
     SMRFB_CHECK(!(h_small[1] & 1), SMRFB_ERR_SINGULAR, "DK: singular kriging system in the final solve");
     if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
+    if (verbose)
+        fprintf(stderr, "[smrfb] dk_build: n=%d cells=%lld tiles=%lld applies=%llu undos=%llu forks=%llu K=%d fallback=%llu "
+                "walk %.1f ms, exact finish %.1f ms\n", n, in.ncell, ntiles, h_cnt[2], h_cnt[3], h_cnt[4], K, h_cnt[1], ms_walk, ms_final);
     return SMRFB_OK;
 }
 
@@ -835,8 +964,12 @@ static int dk_get_weights(DkHandle* h, const std::vector<uint8_t>& nanmask, DkWe
 }
 
 static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T, double vmin, double vmax,
-                  const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
+                  const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st, long long cbase = 0,
+                  long long ncw = -1) {
+    if (ncw < 0) ncw = h->g.ncell;
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    SMRFB_CHECK(cbase >= 0 && ncw > 0 && cbase + ncw <= h->g.ncell, SMRFB_ERR_ARG, "cell window [%lld, +%lld) outside the grid",
+                cbase, ncw);
     const int S = h->S;
     // group the steps by NaN mask, in order of first appearance (dk.py:75-85 recomputes on every change)
     std::vector<std::vector<uint8_t>> masks;
@@ -881,10 +1014,10 @@ static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T
         count_launch();
         SMRFB_CUDA(cudaGetLastError());
         DkDistArgs a;
-        a.ncell = h->g.ncell; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
+        a.ncell = h->g.ncell; a.cbase = cbase; a.ncw = ncw; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
         a.vt = h->d_vt; a.pvt = h->d_pvt; a.steps = h->d_steps; a.Tm = Tm; a.Tm_pad = Tm_pad;
         a.vmin = vmin; a.vmax = vmax; a.out = d_out;
-        const unsigned nblk = (unsigned)((h->g.ncell + 255) / 256);
+        const unsigned nblk = (unsigned)((ncw + 255) / 256);
         if (W->K <= 8) dk_distribute_kernel<8><<<nblk, 256, 0, st>>>(a);
         else if (W->K <= DK_KREG) dk_distribute_kernel<DK_KREG><<<nblk, 256, 0, st>>>(a);
         else dk_distribute_generic_kernel<<<nblk, 256, 0, st>>>(a);
@@ -934,6 +1067,18 @@ int smrfb_dk_distribute_dev(smrfb_handle_t hh, const double* d_data, const doubl
     SMRFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return dk_run(h, d_data, h_data, T, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+}
+
+int smrfb_dk_distribute_window_dev(smrfb_handle_t hh, const double* d_data, const double* h_data, int T, double vmin,
+                                   double vmax, const double* d_pv_in, double* d_pv_out, int64_t cell_begin,
+                                   int64_t cell_count, double* d_out, void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    DkHandle* h = reinterpret_cast<DkHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_DK, SMRFB_ERR_ARG, "not a DK handle");
+    SMRFB_CHECK(d_data && h_data && d_out, SMRFB_ERR_ARG, "NULL data/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return dk_run(h, d_data, h_data, T, vmin, vmax, d_pv_in, d_pv_out, d_out, st, cell_begin, cell_count);
 }
 
 int smrfb_dk_distribute(smrfb_handle_t hh, const double* data, int T, double vmin, double vmax, const double* pv_in,

@@ -55,15 +55,19 @@ struct IdwArgs {
     int T, T_pad;
     int detrend;
     double vmin, vmax;
-    double* out;
+    double* out;          // [T][ncw]
+    long long cbase;      // first cell of the window this launch distributes
+    long long ncw;        // cells in the window
 };
 
-// 1/x to ~1 ulp for positive normal x: MUFU.RCP64H seed (2^-23) + two Newton steps; no special cases.
+// 1/x for positive normal x: MUFU.RCP64H seed (>= 20 bits) + Newton steps; no special cases.
+// Two steps give ~1 ulp; one step gives <= 1e-12 relative, three orders inside the 1e-9 contract.
+template <int STEPS>
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
+#pragma unroll
+    for (int i = 0; i < STEPS; i++) r = fma(r, fma(-x, r, 1.0), r);
     return r;
 }
 
@@ -110,8 +114,8 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     //      IDW_WU independent chains of one iteration interleave (the loop is latency-bound otherwise)
     {
         const int cl = tid & (IDW_CT - 1), sg = tid >> 6;   // 8 station groups
-        const long long c = cell0 + cl;
-        const bool live = c < a.g.ncell;
+        const long long c = a.cbase + cell0 + cl;          // global cell index
+        const bool live = cell0 + cl < a.ncw;
         double X = 0.0, Y = 0.0;
         if (live) cell_xy(a.g, c, X, Y);
         const double* smx = scratch;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                 const bool ok = live && in && (s < S);
                 const bool zero = (q == 0.0);
                 coincident |= (ok && zero);   // reference weight is inf; handled in the epilogue
-                double w = p2 ? fast_rcp(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
+                double w = p2 ? fast_rcp<2>(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
                 w = (ok && !zero) ? w : 0.0;
                 dsum[u] += w;
                 if (in) Wt[s * IDW_WSTR + cl] = w;
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     const int kh = (warp >> 2) & 1;                   // K half: stations [kh*S_pad/2, (kh+1)*S_pad/2)
     const int wn = warp & 3;                          // cell quarter
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / col
-    const bool even_pairs = ((a.g.ncell & 1) == 0);
+    const bool even_pairs = ((a.ncw & 1) == 0);
     const int khalf = S_pad >> 1;
     // after the exchange this thread finishes step (kh*8 + fr) for cells wn*16 + nt*8 + fc*2 + e
     double dall[2][2], zc[2][2];
@@ -303,12 +307,12 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                 for (int e = 0; e < 2; e++) {
                     const double d = den[nt][e];
                     // fast reciprocal for ordinary positive denominators, IEEE divide otherwise (0, inf, NaN, subnormal)
-                    double val = (d > 1e-290 && d < 1e290) ? num[nt][e] * fast_rcp(d) : num[nt][e] / d;
+                    double val = (d > 1e-290 && d < 1e290) ? num[nt][e] * fast_rcp<2>(d) : num[nt][e] / d;
                     if (anyz && zflag[cl + e]) {  // rare: a station sits exactly on this cell
                         const long long c = cell0 + cl + e;
-                        if (c < a.g.ncell) {
+                        if (c < a.ncw) {
                             double X, Y;
-                            cell_xy(a.g, c, X, Y);
+                            cell_xy(a.g, a.cbase + c, X, Y);
                             const uint8_t* vt = a.valid + (size_t)t * S;
                             bool hit = false, bad = false;
                             for (int s = 0; s < S; s++) {
@@ -325,12 +329,12 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                     v[e] = clamp_nan_keep(val, a.vmin, a.vmax);
                 }
                 const long long c = cell0 + cl;
-                double* op = a.out + (size_t)t * (size_t)a.g.ncell + c;
-                if (c + 1 < a.g.ncell && even_pairs) {
+                double* op = a.out + (size_t)t * (size_t)a.ncw + c;
+                if (c + 1 < a.ncw && even_pairs) {
                     __stcs(reinterpret_cast<double2*>(op), make_double2(v[0], v[1]));
                 } else {
-                    if (c < a.g.ncell) __stcs(op, v[0]);
-                    if (c + 1 < a.g.ncell) __stcs(op + 1, v[1]);
+                    if (c < a.ncw) __stcs(op, v[0]);
+                    if (c + 1 < a.ncw) __stcs(op + 1, v[1]);
                 }
             }
         }
@@ -350,8 +354,12 @@ static size_t idw_smem_bytes(const RecLayout& L) {
 }
 
 static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int slope_flag, double vmin, double vmax,
-                   const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
+                   const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st, long long cbase = 0,
+                   long long ncw = -1) {
+    if (ncw < 0) ncw = h->g.ncell;
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    SMRFB_CHECK(cbase >= 0 && ncw > 0 && cbase + ncw <= h->g.ncell, SMRFB_ERR_ARG, "cell window [%lld, +%lld) outside the grid",
+                cbase, ncw);
     SMRFB_CHECK(!detrend || (h->g.dem && h->d_mz), SMRFB_ERR_ARG, "detrended IDW needs mz and GridZ");
     const int T_pad = (T + IDW_TC - 1) / IDW_TC * IDW_TC;
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_rec, &h->rec_cap, (size_t)T_pad * h->L.RS * sizeof(double)));
@@ -372,7 +380,9 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     a.vmin = vmin;
     a.vmax = vmax;
     a.out = d_out;
-    long long nblk = (h->g.ncell + IDW_CT - 1) / IDW_CT;
+    a.cbase = cbase;
+    a.ncw = ncw;
+    long long nblk = (ncw + IDW_CT - 1) / IDW_CT;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     idw_distribute_kernel<<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);
     count_launch();
@@ -430,6 +440,18 @@ int smrfb_idw_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, int
     SMRFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return idw_run(h, d_data, T, detrend, slope_flag, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+}
+
+int smrfb_idw_distribute_window_dev(smrfb_handle_t hh, const double* d_data, int T, int detrend, int slope_flag,
+                                    double vmin, double vmax, const double* d_pv_in, double* d_pv_out, int64_t cell_begin,
+                                    int64_t cell_count, double* d_out, void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    IdwHandle* h = reinterpret_cast<IdwHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_IDW, SMRFB_ERR_ARG, "not an IDW handle");
+    SMRFB_CHECK(d_data && d_out, SMRFB_ERR_ARG, "NULL data/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return idw_run(h, d_data, T, detrend, slope_flag, vmin, vmax, d_pv_in, d_pv_out, d_out, st, cell_begin, cell_count);
 }
 
 // Host-buffer entry: the batch is cut into sub-batches of steps so that a double-buffered device
