@@ -535,28 +535,12 @@ __global__ void dk_expand_kernel(int K, long long ncell, int n, const uint8_t* w
 // ------------------------------------------------------------------------------------------
 // Steady state (dk.py:86-96): out = sum_k w_k * r[station_k] + p0*Z + p1
 // ------------------------------------------------------------------------------------------
-// rec[steps[tl]][s] -> vt[s][tl], pvt[tl] = (p0, p1) for the steps of one mask group.
-__global__ void dk_gather_kernel(const double* __restrict__ rec, RecLayout L, const int* __restrict__ steps, int Tm,
-                                 int Tm_pad, double* __restrict__ vt, double* __restrict__ pvt) {
-    __shared__ double tile[32][33];
-    const int s0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int tl = t0 + r, s = s0 + threadIdx.x;
-        tile[r][threadIdx.x] = (tl < Tm && s < L.S) ? rec[(size_t)steps[tl] * L.RS + s] : 0.0;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int s = s0 + r, tl = t0 + threadIdx.x;
-        if (s < L.S && tl < Tm_pad) vt[(size_t)s * Tm_pad + tl] = tile[threadIdx.x][r];
-    }
-    if (blockIdx.x == 0 && threadIdx.y == 0) {
-        int tl = t0 + threadIdx.x;
-        if (tl < Tm_pad) {
-            pvt[2 * tl] = tl < Tm ? rec[(size_t)steps[tl] * L.RS + L.meta()] : 0.0;
-            pvt[2 * tl + 1] = tl < Tm ? rec[(size_t)steps[tl] * L.RS + L.meta() + 1] : 0.0;
-        }
-    }
-}
+// One CTA = 256 consecutive cells of the window, one thread per cell.  The thread keeps its cell's
+// (station, weight) pairs in registers; the residuals of DK_TCH timesteps for ALL stations are staged
+// in shared memory as res[step][station] (coalesced copy of the prepared step records), so the
+// per-cell gathers are shared-memory reads: cells of a warp mostly share their station set
+// (broadcast), and different stations fall into different banks.  Stores stream out row by row.
+constexpr int DK_TCH = 16;
 
 struct DkDistArgs {
     long long ncell;     // cells of the whole grid (ELL plane stride)
@@ -566,74 +550,88 @@ struct DkDistArgs {
     int K;
     const uint8_t* widx;
     const double* wval;
-    const double* vt;    // [S][Tm_pad]
-    const double* pvt;   // [Tm_pad][2]
-    const int* steps;    // [Tm] output step index
-    int Tm, Tm_pad;
+    const double* rec;   // prepared step records [T][RS]
+    RecLayout L;
+    const int* steps;    // [Tm] step indices of this mask group
+    int Tm;
     double vmin, vmax;
-    double* out;         // [T][ncell]
+    double* out;         // [T][ncw]
 };
+
+constexpr int DK_RSTR = DK_TCH + 2;   // shared residual tile row stride (doubles): rows 144 B apart, 16-B aligned pairs
 
 template <int KR>
 __global__ void __launch_bounds__(256) dk_distribute_kernel(DkDistArgs a) {
-    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;   // cell within the window
-    if (c >= a.ncw) return;
-    const size_t gc = (size_t)(a.cbase + c);                          // cell within the grid
+    extern __shared__ __align__(16) unsigned char dk_smem[];
+    const int S = a.L.S, SP = a.L.S_pad;
+    double* res = reinterpret_cast<double*>(dk_smem);        // [SP][DK_RSTR]: residual of station s at local step tl
+    double* pv = res + SP * DK_RSTR;                         // [DK_TCH][2]
+    int* stp = reinterpret_cast<int*>(pv + DK_TCH * 2);      // [DK_TCH]
+    const int tid = threadIdx.x;
+    const long long c = (long long)blockIdx.x * 256 + tid;   // cell within the window
+    const bool live = c < a.ncw;
+    const size_t gc = (size_t)(a.cbase + (live ? c : 0));    // cell within the grid
     double wv[KR];
-    const double* vp[KR];
+    const double* wp[KR];
 #pragma unroll
     for (int j = 0; j < KR; j++) {
-        const bool on = j < a.K;
+        const bool on = live && j < a.K;
         wv[j] = on ? __ldg(a.wval + (size_t)j * a.ncell + gc) : 0.0;
-        vp[j] = a.vt + (size_t)(on ? __ldg(a.widx + (size_t)j * a.ncell + gc) : 0) * a.Tm_pad;
+        wp[j] = res + (on ? (int)__ldg(a.widx + (size_t)j * a.ncell + gc) : 0) * DK_RSTR;
     }
-    const double Z = __ldg(a.dem + gc);
-    for (int t0 = 0; t0 < a.Tm; t0 += 2) {
-        double r0 = 0.0, r1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < KR; j++) {
-            if (j < a.K) {
-                double2 x = __ldg(reinterpret_cast<const double2*>(vp[j] + t0));
-                r0 = fma(wv[j], x.x, r0);
-                r1 = fma(wv[j], x.y, r1);
-            }
+    const double Z = live ? __ldg(a.dem + gc) : 0.0;
+    for (int t0 = 0; t0 < a.Tm; t0 += DK_TCH) {
+        __syncthreads();
+        if (tid < DK_TCH) {
+            const int tl = t0 + tid;
+            const int st = tl < a.Tm ? a.steps[tl] : -1;
+            stp[tid] = st;
+            pv[2 * tid] = st >= 0 ? a.rec[(size_t)st * a.L.RS + a.L.meta()] : 0.0;
+            pv[2 * tid + 1] = st >= 0 ? a.rec[(size_t)st * a.L.RS + a.L.meta() + 1] : 0.0;
         }
-        const double2 pa = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0));
-        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
-        const double4 p = make_double4(pa.x, pa.y, pb.x, pb.y);
-        double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(p.x, Z)), p.y);   // dk.py:168, left to right
-        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
-        if (t0 + 1 < a.Tm) {
-            double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(p.z, Z)), p.w);
-            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+        for (int e = tid; e < DK_TCH * SP; e += 256) {      // coalesced over stations, transposed into the tile
+            const int tl = e / SP, sidx = e - tl * SP;
+            const int tt = t0 + tl;
+            res[sidx * DK_RSTR + tl] = (tt < a.Tm && sidx < S) ? a.rec[(size_t)a.steps[tt] * a.L.RS + sidx] : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 2
+            for (int tl = 0; tl < DK_TCH; tl += 2) {
+                const int st0 = stp[tl], st1 = stp[tl + 1];
+                if (st0 < 0) break;
+                double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < KR; j++) {               // dk.py:91 (entries past K have weight 0)
+                    const double2 x = *reinterpret_cast<const double2*>(wp[j] + tl);
+                    r0 = fma(wv[j], x.x, r0);
+                    r1 = fma(wv[j], x.y, r1);
+                }
+                const double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(pv[2 * tl], Z)), pv[2 * tl + 1]);   // dk.py:168, left to right
+                __stcs(a.out + (size_t)st0 * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+                if (st1 >= 0) {
+                    const double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(pv[2 * tl + 2], Z)), pv[2 * tl + 3]);
+                    __stcs(a.out + (size_t)st1 * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+                }
+            }
         }
     }
 }
 
-// generic K (> DK_KREG): weights re-read per step pair (L2)
+// generic K (> DK_KREG): the ELL entries are re-read per step (L2)
 __global__ void __launch_bounds__(256) dk_distribute_generic_kernel(DkDistArgs a) {
     const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
     if (c >= a.ncw) return;
     const size_t gc = (size_t)(a.cbase + c);
     const double Z = __ldg(a.dem + gc);
-    for (int t0 = 0; t0 < a.Tm; t0 += 2) {
-        double r0 = 0.0, r1 = 0.0;
-        for (int j = 0; j < a.K; j++) {
-            double wj = __ldg(a.wval + (size_t)j * a.ncell + gc);
-            const double* v = a.vt + (size_t)__ldg(a.widx + (size_t)j * a.ncell + gc) * a.Tm_pad;
-            double2 x = __ldg(reinterpret_cast<const double2*>(v + t0));
-            r0 = fma(wj, x.x, r0);
-            r1 = fma(wj, x.y, r1);
-        }
-        const double2 pa = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0));
-        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
-        const double4 p = make_double4(pa.x, pa.y, pb.x, pb.y);
-        double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(p.x, Z)), p.y);
-        __stcs(a.out + (size_t)__ldg(a.steps + t0) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
-        if (t0 + 1 < a.Tm) {
-            double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(p.z, Z)), p.w);
-            __stcs(a.out + (size_t)__ldg(a.steps + t0 + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
-        }
+    for (int tl = 0; tl < a.Tm; tl++) {
+        const int st = a.steps[tl];
+        const double* rr = a.rec + (size_t)st * a.L.RS;
+        double r = 0.0;
+        for (int j = 0; j < a.K; j++)
+            r = fma(__ldg(a.wval + (size_t)j * a.ncell + gc), __ldg(rr + __ldg(a.widx + (size_t)j * a.ncell + gc)), r);
+        const double v = __dadd_rn(__dadd_rn(r, __dmul_rn(rr[a.L.meta()], Z)), rr[a.L.meta() + 1]);
+        __stcs(a.out + (size_t)st * a.ncw + c, clamp_nan_keep(v, a.vmin, a.vmax));
     }
 }
 
@@ -660,18 +658,12 @@ struct DkHandle : HandleBase {
     size_t cache_bytes = 0, cache_budget = (size_t)48 << 30;
     long long masks_built = 0, fallback_cells = 0;
     int max_active = 0;
-    double* d_vt = nullptr;
-    size_t vt_cap = 0;
-    double* d_pvt = nullptr;
-    size_t pvt_cap = 0;
     int* d_steps = nullptr;
     size_t steps_cap = 0;
     DkHandle() : HandleBase(HK_DK) {}
     ~DkHandle() override {
         cudaSetDevice(device);
         for (auto& e : cache) delete e.second;
-        cudaFree(d_vt);
-        cudaFree(d_pvt);
         cudaFree(d_steps);
     }
 };
@@ -1002,25 +994,27 @@ static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T
         DkWeights* W = nullptr;
         SMRFB_PROPAGATE(dk_get_weights(h, masks[gi], &W));
         const int Tm = (int)groups[gi].size();
-        const int Tm_pad = (Tm + 31) / 32 * 32;
-        // the staging buffers are reused by the next group: wait for the previous group's kernel
+        // the step-index buffer is reused by the next group: wait for the previous group's kernel
         SMRFB_CUDA(cudaStreamSynchronize(st));
-        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_vt, &h->vt_cap, (size_t)S * Tm_pad * sizeof(double)));
-        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pvt, &h->pvt_cap, (size_t)Tm_pad * 2 * sizeof(double)));
-        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_steps, &h->steps_cap, (size_t)Tm_pad * sizeof(int)));
+        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_steps, &h->steps_cap, (size_t)Tm * sizeof(int)));
         SMRFB_CUDA(cudaMemcpyAsync(h->d_steps, groups[gi].data(), (size_t)Tm * sizeof(int), cudaMemcpyHostToDevice, st));
-        dim3 tb(32, 8), tg((S + 31) / 32, Tm_pad / 32);
-        dk_gather_kernel<<<tg, tb, 0, st>>>(h->d_rec, h->L, h->d_steps, Tm, Tm_pad, h->d_vt, h->d_pvt);
-        count_launch();
-        SMRFB_CUDA(cudaGetLastError());
         DkDistArgs a;
         a.ncell = h->g.ncell; a.cbase = cbase; a.ncw = ncw; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
-        a.vt = h->d_vt; a.pvt = h->d_pvt; a.steps = h->d_steps; a.Tm = Tm; a.Tm_pad = Tm_pad;
+        a.rec = h->d_rec; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
         a.vmin = vmin; a.vmax = vmax; a.out = d_out;
         const unsigned nblk = (unsigned)((ncw + 255) / 256);
-        if (W->K <= 8) dk_distribute_kernel<8><<<nblk, 256, 0, st>>>(a);
-        else if (W->K <= DK_KREG) dk_distribute_kernel<DK_KREG><<<nblk, 256, 0, st>>>(a);
-        else dk_distribute_generic_kernel<<<nblk, 256, 0, st>>>(a);
+        const size_t dsm = ((size_t)DK_RSTR * h->L.S_pad + DK_TCH * 2) * sizeof(double) + DK_TCH * sizeof(int);
+        switch ((W->K + 1) / 2) {   // register-resident (station, weight) pairs, padded to an even count
+            case 1: dk_distribute_kernel<2><<<nblk, 256, dsm, st>>>(a); break;
+            case 2: dk_distribute_kernel<4><<<nblk, 256, dsm, st>>>(a); break;
+            case 3: dk_distribute_kernel<6><<<nblk, 256, dsm, st>>>(a); break;
+            case 4: dk_distribute_kernel<8><<<nblk, 256, dsm, st>>>(a); break;
+            case 5: dk_distribute_kernel<10><<<nblk, 256, dsm, st>>>(a); break;
+            case 6: dk_distribute_kernel<12><<<nblk, 256, dsm, st>>>(a); break;
+            case 7: dk_distribute_kernel<14><<<nblk, 256, dsm, st>>>(a); break;
+            case 8: dk_distribute_kernel<DK_KREG><<<nblk, 256, dsm, st>>>(a); break;
+            default: dk_distribute_generic_kernel<<<nblk, 256, 0, st>>>(a);
+        }
         count_launch();
         SMRFB_CUDA(cudaGetLastError());
     }

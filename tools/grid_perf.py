@@ -1,0 +1,33 @@
+"""Device-resident timing of the GRID-linear kernel on the C5 shape (development aid)."""
+import sys, time
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from smrf_b200 import _lib, synthetic as syn
+from smrf_b200.spatial import GRID
+ny = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+nx = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+x, y, dem = syn.make_dem(ny, nx, dx=10.0, noise=False)
+px, py, pz = syn.make_source_lattice(x, y, dem, spacing=3000.0 * ny / 4000 / 5.0 if ny < 4000 else 600.0, jitter=30.0, seed=5)
+X = np.broadcast_to(x[None, :], (ny, nx)); Y = np.broadcast_to(y[:, None], (ny, nx))
+t0 = time.perf_counter()
+g = GRID({"grid_local": False, "grid_mask": False}, px, py, X, Y, mz=pz, GridZ=dem)
+print("points %d, create (Delaunay + find_simplex on host + upload): %.2f s" % (len(px), time.perf_counter() - t0))
+f = syn.make_source_fields(px, py, pz, T, seed=9)
+L = _lib.lib()
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); st = stream.cuda_stream
+d_f = torch.from_numpy(f).cuda()
+d_out = torch.empty((T, ny * nx), dtype=torch.float64, device="cuda")
+for det in (1, 0):
+    for _ in range(2):
+        _lib.check(L.smrfb_grid_distribute_dev(g._h, d_f.data_ptr(), T, det, -1, -50.0, 50.0, None, None, d_out.data_ptr(), st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        _lib.check(L.smrfb_grid_distribute_dev(g._h, d_f.data_ptr(), T, det, -1, -50.0, 50.0, None, None, d_out.data_ptr(), st))
+    e1.record(stream); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    cs = ny * nx * T / (ms * 1e-3)
+    print("GRID %dx%d P=%d T=%d detrend=%d: %.2f ms  %.1f G cell-steps/s  write %.0f GB/s" % (ny, nx, len(px), T, det, ms, cs / 1e9, cs * 8 / 1e9))
