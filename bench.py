@@ -378,7 +378,11 @@ def main():
     dk_bytes = 8.0 * slab_cells * Tb + slab_cells * (8.0 + dk_stats[2] * 9.0)
     roof = {"kernel": "idw_distribute_kernel (prep_steps_kernel + idw_distribute_kernel per field; the prep launch is < 0.1 % of it)",
             "bound": "tensor", "achieved": idw_flops / (idw_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": idw_flops / (idw_ms * 1e-3) / 1e12 / fp64_peak, "traffic": None,
+            "frac": idw_flops / (idw_ms * 1e-3) / 1e12 / fp64_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact shape (1e7 cells x 720 steps x 200
+            # stations), ncu --set full, profiles/r01_final_ncu.md; null for other shapes
+            "traffic": 57.66e9 if (slab_cells == 10_000_000 and Tb == 720 and S == 200) else None,
+            "traffic_unit": "bytes per launch (algorithmic: %.3e)" % idw_bytes,
             "peak_source": "fp64 tensor (DMMA) peak " + fp64_src + "; MEASURED_PEAKS.json holds no fp64 figure",
             "algorithmic_flops_per_launch": idw_flops, "ms_per_launch": idw_ms,
             "why_tensor": "dense fp64 IDW at 200 stations is 2*S = 400 flop per 8-byte output = 50 flop/B, far right of the fp64 ridge "
