@@ -1,0 +1,119 @@
+"""Mirror of the reference's dispatch layer ``smrf.distribute.image_data.image_data`` for the hot path.
+
+Same attribute and method names as the reference base class (smrf/distribute/image_data.py:8-274) for the two
+methods on the path -- ``_initialize(topo, metadata)`` (:127-208) and ``_distribute(data, other_attribute=None,
+zeros=None)`` (:210-263) -- so a variable class written against the reference (``air_temp.ta`` etc.) can inherit
+from this one unchanged.  Differences:
+
+  * the interpolators are the CUDA-backed ``smrf_b200.spatial`` classes;
+  * ``prefetch(frame)`` (optional) distributes a whole [time x station] DataFrame block in one fused launch and
+    ``_distribute`` then serves the matching timestep from that block (clamp already applied) -- the run-loop façade
+    of SURVEY.md 8f N-d.  Without ``prefetch`` every ``_distribute`` call is one launch, like the reference.
+"""
+import logging
+
+import numpy as np
+
+from ..spatial import dk, grid, idw
+
+
+class image_data:
+    def __init__(self, variable):
+        self.variable = variable
+        setattr(self, variable, None)
+        self.gridded = False
+        self._block = None
+        self._block_index = None
+        self._logger = logging.getLogger(__name__)
+
+    def getConfig(self, cfg):
+        # image_data.py:77-108
+        if "stations" in cfg.keys() and cfg["stations"] is not None and not isinstance(cfg["stations"], list):
+            cfg["stations"] = [cfg["stations"]]
+        self.gridded = cfg.get("distribution") == "grid"
+        self.getStations(cfg)
+        self.config = cfg
+
+    def getStations(self, config):
+        # image_data.py:110-125: list.sort() returns None, so the station order always comes from the metadata;
+        # reproduced on purpose (SURVEY.md 8a note)
+        stations = None
+        if "stations" in config.keys() and config["stations"] is not None:
+            stations = config["stations"].sort()
+        self.stations = stations
+
+    def _initialize(self, topo, metadata):
+        # image_data.py:127-208
+        self.min = -np.inf if self.config.get("min") is None else self.config["min"]
+        self.max = np.inf if self.config.get("max") is None else self.config["max"]
+        if self.stations is not None:
+            metadata = metadata.loc[self.stations]
+        else:
+            self.stations = metadata.index.values
+        self.metadata = metadata
+        try:
+            self.mx = metadata.utm_x.values
+            self.my = metadata.utm_y.values
+        except Exception:
+            self.mx = metadata.X.values
+            self.my = metadata.Y.values
+        self.mz = metadata.elevation.values
+        dist = self.config.get("distribution")
+        if dist == "idw":
+            self.idw = idw.IDW(self.mx, self.my, topo.X, topo.Y, mz=self.mz, GridZ=topo.dem, power=self.config["idw_power"])
+        elif dist == "dk":
+            self.dk = dk.DK(self.mx, self.my, self.mz, topo.X, topo.Y, topo.dem, self.config)
+        elif dist == "grid":
+            self.grid = grid.GRID(self.config, self.mx, self.my, topo.X, topo.Y, mz=self.mz, GridZ=topo.dem,
+                                  mask=getattr(topo, "mask", None), metadata=metadata)
+        else:
+            raise Exception("Could not determine the distribution method for {}".format(self.variable))
+
+    # ------------------------------------------------------------------ block façade
+    def prefetch(self, frame):
+        """Distribute every row of ``frame`` ([time x station] DataFrame) now; clamp to min/max fused."""
+        rows = frame[self.stations]
+        vals = np.ascontiguousarray(rows.values, dtype=np.float64)
+        if np.isnan(vals).all(axis=1).any():
+            raise Exception("{}: All data values are NaN".format(self.variable))
+        dist = self.config["distribution"]
+        if dist == "idw":
+            blk = self.idw.distribute_block(vals, detrend=bool(self.config["detrend"]), flag=self.config.get("detrend_slope", 0),
+                                            vmin=self.min, vmax=self.max)
+        elif dist == "dk":
+            blk = self.dk.distribute_block(vals, vmin=self.min, vmax=self.max)
+        else:
+            blk = self.grid.distribute_block(vals, detrend=bool(self.config["detrend"]), flag=self.config.get("detrend_slope", 0),
+                                             vmin=self.min, vmax=self.max)
+        self._block = blk
+        self._block_index = {k: i for i, k in enumerate(rows.index)}
+        return blk
+
+    def _distribute(self, data, other_attribute=None, zeros=None):
+        # image_data.py:210-263
+        key = getattr(data, "name", None)
+        if self._block is not None and key in self._block_index:
+            v = self._block[self._block_index[key]]
+        else:
+            data = data[self.stations]
+            if np.sum(data.isnull()) == data.shape[0]:
+                raise Exception("{}: All data values are NaN".format(self.variable))
+            dist = self.config["distribution"]
+            if dist == "idw":
+                if self.config["detrend"]:
+                    v = self.idw.detrendedIDW(data.values, self.config["detrend_slope"], zeros=zeros)
+                else:
+                    v = self.idw.calculateIDW(data.values)
+            elif dist == "dk":
+                v = self.dk.calculate(data.values)
+            elif dist == "grid":
+                if self.config["detrend"]:
+                    v = self.grid.detrendedInterpolation(data, self.config["detrend_slope"], self.config["grid_method"])
+                else:
+                    v = self.grid.calculateInterpolation(data.values, self.config["grid_method"])
+            else:
+                raise Exception("unknown distribution")
+        if other_attribute is not None:
+            setattr(self, other_attribute, v)
+        else:
+            setattr(self, self.variable, v)
