@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libsmrfb.so")
 SOURCES = ["common.cu", "idw.cu", "grid.cu", "dk.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("SMRFB_NVCC_DEFS", "").split()
 
 
 def _stale(target, deps):

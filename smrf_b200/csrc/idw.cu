@@ -33,7 +33,7 @@ constexpr int IDW_NBUF = 3;            // record ring depth
 constexpr int IDW_WSTR = IDW_CT + 4;   // weight-tile row stride (doubles), = 4 (mod 16): conflict-free B frags
 constexpr int IDW_THREADS = 512;
 constexpr int IDW_GROUP = IDW_THREADS / 2;
-constexpr int IDW_MAXM = 15;           // missing-station list length carried in a record (16 int32 with the count)
+constexpr int IDW_MAXM = 47;           // missing-station list length carried in a record (48 int32 with the count)
 constexpr int IDW_WU = 5;              // independent weight chains per thread and iteration
 constexpr int IDW_XSTR = 18;           // exchange tile row stride (doubles)
 
@@ -54,14 +54,16 @@ struct IdwArgs {
     const uint8_t* valid;
     int T, T_pad;
     int detrend;
+    int clamp;            // 0 when both bounds are infinite: the compare / select instructions are skipped
     double vmin, vmax;
     double* out;          // [T][ncw]
     long long cbase;      // first cell of the window this launch distributes
     long long ncw;        // cells in the window
 };
 
-// 1/x for positive normal x: MUFU.RCP64H seed (>= 20 bits) + Newton steps; no special cases.
-// Two steps give ~1 ulp; one step gives <= 1e-12 relative, three orders inside the 1e-9 contract.
+// 1/x for positive normal x: MUFU.RCP64H seed (measured ~2^-10 relative) + Newton steps; no special cases.
+// Two steps give <= ~4e-13 relative (weights: far inside the 1e-9 contract, and numerator and denominator
+// use the same weight values); the quotient in the epilogue adds a residual correction to reach ~1 ulp.
 template <int STEPS>
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
@@ -183,7 +185,9 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
         const int buf = ch % IDW_NBUF;
         const double* rb = recbuf + buf * chunk_elems;
         mbar_wait(&bars[buf], (ch / IDW_NBUF) & 1);
+#ifndef IDW_FREERUN
         if (ch > 0) named_bar_sync(1 + grp, IDW_THREADS);    // my group's turn on the tensor pipe
+#endif
 
         double acc[2][2][2];
 #pragma unroll
@@ -208,7 +212,9 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
             dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
         }
+#ifndef IDW_FREERUN
         if (ch + 1 < nchunk) named_bar_arrive(2 - grp, IDW_THREADS);   // hand the tensor pipe to the other group
+#endif
 
         // ---- swap halves with the other K-half warp of this tile: I keep m-tile kh, give away m-tile 1-kh
         {
@@ -274,11 +280,14 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             }
             // per-cell decision, so a cell's value never depends on which other cells share its thread / tile
             bool need[2][2], redo = false;
+            const bool over = nmiss > a.L.maxm;
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    need[nt][e] = (nmiss > a.L.maxm) || !(den[nt][e] > 1e-5 * dall[nt][e]);
+                    // den < D * 2^-17 (or den <= 0): compared on the high words with integer instructions --
+                    // every fp64 instruction issued here costs tensor-pipe time (profiles/r01_fp64_mix_probe.txt)
+                    need[nt][e] = over || (__double2hiint(den[nt][e]) < __double2hiint(dall[nt][e]) - (17 << 20));
                     redo |= need[nt][e];
                 }
             if (redo) {   // rare: exact masked sum over the valid stations
@@ -306,8 +315,12 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const double d = den[nt][e];
-                    // fast reciprocal for ordinary positive denominators, IEEE divide otherwise (0, inf, NaN, subnormal)
-                    double val = (d > 1e-290 && d < 1e290) ? num[nt][e] * fast_rcp<2>(d) : num[nt][e] / d;
+                    // num / den: reciprocal seed (MUFU.RCP64H, ~2^-10) + two Newton steps, then one residual
+                    // correction of the quotient (7 fp64 instructions, ~1 ulp; den is a positive normal number for
+                    // every live cell)
+                    const double r = fast_rcp<2>(d);
+                    double val = num[nt][e] * r;
+                    val = fma(fma(-d, val, num[nt][e]), r, val);
                     if (anyz && zflag[cl + e]) {  // rare: a station sits exactly on this cell
                         const long long c = cell0 + cl + e;
                         if (c < a.ncw) {
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
                         }
                     }
                     if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, zc[nt][e])), pp.y);   // idw.py:144, left to right
-                    v[e] = clamp_nan_keep(val, a.vmin, a.vmax);
+                    v[e] = a.clamp ? clamp_nan_keep(val, a.vmin, a.vmax) : val;
                 }
                 const long long c = cell0 + cl;
                 double* op = a.out + (size_t)t * (size_t)a.ncw + c;
@@ -379,6 +392,7 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     a.detrend = detrend;
     a.vmin = vmin;
     a.vmax = vmax;
+    a.clamp = !(std::isinf(vmin) && vmin < 0 && std::isinf(vmax) && vmax > 0);
     a.out = d_out;
     a.cbase = cbase;
     a.ncw = ncw;

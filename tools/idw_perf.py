@@ -17,7 +17,8 @@ def main():
     T = int(sys.argv[4]) if len(sys.argv) > 4 else 128
     x, y, dem = syn.make_dem(ny, nx, dx=30.0, noise=False)
     mx, my, mz = syn.make_stations(S, x, y, dem)
-    data = syn.dropouts_iid(syn.make_series("air_temp", mz, T), p=0.02)
+    import os
+    data = syn.dropouts_iid(syn.make_series("air_temp", mz, T), p=float(os.environ.get("DROP_P", "0.02")))
     L = _lib.lib()
     h = _lib.handle_t()
     _lib.check(L.smrfb_idw_create(S, _lib.dptr(mx), _lib.dptr(my), _lib.dptr(mz), ny, nx, 0, _lib.dptr(x), _lib.dptr(y),
