@@ -12,15 +12,16 @@
 //     through a 3-deep shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier);
 //   * the numerator is an fp64 tensor-core contraction  C[16 steps x 64 cells] += R[16 x S] * W[S x 64]
 //     on DMMA m8n8k4.  A warp owns a 16 x 16 output tile (2x2 MMA tiles) over HALF of the stations;
-//     the two K-halves of a tile swap one 8 x 16 half through shared memory, so each of them
-//     finishes 8 steps x 16 cells;
+//     the partial tiles of the two K-halves go through a shared-memory transpose buffer, after which
+//     every warp finishes two whole steps x 64 cells: all lanes of a warp then share the step (uniform
+//     missing-station loop, broadcast metadata reads, conflict-free weight reads, 512 B contiguous stores);
 //   * the CTA's 16 warps form two groups of 8 that alternate step blocks: while one group issues
 //     DMMAs (tensor pipe, two warps per scheduler -- one warp alone reaches only ~55 % of the DMMA
 //     rate) the other runs its epilogue (fp64 pipe + LSU); the tensor pipe is handed over through
 //     named barriers, so it never waits for an epilogue;
 //   * the masked denominator is D[c] minus the weights of that step's missing stations; if that
-//     subtraction cancels more than 5 digits (a missing station dominates D) the
-//     valid weights are re-summed directly, so the result keeps >= 10 digits;
+//     subtraction cancels more than ~2 digits (a missing station dominates D) the
+//     valid weights are re-summed directly, so the result keeps >= 13 digits;
 //   * epilogue: reciprocal (rcp.approx + 2 Newton steps), retrend against the DEM, NaN-preserving
 //     clamp, 128-bit streaming stores.
 #include "common.cuh"
@@ -35,7 +36,7 @@ constexpr int IDW_THREADS = 512;
 constexpr int IDW_GROUP = IDW_THREADS / 2;
 constexpr int IDW_MAXM = 47;           // missing-station list length carried in a record (48 int32 with the count)
 constexpr int IDW_WU = 5;              // independent weight chains per thread and iteration
-constexpr int IDW_XSTR = 18;           // exchange tile row stride (doubles)
+constexpr int IDW_XSTR = 72;           // transpose buffer row stride (doubles): = 16 (mod 32) words, conflict-free tile writes
 
 struct IdwHandle : HandleBase {
     double power = 2.0;
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     double* recbuf = Wt + (size_t)S_pad * IDW_WSTR;                    // [NBUF][TC][RS]
     double* Dall = recbuf + (size_t)IDW_NBUF * IDW_TC * RS;            // [CT] sum of all S weights per cell
     double* Zc = Dall + IDW_CT;                                        // [CT]
-    double* xbuf = Zc + IDW_CT;                                        // [2 groups][4 quarters][2 halves][8][XSTR]
-    double* scratch = xbuf + 2 * 4 * 2 * 8 * IDW_XSTR;                 // [2*S_pad] station coordinates
+    double* xbuf = Zc + IDW_CT;                                        // [2 K-halves][TC][XSTR] partial numerator tiles
+    double* scratch = xbuf + 2 * IDW_TC * IDW_XSTR;                    // [2*S_pad] station coordinates
     double* scratch2 = scratch + 2 * S_pad;                            // [8*CT] partial weight sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch2 + 8 * IDW_CT);  // [NBUF]
     int* zflag = reinterpret_cast<int*>(bars + IDW_NBUF + 1);          // [CT]
@@ -166,20 +167,17 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / col
     const bool even_pairs = ((a.ncw & 1) == 0);
     const int khalf = S_pad >> 1;
-    // after the exchange this thread finishes step (kh*8 + fr) for cells wn*16 + nt*8 + fc*2 + e
-    double dall[2][2], zc[2][2];
+    // after the transpose this thread finishes steps (wg, wg + 8) of its group's block for cells 2*lane, 2*lane + 1
+    const int wg = warp & 7;
+    double dall[2], zc[2];
     bool anyz = false;
 #pragma unroll
-    for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int c1 = wn * 16 + nt * 8 + fc * 2 + e;
-            dall[nt][e] = Dall[c1];
-            zc[nt][e] = Zc[c1];
-            anyz |= (zflag[c1] != 0);
-        }
-    double* xmine = xbuf + (size_t)((grp * 4 + wn) * 2) * 8 * IDW_XSTR;   // [half][8][XSTR] of my warp pair
-    const double* wcol = Wt + wn * 16 + fc * 2;
+    for (int e = 0; e < 2; e++) {
+        dall[e] = Dall[2 * lane + e];
+        zc[e] = Zc[2 * lane + e];
+        anyz |= (zflag[2 * lane + e] != 0);
+    }
+    const double* wcol = Wt + 2 * lane;
 
     for (int ch = grp; ch < nchunk; ch += 2) {
         const int buf = ch % IDW_NBUF;
@@ -216,132 +214,155 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
         if (ch + 1 < nchunk) named_bar_arrive(2 - grp, IDW_THREADS);   // hand the tensor pipe to the other group
 #endif
 
-        // ---- swap halves with the other K-half warp of this tile: I keep m-tile kh, give away m-tile 1-kh
+        // ---- transpose the partial tiles through shared memory (one buffer, used by the two groups in turn)
+        if (ch > 0) named_bar_sync(5 + grp, IDW_THREADS);              // the other group has read its tile out
         {
-            double* xo = xmine + (size_t)(1 - kh) * 8 * IDW_XSTR + fr * IDW_XSTR + fc * 2;   // slot read by my partner
+            double* xo = xbuf + (size_t)kh * IDW_TC * IDW_XSTR + (size_t)fr * IDW_XSTR + wn * 16 + fc * 2;
 #pragma unroll
-            for (int nt = 0; nt < 2; nt++)
-                *reinterpret_cast<double2*>(xo + nt * 8) = make_double2(kh == 0 ? acc[1][nt][0] : acc[0][nt][0],
-                                                                        kh == 0 ? acc[1][nt][1] : acc[0][nt][1]);
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++)
+                    *reinterpret_cast<double2*>(xo + mt * 8 * IDW_XSTR + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         }
         named_bar_sync(3 + grp, IDW_GROUP);
         double num[2][2];
-        {
-            const double* xi = xmine + (size_t)kh * 8 * IDW_XSTR + fr * IDW_XSTR + fc * 2;
 #pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-                const double2 o = *reinterpret_cast<const double2*>(xi + nt * 8);
-                num[nt][0] = (kh == 0 ? acc[0][nt][0] : acc[1][nt][0]) + o.x;
-                num[nt][1] = (kh == 0 ? acc[0][nt][1] : acc[1][nt][1]) + o.y;
-            }
+        for (int h = 0; h < 2; h++) {
+            const double* xi = xbuf + (size_t)(wg + 8 * h) * IDW_XSTR + 2 * lane;
+            const double2 p0v = *reinterpret_cast<const double2*>(xi);
+            const double2 p1v = *reinterpret_cast<const double2*>(xi + IDW_TC * IDW_XSTR);
+            num[h][0] = p0v.x + p1v.x;
+            num[h][1] = p0v.y + p1v.y;
         }
+        if (ch + 1 < nchunk) named_bar_arrive(6 - grp, IDW_THREADS);   // buffer free for the other group
 
-        // ---- epilogue: step tl = kh*8 + fr, cells wn*16 + nt*8 + fc*2 + {0,1}
-        // masked denominator = (sum of all weights) - (weights of this step's missing stations); when that
-        // subtraction cancels more than 5 digits (a missing station almost on the cell) or the
+        // ---- epilogue: steps tl = wg + 8h (h = 0, 1), cells 2*lane + {0,1}; the whole warp works on one step.
+        // Written in phases so that the four outputs of a thread advance together: on an SM sub-partition that
+        // another group keeps saturated with DMMAs every dependent instruction waits ~16 cycles for an issue slot,
+        // so the length of the dependent chain, not the instruction count, decides when this group is ready again.
+        // Masked denominator = (sum of all weights) - (weights of this step's missing stations); when that
+        // subtraction cancels more than ~2 digits (a missing station almost on the cell) or the
         // list overflowed, the valid weights are summed directly instead.
-        const int tl = kh * 8 + fr;
-        const int t = ch * IDW_TC + tl;
-        if (t < a.T) {
-            const double* meta = rb + (size_t)tl * RS + S_pad;
-            const double2 pp = *reinterpret_cast<const double2*>(meta);
-            const int4* mi = reinterpret_cast<const int4*>(meta + 2);
-            int4 q4 = mi[0];
-            const int nmiss = q4.x;
-            double den[2][2];
+        double den[2][2];
+        double2 pp[2];
+        int nmiss2[2];
+        {
+            const int4* mi0 = reinterpret_cast<const int4*>(rb + (size_t)wg * RS + S_pad + 2);
+            const int4* mi1 = reinterpret_cast<const int4*>(rb + (size_t)(wg + 8) * RS + S_pad + 2);
+            pp[0] = *reinterpret_cast<const double2*>(rb + (size_t)wg * RS + S_pad);
+            pp[1] = *reinterpret_cast<const double2*>(rb + (size_t)(wg + 8) * RS + S_pad);
+            int4 qa = mi0[0], qb = mi1[0];
+            nmiss2[0] = qa.x;
+            nmiss2[1] = qb.x;
+            den[0][0] = den[1][0] = dall[0];
+            den[0][1] = den[1][1] = dall[1];
+            const int n0 = min(qa.x, a.L.maxm), n1 = min(qb.x, a.L.maxm);
+            const int nmax = max(n0, n1);
+            // entry j of a list sits at int position j + 1: positions 1..3 ride in the first quad
+            int ia[4] = {qa.y, qa.z, qa.w, 0}, ib[4] = {qb.y, qb.z, qb.w, 0};
+            int base = 0, cnt = 3;
+            for (;;) {
 #pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-                den[nt][0] = dall[nt][0];
-                den[nt][1] = dall[nt][1];
-            }
-            {
-                const int nlist = min(nmiss, a.L.maxm);
-                int idx[4] = {q4.y, q4.z, q4.w, 0};   // entries 0..2 ride in the first quad, then whole quads
-                int base = 0, cnt = 3;
-                for (;;) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (j < cnt && base + j < nlist) {
-                            const double* wr = wcol + (size_t)idx[j] * IDW_WSTR;
-                            const double2 w0 = *reinterpret_cast<const double2*>(wr);
-                            const double2 w1 = *reinterpret_cast<const double2*>(wr + 8);
+                for (int j = 0; j < 4; j++) {
+                    if (j < cnt) {
+                        if (base + j < n0) {
+                            const double2 w0 = *reinterpret_cast<const double2*>(wcol + (size_t)ia[j] * IDW_WSTR);
                             den[0][0] -= w0.x;
                             den[0][1] -= w0.y;
+                        }
+                        if (base + j < n1) {
+                            const double2 w1 = *reinterpret_cast<const double2*>(wcol + (size_t)ib[j] * IDW_WSTR);
                             den[1][0] -= w1.x;
                             den[1][1] -= w1.y;
                         }
                     }
-                    base += cnt;
-                    if (base >= nlist) break;
-                    q4 = mi[(base + 1) >> 2];
-                    idx[0] = q4.x; idx[1] = q4.y; idx[2] = q4.z; idx[3] = q4.w;
-                    cnt = 4;
                 }
+                base += cnt;
+                if (base >= nmax) break;
+                qa = mi0[(base + 1) >> 2];
+                qb = mi1[(base + 1) >> 2];
+                ia[0] = qa.x; ia[1] = qa.y; ia[2] = qa.z; ia[3] = qa.w;
+                ib[0] = qb.x; ib[1] = qb.y; ib[2] = qb.z; ib[3] = qb.w;
+                cnt = 4;
             }
-            // per-cell decision, so a cell's value never depends on which other cells share its thread / tile
-            bool need[2][2], redo = false;
-            const bool over = nmiss > a.L.maxm;
+        }
+        // per-cell decision, so a cell's value never depends on which other cells share its thread / tile:
+        // den < ~D * 2^-7 (or den <= 0), compared on the high words with integer instructions (every fp64
+        // instruction issued here costs tensor-pipe time, profiles/r01_fp64_mix_probe.txt)
+        bool need[2][2], redo = false;
 #pragma unroll
-            for (int nt = 0; nt < 2; nt++)
+        for (int h = 0; h < 2; h++)
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    // den < D * 2^-17 (or den <= 0): compared on the high words with integer instructions --
-                    // every fp64 instruction issued here costs tensor-pipe time (profiles/r01_fp64_mix_probe.txt)
-                    need[nt][e] = over || (__double2hiint(den[nt][e]) < __double2hiint(dall[nt][e]) - (17 << 20));
-                    redo |= need[nt][e];
-                }
-            if (redo) {   // rare: exact masked sum over the valid stations
-                const uint8_t* vt = a.valid + (size_t)t * S;
-                double ds[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                for (int s = 0; s < S; s++)
-                    if (vt[s]) {
-                        const double* wr = wcol + (size_t)s * IDW_WSTR;
+            for (int e = 0; e < 2; e++) {
+                need[h][e] = (nmiss2[h] > a.L.maxm) || (__double2hiint(den[h][e]) < __double2hiint(dall[e]) - (7 << 20));
+                redo |= need[h][e];
+            }
+        if (redo) {   // rare: exact masked sum over the valid stations
 #pragma unroll
-                        for (int nt = 0; nt < 2; nt++) {
-                            ds[nt][0] += wr[nt * 8];
-                            ds[nt][1] += wr[nt * 8 + 1];
+            for (int h = 0; h < 2; h++) {
+                const int t = ch * IDW_TC + wg + 8 * h;
+                if ((need[h][0] || need[h][1]) && t < a.T) {
+                    const uint8_t* vt = a.valid + (size_t)t * S;
+                    double ds0 = 0.0, ds1 = 0.0;
+                    for (int s = 0; s < S; s++)
+                        if (vt[s]) {
+                            const double2 w0 = *reinterpret_cast<const double2*>(wcol + (size_t)s * IDW_WSTR);
+                            ds0 += w0.x;
+                            ds1 += w0.y;
                         }
-                    }
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-                        if (need[nt][e]) den[nt][e] = ds[nt][e];
+                    if (need[h][0]) den[h][0] = ds0;
+                    if (need[h][1]) den[h][1] = ds1;
+                }
             }
+        }
+        // num / den: reciprocal seed (MUFU.RCP64H, ~2^-10) + two Newton steps, then one residual correction of
+        // the quotient (~1 ulp; den is a positive normal number for every live cell); four independent chains
+        double val[2][2];
 #pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-                const int cl = wn * 16 + nt * 8 + fc * 2;
-                double v[2];
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const double d = den[h][e];
+                const double r = fast_rcp<2>(d);
+                const double q = num[h][e] * r;
+                val[h][e] = fma(fma(-d, q, num[h][e]), r, q);
+            }
+        if (anyz) {   // rare: a station sits exactly on one of this thread's cells
+#pragma unroll
+            for (int h = 0; h < 2; h++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const double d = den[nt][e];
-                    // num / den: reciprocal seed (MUFU.RCP64H, ~2^-10) + two Newton steps, then one residual
-                    // correction of the quotient (7 fp64 instructions, ~1 ulp; den is a positive normal number for
-                    // every live cell)
-                    const double r = fast_rcp<2>(d);
-                    double val = num[nt][e] * r;
-                    val = fma(fma(-d, val, num[nt][e]), r, val);
-                    if (anyz && zflag[cl + e]) {  // rare: a station sits exactly on this cell
-                        const long long c = cell0 + cl + e;
-                        if (c < a.ncw) {
-                            double X, Y;
-                            cell_xy(a.g, a.cbase + c, X, Y);
-                            const uint8_t* vt = a.valid + (size_t)t * S;
-                            bool hit = false, bad = false;
-                            for (int s = 0; s < S; s++) {
-                                double dx = __dsub_rn(X, a.mx[s]), dy = __dsub_rn(Y, a.my[s]);
-                                if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) == 0.0 && vt[s]) {
-                                    hit = true;
-                                    if (rb[(size_t)tl * RS + s] != 0.0) bad = true;   // inf * r: +-inf / inf
-                                }
+                    const int tl = wg + 8 * h;
+                    const int t = ch * IDW_TC + tl;
+                    const long long c = cell0 + 2 * lane + e;
+                    if (zflag[2 * lane + e] && c < a.ncw && t < a.T) {
+                        double X, Y;
+                        cell_xy(a.g, a.cbase + c, X, Y);
+                        const uint8_t* vt = a.valid + (size_t)t * S;
+                        bool hit = false, bad = false;
+                        for (int s = 0; s < S; s++) {
+                            double dx = __dsub_rn(X, a.mx[s]), dy = __dsub_rn(Y, a.my[s]);
+                            if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) == 0.0 && vt[s]) {
+                                hit = true;
+                                if (rb[(size_t)tl * RS + s] != 0.0) bad = true;   // inf * r: +-inf / inf
                             }
-                            if (hit) val = bad ? nan("") : 0.0;                      // inf * 0 dropped by nansum: finite / inf
                         }
+                        if (hit) val[h][e] = bad ? nan("") : 0.0;                // inf * 0 dropped by nansum: finite / inf
                     }
-                    if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, zc[nt][e])), pp.y);   // idw.py:144, left to right
-                    v[e] = a.clamp ? clamp_nan_keep(val, a.vmin, a.vmax) : val;
                 }
-                const long long c = cell0 + cl;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int t = ch * IDW_TC + wg + 8 * h;
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                double x = val[h][e];
+                if (a.detrend) x = __dadd_rn(__dadd_rn(x, __dmul_rn(pp[h].x, zc[e])), pp[h].y);   // idw.py:144, left to right
+                v[e] = a.clamp ? clamp_nan_keep(x, a.vmin, a.vmax) : x;
+            }
+            if (t < a.T) {
+                const long long c = cell0 + 2 * lane;
                 double* op = a.out + (size_t)t * (size_t)a.ncw + c;
                 if (c + 1 < a.ncw && even_pairs) {
                     __stcs(reinterpret_cast<double2*>(op), make_double2(v[0], v[1]));
@@ -352,7 +373,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             }
         }
 
-        named_bar_sync(3 + grp, IDW_GROUP);  // the whole group is done with rb (and xbuf) before the TMA engine overwrites it
+        named_bar_sync(3 + grp, IDW_GROUP);  // the whole group is done with rb before the TMA engine overwrites it
         if ((tid & (IDW_GROUP - 1)) == 0 && ch + IDW_NBUF < nchunk) {
             mbar_arrive_expect_tx(&bars[buf], chunk_bytes);
             bulk_g2s(recbuf + buf * chunk_elems, a.rec + (size_t)(ch + IDW_NBUF) * chunk_elems, chunk_bytes, &bars[buf]);
@@ -361,7 +382,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
 }
 
 static size_t idw_smem_bytes(const RecLayout& L) {
-    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * 4 * 2 * 8 * IDW_XSTR +
+    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * IDW_TC * IDW_XSTR +
                2 * (size_t)L.S_pad + 8 * IDW_CT;
     return d * sizeof(double) + (IDW_NBUF + 1) * sizeof(uint64_t) + IDW_CT * sizeof(int);
 }
