@@ -536,11 +536,19 @@ __global__ void dk_expand_kernel(int K, long long ncell, int n, const uint8_t* w
 // Steady state (dk.py:86-96): out = sum_k w_k * r[station_k] + p0*Z + p1
 // ------------------------------------------------------------------------------------------
 // One CTA = 256 consecutive cells of the window, one thread per cell.  The thread keeps its cell's
-// (station, weight) pairs in registers; the residuals of DK_TCH timesteps for ALL stations are staged
-// in shared memory as res[step][station] (coalesced copy of the prepared step records), so the
-// per-cell gathers are shared-memory reads: cells of a warp mostly share their station set
-// (broadcast), and different stations fall into different banks.  Stores stream out row by row.
-constexpr int DK_TCH = 16;
+// (station, weight) pairs in registers; the prepared step records (residuals of ALL stations + p0, p1) of
+// DK_TCH timesteps are staged in shared memory by 1-D TMA bulk copies (one per step record, completion on
+// an mbarrier), double buffered so the copy of the next block overlaps the arithmetic of this one.  The
+// per-cell gathers are shared-memory reads: cells of a warp mostly share their station set (broadcast),
+// and different stations fall into different banks.  Stores stream out row by row.
+#ifndef DK_TCH_DEF
+#define DK_TCH_DEF 16
+#endif
+#ifndef DK_DT_DEF
+#define DK_DT_DEF 256
+#endif
+constexpr int DK_TCH = DK_TCH_DEF;
+constexpr int DK_DT = DK_DT_DEF;     // threads (= cells) per CTA of the distribute kernel
 
 struct DkDistArgs {
     long long ncell;     // cells of the whole grid (ELL plane stride)
@@ -558,63 +566,81 @@ struct DkDistArgs {
     double* out;         // [T][ncw]
 };
 
-constexpr int DK_RSTR = DK_TCH + 2;   // shared residual tile row stride (doubles): rows 144 B apart, 16-B aligned pairs
-
 template <int KR>
-__global__ void __launch_bounds__(256) dk_distribute_kernel(DkDistArgs a) {
+__global__ void __launch_bounds__(DK_DT) dk_distribute_kernel(DkDistArgs a) {
     extern __shared__ __align__(16) unsigned char dk_smem[];
-    const int S = a.L.S, SP = a.L.S_pad;
-    double* res = reinterpret_cast<double*>(dk_smem);        // [SP][DK_RSTR]: residual of station s at local step tl
-    double* pv = res + SP * DK_RSTR;                         // [DK_TCH][2]
-    int* stp = reinterpret_cast<int*>(pv + DK_TCH * 2);      // [DK_TCH]
+    const int ROW = a.L.S_pad + 2;                            // residuals + p0, p1 (doubles); 16-byte multiple
+    double* res = reinterpret_cast<double*>(dk_smem);        // [2][DK_TCH][ROW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res + 2 * DK_TCH * ROW);   // [2]
+    int* stp = reinterpret_cast<int*>(bars + 2);              // [2][DK_TCH]
     const int tid = threadIdx.x;
-    const long long c = (long long)blockIdx.x * 256 + tid;   // cell within the window
+    const long long c = (long long)blockIdx.x * DK_DT + tid; // cell within the window
     const bool live = c < a.ncw;
     const size_t gc = (size_t)(a.cbase + (live ? c : 0));    // cell within the grid
+    const int nchunk = (a.Tm + DK_TCH - 1) / DK_TCH;
+    const uint32_t row_bytes = (uint32_t)(ROW * sizeof(double));
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int chn) {     // one thread: bulk-copy the step records of block chn into buffer chn & 1
+        const int b = chn & 1;
+        const int t0 = chn * DK_TCH;
+        const int nrow = min(DK_TCH, a.Tm - t0);
+        mbar_arrive_expect_tx(&bars[b], row_bytes * nrow);
+        for (int r = 0; r < nrow; r++) {
+            const int st = a.steps[t0 + r];
+            stp[b * DK_TCH + r] = st;
+            bulk_g2s(res + (size_t)(b * DK_TCH + r) * ROW, a.rec + (size_t)st * a.L.RS, row_bytes, &bars[b]);
+        }
+        for (int r = nrow; r < DK_TCH; r++) stp[b * DK_TCH + r] = -1;
+    };
+    if (tid == 0) {
+        issue(0);
+        if (nchunk > 1) issue(1);
+    }
     double wv[KR];
-    const double* wp[KR];
+    int wo[KR];
 #pragma unroll
     for (int j = 0; j < KR; j++) {
         const bool on = live && j < a.K;
         wv[j] = on ? __ldg(a.wval + (size_t)j * a.ncell + gc) : 0.0;
-        wp[j] = res + (on ? (int)__ldg(a.widx + (size_t)j * a.ncell + gc) : 0) * DK_RSTR;
+        wo[j] = on ? (int)__ldg(a.widx + (size_t)j * a.ncell + gc) : 0;
     }
     const double Z = live ? __ldg(a.dem + gc) : 0.0;
-    for (int t0 = 0; t0 < a.Tm; t0 += DK_TCH) {
-        __syncthreads();
-        if (tid < DK_TCH) {
-            const int tl = t0 + tid;
-            const int st = tl < a.Tm ? a.steps[tl] : -1;
-            stp[tid] = st;
-            pv[2 * tid] = st >= 0 ? a.rec[(size_t)st * a.L.RS + a.L.meta()] : 0.0;
-            pv[2 * tid + 1] = st >= 0 ? a.rec[(size_t)st * a.L.RS + a.L.meta() + 1] : 0.0;
-        }
-        for (int e = tid; e < DK_TCH * SP; e += 256) {      // coalesced over stations, transposed into the tile
-            const int tl = e / SP, sidx = e - tl * SP;
-            const int tt = t0 + tl;
-            res[sidx * DK_RSTR + tl] = (tt < a.Tm && sidx < S) ? a.rec[(size_t)a.steps[tt] * a.L.RS + sidx] : 0.0;
-        }
-        __syncthreads();
+    const int SP = a.L.S_pad;
+    for (int chn = 0; chn < nchunk; chn++) {
+        const int b = chn & 1;
+        __syncthreads();                                      // stp[] of this block is visible (written before the barrier below)
+        mbar_wait(&bars[b], (chn >> 1) & 1);
+        const double* rb = res + (size_t)b * DK_TCH * ROW;
+        const int* sb = stp + b * DK_TCH;
         if (live) {
 #pragma unroll 2
             for (int tl = 0; tl < DK_TCH; tl += 2) {
-                const int st0 = stp[tl], st1 = stp[tl + 1];
+                const int st0 = sb[tl], st1 = sb[tl + 1];
                 if (st0 < 0) break;
+                const double* r0p = rb + (size_t)tl * ROW;
+                const double* r1p = r0p + ROW;
                 double r0 = 0.0, r1 = 0.0;
 #pragma unroll
-                for (int j = 0; j < KR; j++) {               // dk.py:91 (entries past K have weight 0)
-                    const double2 x = *reinterpret_cast<const double2*>(wp[j] + tl);
-                    r0 = fma(wv[j], x.x, r0);
-                    r1 = fma(wv[j], x.y, r1);
+                for (int j = 0; j < KR; j++) {                // dk.py:91 (entries past K have weight 0)
+                    r0 = fma(wv[j], r0p[wo[j]], r0);
+                    r1 = fma(wv[j], r1p[wo[j]], r1);
                 }
-                const double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(pv[2 * tl], Z)), pv[2 * tl + 1]);   // dk.py:168, left to right
+                const double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(r0p[SP], Z)), r0p[SP + 1]);   // dk.py:168, left to right
                 __stcs(a.out + (size_t)st0 * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
                 if (st1 >= 0) {
-                    const double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(pv[2 * tl + 2], Z)), pv[2 * tl + 3]);
+                    const double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(r1p[SP], Z)), r1p[SP + 1]);
                     __stcs(a.out + (size_t)st1 * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
                 }
             }
         }
+        __syncthreads();                                      // everyone is done with buffer b
+        if (tid == 0 && chn + 2 < nchunk) issue(chn + 2);
     }
 }
 
@@ -1003,18 +1029,25 @@ static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T
         a.rec = h->d_rec; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
         a.vmin = vmin; a.vmax = vmax; a.out = d_out;
         const unsigned nblk = (unsigned)((ncw + 255) / 256);
-        const size_t dsm = ((size_t)DK_RSTR * h->L.S_pad + DK_TCH * 2) * sizeof(double) + DK_TCH * sizeof(int);
+        const unsigned nblk_d = (unsigned)((ncw + DK_DT - 1) / DK_DT);
+        const size_t dsm = (size_t)2 * DK_TCH * (h->L.S_pad + 2) * sizeof(double) + 2 * sizeof(uint64_t) + 2 * DK_TCH * sizeof(int);
+#define DK_LAUNCH(KRV)                                                                                           \
+    do {                                                                                                         \
+        SMRFB_CUDA(cudaFuncSetAttribute(dk_distribute_kernel<KRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); \
+        dk_distribute_kernel<KRV><<<nblk_d, DK_DT, dsm, st>>>(a);                                                 \
+    } while (0)
         switch ((W->K + 1) / 2) {   // register-resident (station, weight) pairs, padded to an even count
-            case 1: dk_distribute_kernel<2><<<nblk, 256, dsm, st>>>(a); break;
-            case 2: dk_distribute_kernel<4><<<nblk, 256, dsm, st>>>(a); break;
-            case 3: dk_distribute_kernel<6><<<nblk, 256, dsm, st>>>(a); break;
-            case 4: dk_distribute_kernel<8><<<nblk, 256, dsm, st>>>(a); break;
-            case 5: dk_distribute_kernel<10><<<nblk, 256, dsm, st>>>(a); break;
-            case 6: dk_distribute_kernel<12><<<nblk, 256, dsm, st>>>(a); break;
-            case 7: dk_distribute_kernel<14><<<nblk, 256, dsm, st>>>(a); break;
-            case 8: dk_distribute_kernel<DK_KREG><<<nblk, 256, dsm, st>>>(a); break;
+            case 1: DK_LAUNCH(2); break;
+            case 2: DK_LAUNCH(4); break;
+            case 3: DK_LAUNCH(6); break;
+            case 4: DK_LAUNCH(8); break;
+            case 5: DK_LAUNCH(10); break;
+            case 6: DK_LAUNCH(12); break;
+            case 7: DK_LAUNCH(14); break;
+            case 8: DK_LAUNCH(16); break;
             default: dk_distribute_generic_kernel<<<nblk, 256, 0, st>>>(a);
         }
+#undef DK_LAUNCH
         count_launch();
         SMRFB_CUDA(cudaGetLastError());
     }
