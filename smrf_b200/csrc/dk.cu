@@ -10,9 +10,9 @@
 //   2. dk_build_kernel -- one persistent CTA per SM, B (packed symmetric, <=162 KB) lives in shared
 //      memory.  A tile of 32 neighbouring cells (one per warp) walks the elimination tree depth
 //      first: cells that agree on the station to drop share ONE rank-1 downdate of B
-//      (B -= b b'/beta, w -= (w_k/beta) b); where they disagree the tile forks, and on the way
-//      back every downdate is undone with the saved column (B += b b'/beta), so B returns to B0
-//      without ever being re-read.  Output: the final active set of every cell (bit mask).
+//      (B -= b b'/beta, w -= (w_k/beta) b); where they disagree the tile forks: the inverse is
+//      snapshotted once to global memory (L2) and every further child of the fork starts from that
+//      exact copy.  Output: the final active set of every cell (bit mask).
 //   3. dk_final_kernel -- one thread per cell: a fresh solve on the final active set in station
 //      order with the reference's exact arithmetic (Crout LU, implicit scaling, >= pivot rule,
 //      no FMA), which is precisely what the reference's last loop iteration computes; if a negative
@@ -37,12 +37,13 @@ constexpr int DK_WORDS = 8;           // 256 active-set bits per cell
 constexpr int DK_NSMAX = 31;          // largest final active set solved in thread-local memory
 constexpr int DK_KREG = 16;           // ELL entries kept in registers by the distribute kernel
 constexpr int DK_QMAX = (DK_MAXN + 1 + 31) / 32;  // 7 column slots per lane
+constexpr int DK_MAXSNAP = 32;         // nested forks of a 32-cell tile
 
 struct DkPending {
-    int k;
-    unsigned mask;
-    int depth;
-    int pad;
+    int k;          // station (rank index) this subgroup drops next
+    unsigned mask;  // cells of the subgroup
+    int depth;      // number of stations already dropped at the fork
+    int snap;       // snapshot level holding the inverse at the fork
 };
 
 struct DkBuildArgs {
@@ -55,7 +56,7 @@ struct DkBuildArgs {
     const double* dgrid;   // optional [ncell][n], COMPRESSED station order (krige_grid mode)
     const int* perm;       // [n] rank -> compressed station index
     const double* B0p;     // packed upper triangle of the inverse, rank order, NN*(NN+1)/2
-    double* undo;          // [gridDim.x][n][NNP]
+    double* snap;          // [gridDim.x][DK_MAXSNAP][npk] fork snapshots of the packed inverse
     uint32_t* final_act;   // [ncell][DK_WORDS], bits over RANK index
     unsigned long long* tile_counter;
     int* maxcount;
@@ -81,33 +82,27 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, NN = a.NN, NNP = a.NNP;
     const int npk = NN * (NN + 1) / 2;
-    double* Bp = reinterpret_cast<double*>(smem_raw);           // [npk]
-    double* w = Bp + npk;                                       // [32][NN]
+    double* Bp = reinterpret_cast<double*>(smem_raw);           // [npk] packed upper triangle of the current inverse
+    double* w = Bp + npk;                                       // [32][NN] current weights of the tile's cells
     double* bcol = w + DK_TILE * NN;                            // [NNP] column k of B (zeros = inactive)
     double* bsm = bcol + NNP;                                   // [NNP] bcol / beta
-    double* betastack = bsm + NNP;                              // [NN]
-    int* rowoff = reinterpret_cast<int*>(betastack + NN);       // [NNP]
-    int* kstack = rowoff + NNP;                                 // [NN]
+    int* rowoff = reinterpret_cast<int*>(bsm + NNP);            // [NNP]
+    int* kstack = rowoff + NNP;                                 // [NN] stations dropped along the current path
     int* kc = kstack + NN;                                      // [32]
     int* ctrl = kc + DK_TILE;                                   // [8]
     DkPending* pend = reinterpret_cast<DkPending*>(ctrl + 8);   // [64]
     unsigned char* act = reinterpret_cast<unsigned char*>(pend + 64);  // [NNP]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* undo_g = a.undo + (size_t)blockIdx.x * n * NNP;
+    double* snap_g = a.snap + (size_t)blockIdx.x * DK_MAXSNAP * npk;   // fork snapshots of this CTA
     const long long ntiles = (a.ncell + DK_TILE - 1) / DK_TILE;
 
     for (int i = tid; i < NNP; i += DK_THREADS) rowoff[i] = i * NN - (i * (i + 1)) / 2;   // idx(i,j>=i) = rowoff[i] + j
-    for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];
-    int since_refresh = 0;
     __syncthreads();
 
-    // rank-1 update of the packed upper triangle with the column in bcol (zeros = skip):
-    //   B[i][j] += sgn * bsm[i] * bcol[j]   for j >= i,   bsm[i] = bcol[i]/beta
-    // Rows are dealt round-robin to the warps.  (Measured on B200, 1e6 cells x 200 stations: 1024 threads with
-    // this plain loop 1.19 s; 512 threads with loads staged ahead of the stores 1.40 s -- the walk is bound by
-    // the barrier / dependent-latency chain of each elimination step, not by the update arithmetic.)
-    auto rank1 = [&](double sgn) {
+    // rank-1 downdate of the packed upper triangle with the column in bcol (zeros = skip):
+    //   B[i][j] -= bsm[i] * bcol[j]   for j >= i,   bsm[i] = bcol[i]/beta.  Rows are dealt round-robin to the warps.
+    auto rank1 = [&]() {
         double bj[DK_QMAX];
 #pragma unroll
         for (int q = 0; q < DK_QMAX; q++) {
@@ -117,13 +112,12 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
         for (int i = warp; i < NN; i += DK_WARPS) {
             const double bi = bsm[i];
             if (bi == 0.0) continue;
-            const double bs = sgn * bi;
             double* row = Bp + rowoff[i];
             const int q0 = i >> 5;
 #pragma unroll
             for (int q = 0; q < DK_QMAX; q++) {
                 const int j = lane + 32 * q;
-                if (q >= q0 && j >= i && j < NN) row[j] = fma(bs, bj[q], row[j]);
+                if (q >= q0 && j >= i && j < NN) row[j] = fma(-bi, bj[q], row[j]);
             }
         }
     };
@@ -133,11 +127,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
         __syncthreads();
         const long long tile = (unsigned)ctrl[0];
         if (tile >= ntiles) break;
-        if (++since_refresh == 64) {   // bound the do/undo rounding drift: re-read the pristine inverse
-            since_refresh = 0;
-            for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];
-        }
-        // this warp's cells: warp and warp + DK_WARPS
+        for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];   // every tile starts from the pristine inverse (L2-resident)
         {   // right-hand side [dist to every station ; 1] in rank order
 #pragma unroll
             for (int h = 0; h < DK_CPW; h++) {
@@ -160,7 +150,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
         }
         for (int i = tid; i < NNP; i += DK_THREADS) act[i] = (i < NN) ? 1 : 0;
         __syncthreads();
-        {   // w = B0 * rhs (B symmetric, packed); each B element is loaded once for the warp's two cells
+        {   // w = B0 * rhs (B symmetric, packed); each B element is loaded once for all of the warp's cells
             double acc[DK_CPW][DK_QMAX];
 #pragma unroll
             for (int h = 0; h < DK_CPW; h++)
@@ -191,35 +181,37 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                 }
         }
         const long long rem = a.ncell - tile * DK_TILE;
-        unsigned cur_mask = rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
-        int depth = 0, npend = 0;
-        unsigned n_apply = 0, n_undo = 0, n_fork = 0;
+        const unsigned tile_mask = rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
+        int depth = 0, npend = 0, nsnap = 0;
+        unsigned n_apply = 0, n_restore = 0, n_fork = 0;
         __syncthreads();
 
-        for (;;) {   // ---- depth-first walk of the tile's elimination tree
-            // SELECT: first (= highest elevation) active station with a negative weight
+        // SELECT for the cells in `mask`, excluding station kx (dropped in this very phase, act[kx] is still
+        // being cleared): first (= highest elevation) active station with a negative weight; a cell with none
+        // (or with few enough stations left) leaves the shared walk and publishes its active set.
+        auto select = [&](unsigned mask, int kx, int ndrop) {
 #pragma unroll
             for (int h = 0; h < DK_CPW; h++) {
                 const int ci = warp + DK_WARPS * h;
-                if ((cur_mask >> ci) & 1u) {
+                if ((mask >> ci) & 1u) {
                     const double* wc = w + ci * NN;
                     int k = -1;
                     for (int q = 0; q < DK_QMAX; q++) {
                         const int j = lane + 32 * q;
-                        const bool c = (j < a.nsel) && act[j] && (wc[j] < 0.0);
+                        const bool c = (j < a.nsel) && (j != kx) && act[j] && (wc[j] < 0.0);
                         const unsigned bb = __ballot_sync(0xffffffffu, c);
                         if (bb) {
                             k = 32 * q + __ffs(bb) - 1;
                             break;
                         }
                     }
-                    const bool hand = (k >= 0) && (n - depth <= a.handoff);
-                    if (k < 0 || hand) {   // this cell leaves the shared walk: publish its active set
+                    const bool hand = (k >= 0) && (n - ndrop <= a.handoff);
+                    if (k < 0 || hand) {
                         const long long cell = tile * DK_TILE + ci;
                         unsigned myword = 0;
                         for (int q = 0; q < DK_WORDS; q++) {
                             const int j = lane + 32 * q;
-                            const unsigned bb = __ballot_sync(0xffffffffu, (j < n) && act[j]);
+                            const unsigned bb = __ballot_sync(0xffffffffu, (j < n) && (j != kx) && act[j]);
                             if (lane == q) myword = bb;
                         }
                         if (hand && lane == DK_WORDS - 1) myword |= 0x80000000u;   // bit 255: handed off undecided
@@ -231,72 +223,69 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     kc[ci] = -2;
                 }
             }
-            __syncthreads();
-            if (warp == 0) {   // partition the group by chosen station
-                const int k = kc[lane];
-                const unsigned livem = __ballot_sync(0xffffffffu, k >= 0);
-                const unsigned grp = __match_any_sync(0xffffffffu, k);
-                const bool leader = (k >= 0) && (lane == __ffs(grp) - 1);
-                const unsigned lead = __ballot_sync(0xffffffffu, leader);
-                const int p = __popc(lead);
-                if (p == 1) {
-                    if (leader) {
-                        ctrl[1] = 1;   // APPLY directly
-                        ctrl[2] = k;
-                        ctrl[3] = (int)livem;
-                    }
-                } else {
-                    if (leader) {
-                        const int slot = npend + __popc(lead & ((1u << lane) - 1u));
-                        pend[slot].k = k;
-                        pend[slot].mask = grp;
-                        pend[slot].depth = depth;
-                    }
-                    if (lane == 0) {
-                        ctrl[1] = 0;   // POP (or finish)
-                        ctrl[4] = p;
-                    }
-                }
-            }
-            __syncthreads();
+        };
+        select(tile_mask, -1, 0);
+
+        for (;;) {   // ---- depth-first walk of the tile's elimination tree
+            __syncthreads();   // kc[], w, B, act of the previous phase are in place
+            // every warp partitions the group by chosen station (redundantly: no extra barrier in the common case)
             int k;
             unsigned mask;
-            if (ctrl[1] == 1) {
-                k = ctrl[2];
-                mask = (unsigned)ctrl[3];
-            } else {
-                npend += ctrl[4];
-                n_fork += ctrl[4] > 1;
-                const int target = npend > 0 ? pend[npend - 1].depth : 0;
-                while (depth > target) {   // undo back to the fork point
-                    depth--;
-                    n_undo++;
-                    const int ku = kstack[depth];
-                    const double rbeta = dk_rcp(betastack[depth]);
-                    for (int i = tid; i < NNP; i += DK_THREADS) {
-                        const double v = undo_g[(size_t)depth * NNP + i];
-                        bcol[i] = v;
-                        bsm[i] = v * rbeta;
+            {
+                const int kl = kc[lane];
+                const unsigned livem = __ballot_sync(0xffffffffu, kl >= 0);
+                const unsigned grp = __match_any_sync(0xffffffffu, kl);
+                const bool leader = (kl >= 0) && (lane == __ffs(grp) - 1);
+                const unsigned lead = __ballot_sync(0xffffffffu, leader);
+                const int p = __popc(lead);
+                if (p == 1) {          // the whole group drops the same station: apply directly
+                    k = __shfl_sync(0xffffffffu, kl, __ffs(lead) - 1);
+                    mask = livem;
+                } else {
+                    if (warp == 0 && leader) {   // fork: one pending entry per subgroup, all sharing snapshot level nsnap
+                        const int slot = npend + __popc(lead & ((1u << lane) - 1u));
+                        pend[slot].k = kl;
+                        pend[slot].mask = grp;
+                        pend[slot].depth = depth;
+                        pend[slot].snap = nsnap;
                     }
-                    __syncthreads();
-                    rank1(1.0);
-                    if (tid == 0) act[ku] = 1;
-                    __syncthreads();
-                }
-                if (npend == 0) {        // tile finished, B is back at B0
-                    if (tid == 0) {
-                        atomicAdd(a.tile_counter + 2, (unsigned long long)n_apply);
-                        atomicAdd(a.tile_counter + 3, (unsigned long long)n_undo);
-                        atomicAdd(a.tile_counter + 4, (unsigned long long)n_fork);
+                    bool fresh = false;
+                    if (p > 0) {   // snapshot the inverse once for all children (exact: no rounding drift on the way back)
+                        double* sg = snap_g + (size_t)nsnap * npk;
+                        for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Bp[q];
+                        nsnap++;
+                        npend += p;
+                        n_fork++;
+                        fresh = true;
                     }
-                    break;
+                    __syncthreads();         // pend[] written; snapshot reads of B done
+                    if (npend == 0) {        // tile finished
+                        if (tid == 0) {
+                            atomicAdd(a.tile_counter + 2, (unsigned long long)n_apply);
+                            atomicAdd(a.tile_counter + 3, (unsigned long long)n_restore);
+                            atomicAdd(a.tile_counter + 4, (unsigned long long)n_fork);
+                        }
+                        break;
+                    }
+                    npend--;
+                    k = pend[npend].k;
+                    mask = pend[npend].mask;
+                    const int sdepth = pend[npend].depth, ssnap = pend[npend].snap;
+                    const bool last_child = (npend == 0) || (pend[npend - 1].snap != ssnap);
+                    if (!fresh) {   // come back to the fork point: restore the snapshot and the active flags
+                        const double* sg = snap_g + (size_t)ssnap * npk;
+                        for (int q = tid; q < npk; q += DK_THREADS) Bp[q] = sg[q];
+                        for (int i = tid; i < NNP; i += DK_THREADS) act[i] = (i < NN) ? 1 : 0;
+                        __syncthreads();
+                        for (int d = tid; d < sdepth; d += DK_THREADS) act[kstack[d]] = 0;
+                        depth = sdepth;
+                        n_restore++;
+                    }
+                    if (last_child) nsnap = ssnap;   // the snapshot level is free again
+                    __syncthreads();                 // B / act restored; pend[npend] read by everyone
                 }
-                npend--;
-                k = pend[npend].k;
-                mask = pend[npend].mask;
-                __syncthreads();         // everyone has read pend[npend] before warp 0 may overwrite it
             }
-            // APPLY: drop station k for the cells in mask
+            // EXTRACT column k of the inverse
             n_apply++;
             const double beta = Bp[rowoff[k] + k];
             const double rbeta = dk_rcp(beta);
@@ -305,13 +294,10 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                 if (i < NN && i != k && act[i]) v = (i < k) ? Bp[rowoff[i] + k] : Bp[rowoff[k] + i];
                 bcol[i] = v;
                 bsm[i] = v * rbeta;
-                undo_g[(size_t)depth * NNP + i] = v;
             }
-            if (tid == 0) {
-                kstack[depth] = k;
-                betastack[depth] = beta;
-            }
+            if (tid == 0) kstack[depth] = k;
             __syncthreads();
+            // UPDATE the weights of the cells in mask, pick their next station, downdate the inverse
 #pragma unroll
             for (int h = 0; h < DK_CPW; h++) {
                 const int ci = warp + DK_WARPS * h;
@@ -319,18 +305,14 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     double* wc = w + ci * NN;
                     const double f = wc[k] * rbeta;
                     for (int j = lane; j < NN; j += 32) wc[j] = fma(-f, bcol[j], wc[j]);
+                    if (lane == (k & 31)) wc[k] = 0.0;   // same lane that just updated it
                     __syncwarp();
-                    if (lane == 0) wc[k] = 0.0;
                 }
             }
-            rank1(-1.0);
-            if (tid == 0) {
-                act[k] = 0;
-                ctrl[4] = 0;
-            }
+            select(mask, k, depth + 1);
+            rank1();
+            if (tid == 0) act[k] = 0;
             depth++;
-            cur_mask = mask;
-            __syncthreads();
         }
     }
 }
@@ -809,7 +791,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const long long ntiles = (in.ncell + DK_TILE - 1) / DK_TILE;
     const int grid = (int)std::min<long long>(ntiles, nsm);
-    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + 2 * NNP + NN) * sizeof(double) +
+    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + 2 * NNP) * sizeof(double) +
                   ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
 
@@ -857,7 +839,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
         DK_TRY(dev_upload(&d_rankof, rankof.data(), n));
     }
     DK_TRY(dev_upload(&d_orig, in.orig, n));
-    DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * n * NNP * sizeof(double)));
+    if (n > DK_NSMAX) DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * DK_MAXSNAP * npk * sizeof(double)));
     DK_CUDA(cudaMalloc((void**)&d_final, (size_t)in.ncell * DK_WORDS * sizeof(uint32_t)));
     DK_CUDA(cudaMalloc((void**)&d_cnt, 8 * sizeof(unsigned long long)));
     DK_CUDA(cudaMalloc((void**)&d_small, 4 * sizeof(int)));
@@ -867,7 +849,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     DkBuildArgs ba;
     ba.n = n; ba.NN = NN; ba.NNP = NNP; ba.nsel = nsel;
     ba.ncell = in.ncell; ba.g = in.g;
-    ba.sx = d_sx; ba.sy = d_sy; ba.dgrid = in.d_dgrid; ba.perm = d_perm; ba.B0p = d_B0p; ba.undo = d_undo;
+    ba.sx = d_sx; ba.sy = d_sy; ba.dgrid = in.d_dgrid; ba.perm = d_perm; ba.B0p = d_B0p; ba.snap = d_undo;
     ba.final_act = d_final; ba.tile_counter = d_cnt; ba.maxcount = d_small;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     const bool verbose = getenv("SMRFB_DK_VERBOSE") != nullptr;
@@ -927,7 +909,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     dk_final_kernel<<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
     count_launch();
     DK_CUDA(cudaGetLastError());
-    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long h_cnt[8] = {0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaStreamSynchronize(st));
@@ -937,8 +919,9 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CHECK(!(h_small[1] & 1), SMRFB_ERR_SINGULAR, "DK: singular kriging system in the final solve");
     if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
     if (verbose)
-        fprintf(stderr, "[smrfb] dk_build: n=%d cells=%lld tiles=%lld applies=%llu undos=%llu forks=%llu K=%d fallback=%llu "
+        fprintf(stderr, "[smrfb] dk_build: n=%d cells=%lld tiles=%lld applies=%llu restores=%llu forks=%llu K=%d fallback=%llu "
                 "walk %.1f ms, exact finish %.1f ms\n", n, in.ncell, ntiles, h_cnt[2], h_cnt[3], h_cnt[4], K, h_cnt[1], ms_walk, ms_final);
+
     return SMRFB_OK;
 }
 
