@@ -381,6 +381,136 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Few stations (S_pad <= 16; real basins often have a handful, RME has 2): 2*S flop per 8-byte output
+// is left of the fp64 ridge, so the tensor-core tile machinery above only costs instructions.
+// idw_small_kernel: one thread per cell keeps its S weights in REGISTERS (plus a copy in shared
+// memory for the per-step lookup of missing stations' weights), step records stream through a
+// double-buffered shared-memory ring of 1-D TMA bulk copies, and every output is S FMAs with
+// broadcast shared-memory reads of the residuals, the masked denominator, a reciprocal, retrend,
+// clamp and a coalesced streaming store.  Bound by the output stream once S is small.
+// ------------------------------------------------------------------------------------------
+constexpr int IDWS_THREADS = 256;
+constexpr int IDWS_TCH = 16;
+
+template <int SMAX>
+__global__ void __launch_bounds__(IDWS_THREADS) idw_small_kernel(IdwArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.L.S, S_pad = a.L.S_pad, RS = a.L.RS;
+    double* recbuf = reinterpret_cast<double*>(smem_raw);                 // [2][TCH][RS]
+    double* wsm = recbuf + 2 * IDWS_TCH * RS;                             // [S_pad][THREADS] weights, for missing-station lookups
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)S_pad * IDWS_THREADS);   // [2]
+    const int tid = threadIdx.x;
+    const long long c = (long long)blockIdx.x * IDWS_THREADS + tid;      // cell within the window
+    const bool live = c < a.ncw;
+    const long long gcell = a.cbase + (live ? c : 0);
+    const int nchunk = a.T_pad / IDWS_TCH;
+    const uint32_t chunk_bytes = (uint32_t)(IDWS_TCH * RS * sizeof(double));
+    const size_t chunk_elems = (size_t)IDWS_TCH * RS;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int b = 0; b < 2 && b < nchunk; b++) {
+            mbar_arrive_expect_tx(&bars[b], chunk_bytes);
+            bulk_g2s(recbuf + b * chunk_elems, a.rec + b * chunk_elems, chunk_bytes, &bars[b]);
+        }
+    }
+    // weights of this cell (registers + shared copy), their sum, coincident-station flag
+    double w[SMAX];
+    double dall = 0.0;
+    bool coincident = false;
+    {
+        double X = 0.0, Y = 0.0;
+        if (live) cell_xy(a.g, gcell, X, Y);
+        const bool p2 = (a.power == 2.0);
+#pragma unroll
+        for (int s = 0; s < SMAX; s++) {
+            double ws = 0.0;
+            if (s < S) {
+                const double dx = __dsub_rn(X, __ldg(a.mx + s)), dy = __dsub_rn(Y, __ldg(a.my + s));
+                const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                const bool zero = (q == 0.0);
+                coincident |= (live && zero);
+                ws = p2 ? fast_rcp<2>(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
+                ws = (live && !zero) ? ws : 0.0;
+            }
+            w[s] = ws;
+            dall += ws;
+            if (s < S_pad) wsm[(size_t)s * IDWS_THREADS + tid] = ws;
+        }
+    }
+    const double Z = (live && a.g.dem) ? __ldg(a.g.dem + gcell) : 0.0;
+    const double* wmine = wsm + tid;
+
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int buf = ch & 1;
+        const double* rb = recbuf + buf * chunk_elems;
+        mbar_wait(&bars[buf], (ch >> 1) & 1);
+        if (live) {
+#pragma unroll 2
+            for (int tl = 0; tl < IDWS_TCH; tl++) {
+                const int t = ch * IDWS_TCH + tl;
+                if (t >= a.T) break;
+                const double* rr = rb + (size_t)tl * RS;          // warp-uniform address: broadcast reads
+                double num = 0.0;
+#pragma unroll
+                for (int s = 0; s < SMAX; s += 2) {
+                    const double2 r2 = *reinterpret_cast<const double2*>(rr + s);   // S_pad is a multiple of 8; pad residuals are 0
+                    num = fma(w[s], r2.x, num);
+                    num = fma(w[s + 1], r2.y, num);
+                }
+                const double2 pp = *reinterpret_cast<const double2*>(rr + S_pad);
+                const int* mi = reinterpret_cast<const int*>(rr + S_pad + 2);
+                const int nmiss = mi[0];
+                double den = dall;
+                const int nlist = min(nmiss, a.L.maxm);
+                for (int j = 0; j < nlist; j++) den -= wmine[(size_t)mi[1 + j] * IDWS_THREADS];
+                if (nmiss > a.L.maxm || __double2hiint(den) < __double2hiint(dall) - (7 << 20)) {   // rare: exact masked sum
+                    const uint8_t* vt = a.valid + (size_t)t * S;
+                    double ds = 0.0;
+                    for (int s = 0; s < S; s++)
+                        if (vt[s]) ds += wmine[(size_t)s * IDWS_THREADS];
+                    den = ds;
+                }
+                const double r = fast_rcp<2>(den);
+                const double q = num * r;
+                double val = fma(fma(-den, q, num), r, q);
+                if (coincident) {   // rare: a station sits exactly on this cell
+                    double X, Y;
+                    cell_xy(a.g, gcell, X, Y);
+                    const uint8_t* vt = a.valid + (size_t)t * S;
+                    bool hit = false, bad = false;
+                    for (int s = 0; s < S; s++) {
+                        double dx = __dsub_rn(X, a.mx[s]), dy = __dsub_rn(Y, a.my[s]);
+                        if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) == 0.0 && vt[s]) {
+                            hit = true;
+                            if (rr[s] != 0.0) bad = true;
+                        }
+                    }
+                    if (hit) val = bad ? nan("") : 0.0;
+                }
+                if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, Z)), pp.y);   // idw.py:144, left to right
+                if (a.clamp) val = clamp_nan_keep(val, a.vmin, a.vmax);
+                __stcs(a.out + (size_t)t * (size_t)a.ncw + c, val);
+            }
+        }
+        __syncthreads();   // everyone is done with rb before the TMA engine overwrites it
+        if (tid == 0 && ch + 2 < nchunk) {
+            mbar_arrive_expect_tx(&bars[buf], chunk_bytes);
+            bulk_g2s(recbuf + buf * chunk_elems, a.rec + (size_t)(ch + 2) * chunk_elems, chunk_bytes, &bars[buf]);
+        }
+    }
+}
+
+static size_t idw_small_smem_bytes(const RecLayout& L) {
+    return ((size_t)2 * IDWS_TCH * L.RS + (size_t)L.S_pad * IDWS_THREADS) * sizeof(double) + 2 * sizeof(uint64_t);
+}
+
 static size_t idw_smem_bytes(const RecLayout& L) {
     size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * IDW_TC * IDW_XSTR +
                2 * (size_t)L.S_pad + 8 * IDW_CT;
@@ -417,6 +547,24 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     a.out = d_out;
     a.cbase = cbase;
     a.ncw = ncw;
+    // few stations: register-weight kernel.  Measured on B200 (4000 x 4000 cells, T = 512): S = 2: 348 G cell-steps/s;
+    // S = 20: 178 G with either kernel; S = 32: 148 G here vs 163 G on the tensor-core kernel => switch at 16.
+    if (h->L.S_pad <= 16 && !getenv("SMRFB_IDW_FORCE_MMA")) {
+        const long long nb = (ncw + IDWS_THREADS - 1) / IDWS_THREADS;
+        SMRFB_CHECK(nb < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+        const size_t sm = idw_small_smem_bytes(h->L);
+#define IDWS_LAUNCH(N)                                                                                              \
+    do {                                                                                                            \
+        SMRFB_CUDA(cudaFuncSetAttribute(idw_small_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        idw_small_kernel<N><<<(unsigned)nb, IDWS_THREADS, sm, st>>>(a);                                              \
+    } while (0)
+        if (h->L.S_pad <= 8) IDWS_LAUNCH(8);
+        else IDWS_LAUNCH(16);
+#undef IDWS_LAUNCH
+        count_launch();
+        SMRFB_CUDA(cudaGetLastError());
+        return SMRFB_OK;
+    }
     long long nblk = (ncw + IDW_CT - 1) / IDW_CT;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     idw_distribute_kernel<<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);

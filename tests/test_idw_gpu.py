@@ -158,3 +158,22 @@ def test_idw_all_nan_row_raises(sp):
     from smrf_b200._lib import SmrfbError
     with pytest.raises(SmrfbError):
         idw.distribute_block(data, detrend=True, flag=0)
+
+
+def test_idw_small_station_count_both_kernels(sp, golden, monkeypatch):
+    """S <= 16 normally takes the register-weight kernel; the tensor-core kernel must give the same field."""
+    g = golden("idw_synth")
+    X, Y = np.meshgrid(g["x"], g["y"])
+    from oracle import oracle as orc
+    sel = np.arange(0, 20, 2)                                  # 10 of the 20 stations
+    idw = sp.IDW(g["mx"][sel], g["my"][sel], X, Y, mz=g["mz"][sel], GridZ=g["dem"], power=2.0)
+    o = orc.IDW(g["mx"][sel], g["my"][sel], X, Y, mz=g["mz"][sel], GridZ=g["dem"], power=2.0)
+    data = g["data"][:4, sel]
+    a = idw.distribute_block(data, detrend=True, flag=-1, vmin=-10.0, vmax=30.0)
+    monkeypatch.setenv("SMRFB_IDW_FORCE_MMA", "1")
+    b = idw.distribute_block(data, detrend=True, flag=-1, vmin=-10.0, vmax=30.0)
+    monkeypatch.delenv("SMRFB_IDW_FORCE_MMA")
+    for t in range(len(data)):
+        want = np.clip(o.detrendedIDW(data[t].copy(), -1), -10.0, 30.0)
+        assert parity(a[t], want, step_scale(data[t])) <= TOL
+        assert parity(b[t], want, step_scale(data[t])) <= TOL
