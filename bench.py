@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--stations", type=int, default=200)
     ap.add_argument("--tb", type=int, default=720, help="timesteps per block (30 days of hourly steps)")
     ap.add_argument("--slab-rows", type=int, default=1000, help="DEM rows per cell slab; the device-resident output block is [tb][slab]")
-    ap.add_argument("--te2e", type=int, default=32, help="timesteps per block on the host-buffer (e2e) leg")
+    ap.add_argument("--te2e", type=int, default=8, help="timesteps per block on the host-buffer (e2e) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
