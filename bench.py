@@ -52,7 +52,9 @@ def parse():
     ap.add_argument("--stations", type=int, default=200)
     ap.add_argument("--tb", type=int, default=720, help="timesteps per block (30 days of hourly steps)")
     ap.add_argument("--slab-rows", type=int, default=1000, help="DEM rows per cell slab; the device-resident output block is [tb][slab]")
-    ap.add_argument("--te2e", type=int, default=8, help="timesteps per block on the host-buffer (e2e) leg")
+    ap.add_argument("--te2e", type=int, default=0,
+                    help="timesteps per block on the host-buffer (e2e) leg; 0 = max(8, 32 // n_gpus): 25.6 GB of pinned "
+                         "host memory at 1 GPU, 6.4 GB per rank at 4-8 GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -337,7 +339,7 @@ def main():
     # ---- e2e: public Python API, host buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        Te = min(args.te2e, Tb)
+        Te = min(args.te2e if args.te2e > 0 else max(8, 32 // world), Tb)
         del d_out
         torch.cuda.empty_cache()          # the host-buffer API keeps its own device ring per handle
         host_out = torch.empty((Te, ny, nx), dtype=torch.float64, pin_memory=True).numpy()
@@ -381,7 +383,7 @@ def main():
             "frac": idw_flops / (idw_ms * 1e-3) / 1e12 / fp64_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact shape (1e7 cells x 720 steps x 200
             # stations), ncu --set full, profiles/r01_final_ncu.md; null for other shapes
-            "traffic": 57.66e9 if (slab_cells == 10_000_000 and Tb == 720 and S == 200) else None,
+            "traffic": 57.68e9 if (slab_cells == 10_000_000 and Tb == 720 and S == 200) else None,
             "traffic_unit": "bytes per launch (algorithmic: %.3e)" % idw_bytes,
             "peak_source": "fp64 tensor (DMMA) peak " + fp64_src + "; MEASURED_PEAKS.json holds no fp64 figure",
             "algorithmic_flops_per_launch": idw_flops, "ms_per_launch": idw_ms,
