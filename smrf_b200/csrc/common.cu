@@ -88,7 +88,7 @@ RecLayout make_layout(int S, int k_align, int maxm, bool mma_stride) {
     L.S = S;
     L.S_pad = (S + k_align - 1) / k_align * k_align;
     L.maxm = maxm;
-    int rs = L.S_pad + 2 + (maxm + 1 + 1) / 2;
+    int rs = L.S_pad + 2 + (maxm > 0 ? (4 + maxm + 1) / 2 : 1);
     if (rs & 1) rs++;
     if (mma_stride)
         while ((rs & 15) != 4 && (rs & 15) != 12) rs += 2;
@@ -211,11 +211,12 @@ prep_steps_kernel(const double* __restrict__ data, int T, int S, RecLayout L, co
         if (L.maxm > 0) {
             for (int s = 0; s < S; s++) {
                 if (isnan(row[s])) {
-                    if (nm < L.maxm) mi[1 + nm] = s;
+                    if (nm < L.maxm) mi[4 + nm] = s * L.miss_scale;
                     nm++;
                 }
             }
-            for (int j = (nm < L.maxm ? nm : L.maxm) + 1; j < nints; j++) mi[j] = 0;
+            for (int j = 1; j < 4; j++) mi[j] = 0;
+            for (int j = (nm < L.maxm ? nm : L.maxm) + 4; j < nints; j++) mi[j] = L.miss_fill;
         } else {
             nm = S - (int)cnt_valid;
             for (int j = 1; j < nints; j++) mi[j] = 0;

@@ -68,14 +68,15 @@ __device__ __forceinline__ void cell_xy(const Geom& g, long long c, double& X, d
 // One record per timestep, written by prep_steps_kernel, consumed by the distribute kernels:
 //   rec[t][0 .. S_pad)            residuals d_s - (mz_s*p0 + p1); 0 for missing stations and padding
 //   rec[t][S_pad + 0]             p0 (slope)            rec[t][S_pad + 1]   p1 (intercept)
-//   rec[t][S_pad + 2 ...]         int32 array: [0] = number of missing stations, [1 + j] = index of the
-//                                 j-th missing station, j < min(nmiss, maxm); maxm + 1 is a multiple of 4
-//                                 so a consumer reads 4 entries per 128-bit shared-memory load
+//   rec[t][S_pad + 2 ...]         int32 array: [0] = number of missing stations, [1..3] = 0, [4 + j] = (index of
+//                                 the j-th missing station) * miss_scale for j < min(nmiss, maxm); the unused
+//                                 slots hold miss_fill (a consumer reads whole quads with 128-bit loads and
+//                                 points the fill at a zero weight row); maxm is a multiple of 4
 // RS (record stride, doubles) is chosen = 4 or 12 (mod 16) so that DMMA A-fragment loads from a
 // staged record block are shared-memory bank-conflict free.
 // keep_nan: missing stations keep NaN in the residual slot (GRID: NaN propagates like griddata's).
 struct RecLayout {
-    int S = 0, S_pad = 0, RS = 0, maxm = 0, keep_nan = 0;
+    int S = 0, S_pad = 0, RS = 0, maxm = 0, keep_nan = 0, miss_scale = 1, miss_fill = 0;
     __host__ __device__ int meta() const { return S_pad; }
 };
 RecLayout make_layout(int S, int k_align, int maxm, bool mma_stride);

@@ -34,7 +34,7 @@ constexpr int IDW_NBUF = 3;            // record ring depth
 constexpr int IDW_WSTR = IDW_CT + 4;   // weight-tile row stride (doubles), = 4 (mod 16): conflict-free B frags
 constexpr int IDW_THREADS = 512;
 constexpr int IDW_GROUP = IDW_THREADS / 2;
-constexpr int IDW_MAXM = 47;           // missing-station list length carried in a record (48 int32 with the count)
+constexpr int IDW_MAXM = 44;           // missing-station list length carried in a record (11 quads after the count quad)
 constexpr int IDW_WU = 5;              // independent weight chains per thread and iteration
 constexpr int IDW_XSTR = 72;           // transpose buffer row stride (doubles): = 16 (mod 32) words, conflict-free tile writes
 
@@ -42,6 +42,7 @@ struct IdwHandle : HandleBase {
     double power = 2.0;
     RecLayout L;
     size_t smem_bytes = 0;
+    bool use_small = false;     // register-weight kernel (few stations); decided at create time
     IdwHandle() : HandleBase(HK_IDW) {}
 };
 
@@ -77,11 +78,12 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+template <bool DETREND, bool CLAMP>
 __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.L.S, S_pad = a.L.S_pad, RS = a.L.RS;
-    double* Wt = reinterpret_cast<double*>(smem_raw);                  // [S_pad][WSTR]
-    double* recbuf = Wt + (size_t)S_pad * IDW_WSTR;                    // [NBUF][TC][RS]
+    double* Wt = reinterpret_cast<double*>(smem_raw);                  // [S_pad + 1][WSTR]
+    double* recbuf = Wt + (size_t)(S_pad + 1) * IDW_WSTR;              // [NBUF][TC][RS]   (row S_pad of Wt is all zero)
     double* Dall = recbuf + (size_t)IDW_NBUF * IDW_TC * RS;            // [CT] sum of all S weights per cell
     double* Zc = Dall + IDW_CT;                                        // [CT]
     double* xbuf = Zc + IDW_CT;                                        // [2 K-halves][TC][XSTR] partial numerator tiles
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
         fence_mbar_init();
     }
     if (tid < IDW_CT) zflag[tid] = 0;
+    if (tid < IDW_WSTR) Wt[(size_t)S_pad * IDW_WSTR + tid] = 0.0;     // the zero row the padded missing-list slots point at
     for (int s = tid; s < S_pad; s += IDW_THREADS) {   // station coordinates -> shared memory
         scratch[s] = s < S ? __ldg(a.mx + s) : 0.0;
         scratch[S_pad + s] = s < S ? __ldg(a.my + s) : 0.0;
@@ -251,39 +254,32 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             const int4* mi1 = reinterpret_cast<const int4*>(rb + (size_t)(wg + 8) * RS + S_pad + 2);
             pp[0] = *reinterpret_cast<const double2*>(rb + (size_t)wg * RS + S_pad);
             pp[1] = *reinterpret_cast<const double2*>(rb + (size_t)(wg + 8) * RS + S_pad);
-            int4 qa = mi0[0], qb = mi1[0];
-            nmiss2[0] = qa.x;
-            nmiss2[1] = qb.x;
+            nmiss2[0] = mi0[0].x;
+            nmiss2[1] = mi1[0].x;
             den[0][0] = den[1][0] = dall[0];
             den[0][1] = den[1][1] = dall[1];
-            const int n0 = min(qa.x, a.L.maxm), n1 = min(qb.x, a.L.maxm);
-            const int nmax = max(n0, n1);
-            // entry j of a list sits at int position j + 1: positions 1..3 ride in the first quad
-            int ia[4] = {qa.y, qa.z, qa.w, 0}, ib[4] = {qb.y, qb.z, qb.w, 0};
-            int base = 0, cnt = 3;
-            for (;;) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (j < cnt) {
-                        if (base + j < n0) {
-                            const double2 w0 = *reinterpret_cast<const double2*>(wcol + (size_t)ia[j] * IDW_WSTR);
-                            den[0][0] -= w0.x;
-                            den[0][1] -= w0.y;
-                        }
-                        if (base + j < n1) {
-                            const double2 w1 = *reinterpret_cast<const double2*>(wcol + (size_t)ib[j] * IDW_WSTR);
-                            den[1][0] -= w1.x;
-                            den[1][1] -= w1.y;
-                        }
-                    }
+            // the lists are stored as element offsets (station * WSTR) in whole quads; unused slots point at the zero row
+            const int g0 = (min(nmiss2[0], a.L.maxm) + 3) >> 2, g1 = (min(nmiss2[1], a.L.maxm) + 3) >> 2;
+            const int gmax = max(g0, g1);
+            for (int g = 1; g <= gmax; g++) {
+                if (g <= g0) {
+                    const int4 q = mi0[g];
+                    const double2 wa = *reinterpret_cast<const double2*>(wcol + q.x);
+                    const double2 wb = *reinterpret_cast<const double2*>(wcol + q.y);
+                    const double2 wc2 = *reinterpret_cast<const double2*>(wcol + q.z);
+                    const double2 wd = *reinterpret_cast<const double2*>(wcol + q.w);
+                    den[0][0] -= (wa.x + wb.x) + (wc2.x + wd.x);
+                    den[0][1] -= (wa.y + wb.y) + (wc2.y + wd.y);
                 }
-                base += cnt;
-                if (base >= nmax) break;
-                qa = mi0[(base + 1) >> 2];
-                qb = mi1[(base + 1) >> 2];
-                ia[0] = qa.x; ia[1] = qa.y; ia[2] = qa.z; ia[3] = qa.w;
-                ib[0] = qb.x; ib[1] = qb.y; ib[2] = qb.z; ib[3] = qb.w;
-                cnt = 4;
+                if (g <= g1) {
+                    const int4 q = mi1[g];
+                    const double2 wa = *reinterpret_cast<const double2*>(wcol + q.x);
+                    const double2 wb = *reinterpret_cast<const double2*>(wcol + q.y);
+                    const double2 wc2 = *reinterpret_cast<const double2*>(wcol + q.z);
+                    const double2 wd = *reinterpret_cast<const double2*>(wcol + q.w);
+                    den[1][0] -= (wa.x + wb.x) + (wc2.x + wd.x);
+                    den[1][1] -= (wa.y + wb.y) + (wc2.y + wd.y);
+                }
             }
         }
         // per-cell decision, so a cell's value never depends on which other cells share its thread / tile:
@@ -358,8 +354,8 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 double x = val[h][e];
-                if (a.detrend) x = __dadd_rn(__dadd_rn(x, __dmul_rn(pp[h].x, zc[e])), pp[h].y);   // idw.py:144, left to right
-                v[e] = a.clamp ? clamp_nan_keep(x, a.vmin, a.vmax) : x;
+                if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(pp[h].x, zc[e])), pp[h].y);   // idw.py:144, left to right
+                v[e] = CLAMP ? clamp_nan_keep(x, a.vmin, a.vmax) : x;
             }
             if (t < a.T) {
                 const long long c = cell0 + 2 * lane;
@@ -469,7 +465,7 @@ __global__ void __launch_bounds__(IDWS_THREADS) idw_small_kernel(IdwArgs a) {
                 const int nmiss = mi[0];
                 double den = dall;
                 const int nlist = min(nmiss, a.L.maxm);
-                for (int j = 0; j < nlist; j++) den -= wmine[(size_t)mi[1 + j] * IDWS_THREADS];
+                for (int j = 0; j < nlist; j++) den -= wmine[mi[4 + j]];          // offsets = station * IDWS_THREADS
                 if (nmiss > a.L.maxm || __double2hiint(den) < __double2hiint(dall) - (7 << 20)) {   // rare: exact masked sum
                     const uint8_t* vt = a.valid + (size_t)t * S;
                     double ds = 0.0;
@@ -512,7 +508,7 @@ static size_t idw_small_smem_bytes(const RecLayout& L) {
 }
 
 static size_t idw_smem_bytes(const RecLayout& L) {
-    size_t d = (size_t)L.S_pad * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * IDW_TC * IDW_XSTR +
+    size_t d = (size_t)(L.S_pad + 1) * IDW_WSTR + (size_t)IDW_NBUF * IDW_TC * L.RS + 2 * IDW_CT + 2 * IDW_TC * IDW_XSTR +
                2 * (size_t)L.S_pad + 8 * IDW_CT;
     return d * sizeof(double) + (IDW_NBUF + 1) * sizeof(uint64_t) + IDW_CT * sizeof(int);
 }
@@ -549,7 +545,7 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     a.ncw = ncw;
     // few stations: register-weight kernel.  Measured on B200 (4000 x 4000 cells, T = 512): S = 2: 348 G cell-steps/s;
     // S = 20: 178 G with either kernel; S = 32: 148 G here vs 163 G on the tensor-core kernel => switch at 16.
-    if (h->L.S_pad <= 16 && !getenv("SMRFB_IDW_FORCE_MMA")) {
+    if (h->use_small) {
         const long long nb = (ncw + IDWS_THREADS - 1) / IDWS_THREADS;
         SMRFB_CHECK(nb < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
         const size_t sm = idw_small_smem_bytes(h->L);
@@ -567,7 +563,13 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     }
     long long nblk = (ncw + IDW_CT - 1) / IDW_CT;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
-    idw_distribute_kernel<<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);
+    if (detrend) {
+        if (a.clamp) idw_distribute_kernel<true, true><<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);
+        else idw_distribute_kernel<true, false><<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);
+    } else {
+        if (a.clamp) idw_distribute_kernel<false, true><<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);
+        else idw_distribute_kernel<false, false><<<(unsigned)nblk, IDW_THREADS, h->smem_bytes, st>>>(a);
+    }
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
     return SMRFB_OK;
@@ -590,6 +592,14 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
     int rc = upload_geom(h, nsta, mx, my, mz, ny, nx, grid_kind, gx, gy, dem);
     if (rc == SMRFB_OK) {
         h->L = make_layout(nsta, 8, IDW_MAXM, true);
+        h->use_small = (h->L.S_pad <= 16) && !getenv("SMRFB_IDW_FORCE_MMA");
+        if (h->use_small) {                // register-weight kernel: offsets into wsm[station][thread]
+            h->L.miss_scale = IDWS_THREADS;
+            h->L.miss_fill = 0;
+        } else {                           // tensor-core kernel: offsets into Wt[station][WSTR], fill = the zero row
+            h->L.miss_scale = IDW_WSTR;
+            h->L.miss_fill = h->L.S_pad * IDW_WSTR;
+        }
         h->smem_bytes = idw_smem_bytes(h->L);
         int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -599,8 +609,14 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
         }
     }
     if (rc == SMRFB_OK) {
-        cudaError_t e = cudaFuncSetAttribute(idw_distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(idw_distribute_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)h->smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(idw_distribute_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(idw_distribute_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(idw_distribute_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(%zu B smem): %s", h->smem_bytes, cudaGetErrorString(e));
             rc = SMRFB_ERR_CUDA;

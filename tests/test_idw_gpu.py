@@ -170,9 +170,10 @@ def test_idw_small_station_count_both_kernels(sp, golden, monkeypatch):
     o = orc.IDW(g["mx"][sel], g["my"][sel], X, Y, mz=g["mz"][sel], GridZ=g["dem"], power=2.0)
     data = g["data"][:4, sel]
     a = idw.distribute_block(data, detrend=True, flag=-1, vmin=-10.0, vmax=30.0)
-    monkeypatch.setenv("SMRFB_IDW_FORCE_MMA", "1")
-    b = idw.distribute_block(data, detrend=True, flag=-1, vmin=-10.0, vmax=30.0)
+    monkeypatch.setenv("SMRFB_IDW_FORCE_MMA", "1")          # read when the handle is created
+    idw_mma = sp.IDW(g["mx"][sel], g["my"][sel], X, Y, mz=g["mz"][sel], GridZ=g["dem"], power=2.0)
     monkeypatch.delenv("SMRFB_IDW_FORCE_MMA")
+    b = idw_mma.distribute_block(data, detrend=True, flag=-1, vmin=-10.0, vmax=30.0)
     for t in range(len(data)):
         want = np.clip(o.detrendedIDW(data[t].copy(), -1), -10.0, 30.0)
         assert parity(a[t], want, step_scale(data[t])) <= TOL
