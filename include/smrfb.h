@@ -117,10 +117,14 @@ int smrfb_grid_create(int npts, const double* mx, const double* my, const double
                       const double* dem /* nullable */,
                       int nsimp, const int32_t* simplices, const double* transform,
                       const int32_t* cell_simplex, const uint8_t* point_mask, int device, smrfb_handle_t* out);
-/* detrend = 1: detrendedInterpolationMask (grid.py:179-212); 0: calculateInterpolation (grid.py:214-231). */
-int smrfb_grid_distribute(smrfb_handle_t h, const double* data, int T, int detrend, int slope_flag,
+/* Optional: the nearest source point of every cell (scipy.spatial.cKDTree.query, as griddata's
+ * NearestNDInterpolator does it), enabling grid_method = 'nearest'.  cell_nearest[ncell] in [0, npts). */
+int smrfb_grid_set_nearest(smrfb_handle_t h, const int32_t* cell_nearest);
+/* detrend = 1: detrendedInterpolationMask (grid.py:179-212); 0: calculateInterpolation (grid.py:214-231).
+ * method: 0 = 'linear', 1 = 'nearest' (the reference's grid_method; 'cubic' is not on this path). */
+int smrfb_grid_distribute(smrfb_handle_t h, const double* data, int T, int detrend, int slope_flag, int method,
                           double vmin, double vmax, const double* pv_in, double* pv_out, double* out);
-int smrfb_grid_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int detrend, int slope_flag,
+int smrfb_grid_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int detrend, int slope_flag, int method,
                               double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
                               double* d_out, void* stream);
 

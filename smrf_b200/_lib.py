@@ -59,11 +59,12 @@ _SIGS = {
     "smrfb_grid_create": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, c_i32_p,
                                          c_double_p, c_i32_p, c_u8_p, ctypes.c_int, ctypes.POINTER(handle_t)]),
-    "smrfb_grid_distribute": (ctypes.c_int, [handle_t, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    "smrfb_grid_set_nearest": (ctypes.c_int, [handle_t, c_i32_p]),
+    "smrfb_grid_distribute": (ctypes.c_int, [handle_t, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
     "smrfb_grid_distribute_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                 ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
-                                                 ctypes.c_void_p, ctypes.c_void_p]),
+                                                 ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_set_min_max": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
 }
 

@@ -25,6 +25,7 @@ struct GridHandle : HandleBase {
     int32_t* d_simplices = nullptr;    // [nsimp][3]
     double* d_transform = nullptr;     // [nsimp][3][2]
     int32_t* d_cell_simplex = nullptr; // [ncell]
+    int32_t* d_cell_nearest = nullptr; // [ncell], optional (grid_method 'nearest')
     RecLayout L;
     double* d_vt = nullptr;            // [S][T_pad] transposed residuals
     size_t vt_cap = 0;
@@ -36,6 +37,7 @@ struct GridHandle : HandleBase {
         cudaFree(d_simplices);
         cudaFree(d_transform);
         cudaFree(d_cell_simplex);
+        cudaFree(d_cell_nearest);
         cudaFree(d_vt);
         cudaFree(d_pvt);
     }
@@ -69,6 +71,7 @@ struct GridArgs {
     const int32_t* simplices;
     const double* transform;
     const int32_t* cell_simplex;
+    const int32_t* cell_nearest;   // non-null: nearest-point mode
     const double* vt;
     const double* pvt;
     int T, T_pad, detrend;
@@ -79,9 +82,26 @@ struct GridArgs {
 __global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs a) {
     const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
     if (c >= a.g.ncell) return;
-    const int sx = __ldg(a.cell_simplex + c);
     double* op = a.out + c;
     const size_t ncell = (size_t)a.g.ncell;
+    if (a.cell_nearest) {   // grid_method 'nearest': the value of the nearest source point, no hull, no arithmetic on it
+        const double* vn = a.vt + (size_t)__ldg(a.cell_nearest + c) * a.T_pad;
+        const double Zn = (a.detrend && a.g.dem) ? __ldg(a.g.dem + c) : 0.0;
+        for (int t0 = 0; t0 < a.T; t0 += 2) {
+            const double2 x = __ldg(reinterpret_cast<const double2*>(vn + t0));
+            const double2 pa = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0));
+            const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
+            double v0 = x.x, v1 = x.y;
+            if (a.detrend) {
+                v0 = __dadd_rn(__dadd_rn(v0, __dmul_rn(pa.x, Zn)), pa.y);
+                v1 = __dadd_rn(__dadd_rn(v1, __dmul_rn(pb.x, Zn)), pb.y);
+            }
+            __stcs(op + (size_t)t0 * ncell, clamp_nan_keep(v0, a.vmin, a.vmax));
+            if (t0 + 1 < a.T) __stcs(op + (size_t)(t0 + 1) * ncell, clamp_nan_keep(v1, a.vmin, a.vmax));
+        }
+        return;
+    }
+    const int sx = __ldg(a.cell_simplex + c);
     if (sx < 0) {
         const double qnan = nan("");
         for (int t = 0; t < a.T; t++) __stcs(op + (size_t)t * ncell, qnan);
@@ -129,9 +149,11 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs 
     }
 }
 
-static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int slope_flag, double vmin, double vmax,
-                    const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
+static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int slope_flag, int method, double vmin,
+                    double vmax, const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    SMRFB_CHECK(method == 0 || method == 1, SMRFB_ERR_ARG, "grid method must be 0 (linear) or 1 (nearest)");
+    SMRFB_CHECK(method == 0 || h->d_cell_nearest, SMRFB_ERR_ARG, "grid method 'nearest' needs smrfb_grid_set_nearest() first");
     SMRFB_CHECK(!detrend || (h->g.dem && h->d_mz), SMRFB_ERR_ARG, "detrended GRID needs mz and GridZ");
     const int T_pad = (T + 31) / 32 * 32;
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_rec, &h->rec_cap, (size_t)T_pad * h->L.RS * sizeof(double)));
@@ -148,6 +170,7 @@ static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int
     a.simplices = h->d_simplices;
     a.transform = h->d_transform;
     a.cell_simplex = h->d_cell_simplex;
+    a.cell_nearest = method == 1 ? h->d_cell_nearest : nullptr;
     a.vt = h->d_vt;
     a.pvt = h->d_pvt;
     a.T = T;
@@ -212,19 +235,33 @@ int smrfb_grid_create(int npts, const double* mx, const double* my, const double
     return SMRFB_OK;
 }
 
-int smrfb_grid_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, int detrend, int slope_flag, double vmin,
-                              double vmax, const double* d_pv_in, double* d_pv_out, double* d_out, void* stream) {
+int smrfb_grid_set_nearest(smrfb_handle_t hh, const int32_t* cell_nearest) {
+    SMRFB_CHECK(hh && cell_nearest, SMRFB_ERR_ARG, "NULL handle / array");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    const size_t ncell = (size_t)h->g.ncell;
+    for (size_t c = 0; c < ncell; c++)
+        SMRFB_CHECK(cell_nearest[c] >= 0 && cell_nearest[c] < h->S, SMRFB_ERR_ARG, "cell_nearest[%zu] = %d out of range", c, cell_nearest[c]);
+    if (!h->d_cell_nearest) SMRFB_CUDA(cudaMalloc((void**)&h->d_cell_nearest, ncell * sizeof(int32_t)));
+    SMRFB_CUDA(cudaMemcpy(h->d_cell_nearest, cell_nearest, ncell * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return SMRFB_OK;
+}
+
+int smrfb_grid_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, int detrend, int slope_flag, int method,
+                              double vmin, double vmax, const double* d_pv_in, double* d_pv_out, double* d_out,
+                              void* stream) {
     SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
     GridHandle* h = reinterpret_cast<GridHandle*>(hh);
     SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
     SMRFB_CHECK(d_data && d_out, SMRFB_ERR_ARG, "NULL data/out");
     SMRFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    return grid_run(h, d_data, T, detrend, slope_flag, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+    return grid_run(h, d_data, T, detrend, slope_flag, method, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
 }
 
-int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detrend, int slope_flag, double vmin,
-                          double vmax, const double* pv_in, double* pv_out, double* out) {
+int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detrend, int slope_flag, int method,
+                          double vmin, double vmax, const double* pv_in, double* pv_out, double* out) {
     SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
     GridHandle* h = reinterpret_cast<GridHandle*>(hh);
     SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
@@ -240,7 +277,7 @@ int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detr
         SMRFB_CUDA(cudaMemcpyAsync(d_pvin, pv_in, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     int rc = run_host_batches(h, T, 32, out, [&](int t0, int tn, double* d_out, cudaStream_t st) {
-        return grid_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, vmin, vmax,
+        return grid_run(h, h->d_data + (size_t)t0 * S, tn, detrend, slope_flag, method, vmin, vmax,
                         d_pvin ? d_pvin + (size_t)2 * t0 : nullptr, h->d_pv + (size_t)2 * t0, d_out, st);
     });
     if (rc == SMRFB_OK && pv_out &&

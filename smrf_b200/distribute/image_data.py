@@ -84,7 +84,7 @@ class image_data:
             blk = self.dk.distribute_block(vals, vmin=self.min, vmax=self.max)
         else:
             blk = self.grid.distribute_block(vals, detrend=bool(self.config["detrend"]), flag=self.config.get("detrend_slope", 0),
-                                             vmin=self.min, vmax=self.max)
+                                             vmin=self.min, vmax=self.max, grid_method=self.config.get("grid_method", "linear"))
         self._block = blk
         self._block_index = {k: i for i, k in enumerate(rows.index)}
         return blk

@@ -6,8 +6,8 @@ every cell on every call (scipy.interpolate.griddata); here the Delaunay triangu
 simplex of every cell are built ONCE on the host with scipy -- the same qhull call the reference
 makes -- and the per-timestep work (barycentric interpolation, retrend, clamp) is one CUDA kernel.
 
-Covered: grid_method='linear', grid_local=False (detrendedInterpolationMask, calculateInterpolation).
-'cubic' / 'nearest' / grid_local raise NotImplementedError (SURVEY.md section 8f row N-b).
+Covered: grid_method='linear' and 'nearest', grid_local=False (detrendedInterpolationMask,
+calculateInterpolation).  'cubic' and grid_local raise NotImplementedError (SURVEY.md section 8f row N-b).
 """
 import numpy as np
 
@@ -68,13 +68,25 @@ class GRID:
                 pass
             self._h = None
 
-    @staticmethod
-    def _check_method(grid_method):
-        if grid_method != "linear":
-            raise NotImplementedError("grid_method=%r: only 'linear' is on the B200 path (SURVEY.md 8f N-b)" % grid_method)
+    def _method_code(self, grid_method):
+        if grid_method == "linear":
+            return 0
+        if grid_method == "nearest":
+            if not getattr(self, "_nearest_ready", False):
+                # griddata(method='nearest') = NearestNDInterpolator: cKDTree(points).query(xi); same call, once
+                from scipy.spatial import cKDTree
+                xi = np.column_stack([np.asarray(self.GridX, dtype=np.float64).ravel(),
+                                      np.asarray(self.GridY, dtype=np.float64).ravel()])
+                idx = cKDTree(np.column_stack([self.mx, self.my])).query(xi)[1]
+                self.cell_nearest = np.ascontiguousarray(idx.astype(np.int32))
+                _lib.check(_lib.lib().smrfb_grid_set_nearest(self._h, self.cell_nearest.ctypes.data_as(_lib.c_i32_p)))
+                self._nearest_ready = True
+            return 1
+        raise NotImplementedError("grid_method=%r: 'linear' and 'nearest' are on the B200 path (SURVEY.md 8f N-b)" % grid_method)
 
-    def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None):
-        """[T, npoints] -> float64 [T, ny, nx] in one launch; NaN outside the convex hull."""
+    def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None, grid_method="linear"):
+        """[T, npoints] -> float64 [T, ny, nx] in one launch; 'linear': NaN outside the convex hull."""
+        method = self._method_code(grid_method)
         data = _lib.as_f64(data)
         if data.ndim == 1:
             data = data[None, :]
@@ -88,15 +100,15 @@ class GRID:
         lo = -np.inf if vmin is None else float(vmin)
         hi = np.inf if vmax is None else float(vmax)
         _lib.check(_lib.lib().smrfb_grid_distribute(
-            self._h, _lib.dptr(data), T, int(bool(detrend)), int(flag), lo, hi,
+            self._h, _lib.dptr(data), T, int(bool(detrend)), int(flag), method, lo, hi,
             _lib.dptr(pv_in), _lib.dptr(pv_out), _lib.dptr(out)))
         self.pv_block = pv_out
         return out
 
     def detrendedInterpolation(self, data, flag=0, grid_method="linear"):
         """grid.py:96-113 -> detrendedInterpolationMask (grid.py:179-212). ``data`` may be a pandas Series."""
-        self._check_method(grid_method)
-        v = self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=True, flag=flag)[0]
+        v = self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=True, flag=flag,
+                                  grid_method=grid_method)[0]
         self.pv = self.pv_block[0].copy()
         return v
 
@@ -104,5 +116,4 @@ class GRID:
 
     def calculateInterpolation(self, data, grid_method="linear"):
         """grid.py:214-231."""
-        self._check_method(grid_method)
-        return self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=False)[0]
+        return self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=False, grid_method=grid_method)[0]

@@ -220,6 +220,8 @@ def main():
             res["out_m%d_f%d" % (gm, flag)] = np.stack(outs)
             res["pv_m%d_f%d" % (gm, flag)] = np.stack(pvs)
     res["out_plain"] = np.stack([ref.calculateInterpolation(r.copy(), "linear") for r in fields])
+    res["out_plain_nearest"] = np.stack([ref.calculateInterpolation(r.copy(), "nearest") for r in fields])
+    res["out_m0_f-1_nearest"] = np.stack([ref.detrendedInterpolation(pd.Series(r.copy()), -1, "nearest") for r in fields])
     np.savez_compressed(os.path.join(OUT, "grid_synth.npz"), px=px, py=py, pz=pz, x=x, y=y, dem=dem, mask=mask,
                         fields=fields, **res)
 

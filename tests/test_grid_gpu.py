@@ -42,6 +42,12 @@ def test_grid_golden(sp, golden):
     np.testing.assert_array_equal(np.isnan(v), np.isnan(g["out_m0_f-1"][1]))
     with pytest.raises(NotImplementedError):
         grid.calculateInterpolation(g["fields"][0], "cubic")
+    # grid_method 'nearest' (NearestNDInterpolator): bit-exact copy of the nearest source value, detrended form within 1e-9
+    out = grid.distribute_block(g["fields"], detrend=False, grid_method="nearest")
+    np.testing.assert_array_equal(out, g["out_plain_nearest"])
+    for t in range(len(g["fields"])):
+        v = grid.detrendedInterpolation(g["fields"][t], -1, "nearest")
+        assert parity(v, g["out_m0_f-1_nearest"][t], step_scale(g["fields"][t])) <= TOL
 
 
 def test_grid_vs_oracle_larger(sp):

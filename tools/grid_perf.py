@@ -21,12 +21,12 @@ d_f = torch.from_numpy(f).cuda()
 d_out = torch.empty((T, ny * nx), dtype=torch.float64, device="cuda")
 for det in (1, 0):
     for _ in range(2):
-        _lib.check(L.smrfb_grid_distribute_dev(g._h, d_f.data_ptr(), T, det, -1, -50.0, 50.0, None, None, d_out.data_ptr(), st))
+        _lib.check(L.smrfb_grid_distribute_dev(g._h, d_f.data_ptr(), T, det, -1, 0, -50.0, 50.0, None, None, d_out.data_ptr(), st))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(3):
-        _lib.check(L.smrfb_grid_distribute_dev(g._h, d_f.data_ptr(), T, det, -1, -50.0, 50.0, None, None, d_out.data_ptr(), st))
+        _lib.check(L.smrfb_grid_distribute_dev(g._h, d_f.data_ptr(), T, det, -1, 0, -50.0, 50.0, None, None, d_out.data_ptr(), st))
     e1.record(stream); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     cs = ny * nx * T / (ms * 1e-3)
