@@ -517,20 +517,36 @@ __global__ void dk_expand_kernel(int K, long long ncell, int n, const uint8_t* w
 // ------------------------------------------------------------------------------------------
 // Steady state (dk.py:86-96): out = sum_k w_k * r[station_k] + p0*Z + p1
 // ------------------------------------------------------------------------------------------
+// Step-pair records for one mask group: recp[p] = { r[t0][s], r[t1][s] interleaved over s | p0,p1 of t0 | p0,p1 of t1 }
+// with (t0, t1) = (steps[2p], steps[2p+1]).  Interleaving lets the distribute kernel fetch the residuals of one
+// station for two timesteps with a single 128-bit shared-memory read.
+__global__ void dk_pair_kernel(const double* __restrict__ rec, RecLayout L, const int* __restrict__ steps, int Tm,
+                               double* __restrict__ recp) {
+    const int p = blockIdx.x;
+    const int PR = 2 * L.S_pad + 4;
+    const int t0 = steps[2 * p];
+    const int t1 = (2 * p + 1 < Tm) ? steps[2 * p + 1] : -1;
+    const double* r0 = rec + (size_t)t0 * L.RS;
+    const double* r1 = t1 >= 0 ? rec + (size_t)t1 * L.RS : nullptr;
+    double* o = recp + (size_t)p * PR;
+    for (int s = threadIdx.x; s < L.S_pad; s += blockDim.x) {
+        o[2 * s] = r0[s];
+        o[2 * s + 1] = r1 ? r1[s] : 0.0;
+    }
+    if (threadIdx.x < 4) {
+        const int h = threadIdx.x >> 1, q = threadIdx.x & 1;
+        const double* r = h ? r1 : r0;
+        o[2 * L.S_pad + threadIdx.x] = r ? r[L.meta() + q] : 0.0;
+    }
+}
+
 // One CTA = 256 consecutive cells of the window, one thread per cell.  The thread keeps its cell's
-// (station, weight) pairs in registers; the prepared step records (residuals of ALL stations + p0, p1) of
-// DK_TCH timesteps are staged in shared memory by 1-D TMA bulk copies (one per step record, completion on
-// an mbarrier), double buffered so the copy of the next block overlaps the arithmetic of this one.  The
-// per-cell gathers are shared-memory reads: cells of a warp mostly share their station set (broadcast),
-// and different stations fall into different banks.  Stores stream out row by row.
-#ifndef DK_TCH_DEF
-#define DK_TCH_DEF 16
-#endif
-#ifndef DK_DT_DEF
-#define DK_DT_DEF 256
-#endif
-constexpr int DK_TCH = DK_TCH_DEF;
-constexpr int DK_DT = DK_DT_DEF;     // threads (= cells) per CTA of the distribute kernel
+// (station, weight) pairs in registers; the step-pair records of DK_TCH timesteps are staged in shared memory by
+// one 1-D TMA bulk copy per block (completion on an mbarrier), double buffered so the copy of the next block
+// overlaps the arithmetic of this one.  The per-cell gathers are 128-bit shared-memory reads (two timesteps each):
+// cells of a warp mostly share their station set (broadcast), and different stations fall into different banks.
+constexpr int DK_TCH = 16;
+constexpr int DK_DT = 256;     // threads (= cells) per CTA of the distribute kernel
 
 struct DkDistArgs {
     long long ncell;     // cells of the whole grid (ELL plane stride)
@@ -540,7 +556,8 @@ struct DkDistArgs {
     int K;
     const uint8_t* widx;
     const double* wval;
-    const double* rec;   // prepared step records [T][RS]
+    const double* rec;   // prepared step records [T][RS] (generic kernel)
+    const double* recp;  // step-pair records of this mask group [ceil(Tm/2)][2*S_pad + 4]
     RecLayout L;
     const int* steps;    // [Tm] step indices of this mask group
     int Tm;
@@ -551,16 +568,17 @@ struct DkDistArgs {
 template <int KR>
 __global__ void __launch_bounds__(DK_DT) dk_distribute_kernel(DkDistArgs a) {
     extern __shared__ __align__(16) unsigned char dk_smem[];
-    const int ROW = a.L.S_pad + 2;                            // residuals + p0, p1 (doubles); 16-byte multiple
-    double* res = reinterpret_cast<double*>(dk_smem);        // [2][DK_TCH][ROW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(res + 2 * DK_TCH * ROW);   // [2]
-    int* stp = reinterpret_cast<int*>(bars + 2);              // [2][DK_TCH]
+    const int SP2 = 2 * a.L.S_pad;
+    const int PR = SP2 + 4;                                   // doubles per step-pair record (16-byte multiple)
+    constexpr int NPR = DK_TCH / 2;                           // pair records per block
+    double* res = reinterpret_cast<double*>(dk_smem);        // [2][NPR][PR]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res + 2 * NPR * PR);   // [2]
     const int tid = threadIdx.x;
     const long long c = (long long)blockIdx.x * DK_DT + tid; // cell within the window
     const bool live = c < a.ncw;
     const size_t gc = (size_t)(a.cbase + (live ? c : 0));    // cell within the grid
-    const int nchunk = (a.Tm + DK_TCH - 1) / DK_TCH;
-    const uint32_t row_bytes = (uint32_t)(ROW * sizeof(double));
+    const int npair = (a.Tm + 1) / 2;
+    const int nchunk = (npair + NPR - 1) / NPR;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -568,17 +586,12 @@ __global__ void __launch_bounds__(DK_DT) dk_distribute_kernel(DkDistArgs a) {
         fence_mbar_init();
     }
     __syncthreads();
-    auto issue = [&](int chn) {     // one thread: bulk-copy the step records of block chn into buffer chn & 1
+    auto issue = [&](int chn) {     // one thread: bulk-copy the pair records of block chn into buffer chn & 1
         const int b = chn & 1;
-        const int t0 = chn * DK_TCH;
-        const int nrow = min(DK_TCH, a.Tm - t0);
-        mbar_arrive_expect_tx(&bars[b], row_bytes * nrow);
-        for (int r = 0; r < nrow; r++) {
-            const int st = a.steps[t0 + r];
-            stp[b * DK_TCH + r] = st;
-            bulk_g2s(res + (size_t)(b * DK_TCH + r) * ROW, a.rec + (size_t)st * a.L.RS, row_bytes, &bars[b]);
-        }
-        for (int r = nrow; r < DK_TCH; r++) stp[b * DK_TCH + r] = -1;
+        const int nrow = min(NPR, npair - chn * NPR);
+        const uint32_t bytes = (uint32_t)(nrow * PR * sizeof(double));
+        mbar_arrive_expect_tx(&bars[b], bytes);
+        bulk_g2s(res + (size_t)b * NPR * PR, a.recp + (size_t)chn * NPR * PR, bytes, &bars[b]);
     };
     if (tid == 0) {
         issue(0);
@@ -590,34 +603,33 @@ __global__ void __launch_bounds__(DK_DT) dk_distribute_kernel(DkDistArgs a) {
     for (int j = 0; j < KR; j++) {
         const bool on = live && j < a.K;
         wv[j] = on ? __ldg(a.wval + (size_t)j * a.ncell + gc) : 0.0;
-        wo[j] = on ? (int)__ldg(a.widx + (size_t)j * a.ncell + gc) : 0;
+        wo[j] = on ? 2 * (int)__ldg(a.widx + (size_t)j * a.ncell + gc) : 0;
     }
     const double Z = live ? __ldg(a.dem + gc) : 0.0;
-    const int SP = a.L.S_pad;
     for (int chn = 0; chn < nchunk; chn++) {
         const int b = chn & 1;
-        __syncthreads();                                      // stp[] of this block is visible (written before the barrier below)
         mbar_wait(&bars[b], (chn >> 1) & 1);
-        const double* rb = res + (size_t)b * DK_TCH * ROW;
-        const int* sb = stp + b * DK_TCH;
+        const double* rb = res + (size_t)b * NPR * PR;
         if (live) {
+            const int nrow = min(NPR, npair - chn * NPR);
 #pragma unroll 2
-            for (int tl = 0; tl < DK_TCH; tl += 2) {
-                const int st0 = sb[tl], st1 = sb[tl + 1];
-                if (st0 < 0) break;
-                const double* r0p = rb + (size_t)tl * ROW;
-                const double* r1p = r0p + ROW;
+            for (int pr = 0; pr < nrow; pr++) {
+                const double* rp = rb + (size_t)pr * PR;
                 double r0 = 0.0, r1 = 0.0;
 #pragma unroll
                 for (int j = 0; j < KR; j++) {                // dk.py:91 (entries past K have weight 0)
-                    r0 = fma(wv[j], r0p[wo[j]], r0);
-                    r1 = fma(wv[j], r1p[wo[j]], r1);
+                    const double2 x = *reinterpret_cast<const double2*>(rp + wo[j]);
+                    r0 = fma(wv[j], x.x, r0);
+                    r1 = fma(wv[j], x.y, r1);
                 }
-                const double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(r0p[SP], Z)), r0p[SP + 1]);   // dk.py:168, left to right
-                __stcs(a.out + (size_t)st0 * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
-                if (st1 >= 0) {
-                    const double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(r1p[SP], Z)), r1p[SP + 1]);
-                    __stcs(a.out + (size_t)st1 * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+                const double2 pa = *reinterpret_cast<const double2*>(rp + SP2);
+                const double2 pb = *reinterpret_cast<const double2*>(rp + SP2 + 2);
+                const int tl = 2 * (chn * NPR + pr);
+                const double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(pa.x, Z)), pa.y);   // dk.py:168, left to right
+                __stcs(a.out + (size_t)__ldg(a.steps + tl) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+                if (tl + 1 < a.Tm) {
+                    const double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(pb.x, Z)), pb.y);
+                    __stcs(a.out + (size_t)__ldg(a.steps + tl + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
                 }
             }
         }
@@ -668,11 +680,14 @@ struct DkHandle : HandleBase {
     int max_active = 0;
     int* d_steps = nullptr;
     size_t steps_cap = 0;
+    double* d_recp = nullptr;   // step-pair records of the current mask group
+    size_t recp_cap = 0;
     DkHandle() : HandleBase(HK_DK) {}
     ~DkHandle() override {
         cudaSetDevice(device);
         for (auto& e : cache) delete e.second;
         cudaFree(d_steps);
+        cudaFree(d_recp);
     }
 };
 
@@ -1007,13 +1022,19 @@ static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T
         SMRFB_CUDA(cudaStreamSynchronize(st));
         SMRFB_PROPAGATE(ensure_cap((void**)&h->d_steps, &h->steps_cap, (size_t)Tm * sizeof(int)));
         SMRFB_CUDA(cudaMemcpyAsync(h->d_steps, groups[gi].data(), (size_t)Tm * sizeof(int), cudaMemcpyHostToDevice, st));
+        const int npair = (Tm + 1) / 2;
+        const int PR = 2 * h->L.S_pad + 4;
+        SMRFB_PROPAGATE(ensure_cap((void**)&h->d_recp, &h->recp_cap, (size_t)npair * PR * sizeof(double)));
+        dk_pair_kernel<<<npair, 128, 0, st>>>(h->d_rec, h->L, h->d_steps, Tm, h->d_recp);
+        count_launch();
+        SMRFB_CUDA(cudaGetLastError());
         DkDistArgs a;
         a.ncell = h->g.ncell; a.cbase = cbase; a.ncw = ncw; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
-        a.rec = h->d_rec; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
+        a.rec = h->d_rec; a.recp = h->d_recp; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
         a.vmin = vmin; a.vmax = vmax; a.out = d_out;
         const unsigned nblk = (unsigned)((ncw + 255) / 256);
         const unsigned nblk_d = (unsigned)((ncw + DK_DT - 1) / DK_DT);
-        const size_t dsm = (size_t)2 * DK_TCH * (h->L.S_pad + 2) * sizeof(double) + 2 * sizeof(uint64_t) + 2 * DK_TCH * sizeof(int);
+        const size_t dsm = (size_t)2 * (DK_TCH / 2) * PR * sizeof(double) + 2 * sizeof(uint64_t);
 #define DK_LAUNCH(KRV)                                                                                           \
     do {                                                                                                         \
         SMRFB_CUDA(cudaFuncSetAttribute(dk_distribute_kernel<KRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); \
