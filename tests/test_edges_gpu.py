@@ -115,3 +115,36 @@ def test_idw_dk_c4_slab_properties(sp):
     dk.distribute_block(pr, vmin=0.0)
     built, fallback, kmax = dk.stats()
     assert built == 1 and fallback == 0 and 2 <= kmax <= 31
+
+
+def test_idw_zeros_branch_and_error_paths(sp):
+    """detrendedIDW(..., zeros=mask): trend fitted on the original values, flagged stations set to zeroVal, negatives
+    clipped (idw.py:96-136); and argument errors come back as exceptions with a message, never as exit()."""
+    from oracle import oracle as orc
+    from smrf_b200._lib import SmrfbError
+    from smrf_b200 import synthetic as syn
+    x, y, dem = syn.make_dem(20, 30, dx=30.0, seed=4)
+    X, Y = np.meshgrid(x, y)
+    mx, my, mz = syn.make_stations(12, x, y, dem, seed=2)
+    row = np.abs(syn.make_series("air_temp", mz, 1, seed=8)[0]) * 0.1
+    zeros = np.zeros(12, dtype=bool)
+    zeros[[2, 5]] = True
+    idw = sp.IDW(mx, my, X, Y, mz=mz, GridZ=dem, power=2.0)
+    o = orc.IDW(mx, my, X, Y, mz=mz, GridZ=dem, power=2.0)
+    keep = row.copy()
+    v = idw.detrendedIDW(row, 1, zeros=zeros)
+    np.testing.assert_array_equal(row, keep)                       # caller's row untouched (the reference mutates it)
+    ref = o.detrendedIDW(keep.copy(), 1, zeros=zeros)
+    assert parity(v, ref, max(step_scale(keep), 1.0)) <= TOL
+    assert (v >= 0).all()
+    with pytest.raises(ValueError):
+        idw.distribute_block(np.zeros((2, 11)))                    # wrong station count
+    with pytest.raises(SmrfbError) as e:
+        sp.IDW(mx, my, X, Y, mz=mz, GridZ=dem, power=2.0, device=99)
+    assert "device" in str(e.value)
+    with pytest.raises(SmrfbError):                                # detrend without elevations
+        sp.IDW(mx, my, X, Y).distribute_block(row[None, :], detrend=True)
+    big = np.linspace(0, 1, 300)
+    with pytest.raises(SmrfbError) as e:                           # more stations than a tile's shared memory holds
+        sp.IDW(big, big, X, Y, mz=big, GridZ=dem)
+    assert e.value.code == 4
