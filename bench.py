@@ -396,7 +396,7 @@ def main():
                                      "unit": "GB/s", "frac": dk_bytes / (launch_ms["precip"] * 1e-3) / 1e9 / hbm_peak,
                                      "algorithmic_bytes_per_launch": dk_bytes, "ms_per_launch": launch_ms["precip"]}}
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported baseline, rank 0 at N = 1 only
         cb, _ = cpu_arm(S, 2, 1)
     line = {"metric": "distributed cell-timesteps/sec (IDW+DK)", "value": value, "unit": "cell-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
