@@ -143,3 +143,27 @@ def test_dk_singular_is_an_error_not_exit(sp):
     with pytest.raises(SmrfbError) as e:
         dk.distribute_block(np.array([[1.0, 2.0, 3.0]]))
     assert e.value.code == 3
+
+
+def test_dk_c4_scattered_cells_bit_exact(sp):
+    """2048 cells scattered over the whole 300 km C4 domain (every cell walks its own elimination path,
+    ~190 drops each): active sets and weights bit-identical to the reference algorithm."""
+    from oracle import oracle as orc
+    from smrf_b200 import synthetic as syn
+    x, y, dem = syn.make_dem(10000, 10000, dx=30.0, noise=False)
+    mx, my, mz = syn.make_stations(200, x, y, dem, seed=7)
+    rng = np.random.default_rng(123)
+    ii = rng.integers(0, 10000, size=(32, 64))
+    jj = rng.integers(0, 10000, size=(32, 64))
+    X, Y, Z = x[jj], y[ii], dem[ii, jj]
+    cfg = {"dk_ncores": 16, "detrend_slope": 1}
+    dk = sp.DK(mx, my, mz, X, Y, Z, cfg)
+    dk.nan_val = np.zeros(200, dtype=bool)
+    dk.nan_val[[11, 42, 190]] = True
+    w = dk.calculateWeights()
+    o = orc.DK(mx, my, mz, X, Y, Z, cfg)
+    o.nan_val = dk.nan_val.copy()
+    o.calculateWeights()
+    np.testing.assert_array_equal(w != 0, o.weights != 0)
+    np.testing.assert_array_equal(w, o.weights)
+    assert dk.stats()[1] == 0
