@@ -149,6 +149,69 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs 
     }
 }
 
+// Two adjacent cells per thread, 128-bit streaming stores (needs an even cell count so every row stays 16-byte
+// aligned): each (CTA, step) writes 4 KB contiguous instead of 2 KB.
+struct GridCell {
+    double c0, c1, c2, Z;
+    const double *va, *vb, *vc;
+    bool inside;
+};
+
+__device__ __forceinline__ GridCell grid_cell_setup(const GridArgs& a, long long c) {
+    GridCell g;
+    const int sx = __ldg(a.cell_simplex + c);
+    g.inside = sx >= 0;
+    const int s0 = g.inside ? sx : 0;
+    double X, Y;
+    cell_xy(a.g, c, X, Y);
+    const double* Tm = a.transform + (size_t)s0 * 6;
+    const double dx = __dsub_rn(X, __ldg(Tm + 4)), dy = __dsub_rn(Y, __ldg(Tm + 5));
+    g.c0 = __dadd_rn(__dmul_rn(__ldg(Tm + 0), dx), __dmul_rn(__ldg(Tm + 1), dy));
+    g.c1 = __dadd_rn(__dmul_rn(__ldg(Tm + 2), dx), __dmul_rn(__ldg(Tm + 3), dy));
+    g.c2 = __dsub_rn(__dsub_rn(1.0, g.c0), g.c1);
+    g.va = a.vt + (size_t)__ldg(a.simplices + 3 * s0 + 0) * a.T_pad;
+    g.vb = a.vt + (size_t)__ldg(a.simplices + 3 * s0 + 1) * a.T_pad;
+    g.vc = a.vt + (size_t)__ldg(a.simplices + 3 * s0 + 2) * a.T_pad;
+    g.Z = (a.detrend && a.g.dem) ? __ldg(a.g.dem + c) : 0.0;
+    return g;
+}
+
+__global__ void __launch_bounds__(GRID_THREADS) grid_distribute2_kernel(GridArgs a) {
+    const long long c = ((long long)blockIdx.x * GRID_THREADS + threadIdx.x) * 2;
+    if (c >= a.g.ncell) return;                       // ncell is even: c + 1 is a valid cell too
+    const GridCell g0 = grid_cell_setup(a, c), g1 = grid_cell_setup(a, c + 1);
+    const size_t ncell = (size_t)a.g.ncell;
+    double* op = a.out + c;
+    const double qnan = nan("");
+#pragma unroll 1
+    for (int t0 = 0; t0 < a.T; t0 += 2) {             // T_pad is even: vector loads stay in bounds
+        const double2 a0 = __ldg(reinterpret_cast<const double2*>(g0.va + t0));
+        const double2 b0 = __ldg(reinterpret_cast<const double2*>(g0.vb + t0));
+        const double2 q0 = __ldg(reinterpret_cast<const double2*>(g0.vc + t0));
+        const double2 a1 = __ldg(reinterpret_cast<const double2*>(g1.va + t0));
+        const double2 b1 = __ldg(reinterpret_cast<const double2*>(g1.vb + t0));
+        const double2 q1 = __ldg(reinterpret_cast<const double2*>(g1.vc + t0));
+        const double2 pa = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0));
+        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.pvt + 2 * t0 + 2));
+        double v00 = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g0.c0, a0.x)), __dmul_rn(g0.c1, b0.x)), __dmul_rn(g0.c2, q0.x));
+        double v01 = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g0.c0, a0.y)), __dmul_rn(g0.c1, b0.y)), __dmul_rn(g0.c2, q0.y));
+        double v10 = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g1.c0, a1.x)), __dmul_rn(g1.c1, b1.x)), __dmul_rn(g1.c2, q1.x));
+        double v11 = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g1.c0, a1.y)), __dmul_rn(g1.c1, b1.y)), __dmul_rn(g1.c2, q1.y));
+        if (a.detrend) {                                // grid.py:210, left to right
+            v00 = __dadd_rn(__dadd_rn(v00, __dmul_rn(pa.x, g0.Z)), pa.y);
+            v10 = __dadd_rn(__dadd_rn(v10, __dmul_rn(pa.x, g1.Z)), pa.y);
+            v01 = __dadd_rn(__dadd_rn(v01, __dmul_rn(pb.x, g0.Z)), pb.y);
+            v11 = __dadd_rn(__dadd_rn(v11, __dmul_rn(pb.x, g1.Z)), pb.y);
+        }
+        v00 = g0.inside ? clamp_nan_keep(v00, a.vmin, a.vmax) : qnan;
+        v01 = g0.inside ? clamp_nan_keep(v01, a.vmin, a.vmax) : qnan;
+        v10 = g1.inside ? clamp_nan_keep(v10, a.vmin, a.vmax) : qnan;
+        v11 = g1.inside ? clamp_nan_keep(v11, a.vmin, a.vmax) : qnan;
+        __stcs(reinterpret_cast<double2*>(op + (size_t)t0 * ncell), make_double2(v00, v10));
+        if (t0 + 1 < a.T) __stcs(reinterpret_cast<double2*>(op + (size_t)(t0 + 1) * ncell), make_double2(v01, v11));
+    }
+}
+
 static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int slope_flag, int method, double vmin,
                     double vmax, const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
@@ -181,6 +244,10 @@ static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int
     a.out = d_out;
     long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+    if (method == 0 && (h->g.ncell & 1) == 0 && !getenv("SMRFB_GRID_ONE_CELL")) {
+        const long long nb2 = (h->g.ncell / 2 + GRID_THREADS - 1) / GRID_THREADS;
+        grid_distribute2_kernel<<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
+    } else
     grid_distribute_kernel<<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
