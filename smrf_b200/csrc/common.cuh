@@ -230,4 +230,19 @@ __device__ __forceinline__ double clamp_nan_keep(double v, double vmin, double v
     return v;
 }
 
+// 1/x for positive normal x: MUFU.RCP64H seed (measured ~2^-10 relative) + Newton steps; no special cases.
+// Two steps give <= ~4e-13 relative (weights: far inside the 1e-9 contract, and numerator and denominator
+// use the same weight values); the quotient in the epilogue adds a residual correction to reach ~1 ulp.
+template <int STEPS>
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+    for (int i = 0; i < STEPS; i++) r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 }  // namespace smrfb

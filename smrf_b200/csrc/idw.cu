@@ -25,6 +25,7 @@
 //   * epilogue: reciprocal (rcp.approx + 2 Newton steps), retrend against the DEM, NaN-preserving
 //     clamp, 128-bit streaming stores.
 #include "common.cuh"
+#include "idw_i8.cuh"
 
 namespace smrfb {
 
@@ -43,7 +44,14 @@ struct IdwHandle : HandleBase {
     RecLayout L;
     size_t smem_bytes = 0;
     bool use_small = false;     // register-weight kernel (few stations); decided at create time
+    int i8_mode = 0;            // int8-sliced tcgen05 kernel: 0 = never (SMRFB_IDW_KERNEL=dmma or > 224 stations),
+                                // 1 = batches of >= 32 steps (default), 2 = always (SMRFB_IDW_KERNEL=i8)
+    IdwI8Scratch i8;
     IdwHandle() : HandleBase(HK_IDW) {}
+    ~IdwHandle() override {
+        cudaSetDevice(device);
+        if (i8.d_blob) cudaFree(i8.d_blob);
+    }
 };
 
 struct IdwArgs {
@@ -62,21 +70,6 @@ struct IdwArgs {
     long long cbase;      // first cell of the window this launch distributes
     long long ncw;        // cells in the window
 };
-
-// 1/x for positive normal x: MUFU.RCP64H seed (measured ~2^-10 relative) + Newton steps; no special cases.
-// Two steps give <= ~4e-13 relative (weights: far inside the 1e-9 contract, and numerator and denominator
-// use the same weight values); the quotient in the epilogue adds a residual correction to reach ~1 ulp.
-template <int STEPS>
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#pragma unroll
-    for (int i = 0; i < STEPS; i++) r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <bool DETREND, bool CLAMP>
 __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs a) {
@@ -561,6 +554,11 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
         SMRFB_CUDA(cudaGetLastError());
         return SMRFB_OK;
     }
+    // long batches: the contraction runs on the int8 tensor cores (idw_i8.cu), ~4x the DMMA rate; a chunk there is 80
+    // steps, so short batches stay on the fp64 tensor-core kernel below
+    if (h->i8_mode == 2 || (h->i8_mode == 1 && T >= 32))
+        return idw_i8_run(st, &h->i8, h->g, h->d_mx, h->d_my, h->S, h->power, h->d_rec, h->L.RS, h->L.S_pad, h->d_valid, T,
+                          detrend, vmin, vmax, d_out, cbase, ncw, h->device);
     long long nblk = (ncw + IDW_CT - 1) / IDW_CT;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     if (detrend) {
@@ -599,6 +597,11 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
         } else {                           // tensor-core kernel: offsets into Wt[station][WSTR], fill = the zero row
             h->L.miss_scale = IDW_WSTR;
             h->L.miss_fill = h->L.S_pad * IDW_WSTR;
+        }
+        if (!h->use_small && nsta <= IDW_I8_MAX_STATIONS) {
+            const char* k = getenv("SMRFB_IDW_KERNEL");
+            h->i8_mode = (k && !strcmp(k, "dmma")) ? 0 : (k && !strcmp(k, "i8")) ? 2 : 1;
+            if (h->i8_mode) rc = idw_i8_prepare(device);
         }
         h->smem_bytes = idw_smem_bytes(h->L);
         int smem_max = 0;

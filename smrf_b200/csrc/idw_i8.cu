@@ -1,0 +1,666 @@
+// idw_i8.cu -- inverse-distance weighting (smrf/spatial/idw.py:53-144) on the 5th-generation tensor cores:
+// the fp64 contraction over stations is evaluated EXACTLY in integers (Ozaki-style 8-bit slicing) by
+// tcgen05.mma kind::i8 with s32 accumulators in tensor memory.
+//
+//   out[t][c] = num / den * 2^k(t) + p0[t]*Z[c] + p1[t]
+//   num[c][t] = sum_s W[c][s] * R[t][s]        W = floor(w * 2^ew(c))  55-bit unsigned integers, w = 1/dist^power
+//   den[c][t] = sum_s W[c][s] * V[t][s]        R = rint(r * 2^er(t))   55-bit signed integers (residuals, 0 = missing)
+//                                              V = 1 for a valid station, else 0
+// W and R are cut into seven 8-bit digits (W: unsigned bytes; R: two's complement, top digit signed), and
+//   sum_s W R = sum_{i,j} 2^(8(12-i-j)) sum_s a_i[c][s] b_j[t][s]
+// keeps the 28 digit products with i + j <= 6 (what is dropped is < 2^-53 of max|W| max|R| per station, the
+// size of one fp64 rounding); every digit product is one int8 GEMM whose s32 sums are exact.  den uses all
+// seven digits of W against the 0/1 matrix V: the masked denominator needs no missing-station lists and has
+// no cancellation.  The scale 2^ew(c) of a cell cancels in num / den.
+// Dynamic range: the digits are relative to the LARGEST weight of the cell.  When that station is missing
+// at a step and the remaining weights are below 2^-10 of it, the fixed-point error would no longer be
+// negligible: those (cell, step) pairs -- and cells that coincide with a station (w = inf) --
+// are recomputed in plain fp64 (idw_exact_value).  Error bound of the integer path: 3e-11 * max_s|r[t][s]|
+// in the worst admitted case, ~1e-15 relative typically; the parity contract is 1e-9.
+//
+// One persistent CTA per SM owns tiles of 128 consecutive cells for the whole batch of T steps:
+//   * warps 0-7 ("workers", TMEM lane quarter = warp & 3, step half = warp >> 2) generate the tile's weights
+//     from the coordinates, cut them into digits and write digit planes 0-5 straight into TENSOR MEMORY
+//     (tcgen05.st; the A operand of the MMAs is read from TMEM) and plane 6 into shared memory -- the weight
+//     cube [ncell x S] is never materialised and A stays resident for all T steps;
+//   * the digit planes of R and V are prepared once per call (idw_i8_slice_kernel) in the canonical K-major
+//     core-matrix layout and stream per chunk of 80 steps through shared memory by 1-D TMA bulk copies
+//     (warp 9); R (125 KB) is single-buffered and reloaded under the denominator MMAs, which only read V;
+//   * warp 8 issues the MMAs (M = 128 cells, N = 80 steps, K = 32 stations per instruction): per chunk
+//     7 numerator passes and 7 denominator passes (one per power of 2^8), each pass accumulating its digit
+//     products into one of two 80-column TMEM accumulators;
+//   * the workers drain every pass with tcgen05.ld, fold it into fp64 (num, den per output in registers)
+//     and finish: reciprocal, scale, retrend against the DEM, NaN-preserving clamp, streaming store.
+#include "idw_i8.cuh"
+
+namespace smrfb {
+
+constexpr int I8_M = 128;                      // cells per tile
+constexpr int I8_N = IDW_I8_STEPS;             // steps per chunk
+constexpr int I8_NS = 7;                       // 8-bit digits per operand
+constexpr int I8_WWARPS = 12;                  // worker warps: TMEM lane quarter = warp & 3, step third = warp >> 2
+constexpr int I8_COLS = I8_N / 3;              // steps per worker thread and chunk
+constexpr int I8_WORKERS = I8_WWARPS * 32;
+constexpr int I8_THREADS = I8_WORKERS + 128;   // + warp 12: MMA issuer, warp 13: TMA producer, 14-15 idle (setmaxnreg works on warpgroups)
+constexpr int I8_LBO_B = (I8_N / 8) * 128;     // byte stride between the two 16-byte K chunks of a B core-matrix column
+constexpr int I8_KSTEP_B = 2 * I8_LBO_B;       // bytes of one K = 32 block of a B plane
+constexpr int I8_SBO = 128;                    // byte stride between 8-row groups
+constexpr int I8_META = I8_N * 32;             // per step {2^k, p0, p1, 0}
+constexpr int I8_ACOL = 2 * I8_N;              // TMEM columns [0, 2N): two accumulators; [2N, 2N + 7*8*KB): the A digit planes
+constexpr double I8_DEN_MIN = 35184372088832.0;   // 2^45: den below this (weights scaled to [2^54, 2^55)) -> exact path
+
+struct I8Args {
+    Geom g;
+    const double* mx;
+    const double* my;
+    int S, KB;
+    double power;
+    const uint8_t* blob;
+    unsigned chunk_bytes;
+    int nchunk, T;
+    const double* rec;
+    int RS;
+    const uint8_t* valid;
+    int detrend;
+    double vmin, vmax;
+    double* out;
+    long long cbase, ncw;
+    int ntiles;
+    long long* prof;   // I8_PROFILE builds: per-CTA cycle counters
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {   // arrives on bar when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory operand descriptor: K-major, no swizzle (8 x 16-byte core matrices), Blackwell descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+// instruction descriptor for kind::i8: s32 accumulate, A u8, B u8 / s8, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N, int b_signed) {
+    return (2u << 4) | ((uint32_t)b_signed << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+#ifdef I8_EXP_NOMMA
+    return;
+#endif
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}" ::"r"(d),
+                 "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+        "[%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x as a bit pattern, minus the offset
+__device__ __forceinline__ double s32_to_double(uint32_t x) {
+    return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;
+}
+// exact for |x| < 2^51: the bit pattern of 2^52 + 2^51 + x, minus the offset
+__device__ __forceinline__ double s64_to_double(long long x) { return __longlong_as_double(x + 0x4338000000000000LL) - 6755399441055744.0; }
+__device__ __forceinline__ double u32_to_double(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+
+__device__ __noinline__ double idw_weight_pow(double q, double power) { return 1.0 / pow(sqrt(q), power); }
+__device__ __forceinline__ double idw_weight(double q, bool p2, double power) {   // idw.py:77, q = squared distance > 0
+    return p2 ? fast_rcp<2>(q) : idw_weight_pow(q, power);
+}
+
+// ------------------------------------------------------------------------------------------ operand planes of R and V
+// blob[chunk] = { R digit planes 0..6, V plane : each [2*KB K-chunks][10 step groups][8 steps][16 stations] bytes,
+//                 meta[80] = {2^k, p0, p1, 0} }.   k is chosen per step so that max|R| lies in [2^53, 2^54).
+__global__ void __launch_bounds__(256) idw_i8_slice_kernel(const double* __restrict__ rec, int RS, int S, int S_pad,
+                                                           const uint8_t* __restrict__ valid, int T, int KB,
+                                                           uint8_t* __restrict__ blob, unsigned chunk_bytes) {
+    __shared__ double s_scale[I8_N];
+    const int ch = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* cb = blob + (size_t)ch * chunk_bytes;
+    const int plane = KB * I8_KSTEP_B;
+    double* meta = reinterpret_cast<double*>(cb + (size_t)8 * plane);
+    for (int n = warp; n < I8_N; n += 8) {
+        const int t = ch * I8_N + n;
+        double m = 0.0;
+        if (t < T)
+            for (int s = lane; s < S; s += 32) m = fmax(m, fabs(rec[(size_t)t * RS + s]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) {
+            double sc = 1.0, back = 0.0;
+            if (t < T && m > 0.0 && m < 1e300) {
+                int E = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;
+                E = max(E, -900);
+                sc = __hiloint2double((1023 + 53 - E) << 20, 0);        // max|R| in [2^53, 2^54)
+                back = __hiloint2double((1023 + E - 5) << 20, 0);       // 2^48 / sc: num carries 2^-48 (see the kernel)
+            }
+            s_scale[n] = sc;
+            meta[4 * n + 0] = back;
+            meta[4 * n + 1] = t < T ? rec[(size_t)t * RS + S_pad] : 0.0;
+            meta[4 * n + 2] = t < T ? rec[(size_t)t * RS + S_pad + 1] : 0.0;
+            meta[4 * n + 3] = 0.0;
+        }
+    }
+    __syncthreads();
+    for (int item = tid; item < I8_N * 2 * KB; item += 256) {
+        const int n = item % I8_N, kc = item / I8_N;
+        const int t = ch * I8_N + n;
+        const double sc = s_scale[n];
+        uint32_t w[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[i][j] = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int s = kc * 16 + b;
+            long long R = 0;
+            uint32_t v = 0;
+            if (t < T && s < S) {
+                R = __double2ll_rn(rec[(size_t)t * RS + s] * sc);
+                v = valid[(size_t)t * S + s] ? 1u : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < I8_NS; i++) w[i][b >> 2] |= (uint32_t)((R >> (8 * (6 - i))) & 255) << (8 * (b & 3));
+            w[7][b >> 2] |= v << (8 * (b & 3));
+        }
+        const size_t off = (size_t)kc * I8_LBO_B + (size_t)(n >> 3) * I8_SBO + (size_t)(n & 7) * 16;
+#pragma unroll
+        for (int i = 0; i < 8; i++) *reinterpret_cast<uint4*>(cb + (size_t)i * plane + off) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exact fp64 path (rare)
+__device__ __forceinline__ double idw_exact_value(const double* smx, const double* smy, int S, double X, double Y, double power,
+                                               const double* __restrict__ rrow, const uint8_t* __restrict__ vrow) {
+    const bool p2 = (power == 2.0);
+    bool hit = false, bad = false;
+    double num = 0.0, den = 0.0;
+    for (int s = 0; s < S; s++) {
+        if (!vrow[s]) continue;
+        const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
+        const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        const double r = rrow[s];
+        if (q == 0.0) {            // reference weight is inf: inf * r / inf
+            hit = true;
+            bad |= (r != 0.0);
+            continue;
+        }
+        const double w = idw_weight(q, p2, power);
+        num = fma(w, r, num);
+        den += w;
+    }
+    if (hit) return bad ? nan("") : 0.0;   // inf * 0 is dropped by nansum: finite / inf
+    return num / den;
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+// shared memory: stage[2] = { R planes 0..6, V plane, meta } (one TMA bulk copy per chunk), station coordinates,
+// per-cell scratch of the weight generation, mbarriers
+enum { B_FULL = 0, B_EMPTY = 2, B_ACCFULL = 4, B_ACCEMPTY = 6, B_AREADY = 8, B_COUNT = 9 };
+
+__host__ __device__ inline size_t i8_smem_bytes(int KB) {
+    return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + 2 * 32 * KB * 8 + 4 * 128 * 8 + 4 * 128 * 4 + B_COUNT * 8 + 16 + 128;
+}
+
+#ifdef I8_PROFILE
+#define PROF(var, stmt) do { const long long t__ = clock64(); stmt; var += clock64() - t__; } while (0)
+#else
+#define PROF(var, stmt) stmt
+#endif
+
+template <bool DETREND, bool CLAMP>
+__global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int KB = a.KB, S = a.S;
+    const int plane = KB * I8_KSTEP_B;
+    const uint32_t stage_bytes = 8u * (uint32_t)plane + I8_META;
+    unsigned char* p0 = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    unsigned char* const stage0 = p0;
+    unsigned char* const stage1 = p0 + stage_bytes;
+    double* const smx = reinterpret_cast<double*>(p0 + 2 * (size_t)stage_bytes);
+    double* const smy = smx + 32 * KB;
+    double* const qmin = smy + 32 * KB;                          // [4][128]
+    int* const zf = reinterpret_cast<int*>(qmin + 4 * 128);       // [4][128]
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(zf + 4 * 128);
+    uint32_t* const tbase_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tbase_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 32) {
+        mbar_init(&bars[B_FULL + 0], 1);
+        mbar_init(&bars[B_FULL + 1], 1);
+        mbar_init(&bars[B_EMPTY + 0], 1 + I8_WWARPS);    // MMA commit + the worker warps (they read the step meta)
+        mbar_init(&bars[B_EMPTY + 1], 1 + I8_WWARPS);
+        mbar_init(&bars[B_ACCFULL + 0], 1);
+        mbar_init(&bars[B_ACCFULL + 1], 1);
+        mbar_init(&bars[B_ACCEMPTY + 0], I8_WWARPS);
+        mbar_init(&bars[B_ACCEMPTY + 1], I8_WWARPS);
+        mbar_init(&bars[B_AREADY], I8_WWARPS);
+        fence_mbar_init();
+    }
+    for (int s = tid; s < 32 * KB; s += I8_THREADS) {
+        smx[s] = s < S ? __ldg(a.mx + s) : 0.0;
+        smy[s] = s < S ? __ldg(a.my + s) : 0.0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tbase_s;
+
+    if (warp >= I8_WWARPS) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == I8_WWARPS) {
+        // ====================================================================== MMA issuer
+        // The whole warp walks the loops (descriptors and addresses stay in uniform registers, the UTCIMMAs
+        // issue back to back); one elected lane issues.  Measured (tools/umma_i8_probe.cu): 24.1 clk per
+        // 128 x 48 x 32 MMA with A in TMEM = 8162 MAC/clk/SM, the int8 peak.
+        uint32_t leader;
+        asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(leader));
+        const uint32_t idesc_u = umma_idesc_i8(I8_M, I8_N, 0), idesc_s = umma_idesc_i8(I8_M, I8_N, 1);
+        const uint64_t sdesc[2] = {umma_desc(smem_u32(stage0), I8_LBO_B, I8_SBO), umma_desc(smem_u32(stage1), I8_LBO_B, I8_SBO)};
+        const uint32_t acol = tbase + I8_ACOL;
+        const uint32_t plane16 = (uint32_t)plane >> 4;
+        uint32_t P = 0, G = 0, tc = 0;
+#ifdef I8_PROFILE
+        long long c_a = 0, c_full = 0, c_acc = 0, c_tot = clock64();
+#endif
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
+            PROF(c_a, mbar_wait(&bars[B_AREADY], tc & 1));
+            tc_fence_after();
+            for (int ch = 0; ch < a.nchunk; ch++, G++) {
+                const int s = G & 1;
+                PROF(c_full, mbar_wait(&bars[B_FULL + s], (G >> 1) & 1));
+                tc_fence_after();
+                const uint64_t bdesc = sdesc[s];
+                for (int gg = I8_NS - 1; gg >= 0; gg--, P++) {      // numerator: all digit products with i + j = gg
+                    const int buf = P & 1;
+                    PROF(c_acc, mbar_wait(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t dcol = tbase + buf * I8_N;
+                        for (int i = 0; i <= gg; i++) {
+                            const int j = gg - i;
+                            const uint32_t ac = acol + (uint32_t)(i * KB) * 8;
+                            const uint64_t bd = bdesc + (uint64_t)j * plane16;
+                            const uint32_t idesc = j == 0 ? idesc_s : idesc_u;
+#pragma unroll
+                            for (int kk = 0; kk < 7; kk++)
+                                if (kk < KB) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (I8_KSTEP_B >> 4), idesc, (i | kk) != 0);
+                        }
+                        tc_commit(&bars[B_ACCFULL + buf]);
+                    }
+                    __syncwarp();
+                }
+                for (int i = 0; i < I8_NS; i++, P++) {              // denominator: digit plane i of W against V
+                    const int buf = P & 1;
+                    PROF(c_acc, mbar_wait(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t dcol = tbase + buf * I8_N;
+                        const uint32_t ac = acol + (uint32_t)(i * KB) * 8;
+                        const uint64_t bd = bdesc + (uint64_t)7 * plane16;
+#pragma unroll
+                        for (int kk = 0; kk < 7; kk++)
+                            if (kk < KB) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (I8_KSTEP_B >> 4), idesc_u, kk > 0);
+                        tc_commit(&bars[B_ACCFULL + buf]);
+                    }
+                    __syncwarp();
+                }
+                if (leader) tc_commit(&bars[B_EMPTY + s]);
+                __syncwarp();
+            }
+        }
+#ifdef I8_PROFILE
+        if (a.prof && leader) {
+            long long* pr = a.prof + 16 * blockIdx.x;
+            pr[0] = clock64() - c_tot; pr[1] = c_a; pr[2] = c_full; pr[3] = c_acc;
+        }
+#endif
+      } else if (warp == I8_WWARPS + 1) {
+        // ====================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t G = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int ch = 0; ch < a.nchunk; ch++, G++) {
+                    const int s = G & 1;
+                    mbar_wait(&bars[B_EMPTY + s], ((G >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars[B_FULL + s], stage_bytes);
+                    bulk_g2s(s ? stage1 : stage0, a.blob + (size_t)ch * a.chunk_bytes, stage_bytes, &bars[B_FULL + s]);
+                }
+            }
+        }
+      }
+    } else {
+        // ====================================================================== workers
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        const int q = warp & 3, h = warp >> 2;
+        const int cl = 32 * q + lane;
+        const uint32_t tlane = tbase + ((uint32_t)(32 * q) << 16);
+        const bool p2 = (a.power == 2.0);
+        const int kb0 = h * KB / 3, kb1 = (h + 1) * KB / 3;
+        uint32_t P = 0, G = 0;
+#ifdef I8_PROFILE
+        long long w_gen = 0, w_wait = 0, w_ld = 0, w_fin = 0, w_tot = clock64();
+#endif
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+#ifdef I8_PROFILE
+            const long long tg0 = clock64();
+#endif
+            const long long c = (long long)tile * I8_M + cl;
+            const bool live = c < a.ncw;
+            double X = 0.0, Y = 0.0, Z = 0.0;
+            if (live) {
+                cell_xy(a.g, a.cbase + c, X, Y);
+                if (DETREND && a.g.dem) Z = __ldg(a.g.dem + a.cbase + c);
+            }
+            // ---- weights: smallest squared distance of the cell -> common scale -> digits
+            {
+                double qm = 1e300;
+                int coin = 0;
+                const int s1 = min(kb1 * 32, S);
+                for (int s = kb0 * 32; s < s1; s++) {
+                    const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
+                    const double qq = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    if (qq == 0.0) coin = 1;
+                    else qm = fmin(qm, qq);
+                }
+                qmin[h * 128 + cl] = qm;
+                zf[h * 128 + cl] = coin;
+            }
+            named_bar_sync(1, I8_WORKERS);
+            const double qm = fmin(fmin(qmin[cl], qmin[128 + cl]), qmin[256 + cl]);
+            const bool coincident = live && ((zf[cl] | zf[128 + cl] | zf[256 + cl]) != 0);
+            double scale;
+            {
+                const double wmax = idw_weight(qm, p2, a.power);
+                int E = ((__double2hiint(wmax) >> 20) & 0x7ff) - 1023;
+                E = min(max(E, -900), 900);
+                scale = __hiloint2double((1023 + 54 - E) << 20, 0);      // largest weight of the cell in [2^54, 2^55)
+            }
+            named_bar_sync(1, I8_WORKERS);                                // qmin / zf are rewritten for the next tile
+            for (int kb = kb0; kb < kb1; kb++) {
+                uint32_t wd[I8_NS][8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t lo[4], hi[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int s = kb * 32 + j * 4 + b;
+                        const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
+                        const double qq = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        const bool ok = live && s < S && qq != 0.0;
+                        const double w = idw_weight(ok ? qq : 1.0, p2, a.power);
+                        const unsigned long long W = ok ? __double2ull_rz(w * scale) : 0ull;
+                        lo[b] = (uint32_t)W;
+                        hi[b] = (uint32_t)(W >> 32);
+                    }
+#pragma unroll
+                    for (int i = 0; i < I8_NS; i++) {                    // digit i = byte 6 - i of W
+                        const int byte = 6 - i;
+                        const uint32_t* x = byte >= 4 ? hi : lo;
+                        const uint32_t sel = (uint32_t)(byte & 3) | ((uint32_t)(4 + (byte & 3)) << 4);
+                        const uint32_t t01 = __byte_perm(x[0], x[1], sel), t23 = __byte_perm(x[2], x[3], sel);
+                        wd[i][j] = __byte_perm(t01, t23, 0x5410);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < I8_NS; i++) tmem_st8(tlane + I8_ACOL + (uint32_t)(i * KB + kb) * 8, wd[i]);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_AREADY]);
+#ifdef I8_PROFILE
+            w_gen += clock64() - tg0;
+#endif
+
+            // ---- chunks of 48 steps; this thread owns steps [16h, 16h + 16) of each chunk for its cell.
+            // Every pass is drained with one tcgen05.ld and folded with INTEGER multiply-adds (the s32 sums are
+            // exact, and an fp64 instruction costs two issue slots here): the denominator's digit sums D_i < 2^16
+            // pack three to a 32-bit word, the numerator's group sums go into two 64-bit words.
+            for (int ch = 0; ch < a.nchunk; ch++, G++) {
+                uint32_t v[I8_COLS];
+                auto drain = [&]() {
+                    const int buf = P & 1;
+                    PROF(w_wait, mbar_wait(&bars[B_ACCFULL + buf], (P >> 1) & 1));
+                    tc_fence_after();
+                    PROF(w_ld, tmem_ld16(tlane + (uint32_t)(buf * I8_N + h * I8_COLS), v); tmem_ld_wait());
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
+                    P++;
+                };
+                double num[I8_COLS];
+                {
+                    long long lo[I8_COLS], hi[I8_COLS];     // groups 6..3 and 2..0 in radix 256
+#pragma unroll
+                    for (int j = 0; j < I8_NS; j++) {       // groups arrive as g = 6, 5, ..., 0
+                        drain();
+                        if (j == 0) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) lo[k] = (long long)(int)v[k];
+                        } else if (j < 4) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) lo[k] += (long long)(int)v[k] * (long long)(1 << (8 * j));
+                        } else if (j == 4) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) hi[k] = (long long)(int)v[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) hi[k] += (long long)(int)v[k] * (long long)(1 << (8 * (j - 4)));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < I8_COLS; k++) num[k] = fma(s64_to_double(hi[k]), 4294967296.0, s64_to_double(lo[k]));
+                }
+                double den[I8_COLS];
+                uint32_t slow = 0;
+                {
+                    uint32_t d1[I8_COLS], d2[I8_COLS];     // D0 D1 D2 | D3 D4 D5 in radix 256 (< 2^32: D_i <= 224 * 255)
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        drain();
+                        if (i == 0) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) d1[k] = v[k];
+                        } else if (i < 3) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) d1[k] = d1[k] * 256u + v[k];
+                        } else if (i == 3) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) d2[k] = v[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) d2[k] = d2[k] * 256u + v[k];
+                        }
+                    }
+                    drain();                                // D6
+                    // den = d1 * 2^32 + d2 * 2^8 + D6; weights are scaled so that the largest lies in [2^54, 2^55):
+                    // d1 < 2^13 means den < 2^45, the exact path
+#pragma unroll
+                    for (int k = 0; k < I8_COLS; k++) {
+                        slow |= (uint32_t)(d1[k] < 8192u) << k;
+                        const double dlo = fma(u32_to_double(d2[k]), 256.0, u32_to_double(v[k]));
+                        den[k] = fast_rcp<3>(fma(u32_to_double(d1[k]), 4294967296.0, dlo));
+                    }
+                }
+                // ---- finish: scale back, retrend, clamp, store; exact path where flagged
+#ifdef I8_PROFILE
+                const long long tf0 = clock64();
+#endif
+                const int s = G & 1;
+                const double* meta = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes + (size_t)8 * plane) + 4 * (h * I8_COLS);
+                const int t0 = ch * I8_N + h * I8_COLS;
+                if (coincident) slow = 0xffffffffu;
+#if defined(I8_EXP_NOMMA)
+                slow = 0;
+#endif
+                if (live) {
+                    double* op = a.out + (size_t)t0 * (size_t)a.ncw + c;
+                    const bool whole = t0 + I8_COLS <= a.T;      // no per-step test on the common path: the 16 outputs
+#pragma unroll                                                   // then form one basic block and overlap
+                    for (int k = 0; k < I8_COLS; k++) {
+                        const double2 m01 = *reinterpret_cast<const double2*>(meta + 4 * k);
+                        const double p1 = meta[4 * k + 2];
+                        double x = (num[k] * den[k]) * m01.x;
+                        if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(m01.y, Z)), p1);   // idw.py:144, left to right
+                        if (CLAMP) x = clamp_nan_keep(x, a.vmin, a.vmax);
+                        num[k] = x;
+                    }
+                    if (whole) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++)
+                            if (t0 + k < a.T) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
+                    }
+                    if (slow) {   // rare: rewrite the flagged steps from the exact fp64 sums
+                        for (int k = 0; k < I8_COLS; k++) {
+                            if (!((slow >> k) & 1u) || t0 + k >= a.T) continue;
+                            double x = idw_exact_value(smx, smy, S, X, Y, a.power, a.rec + (size_t)(t0 + k) * a.RS,
+                                                       a.valid + (size_t)(t0 + k) * S);
+                            if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(meta[4 * k + 1], Z)), meta[4 * k + 2]);
+                            if (CLAMP) x = clamp_nan_keep(x, a.vmin, a.vmax);
+                            __stcs(op + (size_t)k * (size_t)a.ncw, x);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_EMPTY + s]);
+#ifdef I8_PROFILE
+                w_fin += clock64() - tf0;
+#endif
+            }
+        }
+#ifdef I8_PROFILE
+        if (a.prof && tid == 0) {
+            long long* pr = a.prof + 16 * blockIdx.x;
+            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld;
+        }
+#endif
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------ host
+int idw_i8_prepare(int device) {
+    (void)device;
+    const int sm = (int)i8_smem_bytes(IDW_I8_MAX_STATIONS / 32);
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    return SMRFB_OK;
+}
+
+int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const double* d_mx, const double* d_my, int S,
+               double power, const double* d_rec, int RS, int S_pad, const uint8_t* d_valid, int T, int detrend,
+               double vmin, double vmax, double* d_out, long long cbase, long long ncw, int device) {
+    SMRFB_CHECK(S <= IDW_I8_MAX_STATIONS, SMRFB_ERR_LIMIT, "the int8 tensor-core IDW kernel takes at most %d stations", IDW_I8_MAX_STATIONS);
+    const int KB = (S + 31) / 32;
+    const int nchunk = (T + I8_N - 1) / I8_N;
+    const unsigned chunk_bytes = 8u * KB * I8_KSTEP_B + I8_META;
+    SMRFB_PROPAGATE(ensure_cap((void**)&scratch->d_blob, &scratch->blob_cap, (size_t)nchunk * chunk_bytes));
+    idw_i8_slice_kernel<<<nchunk, 256, 0, st>>>(d_rec, RS, S, S_pad, d_valid, T, KB, scratch->d_blob, chunk_bytes);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    I8Args a;
+    a.g = g;
+    a.mx = d_mx;
+    a.my = d_my;
+    a.S = S;
+    a.KB = KB;
+    a.power = power;
+    a.blob = scratch->d_blob;
+    a.chunk_bytes = chunk_bytes;
+    a.nchunk = nchunk;
+    a.T = T;
+    a.rec = d_rec;
+    a.RS = RS;
+    a.valid = d_valid;
+    a.detrend = detrend;
+    a.vmin = vmin;
+    a.vmax = vmax;
+    a.out = d_out;
+    a.cbase = cbase;
+    a.ncw = ncw;
+    const long long ntiles = (ncw + I8_M - 1) / I8_M;
+    SMRFB_CHECK(ntiles < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+    a.ntiles = (int)ntiles;
+    a.prof = nullptr;
+#ifdef I8_PROFILE
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc(&d_prof, 16 * 8 * 1024);
+    cudaMemsetAsync(d_prof, 0, 16 * 8 * 1024, st);
+    a.prof = d_prof;
+#endif
+    int sms = 0;
+    SMRFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, sms);
+    const size_t smem = i8_smem_bytes(KB);
+    const bool clamp = !(std::isinf(vmin) && vmin < 0 && std::isinf(vmax) && vmax > 0);
+    if (detrend) {
+        if (clamp) idw_i8_kernel<true, true><<<grid, I8_THREADS, smem, st>>>(a);
+        else idw_i8_kernel<true, false><<<grid, I8_THREADS, smem, st>>>(a);
+    } else {
+        if (clamp) idw_i8_kernel<false, true><<<grid, I8_THREADS, smem, st>>>(a);
+        else idw_i8_kernel<false, false><<<grid, I8_THREADS, smem, st>>>(a);
+    }
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+#ifdef I8_PROFILE
+    {
+        long long hp[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hp, a.prof, sizeof(hp), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, finish %lld\n",
+                (a.ntiles + (int)grid - 1) / (int)grid, nchunk, hp[0], hp[1], hp[2], hp[3], hp[8], hp[9], hp[10], hp[12], hp[11]);
+    }
+#endif
+    return SMRFB_OK;
+}
+
+}  // namespace smrfb

@@ -44,6 +44,19 @@ def main():
         print("IDW S=%d %dx%d T=%d detrend=%d: %.2f ms  %.2f G cell-steps/s  write %.1f GB/s  fp64 %.2f TFLOP/s" %
               (S, ny, nx, T, det, ms, cs / 1e9, cs * 8 / 1e9, cs * 2 * S / 1e12))
     print("finite:", bool(torch.isfinite(d_out).all()), float(d_out.mean()))
+    if os.environ.get("IDW_COMPARE"):      # same call on the other kernel: max difference relative to the step scale
+        os.environ["SMRFB_IDW_KERNEL"] = os.environ["IDW_COMPARE"]
+        h2 = _lib.handle_t()
+        _lib.check(L.smrfb_idw_create(S, _lib.dptr(mx), _lib.dptr(my), _lib.dptr(mz), ny, nx, 0, _lib.dptr(x), _lib.dptr(y),
+                                      _lib.dptr(dem.reshape(-1)), 2.0, 0, h2))
+        d_out2 = torch.empty_like(d_out)
+        _lib.check(L.smrfb_idw_distribute_dev(h2, d_data.data_ptr(), T, 0, -1, -73.0, 47.0, None, None, d_out2.data_ptr(), st))
+        torch.cuda.synchronize()
+        scale = torch.from_numpy(np.nanmax(np.abs(data), axis=1)).cuda()[:, None]
+        err = ((d_out - d_out2).abs() / scale)
+        print("vs %s kernel: max rel diff %.3e  mean %.3e  nan mismatch %d" % (
+            os.environ["IDW_COMPARE"], float(err.nan_to_num(0).max()), float(err.nan_to_num(0).mean()),
+            int((torch.isnan(d_out) != torch.isnan(d_out2)).sum())))
 
 
 if __name__ == "__main__":
