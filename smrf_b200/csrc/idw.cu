@@ -607,11 +607,16 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
         int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         if (h->smem_bytes > (size_t)smem_max) {   // S_pad*68*8 B weight tile + 2*32*RS*8 B record ring <= 227 KB: S <= 200
-            set_error("IDW: %d stations need %zu B of shared memory per CTA, device allows %d", nsta, h->smem_bytes, smem_max);
-            rc = SMRFB_ERR_LIMIT;
+            if (rc == SMRFB_OK && h->i8_mode) {   // 201..224 stations: only the int8 tensor-core kernel holds them
+                h->i8_mode = 2;
+                h->smem_bytes = 0;
+            } else {
+                set_error("IDW: %d stations need %zu B of shared memory per CTA, device allows %d", nsta, h->smem_bytes, smem_max);
+                rc = SMRFB_ERR_LIMIT;
+            }
         }
     }
-    if (rc == SMRFB_OK) {
+    if (rc == SMRFB_OK && h->smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(idw_distribute_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)h->smem_bytes);
         if (e == cudaSuccess)

@@ -47,7 +47,8 @@ constexpr int I8_KSTEP_B = 2 * I8_LBO_B;       // bytes of one K = 32 block of a
 constexpr int I8_SBO = 128;                    // byte stride between 8-row groups
 constexpr int I8_META = I8_N * 32;             // per step {2^k, p0, p1, 0}
 constexpr int I8_ACOL = 2 * I8_N;              // TMEM columns [0, 2N): two accumulators; [2N, 2N + 7*8*KB): the A digit planes
-constexpr double I8_DEN_MIN = 35184372088832.0;   // 2^45: den below this (weights scaled to [2^54, 2^55)) -> exact path
+constexpr int I8_MAXMASK = 32;                 // distinct NaN masks per call up to which the denominators are built per tile
+constexpr int I8_HDR = 64;                     // ints at the head of the mask buffer: [0] = number of distinct masks
 
 struct I8Args {
     Geom g;
@@ -66,6 +67,8 @@ struct I8Args {
     double* out;
     long long cbase, ncw;
     int ntiles;
+    const int* maskhdr;     // [0] = distinct NaN masks among the T steps (idw_i8_mask_kernel)
+    const uint8_t* vu;      // V plane of the distinct masks (rows = mask ids), canonical layout
     long long* prof;   // I8_PROFILE builds: per-CTA cycle counters
 };
 
@@ -74,6 +77,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait with a long suspend-time hint: a waiting warp sleeps in the barrier unit instead of re-issuing
+// try_wait (the MMA-issuing warp shares its scheduler with three worker warps that wait here most of the time)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {   // arrives on bar when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -147,9 +160,58 @@ __device__ __forceinline__ double idw_weight(double q, bool p2, double power) { 
 // ------------------------------------------------------------------------------------------ operand planes of R and V
 // blob[chunk] = { R digit planes 0..6, V plane : each [2*KB K-chunks][10 step groups][8 steps][16 stations] bytes,
 //                 meta[80] = {2^k, p0, p1, 0} }.   k is chosen per step so that max|R| lies in [2^53, 2^54).
+// Distinct NaN masks of the call (first-occurrence order): hdr[0] = count, mask_id[t], and -- when there are at most
+// I8_MAXMASK -- the V plane of the distinct masks.  Station networks drop out in blocks, so a 720-hour batch
+// typically has a handful of masks; the kernel then builds the masked denominators once per tile and mask
+// instead of once per tile and step.  One CTA; O(T^2) 64-bit hash compares.
+__global__ void __launch_bounds__(1024) idw_i8_mask_kernel(const uint8_t* __restrict__ valid, int T, int S, int KB, int* __restrict__ hdr,
+                                                           int* __restrict__ mask_id, uint8_t* __restrict__ vu) {
+    extern __shared__ unsigned long long s_hash[];     // [T] hashes, then [T] ints: representative / id
+    int* s_rep = reinterpret_cast<int*>(s_hash + T);
+    __shared__ int s_count;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < T; t += blockDim.x) {
+        unsigned long long hsh = 1469598103934665603ull;
+        for (int s = 0; s < S; s++) hsh = (hsh ^ (valid[(size_t)t * S + s] ? 1u : 0u)) * 1099511628211ull;
+        s_hash[t] = hsh;
+    }
+    for (int i = tid; i < KB * I8_KSTEP_B / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(vu)[i] = 0;
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) {
+        int r = t;
+        const unsigned long long hsh = s_hash[t];
+        for (int u = 0; u < t; u++) {
+            if (s_hash[u] != hsh) continue;
+            bool same = true;
+            for (int s = 0; s < S && same; s++) same = (valid[(size_t)t * S + s] != 0) == (valid[(size_t)u * S + s] != 0);
+            if (same) { r = u; break; }
+        }
+        s_rep[t] = r;
+    }
+    __syncthreads();
+    if (tid == 0) {                                    // ids in first-occurrence order (serial: T is a few thousand at most)
+        int n = 0;
+        for (int t = 0; t < T; t++) {
+            if (s_rep[t] == t) mask_id[t] = n++;
+            else mask_id[t] = mask_id[s_rep[t]];
+        }
+        s_count = n;
+        hdr[0] = n;
+    }
+    __syncthreads();
+    if (s_count > I8_MAXMASK) return;
+    for (int t = 0; t < T; t++) {                      // few representatives: the block walks them one by one
+        if (s_rep[t] != t) continue;
+        const int n = mask_id[t];
+        for (int k = tid; k < S; k += blockDim.x)
+            vu[(size_t)(k >> 4) * I8_LBO_B + (size_t)(n >> 3) * I8_SBO + (size_t)(n & 7) * 16 + (k & 15)] = valid[(size_t)t * S + k] ? 1 : 0;
+    }
+}
+
 __global__ void __launch_bounds__(256) idw_i8_slice_kernel(const double* __restrict__ rec, int RS, int S, int S_pad,
                                                            const uint8_t* __restrict__ valid, int T, int KB,
-                                                           uint8_t* __restrict__ blob, unsigned chunk_bytes) {
+                                                           const int* __restrict__ mask_id, uint8_t* __restrict__ blob,
+                                                           unsigned chunk_bytes) {
     __shared__ double s_scale[I8_N];
     const int ch = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* cb = blob + (size_t)ch * chunk_bytes;
@@ -174,7 +236,7 @@ __global__ void __launch_bounds__(256) idw_i8_slice_kernel(const double* __restr
             meta[4 * n + 0] = back;
             meta[4 * n + 1] = t < T ? rec[(size_t)t * RS + S_pad] : 0.0;
             meta[4 * n + 2] = t < T ? rec[(size_t)t * RS + S_pad + 1] : 0.0;
-            meta[4 * n + 3] = 0.0;
+            meta[4 * n + 3] = __longlong_as_double(t < T ? (long long)mask_id[t] : 0LL);
         }
     }
     __syncthreads();
@@ -207,27 +269,64 @@ __global__ void __launch_bounds__(256) idw_i8_slice_kernel(const double* __restr
 }
 
 // ------------------------------------------------------------------------------------------ exact fp64 path (rare)
-__device__ __forceinline__ double idw_exact_value(const double* smx, const double* smy, int S, double X, double Y, double power,
-                                               const double* __restrict__ rrow, const uint8_t* __restrict__ vrow) {
+// One (cell, step) pair by the whole warp: lane l sums stations l, l + 32, ...; every lane returns the value.
+__device__ __noinline__ double idw_exact_value(const double* smx, const double* smy, int S, double X, double Y, double power,
+                                               const double* __restrict__ rrow, const uint8_t* __restrict__ vrow, int lane) {
     const bool p2 = (power == 2.0);
     bool hit = false, bad = false;
     double num = 0.0, den = 0.0;
-    for (int s = 0; s < S; s++) {
-        if (!vrow[s]) continue;
+    double rr[7];
+    bool vv[7];
+#pragma unroll
+    for (int u = 0; u < 7; u++) {          // all loads first: S <= 224 = 7 x 32
+        const int s = lane + 32 * u;
+        vv[u] = s < S && __ldg(vrow + s) != 0;
+        rr[u] = s < S ? __ldg(rrow + s) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+        const int s = lane + 32 * u;
+        if (!vv[u]) continue;
         const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
         const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        const double r = rrow[s];
         if (q == 0.0) {            // reference weight is inf: inf * r / inf
             hit = true;
-            bad |= (r != 0.0);
+            bad |= (rr[u] != 0.0);
             continue;
         }
         const double w = idw_weight(q, p2, power);
-        num = fma(w, r, num);
+        num = fma(w, rr[u], num);
         den += w;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, o);
+        den += __shfl_xor_sync(0xffffffffu, den, o);
+    }
+    hit = __any_sync(0xffffffffu, hit);
+    bad = __any_sync(0xffffffffu, bad);
     if (hit) return bad ? nan("") : 0.0;   // inf * 0 is dropped by nansum: finite / inf
     return num / den;
+}
+
+// One digit product D (+)= A_i * B_j over all K blocks, fully unrolled for the K-block count: three uniform-datapath
+// instructions per MMA (the issuing warp shares its scheduler with three worker warps, so its instruction count
+// per MMA decides whether the tensor pipe stays fed).
+template <int KBT>
+__device__ __forceinline__ void i8_product(uint32_t dcol, uint32_t ac, uint64_t bd, uint32_t idesc, bool first) {
+#pragma unroll
+    for (int kk = 0; kk < KBT; kk++) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (I8_KSTEP_B >> 4), idesc, !(first && kk == 0));
+}
+__device__ __forceinline__ void i8_product_any(int KB, uint32_t dcol, uint32_t ac, uint64_t bd, uint32_t idesc, bool first) {
+    switch (KB) {
+        case 7: i8_product<7>(dcol, ac, bd, idesc, first); break;
+        case 6: i8_product<6>(dcol, ac, bd, idesc, first); break;
+        case 5: i8_product<5>(dcol, ac, bd, idesc, first); break;
+        case 4: i8_product<4>(dcol, ac, bd, idesc, first); break;
+        case 3: i8_product<3>(dcol, ac, bd, idesc, first); break;
+        case 2: i8_product<2>(dcol, ac, bd, idesc, first); break;
+        default: i8_product<1>(dcol, ac, bd, idesc, first); break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
@@ -236,7 +335,8 @@ __device__ __forceinline__ double idw_exact_value(const double* smx, const doubl
 enum { B_FULL = 0, B_EMPTY = 2, B_ACCFULL = 4, B_ACCEMPTY = 6, B_AREADY = 8, B_COUNT = 9 };
 
 __host__ __device__ inline size_t i8_smem_bytes(int KB) {
-    return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + 2 * 32 * KB * 8 + 4 * 128 * 8 + 4 * 128 * 4 + B_COUNT * 8 + 16 + 128;
+    return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + (size_t)KB * I8_KSTEP_B + (size_t)I8_MAXMASK * I8_M * 8 + 2 * 32 * KB * 8 +
+           4 * 128 * 8 + 4 * 128 * 4 + B_COUNT * 8 + 16 + 128;
 }
 
 #ifdef I8_PROFILE
@@ -254,7 +354,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
     unsigned char* p0 = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     unsigned char* const stage0 = p0;
     unsigned char* const stage1 = p0 + stage_bytes;
-    double* const smx = reinterpret_cast<double*>(p0 + 2 * (size_t)stage_bytes);
+    unsigned char* const vu_s = p0 + 2 * (size_t)stage_bytes;                          // V plane of the distinct masks
+    double* const rden_s = reinterpret_cast<double*>(vu_s + plane);                     // [I8_MAXMASK][128] 1/den per mask and cell
+    double* const smx = rden_s + I8_MAXMASK * I8_M;
     double* const smy = smx + 32 * KB;
     double* const qmin = smy + 32 * KB;                          // [4][128]
     int* const zf = reinterpret_cast<int*>(qmin + 4 * 128);       // [4][128]
@@ -282,13 +384,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         smx[s] = s < S ? __ldg(a.mx + s) : 0.0;
         smy[s] = s < S ? __ldg(a.my + s) : 0.0;
     }
+    const bool mask_mode = __ldg(a.maskhdr) <= I8_MAXMASK;
+    if (mask_mode) {
+        for (int i = tid; i < plane / 16; i += I8_THREADS) reinterpret_cast<uint4*>(vu_s)[i] = __ldg(reinterpret_cast<const uint4*>(a.vu) + i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tbase_s;
 
     if (warp >= I8_WWARPS) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == I8_WWARPS) {
         // ====================================================================== MMA issuer
         // The whole warp walks the loops (descriptors and addresses stay in uniform registers, the UTCIMMAs
@@ -304,48 +411,87 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #ifdef I8_PROFILE
         long long c_a = 0, c_full = 0, c_acc = 0, c_tot = clock64();
 #endif
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
-            PROF(c_a, mbar_wait(&bars[B_AREADY], tc & 1));
+        const uint32_t idesc_m = umma_idesc_i8(I8_M, I8_MAXMASK, 0);
+        const uint64_t vudesc = umma_desc(smem_u32(vu_s), I8_LBO_B, I8_SBO);
+        // one pass = one accumulator: wait until the workers have drained it, issue, commit
+        auto den_pass = [&](int i, uint64_t vd, uint32_t idesc) {        // digit plane i of W against a V plane
+            const int buf = P & 1;
+            PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
             tc_fence_after();
+            if (leader) {
+                const uint32_t dcol = tbase + buf * I8_N;
+                const uint32_t ac = acol + (uint32_t)(i * KB) * 8;
+                i8_product_any(KB, dcol, ac, vd, idesc, true);
+                tc_commit(&bars[B_ACCFULL + buf]);
+            }
+            __syncwarp();
+            P++;
+        };
+        // 224-station layout (7 K blocks): every descriptor offset is an immediate -- two uniform adds and the MMA
+        // per instruction, no loop or branch inside a pass (gg is a literal at every call site)
+        auto num_pass_full = [&](const int gg, uint32_t blo, uint32_t bhi) {
+            const int buf = P & 1;
+            PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+            tc_fence_after();
+            if (leader) {
+                const uint32_t dcol = tbase + buf * I8_N;
+#pragma unroll
+                for (int i = 0; i < I8_NS; i++) {
+                    if (i > gg) break;
+                    const int j = gg - i;
+                    // an opaque zero per product keeps the compiler from hoisting the address arithmetic of all 28
+                    // products to the top of the pass (it runs out of uniform registers and spills)
+                    uint32_t z;
+                    asm volatile("mov.u32 %0, 0;" : "=r"(z));
+                    const uint64_t bd = ((uint64_t)bhi << 32) | (uint32_t)(blo + z + (uint32_t)(j * 7 * (I8_KSTEP_B >> 4)));
+                    i8_product<7>(dcol, acol + z + (uint32_t)(i * 7 * 8), bd, j == 0 ? idesc_s : idesc_u, i == 0);
+                }
+                tc_commit(&bars[B_ACCFULL + buf]);
+            }
+            __syncwarp();
+            P++;
+        };
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
+            PROF(c_a, mbar_wait_sleep(&bars[B_AREADY], tc & 1));
+            tc_fence_after();
+            if (mask_mode)
+                for (int i = 0; i < I8_NS; i++) den_pass(i, vudesc, idesc_m);
             for (int ch = 0; ch < a.nchunk; ch++, G++) {
                 const int s = G & 1;
-                PROF(c_full, mbar_wait(&bars[B_FULL + s], (G >> 1) & 1));
+                PROF(c_full, mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1));
                 tc_fence_after();
                 const uint64_t bdesc = sdesc[s];
-                for (int gg = I8_NS - 1; gg >= 0; gg--, P++) {      // numerator: all digit products with i + j = gg
-                    const int buf = P & 1;
-                    PROF(c_acc, mbar_wait(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t dcol = tbase + buf * I8_N;
-                        for (int i = 0; i <= gg; i++) {
-                            const int j = gg - i;
-                            const uint32_t ac = acol + (uint32_t)(i * KB) * 8;
-                            const uint64_t bd = bdesc + (uint64_t)j * plane16;
-                            const uint32_t idesc = j == 0 ? idesc_s : idesc_u;
-#pragma unroll
-                            for (int kk = 0; kk < 7; kk++)
-                                if (kk < KB) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (I8_KSTEP_B >> 4), idesc, (i | kk) != 0);
+                // numerator: one pass per group gg = i + j, in the order 6 5 0 4 1 3 2 (long passes first: they run
+                // under the workers' finish of the previous chunk)
+                if (KB == 7) {
+                    const uint32_t blo = (uint32_t)bdesc, bhi = (uint32_t)(bdesc >> 32);
+                    num_pass_full(6, blo, bhi);
+                    num_pass_full(5, blo, bhi);
+                    num_pass_full(0, blo, bhi);
+                    num_pass_full(4, blo, bhi);
+                    num_pass_full(1, blo, bhi);
+                    num_pass_full(3, blo, bhi);
+                    num_pass_full(2, blo, bhi);
+                } else {
+                    for (int oi = 0; oi < I8_NS; oi++, P++) {
+                        const int gg = (0x2314056 >> (4 * oi)) & 7;
+                        const int buf = P & 1;
+                        PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t dcol = tbase + buf * I8_N;
+                            for (int i = 0; i <= gg; i++) {
+                                const int j = gg - i;
+                                i8_product_any(KB, dcol, acol + (uint32_t)(i * KB) * 8, bdesc + (uint64_t)j * plane16, j == 0 ? idesc_s : idesc_u,
+                                               i == 0);
+                            }
+                            tc_commit(&bars[B_ACCFULL + buf]);
                         }
-                        tc_commit(&bars[B_ACCFULL + buf]);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
-                for (int i = 0; i < I8_NS; i++, P++) {              // denominator: digit plane i of W against V
-                    const int buf = P & 1;
-                    PROF(c_acc, mbar_wait(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t dcol = tbase + buf * I8_N;
-                        const uint32_t ac = acol + (uint32_t)(i * KB) * 8;
-                        const uint64_t bd = bdesc + (uint64_t)7 * plane16;
-#pragma unroll
-                        for (int kk = 0; kk < 7; kk++)
-                            if (kk < KB) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (I8_KSTEP_B >> 4), idesc_u, kk > 0);
-                        tc_commit(&bars[B_ACCFULL + buf]);
-                    }
-                    __syncwarp();
-                }
+                if (!mask_mode)
+                    for (int i = 0; i < I8_NS; i++) den_pass(i, bdesc + (uint64_t)7 * plane16, idesc_u);
                 if (leader) tc_commit(&bars[B_EMPTY + s]);
                 __syncwarp();
             }
@@ -363,7 +509,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int ch = 0; ch < a.nchunk; ch++, G++) {
                     const int s = G & 1;
-                    mbar_wait(&bars[B_EMPTY + s], ((G >> 1) & 1) ^ 1);
+                    mbar_wait_sleep(&bars[B_EMPTY + s], ((G >> 1) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars[B_FULL + s], stage_bytes);
                     bulk_g2s(s ? stage1 : stage0, a.blob + (size_t)ch * a.chunk_bytes, stage_bytes, &bars[B_FULL + s]);
                 }
@@ -454,88 +600,127 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             w_gen += clock64() - tg0;
 #endif
 
-            // ---- chunks of 48 steps; this thread owns steps [16h, 16h + 16) of each chunk for its cell.
-            // Every pass is drained with one tcgen05.ld and folded with INTEGER multiply-adds (the s32 sums are
+            // ---- Every pass is drained with one tcgen05.ld and folded with INTEGER multiply-adds (the s32 sums are
             // exact, and an fp64 instruction costs two issue slots here): the denominator's digit sums D_i < 2^16
             // pack three to a 32-bit word, the numerator's group sums go into two 64-bit words.
+            uint32_t v[I8_COLS];
+            auto drain = [&]() {
+                const int buf = P & 1;
+                PROF(w_wait, mbar_wait_sleep(&bars[B_ACCFULL + buf], (P >> 1) & 1));
+                tc_fence_after();
+#ifdef I8_EXP_NOLD
+#pragma unroll
+                for (int k = 0; k < I8_COLS; k++) v[k] = 0x10000u + k + P;
+#else
+                PROF(w_ld, tmem_ld16(tlane + (uint32_t)(buf * I8_N + h * I8_COLS), v); tmem_ld_wait());
+#endif
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
+                P++;
+            };
+            // seven denominator passes -> 1 / den for this thread's 16 columns (NaN where the exact path is needed)
+            auto den_passes = [&](double* rden) {
+                uint32_t d1[I8_COLS], d2[I8_COLS];     // D0 D1 D2 | D3 D4 D5 in radix 256 (< 2^32: D_i <= 224 * 255)
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    drain();
+                    if (i == 0) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) d1[k] = v[k];
+                    } else if (i < 3) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) d1[k] = d1[k] * 256u + v[k];
+                    } else if (i == 3) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) d2[k] = v[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) d2[k] = d2[k] * 256u + v[k];
+                    }
+                }
+                drain();                                // D6
+                // den = d1 * 2^32 + d2 * 2^8 + D6; the weights are scaled so that the largest lies in [2^54, 2^55):
+                // d1 < 2^13 means den < 2^45 = 2^-9 .. 2^-10 of it, where the fixed-point error stops being negligible
+#pragma unroll
+                for (int k = 0; k < I8_COLS; k++) {
+                    const double dlo = fma(u32_to_double(d2[k]), 256.0, u32_to_double(v[k]));
+                    const double r = fast_rcp<3>(fma(u32_to_double(d1[k]), 4294967296.0, dlo));
+                    rden[k] = d1[k] < 8192u ? nan("") : r;
+                }
+            };
+            if (mask_mode) {                            // denominators once per tile: column = mask id
+                double rd[I8_COLS];
+                den_passes(rd);
+                if (h * I8_COLS < I8_MAXMASK) {
+#pragma unroll
+                    for (int k = 0; k < I8_COLS; k++) rden_s[(h * I8_COLS + k) * I8_M + cl] = rd[k];
+                }
+                named_bar_sync(1, I8_WORKERS);
+            }
+
+            // ---- chunks of 48 steps; this thread owns steps [16h, 16h + 16) of each chunk for its cell
             for (int ch = 0; ch < a.nchunk; ch++, G++) {
-                uint32_t v[I8_COLS];
-                auto drain = [&]() {
-                    const int buf = P & 1;
-                    PROF(w_wait, mbar_wait(&bars[B_ACCFULL + buf], (P >> 1) & 1));
-                    tc_fence_after();
-                    PROF(w_ld, tmem_ld16(tlane + (uint32_t)(buf * I8_N + h * I8_COLS), v); tmem_ld_wait());
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
-                    P++;
-                };
+                const int s = G & 1;
+                const double* meta = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes + (size_t)8 * plane) + 4 * (h * I8_COLS);
+                double den[I8_COLS];
+                if (mask_mode) {                            // 1 / den of each step's mask, fetched under the first passes
+                    mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1);
+#pragma unroll
+                    for (int k = 0; k < I8_COLS; k++) den[k] = rden_s[reinterpret_cast<const int*>(meta)[8 * k + 6] * I8_M + cl];
+                }
                 double num[I8_COLS];
                 {
                     long long lo[I8_COLS], hi[I8_COLS];     // groups 6..3 and 2..0 in radix 256
+                    constexpr int order[I8_NS] = {6, 5, 0, 4, 1, 3, 2};
 #pragma unroll
-                    for (int j = 0; j < I8_NS; j++) {       // groups arrive as g = 6, 5, ..., 0
+                    for (int oi = 0; oi < I8_NS; oi++) {
+                        const int g = order[oi];
                         drain();
-                        if (j == 0) {
+                        if (g == 6) {
 #pragma unroll
                             for (int k = 0; k < I8_COLS; k++) lo[k] = (long long)(int)v[k];
-                        } else if (j < 4) {
+                        } else if (g >= 3) {
 #pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) lo[k] += (long long)(int)v[k] * (long long)(1 << (8 * j));
-                        } else if (j == 4) {
+                            for (int k = 0; k < I8_COLS; k++) lo[k] += (long long)(int)v[k] * (long long)(1 << (8 * (6 - g)));
+                        } else if (g == 0) {
 #pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) hi[k] = (long long)(int)v[k];
+                            for (int k = 0; k < I8_COLS; k++) hi[k] = (long long)(int)v[k] * 65536LL;
                         } else {
 #pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) hi[k] += (long long)(int)v[k] * (long long)(1 << (8 * (j - 4)));
+                            for (int k = 0; k < I8_COLS; k++) hi[k] += (long long)(int)v[k] * (long long)(1 << (8 * (2 - g)));
+                        }
+                        // fold now, under the MMAs of the next pass (without this the compiler sinks all seven folds
+                        // below the last drain, where the tensor pipe waits for them)
+                        if (g >= 3) {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(lo[k]));
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(hi[k]));
                         }
                     }
 #pragma unroll
                     for (int k = 0; k < I8_COLS; k++) num[k] = fma(s64_to_double(hi[k]), 4294967296.0, s64_to_double(lo[k]));
                 }
-                double den[I8_COLS];
-                uint32_t slow = 0;
-                {
-                    uint32_t d1[I8_COLS], d2[I8_COLS];     // D0 D1 D2 | D3 D4 D5 in radix 256 (< 2^32: D_i <= 224 * 255)
-#pragma unroll
-                    for (int i = 0; i < 6; i++) {
-                        drain();
-                        if (i == 0) {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) d1[k] = v[k];
-                        } else if (i < 3) {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) d1[k] = d1[k] * 256u + v[k];
-                        } else if (i == 3) {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) d2[k] = v[k];
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) d2[k] = d2[k] * 256u + v[k];
-                        }
-                    }
-                    drain();                                // D6
-                    // den = d1 * 2^32 + d2 * 2^8 + D6; weights are scaled so that the largest lies in [2^54, 2^55):
-                    // d1 < 2^13 means den < 2^45, the exact path
-#pragma unroll
-                    for (int k = 0; k < I8_COLS; k++) {
-                        slow |= (uint32_t)(d1[k] < 8192u) << k;
-                        const double dlo = fma(u32_to_double(d2[k]), 256.0, u32_to_double(v[k]));
-                        den[k] = fast_rcp<3>(fma(u32_to_double(d1[k]), 4294967296.0, dlo));
-                    }
-                }
+                if (!mask_mode) den_passes(den);
                 // ---- finish: scale back, retrend, clamp, store; exact path where flagged
 #ifdef I8_PROFILE
                 const long long tf0 = clock64();
 #endif
-                const int s = G & 1;
-                const double* meta = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes + (size_t)8 * plane) + 4 * (h * I8_COLS);
                 const int t0 = ch * I8_N + h * I8_COLS;
+                uint32_t slow = 0;
+#pragma unroll
+                for (int k = 0; k < I8_COLS; k++) slow |= (uint32_t)(den[k] != den[k]) << k;
                 if (coincident) slow = 0xffffffffu;
-#if defined(I8_EXP_NOMMA)
+#if defined(I8_EXP_NOMMA) || defined(I8_EXP_NOSLOW) || defined(I8_EXP_NOLD) || defined(I8_EXP_NOFINISH)
                 slow = 0;
 #endif
+#ifdef I8_EXP_NOFINISH
+                if (live && num[0] * den[0] == 1.2345e-300) {
+#else
                 if (live) {
+#endif
                     double* op = a.out + (size_t)t0 * (size_t)a.ncw + c;
                     const bool whole = t0 + I8_COLS <= a.T;      // no per-step test on the common path: the 16 outputs
 #pragma unroll                                                   // then form one basic block and overlap
@@ -555,14 +740,24 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                         for (int k = 0; k < I8_COLS; k++)
                             if (t0 + k < a.T) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
                     }
-                    if (slow) {   // rare: rewrite the flagged steps from the exact fp64 sums
-                        for (int k = 0; k < I8_COLS; k++) {
-                            if (!((slow >> k) & 1u) || t0 + k >= a.T) continue;
-                            double x = idw_exact_value(smx, smy, S, X, Y, a.power, a.rec + (size_t)(t0 + k) * a.RS,
-                                                       a.valid + (size_t)(t0 + k) * S);
-                            if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(meta[4 * k + 1], Z)), meta[4 * k + 2]);
-                            if (CLAMP) x = clamp_nan_keep(x, a.vmin, a.vmax);
-                            __stcs(op + (size_t)k * (size_t)a.ncw, x);
+                }
+                if (!live) slow = 0;
+                if (__any_sync(0xffffffffu, slow != 0)) {
+                    // rare: flagged (cell, step) pairs are recomputed from the exact fp64 sums, the whole warp on one pair
+                    for (int k = 0; k < I8_COLS; k++) {
+                        if (t0 + k >= a.T) break;
+                        uint32_t m = __ballot_sync(0xffffffffu, (slow >> k) & 1u);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const double x = idw_exact_value(smx, smy, S, __shfl_sync(0xffffffffu, X, src), __shfl_sync(0xffffffffu, Y, src),
+                                                             a.power, a.rec + (size_t)(t0 + k) * a.RS, a.valid + (size_t)(t0 + k) * S, lane);
+                            if (lane == src) {
+                                double y = x;
+                                if (DETREND) y = __dadd_rn(__dadd_rn(y, __dmul_rn(meta[4 * k + 1], Z)), meta[4 * k + 2]);
+                                if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
+                                __stcs(a.out + (size_t)(t0 + k) * (size_t)a.ncw + c, y);
+                            }
                         }
                     }
                 }
@@ -603,9 +798,26 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
     const int KB = (S + 31) / 32;
     const int nchunk = (T + I8_N - 1) / I8_N;
     const unsigned chunk_bytes = 8u * KB * I8_KSTEP_B + I8_META;
-    SMRFB_PROPAGATE(ensure_cap((void**)&scratch->d_blob, &scratch->blob_cap, (size_t)nchunk * chunk_bytes));
-    idw_i8_slice_kernel<<<nchunk, 256, 0, st>>>(d_rec, RS, S, S_pad, d_valid, T, KB, scratch->d_blob, chunk_bytes);
-    count_launch();
+    // scratch: [chunk blobs][mask header, mask ids][V plane of the distinct masks]
+    const size_t blob_bytes = (size_t)nchunk * chunk_bytes;
+    const size_t ids_bytes = ((size_t)(I8_HDR + T) * sizeof(int) + 255) / 256 * 256;
+    const size_t vu_bytes = (size_t)KB * I8_KSTEP_B;
+    SMRFB_PROPAGATE(ensure_cap((void**)&scratch->d_blob, &scratch->blob_cap, blob_bytes + ids_bytes + vu_bytes));
+    int* d_hdr = reinterpret_cast<int*>(scratch->d_blob + blob_bytes);
+    int* d_ids = d_hdr + I8_HDR;
+    uint8_t* d_vu = scratch->d_blob + blob_bytes + ids_bytes;
+    const size_t mask_smem = (size_t)T * (sizeof(unsigned long long) + sizeof(int));
+    SMRFB_CHECK(mask_smem <= 200 * 1024, SMRFB_ERR_LIMIT, "the int8 IDW kernel takes at most %d steps per call", (int)(200 * 1024 / 12));
+    if (mask_smem > 48 * 1024) {
+        static size_t opted = 0;
+        if (mask_smem > opted) {
+            SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            opted = 200 * 1024;
+        }
+    }
+    idw_i8_mask_kernel<<<1, 1024, mask_smem, st>>>(d_valid, T, S, KB, d_hdr, d_ids, d_vu);
+    idw_i8_slice_kernel<<<nchunk, 256, 0, st>>>(d_rec, RS, S, S_pad, d_valid, T, KB, d_ids, scratch->d_blob, chunk_bytes);
+    count_launch(2);
     SMRFB_CUDA(cudaGetLastError());
     I8Args a;
     a.g = g;
@@ -630,6 +842,8 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
     const long long ntiles = (ncw + I8_M - 1) / I8_M;
     SMRFB_CHECK(ntiles < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     a.ntiles = (int)ntiles;
+    a.maskhdr = d_hdr;
+    a.vu = d_vu;
     a.prof = nullptr;
 #ifdef I8_PROFILE
     static long long* d_prof = nullptr;

@@ -102,7 +102,10 @@ def test_idw_200_stations_vs_oracle(sp):
     Xp[0, 0] += 0.0                                                      # still a mesh -> force points via transpose trick
     idw_pts = sp.IDW(mx, my, X.T.copy(), Y.T.copy(), mz=mz, GridZ=dem.T.copy(), power=2.0)
     out_pts = idw_pts.distribute_block(data[:3], detrend=True, flag=-1, vmin=-73.0, vmax=47.0)
-    np.testing.assert_array_equal(out_pts.transpose(0, 2, 1), out[:3])
+    out_3 = idw.distribute_block(data[:3], detrend=True, flag=-1, vmin=-73.0, vmax=47.0)   # same batch length: same kernel
+    np.testing.assert_array_equal(out_pts.transpose(0, 2, 1), out_3)
+    for t in range(3):                                                                    # short and long batches agree
+        assert parity(out_3[t], out[t], step_scale(data[t])) <= TOL
 
 
 def test_idw_missing_station_next_to_cell(sp):

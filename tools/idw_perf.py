@@ -18,7 +18,11 @@ def main():
     x, y, dem = syn.make_dem(ny, nx, dx=30.0, noise=False)
     mx, my, mz = syn.make_stations(S, x, y, dem)
     import os
-    data = syn.dropouts_iid(syn.make_series("air_temp", mz, T), p=float(os.environ.get("DROP_P", "0.02")))
+    if os.environ.get("DROP_MODE") == "block":       # the bench's outage model: a dozen distinct NaN masks per batch
+        data, nm = syn.dropouts_block(syn.make_series("air_temp", mz, T), max_masks=12, per_year=40.0)
+        print("block outages:", nm, "distinct masks, %.2f %% missing" % (100 * np.isnan(data).mean()))
+    else:
+        data = syn.dropouts_iid(syn.make_series("air_temp", mz, T), p=float(os.environ.get("DROP_P", "0.02")))
     L = _lib.lib()
     h = _lib.handle_t()
     _lib.check(L.smrfb_idw_create(S, _lib.dptr(mx), _lib.dptr(my), _lib.dptr(mz), ny, nx, 0, _lib.dptr(x), _lib.dptr(y),

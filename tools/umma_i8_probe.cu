@@ -179,6 +179,65 @@ __global__ void __launch_bounds__(128) probe(const uint8_t* A, const uint8_t* B,
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
+// Issue pattern of the IDW kernel: 7 x 7 A column blocks in TMEM, 8 B planes x 7 K blocks in 86 KB of shared memory,
+// passes of (g + 1) x 7 MMAs alternating between two accumulators.  Measures clk per MMA without any consumer.
+__global__ void __launch_bounds__(128) probe_cycle(int n, int iters, long long* clk, int commit_each, int signed_top) {
+    extern __shared__ __align__(128) uint8_t dynB[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar2[2];
+    __shared__ uint32_t tbase_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tbase_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init(&bar2[0], 1);
+        mbar_init(&bar2[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    const int lbo = (n / 8) * 128, kstep = 2 * lbo, plane = 7 * kstep;
+    for (int i = tid; i < 8 * plane; i += 128) dynB[i] = (uint8_t)(i * 7);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = tbase_s;
+    const uint32_t idp = make_idesc(128, n, 0, 0), ids = make_idesc(128, n, 0, signed_top);
+    long long t0 = clock64();
+    int count = 0;
+    if (warp == 0) {
+        uint32_t leader;
+        asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(leader));
+        const uint64_t bdesc = make_desc(smem_u32(dynB), lbo, SBO);
+        const uint32_t acol = tbase + 2 * n;
+        for (int it = 0; it < iters; it++) {
+            for (int gg = 6; gg >= 0; gg--) {
+                const uint32_t dcol = tbase + (gg & 1) * n;
+                if (leader) {
+                    for (int i = 0; i <= gg; i++) {
+                        const int j = gg - i;
+#pragma unroll
+                        for (int kk = 0; kk < 7; kk++)
+                            mma_ts(dcol, acol + (i * 7 + kk) * 8, bdesc + (uint64_t)((j * plane + kk * kstep) >> 4), j == 0 ? ids : idp, (i | kk) != 0);
+                    }
+                    if (commit_each) commit(&bar2[gg & 1]);
+                }
+                __syncwarp();
+                count += (gg + 1) * 7;
+            }
+        }
+        if (leader) commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (tid == 0) { clk[2 * blockIdx.x] = t1 - t0; clk[2 * blockIdx.x + 1] = count; }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
 int main() {
     std::vector<uint8_t> A(M * K), B(N * K);
     srand(1);
@@ -235,5 +294,18 @@ int main() {
                 printf("A from %s, %d accumulators, N=%3d: %.1f clk per MMA (128 x %d x 32) = %.0f MAC/clk/SM\n", mode ? "TMEM" : "smem", nacc, pn, per, pn,
                        128.0 * pn * 32 / per);
             }
+    for (int n : {32, 48}) {
+        const int smem = 8 * 7 * 2 * (n / 8) * 128;
+        cudaFuncSetAttribute(probe_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int variant = 0; variant < 4; variant++) {
+            probe_cycle<<<sms, 128, smem>>>(n, 200, dclk, variant & 1, variant >> 1);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("cycle: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+            long long c[2];
+            cudaMemcpy(c, dclk, 16, cudaMemcpyDeviceToHost);
+            printf("IDW issue pattern, N=%d, commit per pass %d, signed top digit %d: %.1f clk per MMA over %lld MMAs\n", n, variant & 1,
+                   variant >> 1, (double)c[0] / c[1], c[1]);
+        }
+    }
     return 0;
 }
