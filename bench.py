@@ -193,6 +193,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+I8_TRAFFIC = None     # dram bytes of one idw_i8_kernel launch at the C4 slab shape (ncu --set full, profiles/r01_i8_ncu.md)
+
+
 def load_peaks():
     hbm, src = 6650.0, "fallback (B200_PROFILING.md)"
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -210,6 +213,20 @@ def load_peaks():
         except Exception:
             pass
     return hbm, src, fp64, fsrc
+
+
+def int8_peak_tops(sm_mhz):
+    """Dense int8 tensor peak of this GPU in TOP/s: tcgen05.mma kind::i8 issue loop measured by tools/umma_i8_probe.cu
+    (profiles/r01_umma_i8_probe.json: MAC per clock and SM) x 2 x SMs x the SM clock."""
+    mac, sms = 8187.0, 148
+    q = os.path.join(ROOT, "profiles", "r01_umma_i8_probe.json")
+    if os.path.exists(q):
+        try:
+            d = json.load(open(q))
+            mac, sms = float(d["int8_mac_per_clk_per_sm"]), int(d["sms"])
+        except Exception:
+            pass
+    return 2.0 * mac * sms * sm_mhz * 1e6 / 1e12
 
 
 def main():
@@ -378,29 +395,60 @@ def main():
     idw_flops = 2.0 * S * slab_cells * Tb     # numerator contraction only (the masked denominator is a sparse correction)
     idw_bytes = 8.0 * slab_cells * Tb + 8.0 * slab_cells
     dk_bytes = 8.0 * slab_cells * Tb + slab_cells * (8.0 + dk_stats[2] * 9.0)
-    roof = {"kernel": "idw_distribute_kernel (prep_steps_kernel + idw_distribute_kernel per field; the prep launch is < 0.1 % of it)",
-            "bound": "tensor", "achieved": idw_flops / (idw_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": idw_flops / (idw_ms * 1e-3) / 1e12 / fp64_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact shape (1e7 cells x 720 steps x 200
-            # stations), ncu --set full, profiles/r01_final_ncu.md; null for other shapes
-            "traffic": 57.68e9 if (slab_cells == 10_000_000 and Tb == 720 and S == 200) else None,
-            "traffic_unit": "bytes per launch (algorithmic: %.3e)" % idw_bytes,
-            "peak_source": "fp64 tensor (DMMA) peak " + fp64_src + "; MEASURED_PEAKS.json holds no fp64 figure",
-            "algorithmic_flops_per_launch": idw_flops, "ms_per_launch": idw_ms,
-            "why_tensor": "dense fp64 IDW at 200 stations is 2*S = 400 flop per 8-byte output = 50 flop/B, far right of the fp64 ridge "
-                          "(37 TFLOP/s / 6.5 TB/s = 5.7 flop/B): the fp64 tensor pipe, not HBM, bounds it",
-            "hbm_view": {"bound": "hbm", "achieved": idw_bytes / (idw_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": idw_bytes / (idw_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                         "algorithmic_bytes_per_launch": idw_bytes},
-            "dk_distribute_kernel": {"bound": "hbm", "achieved": dk_bytes / (launch_ms["precip"] * 1e-3) / 1e9, "peak": hbm_peak,
-                                     "unit": "GB/s", "frac": dk_bytes / (launch_ms["precip"] * 1e-3) / 1e9 / hbm_peak,
-                                     "algorithmic_bytes_per_launch": dk_bytes, "ms_per_launch": launch_ms["precip"]}}
+    # which IDW kernel ran: batches of >= 32 steps and <= 224 stations take the int8-sliced tcgen05 kernel (idw_i8.cu)
+    i8 = (Tb >= 32 and 16 < S <= 224 and os.environ.get("SMRFB_IDW_KERNEL", "") != "dmma")
+    common = {"traffic_unit": "bytes per launch (algorithmic: %.3e)" % idw_bytes, "ms_per_launch": idw_ms,
+              "hbm_view": {"bound": "hbm", "achieved": idw_bytes / (idw_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": idw_bytes / (idw_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                           "algorithmic_bytes_per_launch": idw_bytes},
+              "dk_distribute_kernel": {"bound": "hbm", "achieved": dk_bytes / (launch_ms["precip"] * 1e-3) / 1e9, "peak": hbm_peak,
+                                       "unit": "GB/s", "frac": dk_bytes / (launch_ms["precip"] * 1e-3) / 1e9 / hbm_peak,
+                                       "algorithmic_bytes_per_launch": dk_bytes, "ms_per_launch": launch_ms["precip"]}}
+    c4_shape = (slab_cells == 10_000_000 and Tb == 720 and S == 200)
+    if i8:
+        nm = min(len(np.unique(np.isnan(rows[f]), axis=0)) for f in ("air_temp", "vapor_pressure"))
+        products = 28 + (7 if nm > 32 else 0)        # digit products per output: numerator 28, per-step denominator 7
+        KB = (S + 31) // 32
+        i8_ops = 2.0 * products * 32 * KB * slab_cells * (-(-Tb // 48) * 48)     # executed int8 ops per launch
+        sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+        peak = int8_peak_tops(sm_mhz)
+        roof = {"kernel": "idw_i8_kernel (prep_steps_kernel + idw_i8_mask_kernel + idw_i8_slice_kernel + idw_i8_kernel per field; "
+                          "the three preparation launches are < 0.1 % of it)",
+                "bound": "tensor", "achieved": i8_ops / (idw_ms * 1e-3) / 1e12, "peak": peak, "unit": "TOP/s (int8)",
+                "frac": i8_ops / (idw_ms * 1e-3) / 1e12 / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact shape (ncu --set full,
+                # profiles/r01_i8_ncu.md); null for other shapes
+                "traffic": I8_TRAFFIC if c4_shape else None,
+                "peak_source": "int8 tensor peak measured with a tcgen05.mma kind::i8 issue loop (tools/umma_i8_probe.cu, "
+                               "profiles/r01_umma_i8_probe.json: 8187 MAC/clk/SM) at the SM clock; MEASURED_PEAKS.json holds bf16 only "
+                               "(its dense bf16 figure x 2 = %.0f TOP/s)" % (2 * 1619.0),
+                "algorithmic_int8_ops_per_launch": i8_ops, "digit_products_per_output": products, "distinct_nan_masks": int(nm),
+                "fp64_equivalent": {"achieved": idw_flops / (idw_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                    "vs_fp64_tensor_peak": idw_flops / (idw_ms * 1e-3) / 1e12 / fp64_peak,
+                                    "note": "2*S flop per output as if evaluated in fp64; the DMMA kernel this one replaces reached "
+                                            "0.66 of the %.1f TFLOP/s fp64 tensor peak" % fp64_peak},
+                "why_tensor": "2*S = 400 fp64-equivalent flop per 8-byte output; evaluated exactly as 28-35 int8 digit-product GEMMs "
+                              "(%d int8 op per output) on the 5th-generation tensor cores, s32 accumulators in tensor memory"
+                              % int(2 * products * 32 * KB)}
+    else:            # fp64 tensor-core (DMMA) kernel: short batches, > 224 stations, or SMRFB_IDW_KERNEL=dmma
+        roof = {"kernel": "idw_distribute_kernel (prep_steps_kernel + idw_distribute_kernel per field; the prep launch is < 0.1 % of it)",
+                "bound": "tensor", "achieved": idw_flops / (idw_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": idw_flops / (idw_ms * 1e-3) / 1e12 / fp64_peak,
+                "traffic": 57.68e9 if c4_shape else None,
+                "peak_source": "fp64 tensor (DMMA) peak " + fp64_src + "; MEASURED_PEAKS.json holds no fp64 figure",
+                "algorithmic_flops_per_launch": idw_flops,
+                "why_tensor": "dense fp64 IDW at 200 stations is 2*S = 400 flop per 8-byte output = 50 flop/B, far right of the fp64 ridge "
+                              "(37 TFLOP/s / 6.5 TB/s = 5.7 flop/B): the fp64 tensor pipe, not HBM, bounds it"}
+    roof.update(common)
     cb = None
     if not args.no_cpu_baseline and world == 1:      # reported baseline, rank 0 at N = 1 only
         cb, _ = cpu_arm(S, 2, 1)
     line = {"metric": "distributed cell-timesteps/sec (IDW+DK)", "value": value, "unit": "cell-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "arithmetic": ("IDW: fp64 contraction evaluated exactly in integers -- 7 x 8-bit digit slices per operand on tcgen05.mma kind::i8, "
+                           "s32 accumulate, fp64 epilogue; within 4e-11 of the fp64 tensor-core kernel (DESIGN.md 4.1). DK, epilogues: fp64"
+                           if i8 else "fp64 throughout (DMMA m8n8k4 for the IDW contraction)"),
             "config": {"workload": "C4 (BASELINE.json configs[3]): %dx%d DEM = %d cells, %d stations, hourly; step = %d-hour block x 3 fields "
                                    "(air_temp IDW, vapor_pressure IDW, precip DK) over the whole grid, walked in %d slabs of %d cells"
                                    % (ny, nx, ncell, S, Tb, len(slabs), slab_cells),

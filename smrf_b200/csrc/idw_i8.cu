@@ -31,6 +31,8 @@
 //     products into one of two 80-column TMEM accumulators;
 //   * the workers drain every pass with tcgen05.ld, fold it into fp64 (num, den per output in registers)
 //     and finish: reciprocal, scale, retrend against the DEM, NaN-preserving clamp, streaming store.
+#include <type_traits>
+
 #include "idw_i8.cuh"
 
 namespace smrfb {
@@ -336,7 +338,7 @@ enum { B_FULL = 0, B_EMPTY = 2, B_ACCFULL = 4, B_ACCEMPTY = 6, B_AREADY = 8, B_C
 
 __host__ __device__ inline size_t i8_smem_bytes(int KB) {
     return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + (size_t)KB * I8_KSTEP_B + (size_t)I8_MAXMASK * I8_M * 8 + 2 * 32 * KB * 8 +
-           4 * 128 * 8 + 4 * 128 * 4 + B_COUNT * 8 + 16 + 128;
+           2 * 3 * 128 * 8 + 2 * 3 * 128 * 4 + B_COUNT * 8 + 16 + 128;
 }
 
 #ifdef I8_PROFILE
@@ -351,16 +353,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
     const int KB = a.KB, S = a.S;
     const int plane = KB * I8_KSTEP_B;
     const uint32_t stage_bytes = 8u * (uint32_t)plane + I8_META;
-    unsigned char* p0 = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // 128-byte alignment by pointer arithmetic (an integer round trip would hide the shared address space from the
+    // compiler: every access below would become a generic load)
+    unsigned char* p0 = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     unsigned char* const stage0 = p0;
     unsigned char* const stage1 = p0 + stage_bytes;
     unsigned char* const vu_s = p0 + 2 * (size_t)stage_bytes;                          // V plane of the distinct masks
     double* const rden_s = reinterpret_cast<double*>(vu_s + plane);                     // [I8_MAXMASK][128] 1/den per mask and cell
     double* const smx = rden_s + I8_MAXMASK * I8_M;
     double* const smy = smx + 32 * KB;
-    double* const qmin = smy + 32 * KB;                          // [4][128]
-    int* const zf = reinterpret_cast<int*>(qmin + 4 * 128);       // [4][128]
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(zf + 4 * 128);
+    double* const qmin = smy + 32 * KB;                          // [3][128] smallest squared distance per station third
+    double* const qsec = qmin + 3 * 128;                         // [3][128] second smallest
+    int* const qarg = reinterpret_cast<int*>(qsec + 3 * 128);    // [3][128] station of the smallest
+    int* const zf = qarg + 3 * 128;                              // [3][128] a station coincides with the cell
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(zf + 3 * 128);
     uint32_t* const tbase_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -526,7 +532,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         const int kb0 = h * KB / 3, kb1 = (h + 1) * KB / 3;
         uint32_t P = 0, G = 0;
 #ifdef I8_PROFILE
-        long long w_gen = 0, w_wait = 0, w_ld = 0, w_fin = 0, w_tot = clock64();
+        long long w_gen = 0, w_wait = 0, w_ld = 0, w_fin = 0, w_val = 0, w_st = 0, w_tot = clock64();
 #endif
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
 #ifdef I8_PROFILE
@@ -539,30 +545,52 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 cell_xy(a.g, a.cbase + c, X, Y);
                 if (DETREND && a.g.dem) Z = __ldg(a.g.dem + a.cbase + c);
             }
-            // ---- weights: smallest squared distance of the cell -> common scale -> digits
+            // ---- weights: the two smallest squared distances of the cell -> common scale -> digits.
+            // The digits are relative to the largest weight they hold.  A station that out-weighs the runner-up by
+            // more than 2^9 (the cell sits almost on it) would leave the others too few digits whenever it drops out:
+            // it is taken out of the integer operands and added in fp64 in the epilogue (dom_s, dom_w).
             {
-                double qm = 1e300;
-                int coin = 0;
-                const int s1 = min(kb1 * 32, S);
-                for (int s = kb0 * 32; s < s1; s++) {
+                double q1 = 1e300, q2 = 1e300;
+                int s1 = -1, coin = 0;
+                const int send = min(kb1 * 32, S);
+                for (int s = kb0 * 32; s < send; s++) {
                     const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
                     const double qq = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                     if (qq == 0.0) coin = 1;
-                    else qm = fmin(qm, qq);
+                    else if (qq < q1) { q2 = q1; q1 = qq; s1 = s; }
+                    else q2 = fmin(q2, qq);
                 }
-                qmin[h * 128 + cl] = qm;
+                qmin[h * 128 + cl] = q1;
+                qsec[h * 128 + cl] = q2;
+                qarg[h * 128 + cl] = s1;
                 zf[h * 128 + cl] = coin;
             }
             named_bar_sync(1, I8_WORKERS);
-            const double qm = fmin(fmin(qmin[cl], qmin[128 + cl]), qmin[256 + cl]);
             const bool coincident = live && ((zf[cl] | zf[128 + cl] | zf[256 + cl]) != 0);
-            double scale;
+            double scale, dom_w = 0.0;
+            int dom_s = -1;
             {
-                const double wmax = idw_weight(qm, p2, a.power);
+                double q1 = 1e300, q2 = 1e300;
+                int s1 = -1;
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const double a1 = qmin[u * 128 + cl], a2 = qsec[u * 128 + cl];
+                    if (a1 < q1) { q2 = fmin(q1, a2); q1 = a1; s1 = qarg[u * 128 + cl]; }
+                    else q2 = fmin(q2, a1);
+                }
+                const double w1 = idw_weight(q1, p2, a.power), w2 = idw_weight(q2, p2, a.power);
+                const bool dom = live && s1 >= 0 && w1 > 512.0 * w2;
+                const double wmax = dom ? w2 : w1;
                 int E = ((__double2hiint(wmax) >> 20) & 0x7ff) - 1023;
                 E = min(max(E, -900), 900);
-                scale = __hiloint2double((1023 + 54 - E) << 20, 0);      // largest weight of the cell in [2^54, 2^55)
+                scale = __hiloint2double((1023 + 54 - E) << 20, 0);      // largest weight in the digits in [2^54, 2^55)
+                if (dom) {
+                    dom_s = s1;
+                    dom_w = w1 * scale;
+                }
             }
+            const bool anydom = __any_sync(0xffffffffu, dom_s >= 0);
+            const int dom_i = max(dom_s, 0);
             named_bar_sync(1, I8_WORKERS);                                // qmin / zf are rewritten for the next tile
             for (int kb = kb0; kb < kb1; kb++) {
                 uint32_t wd[I8_NS][8];
@@ -574,7 +602,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                         const int s = kb * 32 + j * 4 + b;
                         const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
                         const double qq = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                        const bool ok = live && s < S && qq != 0.0;
+                        const bool ok = live && s < S && qq != 0.0 && s != dom_s;
                         const double w = idw_weight(ok ? qq : 1.0, p2, a.power);
                         const unsigned long long W = ok ? __double2ull_rz(w * scale) : 0ull;
                         lo[b] = (uint32_t)W;
@@ -619,8 +647,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
                 P++;
             };
-            // seven denominator passes -> 1 / den for this thread's 16 columns (NaN where the exact path is needed)
-            auto den_passes = [&](double* rden) {
+            // seven denominator passes -> 1 / den for this thread's 16 columns (negative where the exact path is needed)
+            auto den_passes = [&](double* rden, auto dom_valid) {     // dom_valid(k): is the dominant station valid in column k
                 uint32_t d1[I8_COLS], d2[I8_COLS];     // D0 D1 D2 | D3 D4 D5 in radix 256 (< 2^32: D_i <= 224 * 255)
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
@@ -640,18 +668,23 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                     }
                 }
                 drain();                                // D6
-                // den = d1 * 2^32 + d2 * 2^8 + D6; the weights are scaled so that the largest lies in [2^54, 2^55):
-                // d1 < 2^13 means den < 2^45 = 2^-9 .. 2^-10 of it, where the fixed-point error stops being negligible
+                // den = d1 * 2^32 + d2 * 2^8 + D6 (+ the dominant station's weight); the digits are scaled so that their
+                // largest weight lies in [2^54, 2^55): den < 2^45 = 2^-9 .. 2^-10 of it is where the fixed-point error
+                // stops being negligible -> a negative value marks the exact path
 #pragma unroll
                 for (int k = 0; k < I8_COLS; k++) {
                     const double dlo = fma(u32_to_double(d2[k]), 256.0, u32_to_double(v[k]));
-                    const double r = fast_rcp<3>(fma(u32_to_double(d1[k]), 4294967296.0, dlo));
-                    rden[k] = d1[k] < 8192u ? nan("") : r;
+                    double d = fma(u32_to_double(d1[k]), 4294967296.0, dlo);
+                    if (anydom) d += dom_valid(k) ? dom_w : 0.0;      // warp-uniform test; dom_w is 0 on the other lanes
+                    rden[k] = d < 35184372088832.0 ? -1.0 : fast_rcp<3>(d);
                 }
             };
             if (mask_mode) {                            // denominators once per tile: column = mask id
                 double rd[I8_COLS];
-                den_passes(rd);
+                den_passes(rd, [&](int k) {
+                    const int n = h * I8_COLS + k;
+                    return vu_s[(dom_i >> 4) * I8_LBO_B + (n >> 3) * I8_SBO + (n & 7) * 16 + (dom_i & 15)] != 0;
+                });
                 if (h * I8_COLS < I8_MAXMASK) {
 #pragma unroll
                     for (int k = 0; k < I8_COLS; k++) rden_s[(h * I8_COLS + k) * I8_M + cl] = rd[k];
@@ -703,15 +736,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #pragma unroll
                     for (int k = 0; k < I8_COLS; k++) num[k] = fma(s64_to_double(hi[k]), 4294967296.0, s64_to_double(lo[k]));
                 }
-                if (!mask_mode) den_passes(den);
+                if (!mask_mode)
+                    den_passes(den, [&](int k) {
+                        const int t = min(ch * I8_N + h * I8_COLS + k, a.T - 1);
+                        return __ldg(a.valid + (size_t)t * S + dom_i) != 0;
+                    });
                 // ---- finish: scale back, retrend, clamp, store; exact path where flagged
 #ifdef I8_PROFILE
                 const long long tf0 = clock64();
 #endif
                 const int t0 = ch * I8_N + h * I8_COLS;
                 uint32_t slow = 0;
+                {
+                    int anyneg = 0;                              // sign bits only: no fp64 compare on the common path
 #pragma unroll
-                for (int k = 0; k < I8_COLS; k++) slow |= (uint32_t)(den[k] != den[k]) << k;
+                    for (int k = 0; k < I8_COLS; k++) anyneg |= __double2hiint(den[k]);
+                    if (anyneg < 0) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) slow |= ((uint32_t)__double2hiint(den[k]) >> 31) << k;
+                    }
+                }
                 if (coincident) slow = 0xffffffffu;
 #if defined(I8_EXP_NOMMA) || defined(I8_EXP_NOSLOW) || defined(I8_EXP_NOLD) || defined(I8_EXP_NOFINISH)
                 slow = 0;
@@ -723,15 +767,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #endif
                     double* op = a.out + (size_t)t0 * (size_t)a.ncw + c;
                     const bool whole = t0 + I8_COLS <= a.T;      // no per-step test on the common path: the 16 outputs
-#pragma unroll                                                   // then form one basic block and overlap
-                    for (int k = 0; k < I8_COLS; k++) {
-                        const double2 m01 = *reinterpret_cast<const double2*>(meta + 4 * k);
-                        const double p1 = meta[4 * k + 2];
-                        double x = (num[k] * den[k]) * m01.x;
-                        if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(m01.y, Z)), p1);   // idw.py:144, left to right
-                        if (CLAMP) x = clamp_nan_keep(x, a.vmin, a.vmax);
-                        num[k] = x;
-                    }
+                    // then form one basic block and overlap; warps without a dominant station (almost all) take the
+                    // variant without its instructions
+                    auto values = [&](auto with_dom) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) {
+                            const double2 m01 = *reinterpret_cast<const double2*>(meta + 4 * k);
+                            double x = (num[k] * den[k]) * m01.x;
+                            if (decltype(with_dom)::value)     // no per-lane branch: dom_w is 0 on lanes without one
+                                x = fma(dom_w * den[k], __ldg(a.rec + (size_t)min(t0 + k, a.T - 1) * a.RS + dom_i), x);
+                            if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(m01.y, Z)), meta[4 * k + 2]);   // idw.py:144, left to right
+                            if (CLAMP) x = clamp_nan_keep(x, a.vmin, a.vmax);
+                            num[k] = x;
+                        }
+                    };
+                    PROF(w_val, if (anydom) values(std::true_type{}); else values(std::false_type{}); asm volatile("" :: "d"(num[0]), "d"(num[15])));
+#ifdef I8_PROFILE
+                    const long long ts0 = clock64();
+#endif
+#ifdef I8_EXP_NOSTORE
+                    double acc_ = 0.0;
+#pragma unroll
+                    for (int k = 0; k < I8_COLS; k++) acc_ += num[k];
+                    if (acc_ == 1.2345e-300) __stcs(op, acc_);
+#else
                     if (whole) {
 #pragma unroll
                         for (int k = 0; k < I8_COLS; k++) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
@@ -740,6 +799,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                         for (int k = 0; k < I8_COLS; k++)
                             if (t0 + k < a.T) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
                     }
+#endif
+#ifdef I8_PROFILE
+                    w_st += clock64() - ts0;
+#endif
                 }
                 if (!live) slow = 0;
                 if (__any_sync(0xffffffffu, slow != 0)) {
@@ -771,7 +834,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #ifdef I8_PROFILE
         if (a.prof && tid == 0) {
             long long* pr = a.prof + 16 * blockIdx.x;
-            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld;
+            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld; pr[13] = w_val; pr[14] = w_st;
         }
 #endif
     }
@@ -870,8 +933,8 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
         long long hp[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hp, a.prof, sizeof(hp), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, finish %lld\n",
-                (a.ntiles + (int)grid - 1) / (int)grid, nchunk, hp[0], hp[1], hp[2], hp[3], hp[8], hp[9], hp[10], hp[12], hp[11]);
+        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, finish %lld (values %lld, stores %lld)\n",
+                (a.ntiles + (int)grid - 1) / (int)grid, nchunk, hp[0], hp[1], hp[2], hp[3], hp[8], hp[9], hp[10], hp[12], hp[11], hp[13], hp[14]);
     }
 #endif
     return SMRFB_OK;
