@@ -47,9 +47,10 @@ constexpr int I8_THREADS = I8_WORKERS + 128;   // + warp 12: MMA issuer, warp 13
 constexpr int I8_LBO_B = (I8_N / 8) * 128;     // byte stride between the two 16-byte K chunks of a B core-matrix column
 constexpr int I8_KSTEP_B = 2 * I8_LBO_B;       // bytes of one K = 32 block of a B plane
 constexpr int I8_SBO = 128;                    // byte stride between 8-row groups
-constexpr int I8_META = I8_N * 32;             // per step {2^k, p0, p1, 0}
+constexpr int I8_META = I8_N * 32;             // per step {p0, p1, 2^k, mask id}
 constexpr int I8_ACOL = 2 * I8_N;              // TMEM columns [0, 2N): two accumulators; [2N, 2N + 7*8*KB): the A digit planes
 constexpr int I8_MAXMASK = 32;                 // distinct NaN masks per call up to which the denominators are built per tile
+constexpr int I8_LBO_M = (I8_MAXMASK / 8) * 128;   // K-chunk stride of the V plane of the distinct masks (rows = mask ids)
 constexpr int I8_HDR = 64;                     // ints at the head of the mask buffer: [0] = number of distinct masks
 
 struct I8Args {
@@ -103,9 +104,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N, int b_signed)
     return (2u << 4) | ((uint32_t)b_signed << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-#ifdef I8_EXP_NOMMA
-    return;
-#endif
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}" ::"r"(d),
                  "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
                  : "memory");
@@ -161,7 +159,7 @@ __device__ __forceinline__ double idw_weight(double q, bool p2, double power) { 
 
 // ------------------------------------------------------------------------------------------ operand planes of R and V
 // blob[chunk] = { R digit planes 0..6, V plane : each [2*KB K-chunks][10 step groups][8 steps][16 stations] bytes,
-//                 meta[80] = {2^k, p0, p1, 0} }.   k is chosen per step so that max|R| lies in [2^53, 2^54).
+//                 meta[steps] = {p0, p1, 2^k, mask id} }.   k is chosen per step so that max|R| lies in [2^53, 2^54).
 // Distinct NaN masks of the call (first-occurrence order): hdr[0] = count, mask_id[t], and -- when there are at most
 // I8_MAXMASK -- the V plane of the distinct masks.  Station networks drop out in blocks, so a 720-hour batch
 // typically has a handful of masks; the kernel then builds the masked denominators once per tile and mask
@@ -177,7 +175,7 @@ __global__ void __launch_bounds__(1024) idw_i8_mask_kernel(const uint8_t* __rest
         for (int s = 0; s < S; s++) hsh = (hsh ^ (valid[(size_t)t * S + s] ? 1u : 0u)) * 1099511628211ull;
         s_hash[t] = hsh;
     }
-    for (int i = tid; i < KB * I8_KSTEP_B / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(vu)[i] = 0;
+    for (int i = tid; i < 2 * KB * I8_LBO_M / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(vu)[i] = 0;
     __syncthreads();
     for (int t = tid; t < T; t += blockDim.x) {
         int r = t;
@@ -206,7 +204,7 @@ __global__ void __launch_bounds__(1024) idw_i8_mask_kernel(const uint8_t* __rest
         if (s_rep[t] != t) continue;
         const int n = mask_id[t];
         for (int k = tid; k < S; k += blockDim.x)
-            vu[(size_t)(k >> 4) * I8_LBO_B + (size_t)(n >> 3) * I8_SBO + (size_t)(n & 7) * 16 + (k & 15)] = valid[(size_t)t * S + k] ? 1 : 0;
+            vu[(size_t)(k >> 4) * I8_LBO_M + (size_t)(n >> 3) * I8_SBO + (size_t)(n & 7) * 16 + (k & 15)] = valid[(size_t)t * S + k] ? 1 : 0;
     }
 }
 
@@ -235,9 +233,9 @@ __global__ void __launch_bounds__(256) idw_i8_slice_kernel(const double* __restr
                 back = __hiloint2double((1023 + E - 5) << 20, 0);       // 2^48 / sc: num carries 2^-48 (see the kernel)
             }
             s_scale[n] = sc;
-            meta[4 * n + 0] = back;
-            meta[4 * n + 1] = t < T ? rec[(size_t)t * RS + S_pad] : 0.0;
-            meta[4 * n + 2] = t < T ? rec[(size_t)t * RS + S_pad + 1] : 0.0;
+            meta[4 * n + 0] = t < T ? rec[(size_t)t * RS + S_pad] : 0.0;          // p0
+            meta[4 * n + 1] = t < T ? rec[(size_t)t * RS + S_pad + 1] : 0.0;      // p1
+            meta[4 * n + 2] = back;
             meta[4 * n + 3] = __longlong_as_double(t < T ? (long long)mask_id[t] : 0LL);
         }
     }
@@ -314,20 +312,21 @@ __device__ __noinline__ double idw_exact_value(const double* smx, const double* 
 // One digit product D (+)= A_i * B_j over all K blocks, fully unrolled for the K-block count: three uniform-datapath
 // instructions per MMA (the issuing warp shares its scheduler with three worker warps, so its instruction count
 // per MMA decides whether the tensor pipe stays fed).
-template <int KBT>
+template <int KBT, int KSTEP = I8_KSTEP_B>       // KSTEP: bytes of one K = 32 block of the B plane
 __device__ __forceinline__ void i8_product(uint32_t dcol, uint32_t ac, uint64_t bd, uint32_t idesc, bool first) {
 #pragma unroll
-    for (int kk = 0; kk < KBT; kk++) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (I8_KSTEP_B >> 4), idesc, !(first && kk == 0));
+    for (int kk = 0; kk < KBT; kk++) mma_ts(dcol, ac + kk * 8, bd + (uint64_t)kk * (KSTEP >> 4), idesc, !(first && kk == 0));
 }
+template <int KSTEP = I8_KSTEP_B>
 __device__ __forceinline__ void i8_product_any(int KB, uint32_t dcol, uint32_t ac, uint64_t bd, uint32_t idesc, bool first) {
     switch (KB) {
-        case 7: i8_product<7>(dcol, ac, bd, idesc, first); break;
-        case 6: i8_product<6>(dcol, ac, bd, idesc, first); break;
-        case 5: i8_product<5>(dcol, ac, bd, idesc, first); break;
-        case 4: i8_product<4>(dcol, ac, bd, idesc, first); break;
-        case 3: i8_product<3>(dcol, ac, bd, idesc, first); break;
-        case 2: i8_product<2>(dcol, ac, bd, idesc, first); break;
-        default: i8_product<1>(dcol, ac, bd, idesc, first); break;
+        case 7: i8_product<7, KSTEP>(dcol, ac, bd, idesc, first); break;
+        case 6: i8_product<6, KSTEP>(dcol, ac, bd, idesc, first); break;
+        case 5: i8_product<5, KSTEP>(dcol, ac, bd, idesc, first); break;
+        case 4: i8_product<4, KSTEP>(dcol, ac, bd, idesc, first); break;
+        case 3: i8_product<3, KSTEP>(dcol, ac, bd, idesc, first); break;
+        case 2: i8_product<2, KSTEP>(dcol, ac, bd, idesc, first); break;
+        default: i8_product<1, KSTEP>(dcol, ac, bd, idesc, first); break;
     }
 }
 
@@ -337,8 +336,8 @@ __device__ __forceinline__ void i8_product_any(int KB, uint32_t dcol, uint32_t a
 enum { B_FULL = 0, B_EMPTY = 2, B_ACCFULL = 4, B_ACCEMPTY = 6, B_AREADY = 8, B_COUNT = 9 };
 
 __host__ __device__ inline size_t i8_smem_bytes(int KB) {
-    return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + (size_t)KB * I8_KSTEP_B + (size_t)I8_MAXMASK * I8_M * 8 + 2 * 32 * KB * 8 +
-           2 * 3 * 128 * 8 + 2 * 3 * 128 * 4 + B_COUNT * 8 + 16 + 128;
+    return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + (size_t)2 * KB * I8_LBO_M + (size_t)I8_MAXMASK * I8_M * 8 + 2 * 32 * KB * 8 +
+           2 * 3 * 128 * 8 + 2 * 3 * 128 * 4 + (size_t)I8_WWARPS * I8_COLS * 16 + B_COUNT * 8 + 16 + 128;
 }
 
 #ifdef I8_PROFILE
@@ -359,14 +358,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
     unsigned char* const stage0 = p0;
     unsigned char* const stage1 = p0 + stage_bytes;
     unsigned char* const vu_s = p0 + 2 * (size_t)stage_bytes;                          // V plane of the distinct masks
-    double* const rden_s = reinterpret_cast<double*>(vu_s + plane);                     // [I8_MAXMASK][128] 1/den per mask and cell
+    double* const rden_s = reinterpret_cast<double*>(vu_s + 2 * KB * I8_LBO_M);                     // [I8_MAXMASK][128] 1/den per mask and cell
     double* const smx = rden_s + I8_MAXMASK * I8_M;
     double* const smy = smx + 32 * KB;
     double* const qmin = smy + 32 * KB;                          // [3][128] smallest squared distance per station third
     double* const qsec = qmin + 3 * 128;                         // [3][128] second smallest
     int* const qarg = reinterpret_cast<int*>(qsec + 3 * 128);    // [3][128] station of the smallest
     int* const zf = qarg + 3 * 128;                              // [3][128] a station coincides with the cell
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(zf + 3 * 128);
+    double2* const pmeta_s = reinterpret_cast<double2*>(zf + 3 * 128);   // [worker warp][16] {p0, p1} of the chunk that is retiring
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(pmeta_s + I8_WWARPS * I8_COLS);
     uint32_t* const tbase_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
     }
     const bool mask_mode = __ldg(a.maskhdr) <= I8_MAXMASK;
     if (mask_mode) {
-        for (int i = tid; i < plane / 16; i += I8_THREADS) reinterpret_cast<uint4*>(vu_s)[i] = __ldg(reinterpret_cast<const uint4*>(a.vu) + i);
+        for (int i = tid; i < 2 * KB * I8_LBO_M / 16; i += I8_THREADS) reinterpret_cast<uint4*>(vu_s)[i] = __ldg(reinterpret_cast<const uint4*>(a.vu) + i);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
@@ -418,16 +418,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         long long c_a = 0, c_full = 0, c_acc = 0, c_tot = clock64();
 #endif
         const uint32_t idesc_m = umma_idesc_i8(I8_M, I8_MAXMASK, 0);
-        const uint64_t vudesc = umma_desc(smem_u32(vu_s), I8_LBO_B, I8_SBO);
+        const uint64_t vudesc = umma_desc(smem_u32(vu_s), I8_LBO_M, I8_SBO);
         // one pass = one accumulator: wait until the workers have drained it, issue, commit
-        auto den_pass = [&](int i, uint64_t vd, uint32_t idesc) {        // digit plane i of W against a V plane
+        auto den_pass = [&](int i, uint64_t vd, uint32_t idesc, auto per_mask) {        // digit plane i of W against a V plane
             const int buf = P & 1;
             PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
             tc_fence_after();
             if (leader) {
                 const uint32_t dcol = tbase + buf * I8_N;
                 const uint32_t ac = acol + (uint32_t)(i * KB) * 8;
-                i8_product_any(KB, dcol, ac, vd, idesc, true);
+                if (decltype(per_mask)::value) i8_product_any<2 * I8_LBO_M>(KB, dcol, ac, vd, idesc, true);
+                else i8_product_any(KB, dcol, ac, vd, idesc, true);
                 tc_commit(&bars[B_ACCFULL + buf]);
             }
             __syncwarp();
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             PROF(c_a, mbar_wait_sleep(&bars[B_AREADY], tc & 1));
             tc_fence_after();
             if (mask_mode)
-                for (int i = 0; i < I8_NS; i++) den_pass(i, vudesc, idesc_m);
+                for (int i = 0; i < I8_NS; i++) den_pass(i, vudesc, idesc_m, std::true_type{});
             for (int ch = 0; ch < a.nchunk; ch++, G++) {
                 const int s = G & 1;
                 PROF(c_full, mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1));
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                     }
                 }
                 if (!mask_mode)
-                    for (int i = 0; i < I8_NS; i++) den_pass(i, bdesc + (uint64_t)7 * plane16, idesc_u);
+                    for (int i = 0; i < I8_NS; i++) den_pass(i, bdesc + (uint64_t)7 * plane16, idesc_u, std::false_type{});
                 if (leader) tc_commit(&bars[B_EMPTY + s]);
                 __syncwarp();
             }
@@ -531,8 +532,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         const bool p2 = (a.power == 2.0);
         const int kb0 = h * KB / 3, kb1 = (h + 1) * KB / 3;
         uint32_t P = 0, G = 0;
+        double2* const wmeta = pmeta_s + warp * I8_COLS;
 #ifdef I8_PROFILE
-        long long w_gen = 0, w_wait = 0, w_ld = 0, w_fin = 0, w_val = 0, w_st = 0, w_tot = clock64();
+        long long w_gen = 0, w_wait = 0, w_ld = 0, w_fin = 0, w_st = 0, w_tot = clock64();
 #endif
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
 #ifdef I8_PROFILE
@@ -636,12 +638,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 const int buf = P & 1;
                 PROF(w_wait, mbar_wait_sleep(&bars[B_ACCFULL + buf], (P >> 1) & 1));
                 tc_fence_after();
-#ifdef I8_EXP_NOLD
-#pragma unroll
-                for (int k = 0; k < I8_COLS; k++) v[k] = 0x10000u + k + P;
-#else
                 PROF(w_ld, tmem_ld16(tlane + (uint32_t)(buf * I8_N + h * I8_COLS), v); tmem_ld_wait());
-#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
@@ -683,7 +680,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 double rd[I8_COLS];
                 den_passes(rd, [&](int k) {
                     const int n = h * I8_COLS + k;
-                    return vu_s[(dom_i >> 4) * I8_LBO_B + (n >> 3) * I8_SBO + (n & 7) * 16 + (dom_i & 15)] != 0;
+                    return vu_s[(dom_i >> 4) * I8_LBO_M + (n >> 3) * I8_SBO + (n & 7) * 16 + (dom_i & 15)] != 0;
                 });
                 if (h * I8_COLS < I8_MAXMASK) {
 #pragma unroll
@@ -692,56 +689,129 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 named_bar_sync(1, I8_WORKERS);
             }
 
-            // ---- chunks of 48 steps; this thread owns steps [16h, 16h + 16) of each chunk for its cell
-            for (int ch = 0; ch < a.nchunk; ch++, G++) {
-                const int s = G & 1;
-                const double* meta = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes + (size_t)8 * plane) + 4 * (h * I8_COLS);
-                double den[I8_COLS];
-                if (mask_mode) {                            // 1 / den of each step's mask, fetched under the first passes
-                    mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1);
+            // ---- chunks of 48 steps; this thread owns steps [16h, 16h + 16) of each chunk for its cell.
+            // Software pipeline: when the last pass of a chunk has been drained its outputs are only brought to their
+            // value before the retrend (xp); the retrend, the clamp and the stores are spread over the drains of the
+            // NEXT chunk's passes.  The accumulators are therefore always drained promptly and the tensor pipe does not
+            // wait for an epilogue.  {p0, p1} of the retiring chunk sit in a private shared-memory slot of the warp, so
+            // the operand stage is released as soon as the chunk's last pass is drained.
+            double xp[I8_COLS];
+            int pt0 = 0;
+            uint32_t pslow = 0, pok = 0;            // flagged for the exact path / to be stored by the ordinary path
+            bool pend = false;
+            const size_t meta_off = (size_t)8 * plane + (size_t)(h * I8_COLS) * 32;
+            double* pop = nullptr;                  // &out[pt0][c]
+            const size_t ostride = (size_t)a.ncw;
+            // retrend, clamp, store outputs [K0, K1) of the pending chunk.  One basic block on the common path, so that
+            // the outputs overlap.
+            auto retire = [&](auto K0, auto K1) {
+                constexpr int k0 = decltype(K0)::value, k1 = decltype(K1)::value;
+#ifdef I8_PROFILE
+                const long long tr0 = clock64();
+#endif
+                double x[k1 - k0];
 #pragma unroll
-                    for (int k = 0; k < I8_COLS; k++) den[k] = rden_s[reinterpret_cast<const int*>(meta)[8 * k + 6] * I8_M + cl];
+                for (int k = k0; k < k1; k++) {
+                    double y = xp[k];
+                    if (DETREND) {
+                        const double2 pp = wmeta[k];
+                        y = __dadd_rn(__dadd_rn(y, __dmul_rn(pp.x, Z)), pp.y);       // idw.py:144, left to right
+                    }
+                    if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
+                    x[k - k0] = y;
                 }
-                double num[I8_COLS];
-                {
-                    long long lo[I8_COLS], hi[I8_COLS];     // groups 6..3 and 2..0 in radix 256
-                    constexpr int order[I8_NS] = {6, 5, 0, 4, 1, 3, 2};
+                double* q = pop + (size_t)k0 * ostride;
+                if (pok == 0xffffu) {
 #pragma unroll
-                    for (int oi = 0; oi < I8_NS; oi++) {
-                        const int g = order[oi];
-                        drain();
-                        if (g == 6) {
+                    for (int k = k0; k < k1; k++, q += ostride) __stcs(q, x[k - k0]);
+                } else {
 #pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) lo[k] = (long long)(int)v[k];
-                        } else if (g >= 3) {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) lo[k] += (long long)(int)v[k] * (long long)(1 << (8 * (6 - g)));
-                        } else if (g == 0) {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) hi[k] = (long long)(int)v[k] * 65536LL;
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) hi[k] += (long long)(int)v[k] * (long long)(1 << (8 * (2 - g)));
-                        }
-                        // fold now, under the MMAs of the next pass (without this the compiler sinks all seven folds
-                        // below the last drain, where the tensor pipe waits for them)
-                        if (g >= 3) {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(lo[k]));
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(hi[k]));
+                    for (int k = k0; k < k1; k++, q += ostride)
+                        if ((pok >> k) & 1u) __stcs(q, x[k - k0]);
+                }
+#ifdef I8_PROFILE
+                w_st += clock64() - tr0;
+#endif
+            };
+            // rare: flagged (cell, step) pairs are recomputed from the exact fp64 sums, the whole warp on one pair, and
+            // stored at once (the ordinary path skips them: pok); called where few registers are live
+            auto exact_pairs = [&]() {
+                for (int k = 0; k < I8_COLS; k++) {
+                    if (pt0 + k >= a.T) break;
+                    uint32_t m = __ballot_sync(0xffffffffu, (pslow >> k) & 1u);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const double x = idw_exact_value(smx, smy, S, __shfl_sync(0xffffffffu, X, src), __shfl_sync(0xffffffffu, Y, src),
+                                                         a.power, a.rec + (size_t)(pt0 + k) * a.RS, a.valid + (size_t)(pt0 + k) * S, lane);
+                        if (lane == src) {
+                            double y = x;
+                            if (DETREND) y = __dadd_rn(__dadd_rn(y, __dmul_rn(wmeta[k].x, Z)), wmeta[k].y);
+                            if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
+                            __stcs(a.out + (size_t)(pt0 + k) * (size_t)a.ncw + c, y);
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < I8_COLS; k++) num[k] = fma(s64_to_double(hi[k]), 4294967296.0, s64_to_double(lo[k]));
                 }
-                if (!mask_mode)
+            };
+            for (int ch = 0; ch < a.nchunk; ch++, G++) {
+                long long lo[I8_COLS], hi[I8_COLS];     // groups 6..3 and 2..0 in radix 256
+                // one numerator pass (group g = i + j of digit products), then a slice of the pending chunk's epilogue
+                auto num_pass = [&](auto OI) {
+                    constexpr int oi = decltype(OI)::value;
+                    constexpr int g = (0x2314056 >> (4 * oi)) & 7;       // order 6 5 0 4 1 3 2, as the MMA warp issues them
+                    // the pending chunk retires in four slices of four outputs, after the drains that are followed by a
+                    // long pass (groups 5, 4, 3, 2: the tensor pipe is busy for >= 500 clocks)
+                    constexpr int sl = oi == 0 ? 0 : oi == 2 ? 1 : oi == 4 ? 2 : oi == 5 ? 3 : -1;
+                    constexpr int k0 = sl < 0 ? 0 : sl * (I8_COLS / 4), k1 = sl < 0 ? 0 : (sl + 1) * (I8_COLS / 4);
+                    drain();
+                    if constexpr (g == 6) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) lo[k] = (long long)(int)v[k];
+                    } else if constexpr (g >= 3) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) lo[k] += (long long)(int)v[k] * (long long)(1 << (8 * (6 - g)));
+                    } else if constexpr (g == 0) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) hi[k] = (long long)(int)v[k] * 65536LL;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) hi[k] += (long long)(int)v[k] * (long long)(1 << (8 * (2 - g)));
+                    }
+                    // fold now, under the MMAs of the next pass (without this the compiler sinks all seven folds
+                    // below the last drain, where the tensor pipe waits for them)
+                    if (g >= 3) {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(lo[k]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(hi[k]));
+                    }
+                    if constexpr (sl >= 0) if (pend) retire(std::integral_constant<int, k0>{}, std::integral_constant<int, k1>{});
+                };
+                num_pass(std::integral_constant<int, 0>{});
+                num_pass(std::integral_constant<int, 1>{});
+                num_pass(std::integral_constant<int, 2>{});
+                num_pass(std::integral_constant<int, 3>{});
+                num_pass(std::integral_constant<int, 4>{});
+                num_pass(std::integral_constant<int, 5>{});
+                num_pass(std::integral_constant<int, 6>{});
+                double num[I8_COLS];
+#pragma unroll
+                for (int k = 0; k < I8_COLS; k++) num[k] = fma(s64_to_double(hi[k]), 4294967296.0, s64_to_double(lo[k]));
+                const int s = G & 1;
+                const double* meta = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes + meta_off);
+                mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1);      // completed long ago: makes the TMA's writes visible
+                double den[I8_COLS];
+                if (mask_mode) {                            // 1 / den of each step's mask
+#pragma unroll
+                    for (int k = 0; k < I8_COLS; k++) den[k] = rden_s[reinterpret_cast<const int*>(meta)[8 * k + 6] * I8_M + cl];
+                } else {
                     den_passes(den, [&](int k) {
                         const int t = min(ch * I8_N + h * I8_COLS + k, a.T - 1);
                         return __ldg(a.valid + (size_t)t * S + dom_i) != 0;
                     });
-                // ---- finish: scale back, retrend, clamp, store; exact path where flagged
+                }
+                // ---- value before the retrend; flags for the exact path
 #ifdef I8_PROFILE
                 const long long tf0 = clock64();
 #endif
@@ -757,84 +827,40 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                     }
                 }
                 if (coincident) slow = 0xffffffffu;
-#if defined(I8_EXP_NOMMA) || defined(I8_EXP_NOSLOW) || defined(I8_EXP_NOLD) || defined(I8_EXP_NOFINISH)
-                slow = 0;
-#endif
-#ifdef I8_EXP_NOFINISH
-                if (live && num[0] * den[0] == 1.2345e-300) {
-#else
-                if (live) {
-#endif
-                    double* op = a.out + (size_t)t0 * (size_t)a.ncw + c;
-                    const bool whole = t0 + I8_COLS <= a.T;      // no per-step test on the common path: the 16 outputs
-                    // then form one basic block and overlap; warps without a dominant station (almost all) take the
-                    // variant without its instructions
-                    auto values = [&](auto with_dom) {
+                // warps without a dominant station (almost all) take the variant without its instructions
+                auto values = [&](auto with_dom) {
 #pragma unroll
-                        for (int k = 0; k < I8_COLS; k++) {
-                            const double2 m01 = *reinterpret_cast<const double2*>(meta + 4 * k);
-                            double x = (num[k] * den[k]) * m01.x;
-                            if (decltype(with_dom)::value)     // no per-lane branch: dom_w is 0 on lanes without one
-                                x = fma(dom_w * den[k], __ldg(a.rec + (size_t)min(t0 + k, a.T - 1) * a.RS + dom_i), x);
-                            if (DETREND) x = __dadd_rn(__dadd_rn(x, __dmul_rn(m01.y, Z)), meta[4 * k + 2]);   // idw.py:144, left to right
-                            if (CLAMP) x = clamp_nan_keep(x, a.vmin, a.vmax);
-                            num[k] = x;
-                        }
-                    };
-                    PROF(w_val, if (anydom) values(std::true_type{}); else values(std::false_type{}); asm volatile("" :: "d"(num[0]), "d"(num[15])));
-#ifdef I8_PROFILE
-                    const long long ts0 = clock64();
-#endif
-#ifdef I8_EXP_NOSTORE
-                    double acc_ = 0.0;
-#pragma unroll
-                    for (int k = 0; k < I8_COLS; k++) acc_ += num[k];
-                    if (acc_ == 1.2345e-300) __stcs(op, acc_);
-#else
-                    if (whole) {
-#pragma unroll
-                        for (int k = 0; k < I8_COLS; k++) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < I8_COLS; k++)
-                            if (t0 + k < a.T) __stcs(op + (size_t)k * (size_t)a.ncw, num[k]);
-                    }
-#endif
-#ifdef I8_PROFILE
-                    w_st += clock64() - ts0;
-#endif
-                }
-                if (!live) slow = 0;
-                if (__any_sync(0xffffffffu, slow != 0)) {
-                    // rare: flagged (cell, step) pairs are recomputed from the exact fp64 sums, the whole warp on one pair
                     for (int k = 0; k < I8_COLS; k++) {
-                        if (t0 + k >= a.T) break;
-                        uint32_t m = __ballot_sync(0xffffffffu, (slow >> k) & 1u);
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const double x = idw_exact_value(smx, smy, S, __shfl_sync(0xffffffffu, X, src), __shfl_sync(0xffffffffu, Y, src),
-                                                             a.power, a.rec + (size_t)(t0 + k) * a.RS, a.valid + (size_t)(t0 + k) * S, lane);
-                            if (lane == src) {
-                                double y = x;
-                                if (DETREND) y = __dadd_rn(__dadd_rn(y, __dmul_rn(meta[4 * k + 1], Z)), meta[4 * k + 2]);
-                                if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
-                                __stcs(a.out + (size_t)(t0 + k) * (size_t)a.ncw + c, y);
-                            }
-                        }
+                        double x = (num[k] * den[k]) * meta[4 * k + 2];
+                        if (decltype(with_dom)::value)     // no per-lane branch: dom_w is 0 on lanes without one
+                            x = fma(dom_w * den[k], __ldg(a.rec + (size_t)min(t0 + k, a.T - 1) * a.RS + dom_i), x);
+                        xp[k] = x;
                     }
-                }
+                };
+                if (anydom) values(std::true_type{});
+                else values(std::false_type{});
+                // {p0, p1} of these steps into the warp's slot (the previous chunk has retired), then release the stage
+                if (lane < I8_COLS) wmeta[lane] = *reinterpret_cast<const double2*>(meta + 4 * lane);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_EMPTY + s]);
+                pt0 = t0;
+                pop = a.out + (size_t)t0 * ostride + c;
+                pslow = live ? slow : 0u;
+                pok = (live ? ~slow : 0u) & (t0 + I8_COLS <= a.T ? 0xffffu : ((1u << max(a.T - t0, 0)) - 1u));
+                pend = true;
+                if (__any_sync(0xffffffffu, pslow != 0)) exact_pairs();
 #ifdef I8_PROFILE
                 w_fin += clock64() - tf0;
 #endif
+            }
+            if (pend) {                                      // the tile's last chunk
+                retire(std::integral_constant<int, 0>{}, std::integral_constant<int, I8_COLS>{});
             }
         }
 #ifdef I8_PROFILE
         if (a.prof && tid == 0) {
             long long* pr = a.prof + 16 * blockIdx.x;
-            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld; pr[13] = w_val; pr[14] = w_st;
+            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld; pr[13] = 0; pr[14] = w_st;
         }
 #endif
     }
@@ -864,7 +890,7 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
     // scratch: [chunk blobs][mask header, mask ids][V plane of the distinct masks]
     const size_t blob_bytes = (size_t)nchunk * chunk_bytes;
     const size_t ids_bytes = ((size_t)(I8_HDR + T) * sizeof(int) + 255) / 256 * 256;
-    const size_t vu_bytes = (size_t)KB * I8_KSTEP_B;
+    const size_t vu_bytes = (size_t)2 * KB * I8_LBO_M;
     SMRFB_PROPAGATE(ensure_cap((void**)&scratch->d_blob, &scratch->blob_cap, blob_bytes + ids_bytes + vu_bytes));
     int* d_hdr = reinterpret_cast<int*>(scratch->d_blob + blob_bytes);
     int* d_ids = d_hdr + I8_HDR;
@@ -933,7 +959,7 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
         long long hp[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hp, a.prof, sizeof(hp), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, finish %lld (values %lld, stores %lld)\n",
+        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, chunk-end values %lld (unused %lld), retire slices %lld\n",
                 (a.ntiles + (int)grid - 1) / (int)grid, nchunk, hp[0], hp[1], hp[2], hp[3], hp[8], hp[9], hp[10], hp[12], hp[11], hp[13], hp[14]);
     }
 #endif
