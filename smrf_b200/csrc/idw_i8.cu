@@ -1,37 +1,45 @@
 // idw_i8.cu -- inverse-distance weighting (smrf/spatial/idw.py:53-144) on the 5th-generation tensor cores:
-// the fp64 contraction over stations is evaluated EXACTLY in integers (Ozaki-style 8-bit slicing) by
+// the fp64 contraction over stations is evaluated in integers (Ozaki-style 8-bit slicing) by
 // tcgen05.mma kind::i8 with s32 accumulators in tensor memory.
 //
 //   out[t][c] = num / den * 2^k(t) + p0[t]*Z[c] + p1[t]
-//   num[c][t] = sum_s W[c][s] * R[t][s]        W = floor(w * 2^ew(c))  55-bit unsigned integers, w = 1/dist^power
+//   num[c][t] = sum_s W[c][s] * R[t][s]        W = rint(w * 2^ew(c))   48-bit unsigned integers, w = 1/dist^power
 //   den[c][t] = sum_s W[c][s] * V[t][s]        R = rint(r * 2^er(t))   55-bit signed integers (residuals, 0 = missing)
 //                                              V = 1 for a valid station, else 0
-// W and R are cut into seven 8-bit digits (W: unsigned bytes; R: two's complement, top digit signed), and
-//   sum_s W R = sum_{i,j} 2^(8(12-i-j)) sum_s a_i[c][s] b_j[t][s]
-// keeps the 28 digit products with i + j <= 6 (what is dropped is < 2^-53 of max|W| max|R| per station, the
-// size of one fp64 rounding); every digit product is one int8 GEMM whose s32 sums are exact.  den uses all
-// seven digits of W against the 0/1 matrix V: the masked denominator needs no missing-station lists and has
-// no cancellation.  The scale 2^ew(c) of a cell cancels in num / den.
-// Dynamic range: the digits are relative to the LARGEST weight of the cell.  When that station is missing
-// at a step and the remaining weights are below 2^-10 of it, the fixed-point error would no longer be
-// negligible: those (cell, step) pairs -- and cells that coincide with a station (w = inf) --
-// are recomputed in plain fp64 (idw_exact_value).  Error bound of the integer path: 3e-11 * max_s|r[t][s]|
-// in the worst admitted case, ~1e-15 relative typically; the parity contract is 1e-9.
+// W is cut into six 8-bit digits a_i (unsigned bytes), R into seven digits b_j (two's complement, top digit signed):
+//   sum_s W R = sum_{i,j} 2^(8(11-i-j)) sum_s a_i[c][s] b_j[t][s]
+// keeps the 27 digit products with i + j <= 6; every digit product is one int8 GEMM whose s32 sums are exact.
+// den uses the six digits of W against the 0/1 matrix V: the masked denominator needs no missing-station lists and
+// has no cancellation.  The scale 2^ew(c) of a cell cancels in num / den.
+// Dynamic range: the digits are relative to the LARGEST weight they hold.  A station that out-weighs the second
+// nearest by more than 2^5 (about 3 % of the cells) is kept out of the digits and added in fp64 (dom_s, dom_w), so
+// its dropping out does not starve the others of digits.  When the valid weights of a step still sum to less than
+// 2^-6 .. 2^-7 of the largest digit weight (both nearest stations missing, ...), or a station coincides with the
+// cell (w = inf), the (cell, step) pair is recomputed in plain fp64 (idw_exact_value).
+// Error bound of the integer path, relative to max_s |r[t][s]|: weight rounding S * 2^-48 * 2 * 2^7 = 2.0e-10,
+// dropped digit products 1.6e-11, residual rounding 2^-54; observed 7e-12 (max) / 2e-14 (mean) against the fp64
+// tensor-core kernel.  The parity contract is 1e-9.
 //
 // One persistent CTA per SM owns tiles of 128 consecutive cells for the whole batch of T steps:
-//   * warps 0-7 ("workers", TMEM lane quarter = warp & 3, step half = warp >> 2) generate the tile's weights
-//     from the coordinates, cut them into digits and write digit planes 0-5 straight into TENSOR MEMORY
-//     (tcgen05.st; the A operand of the MMAs is read from TMEM) and plane 6 into shared memory -- the weight
-//     cube [ncell x S] is never materialised and A stays resident for all T steps;
+//   * warps 0-11 ("workers", TMEM lane quarter = warp & 3, step third = warp >> 2) generate the tile's weights
+//     from the coordinates, cut them into digits and write the six digit planes straight into TENSOR MEMORY
+//     (tcgen05.st; the A operand of the MMAs is read from TMEM, 336 columns at 224 stations) -- the weight cube
+//     [ncell x S] is never materialised and A stays resident for all T steps;
 //   * the digit planes of R and V are prepared once per call (idw_i8_slice_kernel) in the canonical K-major
-//     core-matrix layout and stream per chunk of 80 steps through shared memory by 1-D TMA bulk copies
-//     (warp 9); R (125 KB) is single-buffered and reloaded under the denominator MMAs, which only read V;
-//   * warp 8 issues the MMAs (M = 128 cells, N = 80 steps, K = 32 stations per instruction): per chunk
-//     7 numerator passes and 7 denominator passes (one per power of 2^8), each pass accumulating its digit
-//     products into one of two 80-column TMEM accumulators;
-//   * the workers drain every pass with tcgen05.ld, fold it into fp64 (num, den per output in registers)
-//     and finish: reciprocal, scale, retrend against the DEM, NaN-preserving clamp, streaming store.
+//     core-matrix layout and stream per chunk of 48 steps through two shared-memory stages by 1-D TMA bulk copies
+//     (warp 13);
+//   * warp 12 issues the MMAs (M = 128 cells, N = 48 steps, K = 32 stations per instruction): per chunk 7 numerator
+//     passes (one per power of 2^8) and -- unless the batch has at most 32 distinct NaN masks, whose denominators are
+//     built once per tile -- 6 denominator passes, each pass accumulating its digit products into one slot of a
+//     ring of three 48-column TMEM accumulators;
+//   * the workers drain every pass with tcgen05.ld, fold it with integer multiply-adds (two 64-bit words per
+//     output) and finish: one conversion to fp64, 2^k / den by an exponent add, three DFMAs (retrend included),
+//     NaN-preserving clamp decided on the high words, streaming store.
+// Measured on B200 (tools/umma_alu_mix_probe.cu): fp64 arithmetic (DFMA, DADD, DMUL, DSETP) makes no progress on
+// an SM while tcgen05.mma instructions execute; integer, fp32, conversion, shared-memory and global-memory
+// instructions are unaffected.  Hence integer folds and as little fp64 as possible inside the chunk loop.
 #include <type_traits>
+#include <vector>
 
 #include "idw_i8.cuh"
 
@@ -39,7 +47,10 @@ namespace smrfb {
 
 constexpr int I8_M = 128;                      // cells per tile
 constexpr int I8_N = IDW_I8_STEPS;             // steps per chunk
-constexpr int I8_NS = 7;                       // 8-bit digits per operand
+constexpr int I8_NS = 7;                       // 8-bit digits of a residual (R)
+constexpr int I8_NW = 6;                       // 8-bit digits of a weight (W)
+constexpr int I8_GMAX = 6;                     // digit products a_i b_j with i + j <= I8_GMAX are kept
+constexpr int I8_NACC = 3;                     // accumulators in the TMEM ring
 constexpr int I8_WWARPS = 12;                  // worker warps: TMEM lane quarter = warp & 3, step third = warp >> 2
 constexpr int I8_COLS = I8_N / 3;              // steps per worker thread and chunk
 constexpr int I8_WORKERS = I8_WWARPS * 32;
@@ -47,8 +58,8 @@ constexpr int I8_THREADS = I8_WORKERS + 128;   // + warp 12: MMA issuer, warp 13
 constexpr int I8_LBO_B = (I8_N / 8) * 128;     // byte stride between the two 16-byte K chunks of a B core-matrix column
 constexpr int I8_KSTEP_B = 2 * I8_LBO_B;       // bytes of one K = 32 block of a B plane
 constexpr int I8_SBO = 128;                    // byte stride between 8-row groups
-constexpr int I8_META = I8_N * 32;             // per step {p0, p1, 2^k, mask id}
-constexpr int I8_ACOL = 2 * I8_N;              // TMEM columns [0, 2N): two accumulators; [2N, 2N + 7*8*KB): the A digit planes
+constexpr int I8_META = I8_N * 32;             // per step {p0, p1, 2^k, {mask id, k << 20}}
+constexpr int I8_ACOL = I8_NACC * I8_N;        // TMEM columns [0, 3N): the accumulator ring; [3N, 3N + 6*8*KB): the A digit planes (480 of 512 at KB = 7)
 constexpr int I8_MAXMASK = 32;                 // distinct NaN masks per call up to which the denominators are built per tile
 constexpr int I8_LBO_M = (I8_MAXMASK / 8) * 128;   // K-chunk stride of the V plane of the distinct masks (rows = mask ids)
 constexpr int I8_HDR = 64;                     // ints at the head of the mask buffer: [0] = number of distinct masks
@@ -144,13 +155,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x as a bit pattern, minus the offset
-__device__ __forceinline__ double s32_to_double(uint32_t x) {
-    return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;
+// fp64 arithmetic (DFMA, DADD, DMUL, DSETP) makes no progress on an SM while tcgen05.mma instructions execute
+// (tools/umma_alu_mix_probe.cu), integer, fp32 and conversion instructions do: the workers' epilogue uses the
+// latter wherever it can.
+// Ordered 32-bit key of the high word of a double: key(a) < key(b) implies a < b (equal keys decide nothing).
+__device__ __forceinline__ int f64_key_hi(double x) {
+    const int h = __double2hiint(x);
+    return h ^ ((h >> 31) & 0x7fffffff);
 }
-// exact for |x| < 2^51: the bit pattern of 2^52 + 2^51 + x, minus the offset
-__device__ __forceinline__ double s64_to_double(long long x) { return __longlong_as_double(x + 0x4338000000000000LL) - 6755399441055744.0; }
-__device__ __forceinline__ double u32_to_double(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+// utils.py:137-161 with the comparisons decided on the high words; values whose high word reaches a bound's
+// (and NaN, whose key lies above +inf's) take the exact fp64 comparison
+__device__ __forceinline__ double clamp_nan_keep_fast(double v, double vmin, double vmax, int kmin, int kmax) {
+    const int k = f64_key_hi(v);
+    if (k <= kmin || k >= kmax) v = clamp_nan_keep(v, vmin, vmax);
+    return v;
+}
+// 1 / d for d in [2^40, 2^56): fp32 reciprocal through the conversion and special-function units, one Newton
+// step in fp64: relative error < 2^-43
+__device__ __forceinline__ double rcp_via_f32(double d) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(d)));
+    const double r0 = (double)rf;
+    return fma(r0, fma(-d, r0, 1.0), r0);
+}
 
 __device__ __noinline__ double idw_weight_pow(double q, double power) { return 1.0 / pow(sqrt(q), power); }
 __device__ __forceinline__ double idw_weight(double q, bool p2, double power) {   // idw.py:77, q = squared distance > 0
@@ -226,17 +253,19 @@ __global__ void __launch_bounds__(256) idw_i8_slice_kernel(const double* __restr
         for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) {
             double sc = 1.0, back = 0.0;
+            int eshift = 0;                 // back = 2^eshift as an addend to the exponent field of 1 / den
             if (t < T && m > 0.0 && m < 1e300) {
                 int E = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;
                 E = max(E, -900);
                 sc = __hiloint2double((1023 + 53 - E) << 20, 0);        // max|R| in [2^53, 2^54)
-                back = __hiloint2double((1023 + E - 5) << 20, 0);       // 2^48 / sc: num carries 2^-48 (see the kernel)
+                eshift = E - 53 + 8 * (I8_NW + I8_NS - 2 - I8_GMAX);
+                back = __hiloint2double((1023 + eshift) << 20, 0);       // 2^40 / sc: the kernel's num is in units of 2^40
             }
             s_scale[n] = sc;
             meta[4 * n + 0] = t < T ? rec[(size_t)t * RS + S_pad] : 0.0;          // p0
             meta[4 * n + 1] = t < T ? rec[(size_t)t * RS + S_pad + 1] : 0.0;      // p1
             meta[4 * n + 2] = back;
-            meta[4 * n + 3] = __longlong_as_double(t < T ? (long long)mask_id[t] : 0LL);
+            meta[4 * n + 3] = __hiloint2double(eshift * (1 << 20), t < T ? mask_id[t] : 0);     // {mask id, exponent addend}
         }
     }
     __syncthreads();
@@ -333,13 +362,19 @@ __device__ __forceinline__ void i8_product_any(int KB, uint32_t dcol, uint32_t a
 // ------------------------------------------------------------------------------------------ the kernel
 // shared memory: stage[2] = { R planes 0..6, V plane, meta } (one TMA bulk copy per chunk), station coordinates,
 // per-cell scratch of the weight generation, mbarriers
-enum { B_FULL = 0, B_EMPTY = 2, B_ACCFULL = 4, B_ACCEMPTY = 6, B_AREADY = 8, B_COUNT = 9 };
+enum { B_FULL = 0, B_EMPTY = 2, B_ACCFULL = 4, B_ACCEMPTY = 4 + I8_NACC, B_AREADY = 4 + 2 * I8_NACC, B_COUNT = 5 + 2 * I8_NACC };
 
 __host__ __device__ inline size_t i8_smem_bytes(int KB) {
     return 2 * ((size_t)8 * KB * I8_KSTEP_B + I8_META) + (size_t)2 * KB * I8_LBO_M + (size_t)I8_MAXMASK * I8_M * 8 + 2 * 32 * KB * 8 +
-           2 * 3 * 128 * 8 + 2 * 3 * 128 * 4 + (size_t)I8_WWARPS * I8_COLS * 16 + B_COUNT * 8 + 16 + 128;
+           2 * 3 * 128 * 8 + 2 * 3 * 128 * 4 + B_COUNT * 8 + 16 + 128;
 }
 
+// I8_TRACE builds: lane 0 of every warp of CTA 0 logs (tag, clock) events of its fourth tile
+#ifdef I8_TRACE
+#define TRACE(tag) do { if (tracing && lane == 0 && nev < 1024) trbuf[nev++] = ((long long)(tag) << 48) | (clock64() & 0xffffffffffffLL); } while (0)
+#else
+#define TRACE(tag) do { } while (0)
+#endif
 #ifdef I8_PROFILE
 #define PROF(var, stmt) do { const long long t__ = clock64(); stmt; var += clock64() - t__; } while (0)
 #else
@@ -365,10 +400,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
     double* const qsec = qmin + 3 * 128;                         // [3][128] second smallest
     int* const qarg = reinterpret_cast<int*>(qsec + 3 * 128);    // [3][128] station of the smallest
     int* const zf = qarg + 3 * 128;                              // [3][128] a station coincides with the cell
-    double2* const pmeta_s = reinterpret_cast<double2*>(zf + 3 * 128);   // [worker warp][16] {p0, p1} of the chunk that is retiring
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(pmeta_s + I8_WWARPS * I8_COLS);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(zf + 3 * 128);
     uint32_t* const tbase_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef I8_TRACE
+    long long* const trbuf = a.prof + 16 * 1024 + warp * 1024;
+    int nev = 0;
+    bool tracing = false;
+#endif
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tbase_s)), "r"(512));
@@ -379,10 +418,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         mbar_init(&bars[B_FULL + 1], 1);
         mbar_init(&bars[B_EMPTY + 0], 1 + I8_WWARPS);    // MMA commit + the worker warps (they read the step meta)
         mbar_init(&bars[B_EMPTY + 1], 1 + I8_WWARPS);
-        mbar_init(&bars[B_ACCFULL + 0], 1);
-        mbar_init(&bars[B_ACCFULL + 1], 1);
-        mbar_init(&bars[B_ACCEMPTY + 0], I8_WWARPS);
-        mbar_init(&bars[B_ACCEMPTY + 1], I8_WWARPS);
+        for (int i = 0; i < I8_NACC; i++) {
+            mbar_init(&bars[B_ACCFULL + i], 1);
+            mbar_init(&bars[B_ACCEMPTY + i], I8_WWARPS);
+        }
         mbar_init(&bars[B_AREADY], I8_WWARPS);
         fence_mbar_init();
     }
@@ -413,7 +452,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         const uint64_t sdesc[2] = {umma_desc(smem_u32(stage0), I8_LBO_B, I8_SBO), umma_desc(smem_u32(stage1), I8_LBO_B, I8_SBO)};
         const uint32_t acol = tbase + I8_ACOL;
         const uint32_t plane16 = (uint32_t)plane >> 4;
-        uint32_t P = 0, G = 0, tc = 0;
+        uint32_t abuf = 0, aph = 0, G = 0, tc = 0;     // accumulator ring position and phase
+        auto next_acc = [&]() { if (++abuf == I8_NACC) { abuf = 0; aph ^= 1; } };
 #ifdef I8_PROFILE
         long long c_a = 0, c_full = 0, c_acc = 0, c_tot = clock64();
 #endif
@@ -421,8 +461,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         const uint64_t vudesc = umma_desc(smem_u32(vu_s), I8_LBO_M, I8_SBO);
         // one pass = one accumulator: wait until the workers have drained it, issue, commit
         auto den_pass = [&](int i, uint64_t vd, uint32_t idesc, auto per_mask) {        // digit plane i of W against a V plane
-            const int buf = P & 1;
-            PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+            const uint32_t buf = abuf;
+            TRACE(1);
+            PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], aph ^ 1));
+            TRACE(2);
             tc_fence_after();
             if (leader) {
                 const uint32_t dcol = tbase + buf * I8_N;
@@ -432,40 +474,54 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 tc_commit(&bars[B_ACCFULL + buf]);
             }
             __syncwarp();
-            P++;
+            TRACE(3);
+            next_acc();
         };
         // 224-station layout (7 K blocks): every descriptor offset is an immediate -- two uniform adds and the MMA
         // per instruction, no loop or branch inside a pass (gg is a literal at every call site)
         auto num_pass_full = [&](const int gg, uint32_t blo, uint32_t bhi) {
-            const int buf = P & 1;
-            PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+            const uint32_t buf = abuf;
+            TRACE(1);
+            PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], aph ^ 1));
+            TRACE(2);
             tc_fence_after();
             if (leader) {
                 const uint32_t dcol = tbase + buf * I8_N;
+                bool first = true;
 #pragma unroll
-                for (int i = 0; i < I8_NS; i++) {
+                for (int i = 0; i < I8_NW; i++) {
                     if (i > gg) break;
                     const int j = gg - i;
+                    if (j >= I8_NS) continue;
                     // an opaque zero per product keeps the compiler from hoisting the address arithmetic of all 28
                     // products to the top of the pass (it runs out of uniform registers and spills)
                     uint32_t z;
                     asm volatile("mov.u32 %0, 0;" : "=r"(z));
                     const uint64_t bd = ((uint64_t)bhi << 32) | (uint32_t)(blo + z + (uint32_t)(j * 7 * (I8_KSTEP_B >> 4)));
-                    i8_product<7>(dcol, acol + z + (uint32_t)(i * 7 * 8), bd, j == 0 ? idesc_s : idesc_u, i == 0);
+                    i8_product<7>(dcol, acol + z + (uint32_t)(i * 7 * 8), bd, j == 0 ? idesc_s : idesc_u, first);
+                    first = false;
                 }
                 tc_commit(&bars[B_ACCFULL + buf]);
             }
             __syncwarp();
-            P++;
+            TRACE(3);
+            next_acc();
         };
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
+#ifdef I8_TRACE
+            tracing = blockIdx.x == 0 && tc == 3;
+#endif
+            TRACE(6);
             PROF(c_a, mbar_wait_sleep(&bars[B_AREADY], tc & 1));
+            TRACE(7);
             tc_fence_after();
             if (mask_mode)
-                for (int i = 0; i < I8_NS; i++) den_pass(i, vudesc, idesc_m, std::true_type{});
+                for (int i = 0; i < I8_NW; i++) den_pass(i, vudesc, idesc_m, std::true_type{});
             for (int ch = 0; ch < a.nchunk; ch++, G++) {
                 const int s = G & 1;
+                TRACE(4);
                 PROF(c_full, mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1));
+                TRACE(5);
                 tc_fence_after();
                 const uint64_t bdesc = sdesc[s];
                 // numerator: one pass per group gg = i + j, in the order 6 5 0 4 1 3 2 (long passes first: they run
@@ -480,25 +536,28 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                     num_pass_full(3, blo, bhi);
                     num_pass_full(2, blo, bhi);
                 } else {
-                    for (int oi = 0; oi < I8_NS; oi++, P++) {
+                    for (int oi = 0; oi <= I8_GMAX; oi++) {
                         const int gg = (0x2314056 >> (4 * oi)) & 7;
-                        const int buf = P & 1;
-                        PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], ((P >> 1) & 1) ^ 1));
+                        const uint32_t buf = abuf;
+                        PROF(c_acc, mbar_wait_sleep(&bars[B_ACCEMPTY + buf], aph ^ 1));
                         tc_fence_after();
                         if (leader) {
                             const uint32_t dcol = tbase + buf * I8_N;
-                            for (int i = 0; i <= gg; i++) {
+                            bool first = true;
+                            for (int i = max(0, gg - (I8_NS - 1)); i <= min(gg, I8_NW - 1); i++) {
                                 const int j = gg - i;
                                 i8_product_any(KB, dcol, acol + (uint32_t)(i * KB) * 8, bdesc + (uint64_t)j * plane16, j == 0 ? idesc_s : idesc_u,
-                                               i == 0);
+                                               first);
+                                first = false;
                             }
                             tc_commit(&bars[B_ACCFULL + buf]);
                         }
                         __syncwarp();
+                        next_acc();
                     }
                 }
                 if (!mask_mode)
-                    for (int i = 0; i < I8_NS; i++) den_pass(i, bdesc + (uint64_t)7 * plane16, idesc_u, std::false_type{});
+                    for (int i = 0; i < I8_NW; i++) den_pass(i, bdesc + (uint64_t)7 * plane16, idesc_u, std::false_type{});
                 if (leader) tc_commit(&bars[B_EMPTY + s]);
                 __syncwarp();
             }
@@ -531,12 +590,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
         const uint32_t tlane = tbase + ((uint32_t)(32 * q) << 16);
         const bool p2 = (a.power == 2.0);
         const int kb0 = h * KB / 3, kb1 = (h + 1) * KB / 3;
-        uint32_t P = 0, G = 0;
-        double2* const wmeta = pmeta_s + warp * I8_COLS;
+        uint32_t abuf = 0, aph = 0, G = 0;             // accumulator ring position and phase
+        const int kmin = f64_key_hi(a.vmin), kmax = f64_key_hi(a.vmax);
 #ifdef I8_PROFILE
         long long w_gen = 0, w_wait = 0, w_ld = 0, w_fin = 0, w_st = 0, w_tot = clock64();
 #endif
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        int wtc = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, wtc++) {
+#ifdef I8_TRACE
+            tracing = blockIdx.x == 0 && wtc == 3;
+#endif
+            TRACE(20);
 #ifdef I8_PROFILE
             const long long tg0 = clock64();
 #endif
@@ -549,70 +613,88 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             }
             // ---- weights: the two smallest squared distances of the cell -> common scale -> digits.
             // The digits are relative to the largest weight they hold.  A station that out-weighs the runner-up by
-            // more than 2^9 (the cell sits almost on it) would leave the others too few digits whenever it drops out:
+            // more than 2^5 (the cell sits close to it; ~3 % of the cells) would leave the others too few digits whenever it drops out:
             // it is taken out of the integer operands and added in fp64 in the epilogue (dom_s, dom_w).
+            // Phase 1 tracks the two smallest squared distances on their high words only (positive doubles order like
+            // integers; 20 mantissa bits are plenty for a scale exponent and a ratio test): one integer min / max each.
             {
-                double q1 = 1e300, q2 = 1e300;
+                uint32_t h1 = 0x7ff00000u, h2 = 0x7ff00000u;
                 int s1 = -1, coin = 0;
                 const int send = min(kb1 * 32, S);
                 for (int s = kb0 * 32; s < send; s++) {
-                    const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
-                    const double qq = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    if (qq == 0.0) coin = 1;
-                    else if (qq < q1) { q2 = q1; q1 = qq; s1 = s; }
-                    else q2 = fmin(q2, qq);
+                    const double dx = X - smx[s], dy = Y - smy[s];
+                    const uint32_t qh = (uint32_t)__double2hiint(fma(dx, dx, dy * dy));
+                    if (qh == 0u) { coin = 1; continue; }          // q == 0 exactly: the station sits on the cell
+                    h2 = min(h2, max(h1, qh));
+                    if (qh < h1) s1 = s;
+                    h1 = min(h1, qh);
                 }
-                qmin[h * 128 + cl] = q1;
-                qsec[h * 128 + cl] = q2;
+                reinterpret_cast<uint32_t*>(qmin)[h * 128 + cl] = h1;
+                reinterpret_cast<uint32_t*>(qsec)[h * 128 + cl] = h2;
                 qarg[h * 128 + cl] = s1;
                 zf[h * 128 + cl] = coin;
             }
             named_bar_sync(1, I8_WORKERS);
             const bool coincident = live && ((zf[cl] | zf[128 + cl] | zf[256 + cl]) != 0);
-            double scale, dom_w = 0.0;
-            int dom_s = -1;
+            double dom_w = 0.0;
+            int dom_s = -1, es20;                                   // es20: exponent of the digit scale, << 20
             {
-                double q1 = 1e300, q2 = 1e300;
+                uint32_t h1 = 0x7ff00000u, h2 = 0x7ff00000u;
                 int s1 = -1;
 #pragma unroll
                 for (int u = 0; u < 3; u++) {
-                    const double a1 = qmin[u * 128 + cl], a2 = qsec[u * 128 + cl];
-                    if (a1 < q1) { q2 = fmin(q1, a2); q1 = a1; s1 = qarg[u * 128 + cl]; }
-                    else q2 = fmin(q2, a1);
+                    const uint32_t a1 = reinterpret_cast<const uint32_t*>(qmin)[u * 128 + cl], a2 = reinterpret_cast<const uint32_t*>(qsec)[u * 128 + cl];
+                    h2 = min(min(h2, a2), max(h1, a1));
+                    if (a1 < h1) s1 = qarg[u * 128 + cl];
+                    h1 = min(h1, a1);
                 }
-                const double w1 = idw_weight(q1, p2, a.power), w2 = idw_weight(q2, p2, a.power);
-                const bool dom = live && s1 >= 0 && w1 > 512.0 * w2;
+                // weights of the nearest and the second nearest station (the latter from the high word of its squared
+                // distance: the ratio test and the scale exponent need no more)
+                double q1 = 1.0;
+                if (s1 >= 0) {
+                    const double dx = X - smx[s1], dy = Y - smy[s1];
+                    q1 = fma(dx, dx, dy * dy);
+                }
+                const double w1 = idw_weight(q1, p2, a.power), w2 = idw_weight(__hiloint2double((int)h2, 0), p2, a.power);
+                const bool dom = live && s1 >= 0 && w1 > 32.0 * w2;
                 const double wmax = dom ? w2 : w1;
                 int E = ((__double2hiint(wmax) >> 20) & 0x7ff) - 1023;
                 E = min(max(E, -900), 900);
-                scale = __hiloint2double((1023 + 54 - E) << 20, 0);      // largest weight in the digits in [2^54, 2^55)
+                es20 = (8 * I8_NW - 2 - E) * (1 << 20);             // largest weight in the digits in [2^46, 2^48)
                 if (dom) {
                     dom_s = s1;
-                    dom_w = w1 * scale;
+                    dom_w = __hiloint2double(__double2hiint(w1) + es20, __double2loint(w1));
                 }
             }
             const bool anydom = __any_sync(0xffffffffu, dom_s >= 0);
             const int dom_i = max(dom_s, 0);
             named_bar_sync(1, I8_WORKERS);                                // qmin / zf are rewritten for the next tile
             for (int kb = kb0; kb < kb1; kb++) {
-                uint32_t wd[I8_NS][8];
+                uint32_t wd[I8_NW][8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     uint32_t lo[4], hi[4];
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
                         const int s = kb * 32 + j * 4 + b;
-                        const double dx = __dsub_rn(X, smx[s]), dy = __dsub_rn(Y, smy[s]);
-                        const double qq = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                        const bool ok = live && s < S && qq != 0.0 && s != dom_s;
-                        const double w = idw_weight(ok ? qq : 1.0, p2, a.power);
-                        const unsigned long long W = ok ? __double2ull_rz(w * scale) : 0ull;
+                        const double dx = X - smx[s], dy = Y - smy[s];
+                        const double qq = fma(dx, dx, dy * dy);
+                        const bool ok = live && s < S && __double2hiint(qq) != 0 && s != dom_s;
+                        // w * 2^es: for power 2 the scale goes into the exponent of the squared distance before the
+                        // reciprocal; the integer comes out of a magic-number add (round to nearest, w * 2^es < 2^48)
+                        double ws;
+                        if (p2) ws = fast_rcp<2>(ok ? __hiloint2double(__double2hiint(qq) - es20, __double2loint(qq)) : 1.0);
+                        else {
+                            const double w = idw_weight_pow(ok ? qq : 1.0, a.power);
+                            ws = __hiloint2double(__double2hiint(w) + es20, __double2loint(w));
+                        }
+                        const unsigned long long W = ok ? (unsigned long long)(__double_as_longlong(ws + 4503599627370496.0) - 0x4330000000000000LL) : 0ull;
                         lo[b] = (uint32_t)W;
                         hi[b] = (uint32_t)(W >> 32);
                     }
 #pragma unroll
-                    for (int i = 0; i < I8_NS; i++) {                    // digit i = byte 6 - i of W
-                        const int byte = 6 - i;
+                    for (int i = 0; i < I8_NW; i++) {                    // digit i = byte 5 - i of W
+                        const int byte = I8_NW - 1 - i;
                         const uint32_t* x = byte >= 4 ? hi : lo;
                         const uint32_t sel = (uint32_t)(byte & 3) | ((uint32_t)(4 + (byte & 3)) << 4);
                         const uint32_t t01 = __byte_perm(x[0], x[1], sel), t23 = __byte_perm(x[2], x[3], sel);
@@ -620,12 +702,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < I8_NS; i++) tmem_st8(tlane + I8_ACOL + (uint32_t)(i * KB + kb) * 8, wd[i]);
+                for (int i = 0; i < I8_NW; i++) tmem_st8(tlane + I8_ACOL + (uint32_t)(i * KB + kb) * 8, wd[i]);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[B_AREADY]);
+            TRACE(21);
 #ifdef I8_PROFILE
             w_gen += clock64() - tg0;
 #endif
@@ -635,14 +718,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             // pack three to a 32-bit word, the numerator's group sums go into two 64-bit words.
             uint32_t v[I8_COLS];
             auto drain = [&]() {
-                const int buf = P & 1;
-                PROF(w_wait, mbar_wait_sleep(&bars[B_ACCFULL + buf], (P >> 1) & 1));
+                const uint32_t buf = abuf;
+                TRACE(10);
+                PROF(w_wait, mbar_wait_sleep(&bars[B_ACCFULL + buf], aph));
+                TRACE(11);
                 tc_fence_after();
                 PROF(w_ld, tmem_ld16(tlane + (uint32_t)(buf * I8_N + h * I8_COLS), v); tmem_ld_wait());
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
-                P++;
+                TRACE(12);
+                if (++abuf == I8_NACC) { abuf = 0; aph ^= 1; }
             };
             // seven denominator passes -> 1 / den for this thread's 16 columns (negative where the exact path is needed)
             auto den_passes = [&](double* rden, auto dom_valid) {     // dom_valid(k): is the dominant station valid in column k
@@ -664,16 +750,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                         for (int k = 0; k < I8_COLS; k++) d2[k] = d2[k] * 256u + v[k];
                     }
                 }
-                drain();                                // D6
-                // den = d1 * 2^32 + d2 * 2^8 + D6 (+ the dominant station's weight); the digits are scaled so that their
-                // largest weight lies in [2^54, 2^55): den < 2^45 = 2^-9 .. 2^-10 of it is where the fixed-point error
-                // stops being negligible -> a negative value marks the exact path
+                // den = d1 * 2^24 + d2 (+ the dominant station's weight); the digits are scaled so that their largest
+                // weight lies in [2^46, 2^47): below den = 2^40 = 2^-6 .. 2^-7 of it the fixed-point error would no longer
+                // be negligible -> a negative value marks the exact path
 #pragma unroll
                 for (int k = 0; k < I8_COLS; k++) {
-                    const double dlo = fma(u32_to_double(d2[k]), 256.0, u32_to_double(v[k]));
-                    double d = fma(u32_to_double(d1[k]), 4294967296.0, dlo);
+                    double d = __ll2double_rn((long long)(((unsigned long long)d1[k] << 24) + d2[k]));     // conversion unit
                     if (anydom) d += dom_valid(k) ? dom_w : 0.0;      // warp-uniform test; dom_w is 0 on the other lanes
-                    rden[k] = d < 35184372088832.0 ? -1.0 : fast_rcp<3>(d);
+                    const double r = rcp_via_f32(d);
+                    rden[k] = __double2hiint(d) < ((1023 + 40) << 20) ? -1.0 : r;       // d >= 0: its high word orders it
                 }
             };
             if (mask_mode) {                            // denominators once per tile: column = mask id
@@ -690,36 +775,24 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             }
 
             // ---- chunks of 48 steps; this thread owns steps [16h, 16h + 16) of each chunk for its cell.
-            // Software pipeline: when the last pass of a chunk has been drained its outputs are only brought to their
-            // value before the retrend (xp); the retrend, the clamp and the stores are spread over the drains of the
-            // NEXT chunk's passes.  The accumulators are therefore always drained promptly and the tensor pipe does not
-            // wait for an epilogue.  {p0, p1} of the retiring chunk sit in a private shared-memory slot of the warp, so
-            // the operand stage is released as soon as the chunk's last pass is drained.
-            double xp[I8_COLS];
+            // (Spreading a chunk's clamp and stores over the next chunk's drains, a quiet window for the fp64 part and
+            // polling instead of suspended barrier waits were all measured: no gain)
+            double xp[I8_COLS];                     // outputs of the chunk before the clamp
             int pt0 = 0;
             uint32_t pslow = 0, pok = 0;            // flagged for the exact path / to be stored by the ordinary path
-            bool pend = false;
             const size_t meta_off = (size_t)8 * plane + (size_t)(h * I8_COLS) * 32;
             double* pop = nullptr;                  // &out[pt0][c]
             const size_t ostride = (size_t)a.ncw;
-            // retrend, clamp, store outputs [K0, K1) of the pending chunk.  One basic block on the common path, so that
-            // the outputs overlap.
-            auto retire = [&](auto K0, auto K1) {
-                constexpr int k0 = decltype(K0)::value, k1 = decltype(K1)::value;
+            // clamp and store the chunk's outputs (no fp64 instruction on the common path)
+            auto retire = [&]() {
+                constexpr int k0 = 0, k1 = I8_COLS;
 #ifdef I8_PROFILE
                 const long long tr0 = clock64();
 #endif
+                TRACE(16);
                 double x[k1 - k0];
 #pragma unroll
-                for (int k = k0; k < k1; k++) {
-                    double y = xp[k];
-                    if (DETREND) {
-                        const double2 pp = wmeta[k];
-                        y = __dadd_rn(__dadd_rn(y, __dmul_rn(pp.x, Z)), pp.y);       // idw.py:144, left to right
-                    }
-                    if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
-                    x[k - k0] = y;
-                }
+                for (int k = k0; k < k1; k++) x[k - k0] = CLAMP ? clamp_nan_keep_fast(xp[k], a.vmin, a.vmax, kmin, kmax) : xp[k];
                 double* q = pop + (size_t)k0 * ostride;
                 if (pok == 0xffffu) {
 #pragma unroll
@@ -732,10 +805,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #ifdef I8_PROFILE
                 w_st += clock64() - tr0;
 #endif
+                TRACE(17);
             };
             // rare: flagged (cell, step) pairs are recomputed from the exact fp64 sums, the whole warp on one pair, and
             // stored at once (the ordinary path skips them: pok); called where few registers are live
-            auto exact_pairs = [&]() {
+            auto exact_pairs = [&](const double* meta) {
                 for (int k = 0; k < I8_COLS; k++) {
                     if (pt0 + k >= a.T) break;
                     uint32_t m = __ballot_sync(0xffffffffu, (pslow >> k) & 1u);
@@ -746,7 +820,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                                                          a.power, a.rec + (size_t)(pt0 + k) * a.RS, a.valid + (size_t)(pt0 + k) * S, lane);
                         if (lane == src) {
                             double y = x;
-                            if (DETREND) y = __dadd_rn(__dadd_rn(y, __dmul_rn(wmeta[k].x, Z)), wmeta[k].y);
+                            if (DETREND) y = __dadd_rn(__dadd_rn(y, __dmul_rn(meta[4 * k], Z)), meta[4 * k + 1]);
                             if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
                             __stcs(a.out + (size_t)(pt0 + k) * (size_t)a.ncw + c, y);
                         }
@@ -755,14 +829,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
             };
             for (int ch = 0; ch < a.nchunk; ch++, G++) {
                 long long lo[I8_COLS], hi[I8_COLS];     // groups 6..3 and 2..0 in radix 256
-                // one numerator pass (group g = i + j of digit products), then a slice of the pending chunk's epilogue
+                // one numerator pass (group g = i + j of digit products)
                 auto num_pass = [&](auto OI) {
                     constexpr int oi = decltype(OI)::value;
                     constexpr int g = (0x2314056 >> (4 * oi)) & 7;       // order 6 5 0 4 1 3 2, as the MMA warp issues them
-                    // the pending chunk retires in four slices of four outputs, after the drains that are followed by a
-                    // long pass (groups 5, 4, 3, 2: the tensor pipe is busy for >= 500 clocks)
-                    constexpr int sl = oi == 0 ? 0 : oi == 2 ? 1 : oi == 4 ? 2 : oi == 5 ? 3 : -1;
-                    constexpr int k0 = sl < 0 ? 0 : sl * (I8_COLS / 4), k1 = sl < 0 ? 0 : (sl + 1) * (I8_COLS / 4);
                     drain();
                     if constexpr (g == 6) {
 #pragma unroll
@@ -786,7 +856,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #pragma unroll
                         for (int k = 0; k < I8_COLS; k++) asm volatile("" : "+l"(hi[k]));
                     }
-                    if constexpr (sl >= 0) if (pend) retire(std::integral_constant<int, k0>{}, std::integral_constant<int, k1>{});
                 };
                 num_pass(std::integral_constant<int, 0>{});
                 num_pass(std::integral_constant<int, 1>{});
@@ -795,12 +864,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 num_pass(std::integral_constant<int, 4>{});
                 num_pass(std::integral_constant<int, 5>{});
                 num_pass(std::integral_constant<int, 6>{});
-                double num[I8_COLS];
+                // numerator as one double (the two 64-bit halves go through the conversion unit): halves the registers
+                // that stay live across the denominator passes
+                double nd[I8_COLS];
 #pragma unroll
-                for (int k = 0; k < I8_COLS; k++) num[k] = fma(s64_to_double(hi[k]), 4294967296.0, s64_to_double(lo[k]));
+                for (int k = 0; k < I8_COLS; k++) nd[k] = fma(__ll2double_rn(hi[k]), 4294967296.0, __ll2double_rn(lo[k]));
                 const int s = G & 1;
                 const double* meta = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes + meta_off);
+                TRACE(13);
                 mbar_wait_sleep(&bars[B_FULL + s], (G >> 1) & 1);      // completed long ago: makes the TMA's writes visible
+                TRACE(14);
                 double den[I8_COLS];
                 if (mask_mode) {                            // 1 / den of each step's mask
 #pragma unroll
@@ -811,14 +884,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                         return __ldg(a.valid + (size_t)t * S + dom_i) != 0;
                     });
                 }
-                // ---- value before the retrend; flags for the exact path
+                // ---- flags for the exact path (sign bits only), then the value before the clamp:
+                //      x = num * (2^k / den) + (p0 Z + p1)
+                // 2^k / den is an exponent add; with the numerator's conversion three DFMAs per output remain
 #ifdef I8_PROFILE
                 const long long tf0 = clock64();
 #endif
                 const int t0 = ch * I8_N + h * I8_COLS;
                 uint32_t slow = 0;
                 {
-                    int anyneg = 0;                              // sign bits only: no fp64 compare on the common path
+                    int anyneg = 0;
 #pragma unroll
                     for (int k = 0; k < I8_COLS; k++) anyneg |= __double2hiint(den[k]);
                     if (anyneg < 0) {
@@ -831,7 +906,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 auto values = [&](auto with_dom) {
 #pragma unroll
                     for (int k = 0; k < I8_COLS; k++) {
-                        double x = (num[k] * den[k]) * meta[4 * k + 2];
+                        const int rh = __double2hiint(den[k]) + reinterpret_cast<const int*>(meta)[8 * k + 7];
+                        const double rb = __hiloint2double(rh, __double2loint(den[k]));
+                        double x;
+                        if (DETREND) {
+                            const double2 pp = *reinterpret_cast<const double2*>(meta + 4 * k);
+                            x = fma(nd[k], rb, fma(pp.x, Z, pp.y));
+                        } else {
+                            x = nd[k] * rb;
+                        }
                         if (decltype(with_dom)::value)     // no per-lane branch: dom_w is 0 on lanes without one
                             x = fma(dom_w * den[k], __ldg(a.rec + (size_t)min(t0 + k, a.T - 1) * a.RS + dom_i), x);
                         xp[k] = x;
@@ -839,28 +922,24 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 };
                 if (anydom) values(std::true_type{});
                 else values(std::false_type{});
-                // {p0, p1} of these steps into the warp's slot (the previous chunk has retired), then release the stage
-                if (lane < I8_COLS) wmeta[lane] = *reinterpret_cast<const double2*>(meta + 4 * lane);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[B_EMPTY + s]);
                 pt0 = t0;
                 pop = a.out + (size_t)t0 * ostride + c;
                 pslow = live ? slow : 0u;
                 pok = (live ? ~slow : 0u) & (t0 + I8_COLS <= a.T ? 0xffffu : ((1u << max(a.T - t0, 0)) - 1u));
-                pend = true;
-                if (__any_sync(0xffffffffu, pslow != 0)) exact_pairs();
+                retire();
+                if (__any_sync(0xffffffffu, pslow != 0)) exact_pairs(meta);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_EMPTY + s]);        // the stage's meta has been read
+                TRACE(15);
 #ifdef I8_PROFILE
                 w_fin += clock64() - tf0;
 #endif
-            }
-            if (pend) {                                      // the tile's last chunk
-                retire(std::integral_constant<int, 0>{}, std::integral_constant<int, I8_COLS>{});
             }
         }
 #ifdef I8_PROFILE
         if (a.prof && tid == 0) {
             long long* pr = a.prof + 16 * blockIdx.x;
-            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld; pr[13] = 0; pr[14] = w_st;
+            pr[8] = clock64() - w_tot; pr[9] = w_gen; pr[10] = w_wait; pr[11] = w_fin; pr[12] = w_ld; pr[13] = 0; pr[14] = w_st; pr[15] = 0;
         }
 #endif
     }
@@ -934,10 +1013,10 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
     a.maskhdr = d_hdr;
     a.vu = d_vu;
     a.prof = nullptr;
-#ifdef I8_PROFILE
+#if defined(I8_PROFILE) || defined(I8_TRACE)
     static long long* d_prof = nullptr;
-    if (!d_prof) cudaMalloc(&d_prof, 16 * 8 * 1024);
-    cudaMemsetAsync(d_prof, 0, 16 * 8 * 1024, st);
+    if (!d_prof) cudaMalloc(&d_prof, 32 * 8 * 1024);
+    cudaMemsetAsync(d_prof, 0, 32 * 8 * 1024, st);
     a.prof = d_prof;
 #endif
     int sms = 0;
@@ -959,8 +1038,25 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
         long long hp[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hp, a.prof, sizeof(hp), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, chunk-end values %lld (unused %lld), retire slices %lld\n",
-                (a.ntiles + (int)grid - 1) / (int)grid, nchunk, hp[0], hp[1], hp[2], hp[3], hp[8], hp[9], hp[10], hp[12], hp[11], hp[13], hp[14]);
+        fprintf(stderr, "[i8 prof, CTA 0, %d tiles x %d chunks] MMA warp: total %lld, wait A %lld, wait stage %lld, wait acc %lld | worker 0: total %lld, wgen %lld, wait accfull %lld, tmem ld %lld, chunk-end values %lld (conversion %lld), retire slices %lld, wait stage %lld\n",
+                (a.ntiles + (int)grid - 1) / (int)grid, nchunk, hp[0], hp[1], hp[2], hp[3], hp[8], hp[9], hp[10], hp[12], hp[11], hp[13], hp[14], hp[15]);
+    }
+#endif
+#ifdef I8_TRACE
+    {
+        static int dumped = 0;
+        if (!dumped++) {
+            std::vector<long long> tr(16 * 1024);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(tr.data(), a.prof + 16 * 1024, tr.size() * 8, cudaMemcpyDeviceToHost);
+            FILE* f = fopen("gpurun_out/i8_trace.txt", "w");
+            if (f) {
+                for (int w = 0; w < 16; w++)
+                    for (int e = 0; e < 1024 && tr[w * 1024 + e]; e++)
+                        fprintf(f, "%d %lld %lld\n", w, tr[w * 1024 + e] >> 48, tr[w * 1024 + e] & 0xffffffffffffLL);
+                fclose(f);
+            }
+        }
     }
 #endif
     return SMRFB_OK;
