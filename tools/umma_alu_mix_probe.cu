@@ -37,7 +37,8 @@ constexpr int N = 48, LBO = (N / 8) * 128, SBO = 128;
 enum { OP_DFMA, OP_DADD, OP_DMUL, OP_DSETP, OP_FFMA, OP_IMAD, OP_IMADWIDE, OP_IADD3, OP_LDS, OP_LDS32, OP_STS, OP_SHFL, OP_MUFU, OP_I2F64, OP_F2F, OP_I2F32, OP_STG, OP_LDG, OP_COUNT };
 static const char* op_name[] = {"DFMA", "DADD", "DMUL", "DSETP+FSEL", "FFMA", "IMAD", "IMAD.WIDE", "IADD3", "LDS.64", "LDS.32", "STS.64", "SHFL", "MUFU.RCP", "I2F.F64.S64", "F2F.F64.F32", "I2F.F32.S32", "STG.64", "LDG.64"};
 
-__global__ void __launch_bounds__(13 * 32) mix(int n_mma, int n_alu, int op, long long* clk, double* sink, double* gbuf) {
+template <int op>
+__global__ void __launch_bounds__(13 * 32) mix(int n_mma, int n_alu, long long* clk, double* sink, double* gbuf) {
     __shared__ __align__(128) uint8_t sB[2 * 2 * LBO];
     __shared__ __align__(16) double sD[13 * 32];
     __shared__ __align__(8) uint64_t bar;
@@ -140,7 +141,11 @@ int main() {
     const int n_mma = 8000;
     auto run = [&](int nm, int na, int op, double* mma_clk, double* alu_clk) {
         cudaMemset(dclk, 0, 2 * sms * 8);
-        mix<<<sms, 13 * 32>>>(nm, na, op, dclk, dsink, dgbuf);
+        switch (op) {
+#define CASE(o) case o: mix<o><<<sms, 13 * 32>>>(nm, na, dclk, dsink, dgbuf); break;
+            CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17)
+#undef CASE
+        }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
         long long c[2];
