@@ -193,7 +193,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-I8_TRAFFIC = None     # dram bytes of one idw_i8_kernel launch at the C4 slab shape (ncu --set full, profiles/r01_i8_ncu.md)
+I8_TRAFFIC = 57.64e9  # dram bytes of one idw_i8_kernel launch at the C4 slab shape (ncu --set full, profiles/r01_i8_ncu.md)
 
 
 def load_peaks():
