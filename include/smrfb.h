@@ -128,6 +128,14 @@ int smrfb_grid_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int
                               double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
                               double* d_out, void* stream);
 
+/* detrendedInterpolationLocal (grid.py:115-177) with grid_method = 'linear': fields3[T][3][npts] holds per step the
+ * residual, the slope and the intercept of the per-point local fits (grid.py:125-141,164-166; computed by the
+ * caller, smrf_b200/spatial/grid.py); out[t] = interp(residual) + interp(slope) * GridZ + interp(intercept), each
+ * interpolation as griddata / LinearNDInterpolator evaluates it (utils.py:430-449), NaN outside the hull. */
+int smrfb_grid_distribute_local(smrfb_handle_t h, const double* fields3, int T, double vmin, double vmax, double* out);
+int smrfb_grid_distribute_local_dev(smrfb_handle_t h, const double* d_fields3, int T, double vmin, double vmax,
+                                    double* d_out, void* stream);
+
 /* ------------------------------------------------------------------ clamp (utils.py:137-161) */
 /* In place on a host array: x<=vmin -> vmin, x>=vmax -> vmax, NaN stays NaN. */
 int smrfb_set_min_max(double* data, int64_t n, double vmin, double vmax, int device);

@@ -311,10 +311,47 @@ def linear_apply(plan, values, GridX, GridY):
     return out.reshape(GridX.shape)
 
 
-class GRID:
-    """Reference GRID restricted to what the path covers: linear, mask (non-local) detrend.
+def local_neighbours(lat, lon, k):
+    """grid.py:54-65: for every point the k nearest points in latitude / longitude space (itself first), in the
+    order of pandas' Series.sort_values() = numpy's default (quick)sort of the distances."""
+    lat = np.asarray(lat, dtype=float)
+    lon = np.asarray(lon, dtype=float)
+    nbr = np.empty((len(lat), k), dtype=np.int32)
+    for i in range(len(lat)):
+        d = np.sqrt((lat - lat[i]) ** 2 + (lon - lon[i]) ** 2)
+        nbr[i] = np.argsort(d, kind="quicksort")[:k]
+    return nbr
 
-    grid.py:23-94 (ctor / point mask), :179-212 (detrendedInterpolationMask), :214-231.
+
+def local_fit(data, elevation, nbr, flag):
+    """grid.py:125-141 and :164-166 for one timestep: per point a line through its k neighbours (np.polyfit on the
+    neighbours in table order), the slope constraint, and the residual of the point's FIRST neighbour (the frame is
+    de-duplicated with keep='first').  Returns dtrend, slope, intercept, each [P]."""
+    data = np.asarray(data, dtype=float)
+    elevation = np.asarray(elevation, dtype=float)
+    P = nbr.shape[0]
+    slope = np.empty(P)
+    intercept = np.empty(P)
+    for i in range(P):
+        slope[i], intercept[i] = np.polyfit(elevation[nbr[i]], data[nbr[i]], 1)
+    if flag == 1:
+        z = slope < 0
+    elif flag == -1:
+        z = slope > 0
+    else:
+        z = np.zeros(P, dtype=bool)
+    slope[z] = 0.0
+    intercept[z] = 0.0
+    first = nbr[:, 0]
+    el_trend = elevation[first] * slope + intercept
+    return data[first] - el_trend, slope, intercept
+
+
+class GRID:
+    """Reference GRID restricted to what the path covers: linear / nearest, mask and local detrend.
+
+    grid.py:23-94 (ctor / neighbour table / point mask), :115-177 (detrendedInterpolationLocal), :179-212
+    (detrendedInterpolationMask), :214-231.
     """
 
     def __init__(self, config, mx, my, GridX, GridY, mz=None, GridZ=None, mask=None, metadata=None):
@@ -322,8 +359,10 @@ class GRID:
         self.mx, self.my, self.mz = mx, my, mz
         self.GridX, self.GridY, self.GridZ = GridX, GridY, GridZ
         self.npoints = len(mx)
+        self.metadata = metadata
         if config.get("grid_local"):
-            raise NotImplementedError("grid_local is a 'next' row (SURVEY.md 8f N-b)")
+            self.nbr = local_neighbours(metadata.latitude.values, metadata.longitude.values, config["grid_local_n"])
+            self.tri = None
         if config["grid_mask"]:
             assert mask.shape == GridX.shape
             self.mask = point_mask(mx, my, GridX, GridY, mask)
@@ -334,10 +373,27 @@ class GRID:
         from scipy.interpolate import griddata
 
         data = np.asarray(data, dtype=float)
+        if self.config.get("grid_local"):
+            return self.detrendedInterpolationLocal(data, flag, grid_method)
         self.pv = fit_trend(np.asarray(self.mz)[self.mask].astype(float), data[self.mask], flag)
         dtrend = data - (self.mz * self.pv[0] + self.pv[1])
         idtrend = griddata((self.mx, self.my), dtrend, (self.GridX, self.GridY), method=grid_method)
         return idtrend + self.pv[0] * self.GridZ + self.pv[1]
+
+    def detrendedInterpolationLocal(self, data, flag=0, grid_method="linear"):
+        """grid.py:115-177 with grid_method='linear' (utils.py:430-449: LinearNDInterpolator on the cached tri)."""
+        from scipy.interpolate import LinearNDInterpolator
+        from scipy.spatial import Delaunay
+
+        md = self.metadata
+        dtrend, slope, intercept = local_fit(data, md.elevation.values, self.nbr, flag)
+        if self.tri is None:
+            self.tri = Delaunay(np.column_stack([md.utm_x.values, md.utm_y.values]))
+        pts = (self.GridX, self.GridY)
+        grid_slope = LinearNDInterpolator(self.tri, slope)(pts)
+        grid_intercept = LinearNDInterpolator(self.tri, intercept)(pts)
+        idtrend = LinearNDInterpolator(self.tri, dtrend)(pts)
+        return idtrend + grid_slope * self.GridZ + grid_intercept
 
     def calculateInterpolation(self, data, grid_method="linear"):
         from scipy.interpolate import griddata

@@ -65,6 +65,10 @@ _SIGS = {
     "smrfb_grid_distribute_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_grid_distribute_local": (ctypes.c_int, [handle_t, c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                   c_double_p]),
+    "smrfb_grid_distribute_local_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
+                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_set_min_max": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
 }
 

@@ -31,6 +31,10 @@ struct GridHandle : HandleBase {
     size_t vt_cap = 0;
     double* d_pvt = nullptr;           // [T_pad][2]
     size_t pvt_cap = 0;
+    double* d_l4 = nullptr;            // grid_local: [T][4][S] residual, slope, intercept, 0 per step
+    size_t l4_cap = 0;
+    double* d_l3 = nullptr;            // grid_local: staging of the caller's [T][3][S] block
+    size_t l3_cap = 0;
     GridHandle() : HandleBase(HK_GRID) {}
     ~GridHandle() override {
         cudaSetDevice(device);
@@ -40,6 +44,8 @@ struct GridHandle : HandleBase {
         cudaFree(d_cell_nearest);
         cudaFree(d_vt);
         cudaFree(d_pvt);
+        cudaFree(d_l4);
+        cudaFree(d_l3);
     }
 };
 
@@ -212,6 +218,115 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute2_kernel(GridArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------ grid_local
+// detrendedInterpolationLocal (grid.py:115-177, grid_method 'linear'): three point fields per step -- the residual,
+// the slope and the intercept of the per-point local fits (host side, smrf_b200/spatial/grid.py) -- are interpolated
+// with the same barycentric weights and combined per cell:
+//   out = (interp(residual) + interp(slope) * Z) + interp(intercept)                                (grid.py:175)
+// each interpolation in griddata's operation order.  vt[point][4 t + f]: f = 0 residual, 1 slope, 2 intercept.
+struct GridLocalCell {
+    double c0, c1, c2, Z;
+    const double *va, *vb, *vc;
+    bool inside;
+};
+
+__device__ __forceinline__ GridLocalCell grid_local_setup(const GridArgs& a, long long c) {
+    GridLocalCell g;
+    const int sx = __ldg(a.cell_simplex + c);
+    g.inside = sx >= 0;
+    const int s0 = g.inside ? sx : 0;
+    double X, Y;
+    cell_xy(a.g, c, X, Y);
+    const double* Tm = a.transform + (size_t)s0 * 6;
+    const double dx = __dsub_rn(X, __ldg(Tm + 4)), dy = __dsub_rn(Y, __ldg(Tm + 5));
+    g.c0 = __dadd_rn(__dmul_rn(__ldg(Tm + 0), dx), __dmul_rn(__ldg(Tm + 1), dy));
+    g.c1 = __dadd_rn(__dmul_rn(__ldg(Tm + 2), dx), __dmul_rn(__ldg(Tm + 3), dy));
+    g.c2 = __dsub_rn(__dsub_rn(1.0, g.c0), g.c1);
+    g.va = a.vt + (size_t)__ldg(a.simplices + 3 * s0 + 0) * a.T_pad;     // T_pad: row length of vt (>= 4 T)
+    g.vb = a.vt + (size_t)__ldg(a.simplices + 3 * s0 + 1) * a.T_pad;
+    g.vc = a.vt + (size_t)__ldg(a.simplices + 3 * s0 + 2) * a.T_pad;
+    g.Z = a.g.dem ? __ldg(a.g.dem + c) : 0.0;
+    return g;
+}
+
+__device__ __forceinline__ double grid_local_value(const GridLocalCell& g, int t, double vmin, double vmax) {
+    const double2 a01 = __ldg(reinterpret_cast<const double2*>(g.va + 4 * t));
+    const double2 b01 = __ldg(reinterpret_cast<const double2*>(g.vb + 4 * t));
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.vc + 4 * t));
+    const double a2 = __ldg(g.va + 4 * t + 2), b2 = __ldg(g.vb + 4 * t + 2), c2 = __ldg(g.vc + 4 * t + 2);
+    const double res = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g.c0, a01.x)), __dmul_rn(g.c1, b01.x)), __dmul_rn(g.c2, c01.x));
+    const double slo = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g.c0, a01.y)), __dmul_rn(g.c1, b01.y)), __dmul_rn(g.c2, c01.y));
+    const double icp = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(g.c0, a2)), __dmul_rn(g.c1, b2)), __dmul_rn(g.c2, c2));
+    const double v = __dadd_rn(__dadd_rn(res, __dmul_rn(slo, g.Z)), icp);
+    return g.inside ? clamp_nan_keep(v, vmin, vmax) : nan("");
+}
+
+__global__ void __launch_bounds__(GRID_THREADS) grid_local_kernel(GridArgs a) {          // one cell per thread
+    const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (c >= a.g.ncell) return;
+    const GridLocalCell g = grid_local_setup(a, c);
+    const size_t ncell = (size_t)a.g.ncell;
+    double* op = a.out + c;
+    for (int t = 0; t < a.T; t++) __stcs(op + (size_t)t * ncell, grid_local_value(g, t, a.vmin, a.vmax));
+}
+
+__global__ void __launch_bounds__(GRID_THREADS) grid_local2_kernel(GridArgs a) {         // two adjacent cells, 128-bit stores
+    const long long c = ((long long)blockIdx.x * GRID_THREADS + threadIdx.x) * 2;
+    if (c >= a.g.ncell) return;                       // ncell is even: c + 1 is a valid cell too
+    const GridLocalCell g0 = grid_local_setup(a, c), g1 = grid_local_setup(a, c + 1);
+    const size_t ncell = (size_t)a.g.ncell;
+    double* op = a.out + c;
+#pragma unroll 2
+    for (int t = 0; t < a.T; t++)
+        __stcs(reinterpret_cast<double2*>(op + (size_t)t * ncell),
+               make_double2(grid_local_value(g0, t, a.vmin, a.vmax), grid_local_value(g1, t, a.vmin, a.vmax)));
+}
+
+// d_f3: [T][3][S] on the device (residual, slope, intercept rows per step)
+static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin, double vmax, double* d_out, cudaStream_t st) {
+    SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    SMRFB_CHECK(h->g.dem, SMRFB_ERR_ARG, "grid_local needs GridZ");
+    const size_t S = (size_t)h->S;
+    const int R = 4 * T, R_pad = (R + 31) / 32 * 32;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_l4, &h->l4_cap, (size_t)R * S * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_rec, &h->rec_cap, (size_t)R_pad * h->L.RS * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_vt, &h->vt_cap, (size_t)R_pad * S * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pvt, &h->pvt_cap, (size_t)R_pad * 2 * sizeof(double)));
+    SMRFB_CUDA(cudaMemsetAsync(h->d_l4, 0, (size_t)R * S * sizeof(double), st));
+    SMRFB_CUDA(cudaMemcpy2DAsync(h->d_l4, 4 * S * sizeof(double), d_f3, 3 * S * sizeof(double), 3 * S * sizeof(double), (size_t)T,
+                                 cudaMemcpyDeviceToDevice, st));
+    SMRFB_PROPAGATE(launch_prep(st, h->d_l4, R, R_pad, h->S, h->L, nullptr, nullptr, 0, 0, nullptr, nullptr, h->d_rec, nullptr,
+                                h->d_flags));
+    dim3 tb(32, 8), tg((h->S + 31) / 32, R_pad / 32);
+    grid_transpose_kernel<<<tg, tb, 0, st>>>(h->d_rec, h->L, R_pad, h->d_vt, h->d_pvt);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    GridArgs a;
+    a.g = h->g;
+    a.simplices = h->d_simplices;
+    a.transform = h->d_transform;
+    a.cell_simplex = h->d_cell_simplex;
+    a.cell_nearest = nullptr;
+    a.vt = h->d_vt;
+    a.pvt = h->d_pvt;
+    a.T = T;
+    a.T_pad = R_pad;
+    a.detrend = 1;
+    a.vmin = vmin;
+    a.vmax = vmax;
+    a.out = d_out;
+    const long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
+    SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+    if ((h->g.ncell & 1) == 0 && !getenv("SMRFB_GRID_ONE_CELL")) {
+        const long long nb2 = (h->g.ncell / 2 + GRID_THREADS - 1) / GRID_THREADS;
+        grid_local2_kernel<<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
+    } else
+        grid_local_kernel<<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
 static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int slope_flag, int method, double vmin,
                     double vmax, const double* d_pv_in, double* d_pv_out, double* d_out, cudaStream_t st) {
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
@@ -325,6 +440,31 @@ int smrfb_grid_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, in
     SMRFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return grid_run(h, d_data, T, detrend, slope_flag, method, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+}
+
+int smrfb_grid_distribute_local_dev(smrfb_handle_t hh, const double* d_fields3, int T, double vmin, double vmax, double* d_out,
+                                    void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CHECK(d_fields3 && d_out, SMRFB_ERR_ARG, "NULL fields/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return grid_local_run(h, d_fields3, T, vmin, vmax, d_out, st);
+}
+
+int smrfb_grid_distribute_local(smrfb_handle_t hh, const double* fields3, int T, double vmin, double vmax, double* out) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CHECK(fields3 && out && T > 0, SMRFB_ERR_ARG, "NULL fields/out or T <= 0");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_l3, &h->l3_cap, (size_t)T * 3 * S * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpyAsync(h->d_l3, fields3, (size_t)T * 3 * S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return run_host_batches(h, T, 32, out, [&](int t0, int tn, double* d_out, cudaStream_t st) {
+        return grid_local_run(h, h->d_l3 + (size_t)t0 * 3 * S, tn, vmin, vmax, d_out, st);
+    });
 }
 
 int smrfb_grid_distribute(smrfb_handle_t hh, const double* data, int T, int detrend, int slope_flag, int method,

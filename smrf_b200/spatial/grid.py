@@ -6,8 +6,11 @@ every cell on every call (scipy.interpolate.griddata); here the Delaunay triangu
 simplex of every cell are built ONCE on the host with scipy -- the same qhull call the reference
 makes -- and the per-timestep work (barycentric interpolation, retrend, clamp) is one CUDA kernel.
 
-Covered: grid_method='linear' and 'nearest', grid_local=False (detrendedInterpolationMask,
-calculateInterpolation).  'cubic' and grid_local raise NotImplementedError (SURVEY.md section 8f row N-b).
+Covered: grid_method='linear' and 'nearest' with grid_local=False (detrendedInterpolationMask,
+calculateInterpolation), and grid_method='linear' with grid_local=True (detrendedInterpolationLocal,
+grid.py:115-177: the per-point local fits stay on the host -- P ~ 5000 points x k neighbours -- and the
+three interpolations plus their combination are ONE kernel).  'cubic' raises NotImplementedError
+(SURVEY.md section 8f row N-b).
 """
 import numpy as np
 
@@ -27,8 +30,21 @@ class GRID:
         self.shape = tuple(np.shape(GridX))
         self.metadata = metadata
         self.pv = None
-        if config.get("grid_local", False):
-            raise NotImplementedError("grid_local=True is not on the B200 path yet (SURVEY.md 8f N-b)")
+        self.grid_local = bool(config.get("grid_local", False))
+        if self.grid_local:
+            # neighbour table, grid.py:54-65: the k nearest points in latitude / longitude space, in the order of
+            # pandas' Series.sort_values() (= numpy's default sort), as positions into the metadata frame
+            k = int(config["grid_local_n"])
+            lat = np.asarray(metadata.latitude.values, dtype=np.float64)
+            lon = np.asarray(metadata.longitude.values, dtype=np.float64)
+            self.nbr = np.empty((len(lat), k), dtype=np.int64)
+            for i in range(len(lat)):
+                d = np.sqrt((lat - lat[i]) ** 2 + (lon - lon[i]) ** 2)
+                self.nbr[i] = np.argsort(d, kind="quicksort")[:k]
+            self._elev = np.asarray(metadata.elevation.values, dtype=np.float64)
+            # the local path triangulates the metadata's utm coordinates (grid.py:145-148)
+            self.mx = _lib.as_f64(metadata.utm_x.values)
+            self.my = _lib.as_f64(metadata.utm_y.values)
 
         # point mask, grid.py:80-94 (first minimum wins, like np.argmin)
         if config.get("grid_mask", False):
@@ -105,14 +121,81 @@ class GRID:
         self.pv_block = pv_out
         return out
 
+    # ------------------------------------------------------------------ grid_local (grid.py:115-177)
+    def local_fit(self, data, flag=0, exact=True):
+        """Per-point local trend of a block [T, npoints]: (residual, slope, intercept), each [T, npoints].
+
+        exact=True calls np.polyfit per point and step like the reference's groupby/apply (grid.py:125-128), so the
+        coefficients are bit-identical; exact=False is the closed-form least-squares line, vectorised over the
+        block (agrees to ~1e-13 relative; use it for long blocks)."""
+        data = _lib.as_f64(data)
+        if data.ndim == 1:
+            data = data[None, :]
+        T, P = data.shape
+        ze = self._elev[self.nbr]                                   # [P, k]
+        slope = np.empty((T, P))
+        icpt = np.empty((T, P))
+        if exact:
+            for t in range(T):
+                zd = data[t][self.nbr]
+                for i in range(P):
+                    slope[t, i], icpt[t, i] = np.polyfit(ze[i], zd[i], 1)
+        else:
+            zm = ze.mean(axis=1)
+            zc = ze - zm[:, None]
+            szz = (zc * zc).sum(axis=1)
+            dn = data[:, self.nbr]                                  # [T, P, k]
+            dm = dn.mean(axis=2)
+            slope = ((dn - dm[:, :, None]) * zc[None]).sum(axis=2) / szz[None]
+            icpt = dm - slope * zm[None]
+        if flag == 1:
+            z = slope < 0
+        elif flag == -1:
+            z = slope > 0
+        else:
+            z = np.zeros_like(slope, dtype=bool)
+        slope[z] = 0.0
+        icpt[z] = 0.0
+        first = self.nbr[:, 0]                                      # drop_duplicates(keep='first'), grid.py:131-133
+        res = data[:, first] - (self._elev[first][None] * slope + icpt)
+        return res, slope, icpt
+
+    def distribute_block_local(self, data, flag=0, vmin=None, vmax=None, out=None, exact=False):
+        """[T, npoints] -> float64 [T, ny, nx]: detrendedInterpolationLocal for a block of steps, one launch."""
+        res, slope, icpt = self.local_fit(data, flag, exact=exact)
+        T = res.shape[0]
+        f3 = np.ascontiguousarray(np.stack([res, slope, icpt], axis=1))      # [T, 3, P]
+        if out is None:
+            out = np.empty((T,) + self.shape, dtype=np.float64)
+        lo = -np.inf if vmin is None else float(vmin)
+        hi = np.inf if vmax is None else float(vmax)
+        _lib.check(_lib.lib().smrfb_grid_distribute_local(self._h, _lib.dptr(f3), T, lo, hi, _lib.dptr(out)))
+        return out
+
+    def detrendedInterpolationLocal(self, data, flag=0, grid_method="linear"):
+        """grid.py:115-177.  ``data``: pandas Series indexed like the metadata, or an array in metadata order."""
+        if grid_method != "linear":
+            raise NotImplementedError("grid_local with grid_method=%r: only 'linear' is on the B200 path" % grid_method)
+        if hasattr(data, "loc") and self.metadata is not None:
+            data = data.loc[self.metadata.index].values
+        return self.distribute_block_local(np.asarray(data, dtype=np.float64)[None, :], flag=flag, exact=True)[0]
+
     def detrendedInterpolation(self, data, flag=0, grid_method="linear"):
-        """grid.py:96-113 -> detrendedInterpolationMask (grid.py:179-212). ``data`` may be a pandas Series."""
+        """grid.py:96-113 -> detrendedInterpolationLocal (grid_local) or detrendedInterpolationMask (grid.py:179-212).
+        ``data`` may be a pandas Series."""
+        if self.grid_local:
+            return self.detrendedInterpolationLocal(data, flag, grid_method)
         v = self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=True, flag=flag,
                                   grid_method=grid_method)[0]
         self.pv = self.pv_block[0].copy()
         return v
 
-    detrendedInterpolationMask = detrendedInterpolation
+    def detrendedInterpolationMask(self, data, flag=0, grid_method="linear"):
+        """grid.py:179-212."""
+        v = self.distribute_block(np.asarray(data, dtype=np.float64)[None, :], detrend=True, flag=flag,
+                                  grid_method=grid_method)[0]
+        self.pv = self.pv_block[0].copy()
+        return v
 
     def calculateInterpolation(self, data, grid_method="linear"):
         """grid.py:214-231."""

@@ -78,3 +78,60 @@ def test_grid_vs_oracle_larger(sp):
     out = grid.distribute_block(f, detrend=False)
     uses = np.any(plan["simplices"][np.maximum(plan["simplex"], 0)] == 40, axis=1) & (plan["simplex"] >= 0)
     np.testing.assert_array_equal(np.isnan(out[1]).ravel(), uses | (plan["simplex"] < 0))
+
+
+def _local_metadata(g):
+    import pandas as pd
+    idx = ["p%03d" % i for i in range(len(g["px"]))]
+    return pd.DataFrame({"utm_x": g["px"], "utm_y": g["py"], "elevation": g["pz"], "latitude": g["lat"],
+                         "longitude": g["lon"]}, index=idx)
+
+
+def test_grid_local_golden(sp, golden, monkeypatch):
+    """grid_local=True, grid_method='linear' (detrendedInterpolationLocal, grid.py:115-177) against the vectors the
+    reference produced: neighbour table and values bit-exact (the per-point fits are np.polyfit on the host like the
+    reference's, the three interpolations and their combination run in one kernel in griddata's operation order)."""
+    import pandas as pd
+    g = golden("grid_local")
+    X, Y = np.meshgrid(g["x"], g["y"])
+    md = _local_metadata(g)
+    cfg = {"grid_local": True, "grid_local_n": int(g["k"]), "grid_mask": False}
+    grid = sp.GRID(cfg, g["px"], g["py"], X, Y, mz=g["pz"], GridZ=g["dem"], metadata=md)
+    np.testing.assert_array_equal(grid.nbr, g["nbr"])
+    for flag in (-1, 0, 1):
+        ref = g["out_f%d" % flag]
+        for t, row in enumerate(g["fields"]):
+            v = grid.detrendedInterpolation(pd.Series(row.copy(), index=md.index), flag, "linear")
+            np.testing.assert_array_equal(v, ref[t])                              # bit-exact, NaN outside the hull
+        out = grid.distribute_block_local(g["fields"], flag=flag, exact=True)
+        np.testing.assert_array_equal(out, ref)
+        fast = grid.distribute_block_local(g["fields"], flag=flag)               # closed-form fits, vectorised
+        for t in range(len(ref)):
+            assert parity(fast[t], ref[t], step_scale(g["fields"][t])) <= TOL
+    # clamp fused; one-cell-per-thread kernel (odd cell counts take it) agrees bit for bit
+    lo, hi = float(np.nanpercentile(g["out_f0"], 20)), float(np.nanpercentile(g["out_f0"], 80))
+    clamped = grid.distribute_block_local(g["fields"], flag=0, vmin=lo, vmax=hi, exact=True)
+    np.testing.assert_array_equal(clamped, np.where(np.isnan(g["out_f0"]), np.nan, np.clip(g["out_f0"], lo, hi)))
+    monkeypatch.setenv("SMRFB_GRID_ONE_CELL", "1")
+    np.testing.assert_array_equal(grid.distribute_block_local(g["fields"], flag=-1, exact=True), g["out_f-1"])
+    with pytest.raises(NotImplementedError):
+        grid.detrendedInterpolation(g["fields"][0], 0, "cubic")
+
+
+def test_grid_local_vs_oracle_larger(sp):
+    """A larger synthetic basin (more points than the golden case, 37 steps = two transposition tiles)."""
+    import pandas as pd
+    from oracle import oracle as orc
+    from smrf_b200 import synthetic as syn
+    x, y, dem = syn.make_dem(90, 131, dx=60.0, seed=4)
+    X, Y = np.meshgrid(x, y)
+    px, py, pz = syn.make_source_lattice(x, y, dem, spacing=700.0, jitter=80.0, seed=8)
+    md = pd.DataFrame({"utm_x": px, "utm_y": py, "elevation": pz, "latitude": 43.0 + (py - py.min()) / 111000.0,
+                       "longitude": -116.0 + (px - px.min()) / 82000.0})
+    f = syn.make_source_fields(px, py, pz, 37, seed=2)
+    cfg = {"grid_local": True, "grid_local_n": 12, "grid_mask": False}
+    grid = sp.GRID(cfg, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+    o = orc.GRID(cfg, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+    out = grid.distribute_block_local(f, flag=-1)
+    for t in (0, 17, 36):
+        assert parity(out[t], o.detrendedInterpolation(f[t].copy(), -1, "linear"), step_scale(f[t])) <= TOL

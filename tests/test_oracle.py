@@ -141,3 +141,28 @@ def test_grid_synth_bitwise(golden):
                 np.testing.assert_array_equal(v2, v)
     for t, row in enumerate(g["fields"]):
         np.testing.assert_array_equal(orc.linear_apply(plan, row, X, Y), g["out_plain"][t])
+
+
+def _local_metadata(g):
+    import pandas as pd
+    return pd.DataFrame({"utm_x": g["px"], "utm_y": g["py"], "elevation": g["pz"], "latitude": g["lat"],
+                         "longitude": g["lon"]})
+
+
+def test_grid_local_bitwise(golden):
+    """detrendedInterpolationLocal (grid.py:115-177, executed by the reference: tests/golden/make_golden_local.py):
+    neighbour table, per-point fits with the slope constraint, three interpolations and their combination."""
+    g = golden("grid_local")
+    X, Y = np.meshgrid(g["x"], g["y"])
+    cfg = {"grid_local": True, "grid_local_n": int(g["k"]), "grid_mask": False}
+    o = orc.GRID(cfg, g["px"], g["py"], X, Y, mz=g["pz"], GridZ=g["dem"], metadata=_local_metadata(g))
+    np.testing.assert_array_equal(o.nbr, g["nbr"])
+    assert np.isnan(g["out_f0"][0]).sum() > 0
+    for flag in (-1, 0, 1):
+        for t, row in enumerate(g["fields"]):
+            np.testing.assert_array_equal(o.detrendedInterpolation(row.copy(), flag, "linear"), g["out_f%d" % flag][t])
+    # the constraint bites: flag +1 zeroes the fits with a negative slope (these fields have a lapse rate)
+    res, slope, icpt = orc.local_fit(g["fields"][0], g["pz"], g["nbr"], 1)
+    res0, slope0, _ = orc.local_fit(g["fields"][0], g["pz"], g["nbr"], 0)
+    assert (slope0 < 0).any() and not (slope < 0).any() and np.all(icpt[slope0 < 0] == 0.0)
+    assert not np.array_equal(g["out_f1"], g["out_f0"])

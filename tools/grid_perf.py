@@ -31,3 +31,26 @@ for det in (1, 0):
     ms = e0.elapsed_time(e1) / 3
     cs = ny * nx * T / (ms * 1e-3)
     print("GRID %dx%d P=%d T=%d detrend=%d: %.2f ms  %.1f G cell-steps/s  write %.0f GB/s" % (ny, nx, len(px), T, det, ms, cs / 1e9, cs * 8 / 1e9))
+
+# grid_local (detrendedInterpolationLocal): three point fields per step, one kernel
+import pandas as pd
+md = pd.DataFrame({"utm_x": px, "utm_y": py, "elevation": pz, "latitude": 43.0 + (py - py.min()) / 111000.0,
+                   "longitude": -116.0 + (px - px.min()) / 82000.0})
+t0 = time.perf_counter()
+gl = GRID({"grid_local": True, "grid_local_n": 25, "grid_mask": False}, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+print("grid_local create (neighbour table as the reference builds it + Delaunay + upload): %.2f s" % (time.perf_counter() - t0))
+t0 = time.perf_counter()
+res, slope, icpt = gl.local_fit(f, flag=-1, exact=False)
+print("local fits of %d steps x %d points (closed form, host): %.3f s" % (T, len(px), time.perf_counter() - t0))
+d_f3 = torch.from_numpy(np.ascontiguousarray(np.stack([res, slope, icpt], axis=1))).cuda()
+for _ in range(2):
+    _lib.check(L.smrfb_grid_distribute_local_dev(gl._h, d_f3.data_ptr(), T, -50.0, 50.0, d_out.data_ptr(), st))
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+for _ in range(3):
+    _lib.check(L.smrfb_grid_distribute_local_dev(gl._h, d_f3.data_ptr(), T, -50.0, 50.0, d_out.data_ptr(), st))
+e1.record(stream); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 3
+cs = ny * nx * T / (ms * 1e-3)
+print("GRID local %dx%d P=%d T=%d: %.2f ms  %.1f G cell-steps/s  write %.0f GB/s" % (ny, nx, len(px), T, ms, cs / 1e9, cs * 8 / 1e9))
