@@ -82,6 +82,8 @@ class image_data:
                                             vmin=self.min, vmax=self.max)
         elif dist == "dk":
             blk = self.dk.distribute_block(vals, vmin=self.min, vmax=self.max)
+        elif self.config.get("grid_local") and self.config["detrend"]:     # grid.py:96-113 dispatches on grid_local
+            blk = self.grid.distribute_block_local(vals, flag=self.config.get("detrend_slope", 0), vmin=self.min, vmax=self.max)
         else:
             blk = self.grid.distribute_block(vals, detrend=bool(self.config["detrend"]), flag=self.config.get("detrend_slope", 0),
                                              vmin=self.min, vmax=self.max, grid_method=self.config.get("grid_method", "linear"))
