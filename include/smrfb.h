@@ -39,6 +39,7 @@
 #ifndef SMRFB_H
 #define SMRFB_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -64,6 +65,15 @@ int smrfb_destroy(smrfb_handle_t h);
 int smrfb_synchronize(smrfb_handle_t h);
 /* Number of kernels this library has launched since load (all handles); bench.py's gpu_launches. */
 int64_t smrfb_launch_count(void);
+/* Output element type of every later distribute call on this handle: 0 = float64 (default; the parity contract of
+ * 1e-9), 1 = float32 (the type the reference's output files hold, smrf/output/output_netcdf.py:58,90-93 and
+ * CoreConfig.ini:1167-1170; contract 1e-5).  The arithmetic stays fp64; the value is rounded once at the store.
+ * With dtype 1 every `out` / `d_out` argument below points to float [T][ncell] although it is declared double*. */
+int smrfb_set_output_dtype(smrfb_handle_t h, int dtype);
+/* Page-locked host memory for outputs (D2H copies into pageable memory are staged by the driver at a fraction of the
+ * PCIe rate).  The drop-in classes return NumPy arrays that live in such blocks and give them back when collected. */
+int smrfb_host_alloc(size_t bytes, void** out);
+int smrfb_host_free(void* p);
 
 /* ------------------------------------------------------------------ IDW (idw.py) */
 int smrfb_idw_create(int nsta, const double* mx, const double* my, const double* mz /* nullable */,
@@ -121,7 +131,7 @@ int smrfb_grid_create(int npts, const double* mx, const double* my, const double
  * NearestNDInterpolator does it), enabling grid_method = 'nearest'.  cell_nearest[ncell] in [0, npts). */
 int smrfb_grid_set_nearest(smrfb_handle_t h, const int32_t* cell_nearest);
 /* detrend = 1: detrendedInterpolationMask (grid.py:179-212); 0: calculateInterpolation (grid.py:214-231).
- * method: 0 = 'linear', 1 = 'nearest' (the reference's grid_method; 'cubic' is not on this path). */
+ * method: 0 = 'linear', 1 = 'nearest' (the reference's grid_method; 'cubic' has its own entry below). */
 int smrfb_grid_distribute(smrfb_handle_t h, const double* data, int T, int detrend, int slope_flag, int method,
                           double vmin, double vmax, const double* pv_in, double* pv_out, double* out);
 int smrfb_grid_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int detrend, int slope_flag, int method,
@@ -136,8 +146,27 @@ int smrfb_grid_distribute_local(smrfb_handle_t h, const double* fields3, int T, 
 int smrfb_grid_distribute_local_dev(smrfb_handle_t h, const double* d_fields3, int T, double vmin, double vmax,
                                     double* d_out, void* stream);
 
+/* grid_method = 'cubic' (the reference's default, CoreConfig.ini:183-186): scipy's CloughTocher2DInterpolator, reached
+ * through griddata(method='cubic') at grid.py:204-207 / :226-229 and through utils.py:447 on the cached triangulation.
+ * ct_geom[nsimp][9] = per simplex the edge vectors e12, e23, e31 (x, y each) and the three cross-edge coefficients g
+ * (neighbour centroids in barycentric form; smrf_b200/spatial/grid.py builds them from scipy.spatial.Delaunay).
+ * fields[T][nf][3][npts]: per step and field the point values and their gradients d/dx, d/dy (scipy's estimator,
+ * run by the caller like the Delaunay triangulation).
+ *   nf = 1: out = patch(field 0) [+ pv[t][0] * GridZ + pv[t][1] when pv != NULL: detrendedInterpolationMask with the
+ *           residuals formed by the caller, grid.py:188-210; pv == NULL: calculateInterpolation]
+ *   nf = 2: out = patch(field 0) + GridZ * patch(field 1)      (detrendedInterpolationLocal, grid.py:164-175, with
+ *           field 0 = residual + intercept, field 1 = slope)
+ * NaN outside the hull; clamp fused. */
+int smrfb_grid_set_cubic(smrfb_handle_t h, const double* ct_geom);
+int smrfb_grid_distribute_cubic(smrfb_handle_t h, const double* fields, int T, int nf, const double* pv /* nullable [T][2] */,
+                                double vmin, double vmax, double* out);
+int smrfb_grid_distribute_cubic_dev(smrfb_handle_t h, const double* d_fields, int T, int nf, const double* d_pv,
+                                    double vmin, double vmax, double* d_out, void* stream);
+
 /* ------------------------------------------------------------------ clamp (utils.py:137-161) */
-/* In place on a host array: x<=vmin -> vmin, x>=vmax -> vmax, NaN stays NaN. */
+/* In place on a host array: x<=vmin -> vmin, x>=vmax -> vmax, NaN stays NaN.  The distribute calls fuse this clamp
+ * (vmin / vmax arguments); the stand-alone form is for call sites that clamp afterwards.  Arrays from smrfb_host_alloc
+ * are clamped in place through their device mapping (no allocation, no staging copy); pageable arrays are staged. */
 int smrfb_set_min_max(double* data, int64_t n, double vmin, double vmax, int device);
 
 #ifdef __cplusplus

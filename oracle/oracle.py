@@ -311,6 +311,140 @@ def linear_apply(plan, values, GridX, GridY):
     return out.reshape(GridX.shape)
 
 
+# --------------------------------------------------------------------------------------------
+# GRID, cubic  (grid_method='cubic': scipy.interpolate.CloughTocher2DInterpolator)
+# --------------------------------------------------------------------------------------------
+# Third-party algorithm (SciPy, _interpnd.pyx: `_clough_tocher_2d_single`, Alfeld 1984 / Farin 1986 with SciPy's
+# affine-invariant choice of the cross-edge directions), reached from the reference at grid.py:204-207 / :226-229
+# (griddata(method='cubic')) and utils.py:447 (CloughTocher2DInterpolator(tri, values)).  ``GRID`` calls SciPy
+# where the reference does; ``cubic_plan`` / ``cubic_apply`` restate the evaluation in the decomposed form the
+# CUDA path uses: the Bezier patch is LINEAR in the nine data of a simplex (three vertex values f_v and three vertex
+# gradients), so per cell nine weights are formed once and a timestep costs nine multiply-adds.  The vertex gradients
+# themselves come from SciPy's own estimator (estimate_gradients_2d_global, an iteration whose stopping point
+# decides the low digits): both the oracle and the product call it, as the reference's CloughTocher2DInterpolator does.
+def estimate_gradients(tri, values, tol=1e-6, maxiter=400):
+    """[P] or [P, ncol] -> [P, ncol, 2]: what CloughTocher2DInterpolator(tri, values).grad holds."""
+    from scipy.interpolate import _interpnd
+
+    v = np.asarray(values, dtype=float)
+    if v.ndim == 1:
+        v = v[:, None]
+    return _interpnd.estimate_gradients_2d_global(tri, np.ascontiguousarray(v), maxiter=maxiter, tol=tol)
+
+
+def cubic_geometry(tri):
+    """Per simplex: the edge vectors e12, e23, e31 and the three cross-edge coefficients g (centroid of the
+    neighbour across each edge in this simplex's barycentric coordinates; -1/2 where there is no neighbour)."""
+    P = tri.points
+    S = tri.simplices
+    e12 = P[S[:, 1]] - P[S[:, 0]]
+    e23 = P[S[:, 2]] - P[S[:, 1]]
+    e31 = P[S[:, 0]] - P[S[:, 2]]
+    g = np.full((len(S), 3), -0.5)
+    Tm = tri.transform
+    for k in range(3):
+        nb = tri.neighbors[:, k]
+        has = nb >= 0
+        y = P[S[np.where(has, nb, 0)]].sum(axis=1) / 3.0           # neighbour centroid
+        d = y - Tm[:, 2, :]
+        c0 = Tm[:, 0, 0] * d[:, 0] + Tm[:, 0, 1] * d[:, 1]
+        c1 = Tm[:, 1, 0] * d[:, 0] + Tm[:, 1, 1] * d[:, 1]
+        c = np.stack([c0, c1, (1.0 - c0) - c1], axis=1)
+        a, b = [(2, 1), (0, 2), (1, 0)][k]
+        gk = (2 * c[:, a] + c[:, b] - 1) / (2 - 3 * c[:, a] - 3 * c[:, b])
+        g[:, k] = np.where(has, gk, -0.5)
+    return np.concatenate([e12, e23, e31, g], axis=1)               # [nsimp, 9]
+
+
+def _ct_patch(b, geo, f, df):
+    """The Clough-Tocher patch value for barycentrics b [n,3], geometry geo [n,9], vertex values f [n,3] and vertex
+    gradients df [n,3,2] -- SciPy's `_clough_tocher_2d_single`, vectorised over n."""
+    e12x, e12y, e23x, e23y, e31x, e31y, g0, g1, g2 = [geo[:, i] for i in range(9)]
+    f1, f2, f3 = f[:, 0], f[:, 1], f[:, 2]
+    df12 = +(df[:, 0, 0] * e12x + df[:, 0, 1] * e12y)
+    df21 = -(df[:, 1, 0] * e12x + df[:, 1, 1] * e12y)
+    df23 = +(df[:, 1, 0] * e23x + df[:, 1, 1] * e23y)
+    df32 = -(df[:, 2, 0] * e23x + df[:, 2, 1] * e23y)
+    df31 = +(df[:, 2, 0] * e31x + df[:, 2, 1] * e31y)
+    df13 = -(df[:, 0, 0] * e31x + df[:, 0, 1] * e31y)
+    c3000 = f1
+    c2100 = (df12 + 3 * c3000) / 3
+    c2010 = (df13 + 3 * c3000) / 3
+    c0300 = f2
+    c1200 = (df21 + 3 * c0300) / 3
+    c0210 = (df23 + 3 * c0300) / 3
+    c0030 = f3
+    c1020 = (df31 + 3 * c0030) / 3
+    c0120 = (df32 + 3 * c0030) / 3
+    c2001 = (c2100 + c2010 + c3000) / 3
+    c0201 = (c1200 + c0300 + c0210) / 3
+    c0021 = (c1020 + c0120 + c0030) / 3
+    c0111 = (g0 * (-c0300 + 3 * c0210 - 3 * c0120 + c0030) + (-c0300 + 2 * c0210 - c0120 + c0021 + c0201)) / 2
+    c1011 = (g1 * (-c0030 + 3 * c1020 - 3 * c2010 + c3000) + (-c0030 + 2 * c1020 - c2010 + c2001 + c0021)) / 2
+    c1101 = (g2 * (-c3000 + 3 * c2100 - 3 * c1200 + c0300) + (-c3000 + 2 * c2100 - c1200 + c2001 + c0201)) / 2
+    c1002 = (c1101 + c1011 + c2001) / 3
+    c0102 = (c1101 + c0111 + c0201) / 3
+    c0012 = (c1011 + c0111 + c0021) / 3
+    c0003 = (c1002 + c0102 + c0012) / 3
+    minval = b.min(axis=1)
+    b1, b2, b3 = b[:, 0] - minval, b[:, 1] - minval, b[:, 2] - minval
+    b4 = 3 * minval
+    return (b1 ** 3 * c3000 + 3 * b1 ** 2 * b2 * c2100 + 3 * b1 ** 2 * b3 * c2010 + 3 * b1 ** 2 * b4 * c2001
+            + 3 * b1 * b2 ** 2 * c1200 + 6 * b1 * b2 * b4 * c1101 + 3 * b1 * b3 ** 2 * c1020 + 6 * b1 * b3 * b4 * c1011
+            + 3 * b1 * b4 ** 2 * c1002 + b2 ** 3 * c0300 + 3 * b2 ** 2 * b3 * c0210 + 3 * b2 ** 2 * b4 * c0201
+            + 3 * b2 * b3 ** 2 * c0120 + 6 * b2 * b3 * b4 * c0111 + 3 * b2 * b4 ** 2 * c0102 + b3 ** 3 * c0030
+            + 3 * b3 ** 2 * b4 * c0021 + 3 * b3 * b4 ** 2 * c0012 + b4 ** 3 * c0003)
+
+
+def cubic_plan(mx, my, GridX, GridY, tri=None):
+    """Delaunay + find_simplex once, then per cell the nine Clough-Tocher weights: out = sum_v (wf[v] f_v +
+    wx[v] df_v/dx + wy[v] df_v/dy) over the simplex's three vertices; NaN outside the hull."""
+    from scipy.spatial import Delaunay
+
+    if tri is None:
+        tri = Delaunay(np.column_stack([np.asarray(mx, float), np.asarray(my, float)]))
+    xi = np.column_stack([GridX.ravel(), GridY.ravel()])
+    simplex = tri.find_simplex(xi).astype(np.int32)
+    inside = simplex >= 0
+    si = np.where(inside, simplex, 0)
+    Tm = tri.transform[si]
+    dx = xi[:, 0] - Tm[:, 2, 0]
+    dy = xi[:, 1] - Tm[:, 2, 1]
+    c0 = Tm[:, 0, 0] * dx + Tm[:, 0, 1] * dy
+    c1 = Tm[:, 1, 0] * dx + Tm[:, 1, 1] * dy
+    b = np.stack([c0, c1, (1.0 - c0) - c1], axis=1)
+    geo = cubic_geometry(tri)[si]
+    n = len(si)
+    w = np.empty((n, 9))
+    for i in range(9):                                   # the patch is linear: evaluate it on the nine unit data
+        f = np.zeros((n, 3))
+        df = np.zeros((n, 3, 2))
+        if i < 3:
+            f[:, i] = 1.0
+        else:
+            df[:, (i - 3) // 2, (i - 3) % 2] = 1.0
+        w[:, i] = _ct_patch(b, geo, f, df)
+    return {"tri": tri, "simplex": simplex, "simplices": tri.simplices.astype(np.int32), "weights": w,
+            "bary": b, "geo": geo}
+
+
+def cubic_apply(plan, values, grad, shape):
+    """values [P], grad [P, 2] -> [ny, nx]."""
+    s = plan["simplex"]
+    inside = s >= 0
+    vt = plan["simplices"][np.where(inside, s, 0)]
+    w = plan["weights"]
+    v = np.asarray(values, dtype=float)
+    g = np.asarray(grad, dtype=float)
+    out = np.zeros(len(s))
+    for k in range(3):
+        out = out + w[:, k] * v[vt[:, k]]
+    for k in range(3):
+        out = out + w[:, 3 + 2 * k] * g[vt[:, k], 0] + w[:, 4 + 2 * k] * g[vt[:, k], 1]
+    out[~inside] = np.nan
+    return out.reshape(shape)
+
+
 def local_neighbours(lat, lon, k):
     """grid.py:54-65: for every point the k nearest points in latitude / longitude space (itself first), in the
     order of pandas' Series.sort_values() = numpy's default (quick)sort of the distances."""
@@ -348,7 +482,7 @@ def local_fit(data, elevation, nbr, flag):
 
 
 class GRID:
-    """Reference GRID restricted to what the path covers: linear / nearest, mask and local detrend.
+    """Reference GRID restricted to what the path covers: linear / nearest / cubic, mask and local detrend.
 
     grid.py:23-94 (ctor / neighbour table / point mask), :115-177 (detrendedInterpolationLocal), :179-212
     (detrendedInterpolationMask), :214-231.
@@ -381,9 +515,12 @@ class GRID:
         return idtrend + self.pv[0] * self.GridZ + self.pv[1]
 
     def detrendedInterpolationLocal(self, data, flag=0, grid_method="linear"):
-        """grid.py:115-177 with grid_method='linear' (utils.py:430-449: LinearNDInterpolator on the cached tri)."""
-        from scipy.interpolate import LinearNDInterpolator
+        """grid.py:115-177 (utils.py:430-449: LinearNDInterpolator / CloughTocher2DInterpolator on the cached tri)."""
+        from scipy.interpolate import CloughTocher2DInterpolator, LinearNDInterpolator
         from scipy.spatial import Delaunay
+
+        if grid_method == "cubic":
+            LinearNDInterpolator = CloughTocher2DInterpolator          # noqa: F811  (utils.py:447)
 
         md = self.metadata
         dtrend, slope, intercept = local_fit(data, md.elevation.values, self.nbr, flag)

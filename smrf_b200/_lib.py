@@ -29,6 +29,9 @@ _SIGS = {
     "smrfb_destroy": (ctypes.c_int, [handle_t]),
     "smrfb_synchronize": (ctypes.c_int, [handle_t]),
     "smrfb_launch_count": (ctypes.c_int64, []),
+    "smrfb_set_output_dtype": (ctypes.c_int, [handle_t, ctypes.c_int]),
+    "smrfb_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "smrfb_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "smrfb_idw_create": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_int,
                                         ctypes.POINTER(handle_t)]),
@@ -69,6 +72,11 @@ _SIGS = {
                                                    c_double_p]),
     "smrfb_grid_distribute_local_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
                                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_grid_set_cubic": (ctypes.c_int, [handle_t, c_double_p]),
+    "smrfb_grid_distribute_cubic": (ctypes.c_int, [handle_t, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p,
+                                                   ctypes.c_double, ctypes.c_double, c_double_p]),
+    "smrfb_grid_distribute_cubic_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                       ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_set_min_max": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
 }
 
@@ -117,6 +125,96 @@ def mesh_or_points(GridX, GridY):
             np.array_equal(GridY, np.broadcast_to(y[:, None], GridY.shape)):
         return 0, np.ascontiguousarray(x), np.ascontiguousarray(y)
     return 1, np.ascontiguousarray(GridX.ravel()), np.ascontiguousarray(GridY.ravel())
+
+
+class _PinnedPool:
+    """Page-locked output blocks (smrfb_host_alloc), recycled by size: a per-timestep run loop gets its [ny, nx]
+    result in pinned memory (full-rate D2H) without paying cudaHostAlloc on every call -- the array of step n-1 is
+    usually collected before step n+1 asks for a block."""
+
+    def __init__(self, max_free_bytes=8 << 30):
+        import threading
+        self.free = {}
+        self.free_bytes = 0
+        self.max_free_bytes = max_free_bytes
+        self.lock = threading.Lock()
+
+    def take(self, nbytes):
+        with self.lock:
+            lst = self.free.get(nbytes)
+            if lst:
+                self.free_bytes -= nbytes
+                return lst.pop()
+        p = ctypes.c_void_p()
+        check(lib().smrfb_host_alloc(nbytes, ctypes.byref(p)))
+        return p.value
+
+    def give(self, ptr, nbytes):
+        with self.lock:
+            if self.free_bytes + nbytes <= self.max_free_bytes:
+                self.free.setdefault(nbytes, []).append(ptr)
+                self.free_bytes += nbytes
+                return
+        try:
+            lib().smrfb_host_free(ptr)
+        except Exception:
+            pass
+
+
+_pool = _PinnedPool()
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """np.empty(shape, dtype) in page-locked memory from the pool; the block returns to the pool when the array
+    (and every view of it) has been collected.  The array is an ordinary C-contiguous ndarray owned by Python."""
+    import weakref
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    nbytes = max(n * dtype.itemsize, 1)
+    ptr = _pool.take(nbytes)
+    buf = (ctypes.c_char * nbytes).from_address(ptr)
+    weakref.finalize(buf, _pool.give, ptr, nbytes)
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def out_array(T, shape, out, f32):
+    """The [T, ny, nx] result array of a distribute call: the caller's, or a pinned one."""
+    dt = np.float32 if f32 else np.float64
+    if out is None:
+        return pinned_empty((T,) + tuple(shape), dt)
+    if not (isinstance(out, np.ndarray) and out.dtype == dt and out.flags["C_CONTIGUOUS"] and out.shape == (T,) + tuple(shape)):
+        raise ValueError("out must be a C-contiguous %s array of shape %r" % (np.dtype(dt).name, (T,) + tuple(shape)))
+    return out
+
+
+def vptr(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+class HandleMixin:
+    """Shared by the drop-in classes: handle lifetime and the output element type of the next call."""
+    _h = None
+    _f32 = False
+
+    def _select_dtype(self, out_dtype, out):
+        dt = out_dtype if out_dtype is not None else (out.dtype if out is not None else np.float64)
+        dt = np.dtype(dt)
+        if dt not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("out_dtype must be float64 (parity contract 1e-9) or float32 (1e-5), got %s" % dt)
+        f32 = dt == np.dtype(np.float32)
+        if f32 != self._f32:
+            check(lib().smrfb_set_output_dtype(self._h, int(f32)))
+            self._f32 = f32
+        return f32
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().smrfb_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
 
 def default_device():

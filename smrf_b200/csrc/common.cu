@@ -169,12 +169,35 @@ prep_steps_kernel(const double* __restrict__ data, int T, int S, RecLayout L, co
                 }
                 szz = block_sum(szz, sh);
                 szd = block_sum(szd, sh);
-                if (szz > 0.0) {
+                // np.polyfit solves the column-scaled Vandermonde system [z/|z|, 1/sqrt(n)] with rcond = n * eps: its
+                // singular values are sqrt(1 -+ |c|), c = sum(z) / (|z| sqrt(n)), and 1 - c^2 = szz / sum(z^2), so the
+                // fit is rank-deficient when szz < (rcond (1 + |c|))^2 sum(z^2) (all fitted stations at one elevation,
+                // exactly or up to rounding); lstsq then returns the minimum-norm solution along (1, sign c).
+                double szsq = 0.0, szdd = 0.0;
+                for (int s = threadIdx.x; s < S; s += PREP_THREADS) {
+                    double d = row[s];
+                    bool fit = !isnan(d) && (!fitmask || fitmask[s]);
+                    if (fit) {
+                        szsq += mz[s] * mz[s];
+                        szdd += mz[s] * d;
+                    }
+                }
+                szsq = block_sum(szsq, sh);
+                szdd = block_sum(szdd, sh);
+                const double znorm = sqrt(szsq), rn = sqrt(n);
+                const double cc = znorm > 0.0 ? sz / (znorm * rn) : 0.0;
+                const double rc = n * 2.220446049250313e-16 * (1.0 + fabs(cc));
+                if (szz > rc * rc * szsq) {
                     p0 = szd / szz;
                     p1 = dbar - p0 * zbar;
-                } else {  // rank-deficient fit: numpy lstsq minimum-norm solution
-                    p0 = dbar / (2.0 * zbar);
-                    p1 = 0.5 * dbar;
+                } else if (znorm > 0.0) {
+                    const double sg = cc < 0.0 ? -1.0 : 1.0;
+                    const double xs = (szdd / znorm + sg * sd / rn) / (2.0 * (1.0 + fabs(cc)));
+                    p0 = xs / znorm;
+                    p1 = sg * xs / rn;
+                } else {  // every fitted elevation is exactly 0: the slope column vanishes
+                    p0 = 0.0;
+                    p1 = dbar;
                 }
                 if ((slope_flag == 1 && p0 < 0.0) || (slope_flag == -1 && p0 > 0.0)) {
                     p0 = 0.0;
@@ -274,15 +297,51 @@ int smrfb_synchronize(smrfb_handle_t h) {
     return SMRFB_OK;
 }
 
+int smrfb_set_output_dtype(smrfb_handle_t h, int dtype) {
+    SMRFB_CHECK(h, SMRFB_ERR_ARG, "NULL handle");
+    SMRFB_CHECK(dtype == 0 || dtype == 1, SMRFB_ERR_ARG, "dtype must be 0 (float64) or 1 (float32)");
+    reinterpret_cast<HandleBase*>(h)->out_f32 = dtype;
+    return SMRFB_OK;
+}
+
+int smrfb_host_alloc(size_t bytes, void** out) {
+    SMRFB_CHECK(out, SMRFB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    // portable (pinned for every device) and mapped (kernels may address it directly: smrfb_set_min_max)
+    SMRFB_CUDA(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable | cudaHostAllocMapped));
+    return SMRFB_OK;
+}
+
+int smrfb_host_free(void* p) {
+    if (p) SMRFB_CUDA(cudaFreeHost(p));
+    return SMRFB_OK;
+}
+
 int smrfb_set_min_max(double* data, int64_t n, double vmin, double vmax, int device) {
     SMRFB_CHECK(data || n == 0, SMRFB_ERR_ARG, "data is NULL");
     if (n == 0) return SMRFB_OK;
     SMRFB_CUDA(cudaSetDevice(device));
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    // Arrays that came out of this library's pinned pool (smrfb_host_alloc; the drop-in classes return those) are
+    // mapped into the device's address space: the kernel clamps them in place over PCIe -- no device allocation,
+    // no staging copies.  Anything else (ordinary pageable NumPy memory) is staged through a device buffer.
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        clamp_kernel<<<blocks, 256>>>(reinterpret_cast<double*>(at.devicePointer), n, vmin, vmax);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            set_error("smrfb_set_min_max: %s", cudaGetErrorString(e));
+            return SMRFB_ERR_CUDA;
+        }
+        return SMRFB_OK;
+    }
+    cudaGetLastError();
     double* d = nullptr;
     SMRFB_CUDA(cudaMalloc((void**)&d, (size_t)n * sizeof(double)));
     cudaError_t e = cudaMemcpy(d, data, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
         clamp_kernel<<<blocks, 256>>>(d, n, vmin, vmax);
         count_launch();
         e = cudaGetLastError();

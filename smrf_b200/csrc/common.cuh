@@ -104,6 +104,7 @@ struct HandleBase {
     int* d_flags = nullptr;      // [1] device-side status flags (bit0: a step had no valid station)
     double* d_ring = nullptr;    // host-API output ring (up to 2 slots), kept across calls
     size_t ring_cap = 0;
+    int out_f32 = 0;             // smrfb_set_output_dtype: 1 = outputs are written as float32 (the reference's NetCDF type)
     explicit HandleBase(int k) : kind(k) {}
     virtual ~HandleBase();
 };
@@ -124,8 +125,10 @@ int launch_prep(cudaStream_t st, const double* d_data, int T, int T_pad, int S, 
 // one sub-batch (copy_stream) overlaps the kernels of the next (stream).  run(t0, tn, d_out, stream)
 // enqueues the kernels for steps [t0, t0+tn).  Synchronises before returning.
 template <class RunFn>
-int run_host_batches(HandleBase* h, int T, int step_align, double* out, RunFn run) {
-    const size_t ncell = (size_t)h->g.ncell;
+int run_host_batches(HandleBase* h, int T, int step_align, double* out_, RunFn run) {
+    const size_t esz = h->out_f32 ? sizeof(float) : sizeof(double);      // bytes per output element
+    const size_t ncell = ((size_t)h->g.ncell * esz + sizeof(double) - 1) / sizeof(double);   // doubles per step in the ring
+    char* out = reinterpret_cast<char*>(out_);
     size_t budget = (size_t)8 << 30;
     {   // at least one full staged block of steps per slot when memory allows (large grids)
         size_t free_b = 0, total_b = 0;
@@ -162,7 +165,7 @@ int run_host_batches(HandleBase* h, int T, int step_align, double* out, RunFn ru
         if (rc != SMRFB_OK) break;
         cudaEventRecord(done[slot], h->stream);
         cudaStreamWaitEvent(h->copy_stream, done[slot], 0);
-        if (cudaMemcpyAsync(out + (size_t)t0 * ncell, ring[slot], (size_t)tn * ncell * sizeof(double),
+        if (cudaMemcpyAsync(out + (size_t)t0 * (size_t)h->g.ncell * esz, ring[slot], (size_t)tn * (size_t)h->g.ncell * esz,
                             cudaMemcpyDeviceToHost, h->copy_stream) != cudaSuccess) {
             set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = SMRFB_ERR_CUDA;
@@ -221,6 +224,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+// Output element store: fp64, or float32 when the handle was switched with smrfb_set_output_dtype (the flag is
+// uniform across the grid).  Streaming (evict-first) stores: the output is written once and never read back.
+__device__ __forceinline__ void store_out(double* base, size_t idx, double v, int f32) {
+    if (f32) __stcs(reinterpret_cast<float*>(base) + idx, (float)v);
+    else __stcs(base + idx, v);
+}
+// two adjacent elements, idx even and the row 16-byte (f32: 8-byte) aligned
+__device__ __forceinline__ void store_out2(double* base, size_t idx, double v0, double v1, int f32) {
+    if (f32) __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + idx), make_float2((float)v0, (float)v1));
+    else __stcs(reinterpret_cast<double2*>(base + idx), make_double2(v0, v1));
 }
 
 __device__ __forceinline__ double clamp_nan_keep(double v, double vmin, double vmax) {

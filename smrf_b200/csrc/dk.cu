@@ -38,6 +38,8 @@ constexpr int DK_NSMAX = 31;          // largest final active set solved in thre
 constexpr int DK_KREG = 16;           // ELL entries kept in registers by the distribute kernel
 constexpr int DK_QMAX = (DK_MAXN + 1 + 31) / 32;  // 7 column slots per lane
 constexpr int DK_MAXSNAP = 32;         // nested forks of a 32-cell tile
+constexpr int DK_PEND = 4;             // rank-1 downdates of the inverse deferred and applied together (one pass over B)
+constexpr int DK_TX = 8, DK_TY = 4;    // a tile is an 8 x 4 block of mesh cells (neighbours agree longest on what to drop)
 
 struct DkPending {
     int k;          // station (rank index) this subgroup drops next
@@ -78,15 +80,40 @@ __device__ __forceinline__ double dk_rcp(double x) {
     return r;
 }
 
+// Cells of a tile: an 8 x 4 block of the mesh (grid_kind 0, coordinate mode), else 32 consecutive cells.
+struct DkTiling {
+    int blocked, tiles_x;
+    long long ntiles;
+};
+__host__ __device__ inline DkTiling dk_tiling(const Geom& g, long long ncell, bool has_dgrid) {
+    DkTiling t;
+    t.blocked = (!has_dgrid && g.kind == 0 && g.nx > 0 && (long long)g.ny * g.nx == ncell) ? 1 : 0;
+    t.tiles_x = t.blocked ? (g.nx + DK_TX - 1) / DK_TX : 0;
+    t.ntiles = t.blocked ? (long long)t.tiles_x * ((g.ny + DK_TY - 1) / DK_TY) : (ncell + DK_TILE - 1) / DK_TILE;
+    return t;
+}
+// flat cell index of cell ci of a tile, -1 if it falls outside the grid
+__device__ __forceinline__ long long dk_tile_cell(const DkTiling& tl, const Geom& g, long long ncell, long long tile, int ci) {
+    if (tl.blocked) {
+        const long long ty = tile / tl.tiles_x;
+        const int tx = (int)(tile - ty * tl.tiles_x);
+        const long long i = ty * DK_TY + (ci / DK_TX);
+        const int j = tx * DK_TX + (ci % DK_TX);
+        return (i < g.ny && j < g.nx) ? i * g.nx + j : -1;
+    }
+    const long long c = tile * DK_TILE + ci;
+    return c < ncell ? c : -1;
+}
+
 __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, NN = a.NN, NNP = a.NNP;
     const int npk = NN * (NN + 1) / 2;
-    double* Bp = reinterpret_cast<double*>(smem_raw);           // [npk] packed upper triangle of the current inverse
+    double* Bp = reinterpret_cast<double*>(smem_raw);           // [npk] packed upper triangle of the inverse, WITHOUT the pending downdates
     double* w = Bp + npk;                                       // [32][NN] current weights of the tile's cells
-    double* bcol = w + DK_TILE * NN;                            // [NNP] column k of B (zeros = inactive)
-    double* bsm = bcol + NNP;                                   // [NNP] bcol / beta
-    int* rowoff = reinterpret_cast<int*>(bsm + NNP);            // [NNP]
+    double* pcol = w + DK_TILE * NN;                            // [DK_PEND][NNP] extracted columns (zeros = inactive), pending ones first
+    double* psm = pcol + DK_PEND * NNP;                         // [DK_PEND][NNP] column / beta
+    int* rowoff = reinterpret_cast<int*>(psm + DK_PEND * NNP);  // [NNP]
     int* kstack = rowoff + NNP;                                 // [NN] stations dropped along the current path
     int* kc = kstack + NN;                                      // [32]
     int* ctrl = kc + DK_TILE;                                   // [8]
@@ -95,31 +122,65 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* snap_g = a.snap + (size_t)blockIdx.x * DK_MAXSNAP * npk;   // fork snapshots of this CTA
-    const long long ntiles = (a.ncell + DK_TILE - 1) / DK_TILE;
+    const DkTiling tiling = dk_tiling(a.g, a.ncell, a.dgrid != nullptr);
+    const long long ntiles = tiling.ntiles;
 
     for (int i = tid; i < NNP; i += DK_THREADS) rowoff[i] = i * NN - (i * (i + 1)) / 2;   // idx(i,j>=i) = rowoff[i] + j
     __syncthreads();
 
-    // rank-1 downdate of the packed upper triangle with the column in bcol (zeros = skip):
-    //   B[i][j] -= bsm[i] * bcol[j]   for j >= i,   bsm[i] = bcol[i]/beta.  Rows are dealt round-robin to the warps.
-    auto rank1 = [&]() {
-        double bj[DK_QMAX];
+    // The rank-1 downdates B[i][j] -= (b[i]/beta) * b[j] (j >= i) of the last np eliminations are DEFERRED: Bp holds
+    // the inverse without them, and a column is corrected for them when it is extracted (np FMAs per element, in the
+    // order and with the operand roles the eager update would have used: bit-identical).  flush() applies them to the
+    // packed triangle in ONE pass -- B (162 KB at 200 stations) is read and written once per DK_PEND eliminations
+    // instead of once per elimination, and that shared-memory traffic was what an elimination step cost.
+    // Rows are dealt round-robin to the warps; zero entries (inactive stations) are no-ops, whole zero rows skipped.
+    int np = 0;                                                // pending downdates (uniform across the CTA)
+    auto flush = [&]() {
+        if (np == 0) return;
 #pragma unroll
-        for (int q = 0; q < DK_QMAX; q++) {
-            const int j = lane + 32 * q;
-            bj[q] = (j < NN) ? bcol[j] : 0.0;
-        }
-        for (int i = warp; i < NN; i += DK_WARPS) {
-            const double bi = bsm[i];
-            if (bi == 0.0) continue;
-            double* row = Bp + rowoff[i];
-            const int q0 = i >> 5;
+        for (int half = 0; half < 2; half++) {
+            constexpr int QH = (DK_QMAX + 1) / 2;
+            const int qa = half * QH, qb = half ? DK_QMAX : QH;
+            double bj[DK_PEND][QH];
 #pragma unroll
-            for (int q = 0; q < DK_QMAX; q++) {
-                const int j = lane + 32 * q;
-                if (q >= q0 && j >= i && j < NN) row[j] = fma(-bi, bj[q], row[j]);
+            for (int d = 0; d < DK_PEND; d++)
+#pragma unroll
+                for (int q = 0; q < QH; q++) {
+                    const int j = lane + 32 * (qa + q);
+                    bj[d][q] = (d < np && qa + q < qb && j < NN) ? pcol[d * NNP + j] : 0.0;
+                }
+            for (int i = warp; i < NN; i += DK_WARPS) {
+                if ((i >> 5) >= qb) continue;                  // the row starts right of this half
+                double bi[DK_PEND];
+                bool any = false;
+#pragma unroll
+                for (int d = 0; d < DK_PEND; d++) {
+                    bi[d] = d < np ? psm[d * NNP + i] : 0.0;
+                    any |= bi[d] != 0.0;
+                }
+                if (!any) continue;
+                double* row = Bp + rowoff[i];
+                const int q0 = i >> 5;
+#pragma unroll
+                for (int q = 0; q < QH; q++) {
+                    const int j = lane + 32 * (qa + q);
+                    if (qa + q < qb && qa + q >= q0 && j >= i && j < NN) {
+                        double v = row[j];
+#pragma unroll
+                        for (int d = 0; d < DK_PEND; d++) v = fma(-bi[d], bj[d][q], v);   // slots >= np hold zeros here
+                        row[j] = v;
+                    }
+                }
             }
         }
+        np = 0;
+    };
+    // element (i, k) of the CURRENT inverse: the stored value corrected for the pending downdates
+    auto current = [&](int i, int k) {
+        const int r = min(i, k), c = max(i, k);
+        double v = Bp[rowoff[r] + c];
+        for (int d = 0; d < np; d++) v = fma(-psm[d * NNP + r], pcol[d * NNP + c], v);
+        return v;
     };
 
     for (;;) {
@@ -128,12 +189,15 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
         const long long tile = (unsigned)ctrl[0];
         if (tile >= ntiles) break;
         for (int p = tid; p < npk; p += DK_THREADS) Bp[p] = a.B0p[p];   // every tile starts from the pristine inverse (L2-resident)
+        np = 0;
+        long long mycell[DK_CPW];
         {   // right-hand side [dist to every station ; 1] in rank order
 #pragma unroll
             for (int h = 0; h < DK_CPW; h++) {
                 const int ci = warp + DK_WARPS * h;
-                const long long cell = tile * DK_TILE + ci;
-                const bool live = cell < a.ncell;
+                const long long cell = dk_tile_cell(tiling, a.g, a.ncell, tile, ci);
+                mycell[h] = cell;
+                const bool live = cell >= 0;
                 double* wc = w + ci * NN;
                 double X = 0.0, Y = 0.0;
                 if (live && !a.dgrid) cell_xy(a.g, cell, X, Y);
@@ -180,8 +244,11 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     if (j < NN) w[(warp + DK_WARPS * h) * NN + j] = acc[h][q];
                 }
         }
-        const long long rem = a.ncell - tile * DK_TILE;
-        const unsigned tile_mask = rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
+        unsigned tile_mask = 0;
+        {
+            const long long cl = dk_tile_cell(tiling, a.g, a.ncell, tile, lane);
+            tile_mask = __ballot_sync(0xffffffffu, cl >= 0);
+        }
         int depth = 0, npend = 0, nsnap = 0;
         unsigned n_apply = 0, n_restore = 0, n_fork = 0;
         __syncthreads();
@@ -207,7 +274,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     }
                     const bool hand = (k >= 0) && (n - ndrop <= a.handoff);
                     if (k < 0 || hand) {
-                        const long long cell = tile * DK_TILE + ci;
+                        const long long cell = mycell[h];
                         unsigned myword = 0;
                         for (int q = 0; q < DK_WORDS; q++) {
                             const int j = lane + 32 * q;
@@ -251,6 +318,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     }
                     bool fresh = false;
                     if (p > 0) {   // snapshot the inverse once for all children (exact: no rounding drift on the way back)
+                        flush();             // the snapshot holds the CURRENT inverse
+                        __syncthreads();
                         double* sg = snap_g + (size_t)nsnap * npk;
                         for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Bp[q];
                         nsnap++;
@@ -275,6 +344,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     if (!fresh) {   // come back to the fork point: restore the snapshot and the active flags
                         const double* sg = snap_g + (size_t)ssnap * npk;
                         for (int q = tid; q < npk; q += DK_THREADS) Bp[q] = sg[q];
+                        np = 0;              // the pending downdates belonged to the branch just left
                         for (int i = tid; i < NNP; i += DK_THREADS) act[i] = (i < NN) ? 1 : 0;
                         __syncthreads();
                         for (int d = tid; d < sdepth; d += DK_THREADS) act[kstack[d]] = 0;
@@ -285,13 +355,15 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                     __syncthreads();                 // B / act restored; pend[npend] read by everyone
                 }
             }
-            // EXTRACT column k of the inverse
+            // EXTRACT column k of the current inverse into pending slot np
             n_apply++;
-            const double beta = Bp[rowoff[k] + k];
+            double* bcol = pcol + np * NNP;
+            double* bsm = psm + np * NNP;
+            const double beta = current(k, k);
             const double rbeta = dk_rcp(beta);
             for (int i = tid; i < NNP; i += DK_THREADS) {
                 double v = 0.0;
-                if (i < NN && i != k && act[i]) v = (i < k) ? Bp[rowoff[i] + k] : Bp[rowoff[k] + i];
+                if (i < NN && i != k && act[i]) v = current(i, k);
                 bcol[i] = v;
                 bsm[i] = v * rbeta;
             }
@@ -310,7 +382,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
                 }
             }
             select(mask, k, depth + 1);
-            rank1();
+            np++;
+            if (np == DK_PEND) flush();
             if (tid == 0) act[k] = 0;
             depth++;
         }
@@ -336,7 +409,10 @@ struct DkFinalArgs {
     uint32_t* final_act;
     uint8_t* widx;           // [K][ncell]
     double* wval;            // [K][ncell]
-    int* status;             // bit0 singular, bit1 active set larger than DK_NSMAX
+    int* status;             // bit0 singular, bit1 some cell has more than DK_NSMAX active stations (BIG pass needed)
+    double* big_scratch;     // BIG variant: per thread (n+1)(n+2) + (n+1) doubles
+    int* big_iscratch;       //              per thread 2(n+1) ints
+    int big_threshold;       // DK_NSMAX (tests lower it through SMRFB_DK_BIG_THRESHOLD to exercise the BIG variant)
     unsigned long long* fallback_cells;
     int* maxcount_final;
 };
@@ -405,17 +481,47 @@ __device__ int crout_solve_exact(double* a, int nn, int lda, int* indx, double* 
     return 0;
 }
 
+// BIG = false: thread-local workspace, active sets up to DK_NSMAX (every cell in practice: 8-11 stations survive at 200).
+// BIG = true : the cells the first variant skipped (more than DK_NSMAX active stations when they leave the walk; the
+//              reference has no such limit), workspace in global memory, a few thousand threads striding over the grid.
+template <bool BIG>
 __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
-    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.ncell) return;
-    constexpr int LDA = DK_NSMAX + 2;
-    double A[(DK_NSMAX + 1) * LDA];
-    double vv[DK_NSMAX + 1];
-    int indx[DK_NSMAX + 1];
-    int ids[DK_NSMAX + 1];
+    constexpr int LDA_S = DK_NSMAX + 2;
+    double A_s[BIG ? 1 : (DK_NSMAX + 1) * LDA_S];
+    double vv_s[BIG ? 1 : DK_NSMAX + 1];
+    int indx_s[BIG ? 1 : DK_NSMAX + 1];
+    int ids_s[BIG ? 1 : DK_NSMAX + 1];
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = BIG ? (long long)gridDim.x * blockDim.x : a.ncell;
+    const int LDA = BIG ? a.n + 2 : LDA_S;
+    const int cap = BIG ? a.n : DK_NSMAX;
+    double* A = A_s;
+    double* vv = vv_s;
+    int* indx = indx_s;
+    int* ids = ids_s;
+    if (BIG) {
+        const size_t per = (size_t)(a.n + 1) * (a.n + 2) + (a.n + 1);
+        A = a.big_scratch + (size_t)gtid * per;
+        vv = A + (size_t)(a.n + 1) * (a.n + 2);
+        indx = a.big_iscratch + (size_t)gtid * 2 * (a.n + 1);
+        ids = indx + (a.n + 1);
+    }
+    for (long long cell = gtid; cell < a.ncell; cell += gstride) {
     int ns = 0;
-    bool over = false;
     bool handed = false;
+    {
+        int cnt = 0;
+        for (int q = 0; q < DK_WORDS; q++) {
+            unsigned b = a.final_act[(size_t)cell * DK_WORDS + q];
+            if (q == DK_WORDS - 1) b &= 0x7fffffffu;
+            cnt += __popc(b);
+        }
+        const bool big = cnt > a.big_threshold;
+        if (big != BIG) {
+            if (!BIG && a.mode == 0) atomicOr(a.status, 2);      // a pass of the BIG variant is needed
+            continue;
+        }
+    }
     for (int q = 0; q < DK_WORDS; q++) {
         unsigned b = a.final_act[(size_t)cell * DK_WORDS + q];
         if (q == DK_WORDS - 1) {
@@ -425,14 +531,9 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
         while (b) {
             int bit = __ffs(b) - 1;
             b &= b - 1;
-            if (ns < DK_NSMAX) ids[ns] = a.perm[32 * q + bit];
-            else over = true;
+            if (ns < cap) ids[ns] = a.perm[32 * q + bit];
             ns++;
         }
-    }
-    if (over) {
-        atomicOr(a.status, 2);
-        return;
     }
     for (int i = 1; i < ns; i++) {   // station (compressed index) order, as the reference loops m = 0..nsta-1
         int v = ids[i], j = i - 1;
@@ -444,7 +545,7 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
     }
     double X = 0.0, Y = 0.0;
     if (!a.dgrid) cell_xy(a.g, cell, X, Y);
-    bool fell_back = false;
+    bool fell_back = false, singular = false;
     for (;;) {
         for (int m = 0; m < ns; m++) {
             const int sm = ids[m];
@@ -457,7 +558,8 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
         A[ns * LDA + ns + 1] = 1.0;
         if (crout_solve_exact(A, ns + 1, LDA, indx, vv)) {
             atomicOr(a.status, 1);
-            return;
+            singular = true;
+            break;
         }
         double esave = 0.0;   // krige.c:169-185
         int msave = -1;
@@ -472,6 +574,7 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
         for (int m = msave; m + 1 < ns; m++) ids[m] = ids[m + 1];
         ns--;
     }
+    if (singular) continue;
     if (a.mode == 0) {   // write the final active set back (rank-indexed bits) for the second pass
         if (fell_back && !handed) atomicAdd(a.fallback_cells, 1ULL);
         atomicMax(a.maxcount_final, ns);
@@ -482,12 +585,13 @@ __global__ void __launch_bounds__(128) dk_final_kernel(DkFinalArgs a) {
             words[r >> 5] |= 1u << (r & 31);
         }
         for (int q = 0; q < DK_WORDS; q++) a.final_act[(size_t)cell * DK_WORDS + q] = words[q];
-        return;
+        continue;
     }
     for (int j = 0; j < a.K; j++) {
         const bool on = j < ns;
         a.widx[(size_t)j * a.ncell + cell] = on ? (uint8_t)a.orig[ids[j]] : 0;
         a.wval[(size_t)j * a.ncell + cell] = on ? A[j * LDA + ns + 1] : 0.0;
+    }
     }
 }
 
@@ -563,6 +667,7 @@ struct DkDistArgs {
     int Tm;
     double vmin, vmax;
     double* out;         // [T][ncw]
+    int out_f32;         // 1: out is float32
 };
 
 template <int KR>
@@ -626,10 +731,10 @@ __global__ void __launch_bounds__(DK_DT) dk_distribute_kernel(DkDistArgs a) {
                 const double2 pb = *reinterpret_cast<const double2*>(rp + SP2 + 2);
                 const int tl = 2 * (chn * NPR + pr);
                 const double v0 = __dadd_rn(__dadd_rn(r0, __dmul_rn(pa.x, Z)), pa.y);   // dk.py:168, left to right
-                __stcs(a.out + (size_t)__ldg(a.steps + tl) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax));
+                store_out(a.out, (size_t)__ldg(a.steps + tl) * a.ncw + c, clamp_nan_keep(v0, a.vmin, a.vmax), a.out_f32);
                 if (tl + 1 < a.Tm) {
                     const double v1 = __dadd_rn(__dadd_rn(r1, __dmul_rn(pb.x, Z)), pb.y);
-                    __stcs(a.out + (size_t)__ldg(a.steps + tl + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax));
+                    store_out(a.out, (size_t)__ldg(a.steps + tl + 1) * a.ncw + c, clamp_nan_keep(v1, a.vmin, a.vmax), a.out_f32);
                 }
             }
         }
@@ -651,7 +756,7 @@ __global__ void __launch_bounds__(256) dk_distribute_generic_kernel(DkDistArgs a
         for (int j = 0; j < a.K; j++)
             r = fma(__ldg(a.wval + (size_t)j * a.ncell + gc), __ldg(rr + __ldg(a.widx + (size_t)j * a.ncell + gc)), r);
         const double v = __dadd_rn(__dadd_rn(r, __dmul_rn(rr[a.L.meta()], Z)), rr[a.L.meta() + 1]);
-        __stcs(a.out + (size_t)st * a.ncw + c, clamp_nan_keep(v, a.vmin, a.vmax));
+        store_out(a.out, (size_t)st * a.ncw + c, clamp_nan_keep(v, a.vmin, a.vmax), a.out_f32);
     }
 }
 
@@ -804,22 +909,22 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CUDA(cudaGetDevice(&dev));
     SMRFB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const long long ntiles = (in.ncell + DK_TILE - 1) / DK_TILE;
+    const long long ntiles = dk_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles;
     const int grid = (int)std::min<long long>(ntiles, nsm);
-    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + 2 * NNP) * sizeof(double) +
+    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + 2 * DK_PEND * NNP) * sizeof(double) +
                   ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
 
     double *d_sx = nullptr, *d_sy = nullptr, *d_cx = nullptr, *d_cy = nullptr, *d_elev = nullptr, *d_ad = nullptr,
-           *d_B0p = nullptr, *d_undo = nullptr;
-    int *d_perm = nullptr, *d_orig = nullptr, *d_small = nullptr, *d_rankof = nullptr;
+           *d_B0p = nullptr, *d_undo = nullptr, *d_big = nullptr;
+    int *d_perm = nullptr, *d_orig = nullptr, *d_small = nullptr, *d_rankof = nullptr, *d_ibig = nullptr;
     uint32_t* d_final = nullptr;
     unsigned long long* d_cnt = nullptr;
     int rc = SMRFB_OK;
     auto cleanup = [&]() {
         cudaFree(d_sx); cudaFree(d_sy); cudaFree(d_cx); cudaFree(d_cy); cudaFree(d_elev); cudaFree(d_ad);
         cudaFree(d_B0p); cudaFree(d_undo); cudaFree(d_perm); cudaFree(d_rankof); cudaFree(d_orig); cudaFree(d_small); cudaFree(d_final);
-        cudaFree(d_cnt);
+        cudaFree(d_cnt); cudaFree(d_big); cudaFree(d_ibig);
     };
 #define DK_TRY(x)                 \
     do {                          \
@@ -889,23 +994,36 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     fa.orig = d_orig; fa.final_act = d_final; fa.widx = nullptr; fa.wval = nullptr; fa.status = d_small + 1;
     fa.fallback_cells = d_cnt + 1; fa.maxcount_final = d_small + 2;
     fa.mode = 0;
-    dk_final_kernel<<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
+    fa.big_scratch = nullptr;
+    fa.big_iscratch = nullptr;
+    fa.big_threshold = DK_NSMAX;
+    if (const char* e = getenv("SMRFB_DK_BIG_THRESHOLD")) fa.big_threshold = std::min(DK_NSMAX, std::max(1, atoi(e)));
+    dk_final_kernel<false><<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
     count_launch();
     DK_CUDA(cudaGetLastError());
-    if (verbose) cudaEventRecord(ev2, st);
     int h_small[4] = {0, 0, 0, 0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaStreamSynchronize(st));
+    constexpr int BIG_BLOCKS = 16;       // x 128 threads, each with its own (n+1)(n+2) workspace in global memory
+    if (h_small[1] & 2) {                // rare: cells that left the walk with more than DK_NSMAX active stations
+        const size_t per = (size_t)(n + 1) * (n + 2) + (n + 1);
+        DK_CUDA(cudaMalloc((void**)&d_big, (size_t)BIG_BLOCKS * 128 * per * sizeof(double)));
+        DK_CUDA(cudaMalloc((void**)&d_ibig, (size_t)BIG_BLOCKS * 128 * 2 * (n + 1) * sizeof(int)));
+        fa.big_scratch = d_big;
+        fa.big_iscratch = d_ibig;
+        dk_final_kernel<true><<<BIG_BLOCKS, 128, 0, st>>>(fa);
+        count_launch();
+        DK_CUDA(cudaGetLastError());
+        DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+        DK_CUDA(cudaStreamSynchronize(st));
+    }
+    if (verbose) cudaEventRecord(ev2, st);
+    if (verbose) cudaEventSynchronize(ev2);
     float ms_walk = 0.f, ms_final = 0.f;
     if (verbose) {
         cudaEventElapsedTime(&ms_walk, ev0, ev1);
         cudaEventElapsedTime(&ms_final, ev1, ev2);
         cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
-    }
-    if (h_small[1] & 2) {
-        set_error("DK: a cell ends the shared walk with more than %d active stations", DK_NSMAX);
-        cleanup();
-        return SMRFB_ERR_LIMIT;
     }
     if (h_small[1] & 1) {
         set_error("DK: singular kriging system (co-located stations?)");
@@ -921,9 +1039,14 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     DK_CUDA(cudaMalloc((void**)&W->wval, (size_t)K * in.ncell * sizeof(double)));
     fa.K = K; fa.widx = W->widx; fa.wval = W->wval;
     fa.mode = 1;
-    dk_final_kernel<<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
+    dk_final_kernel<false><<<(unsigned)((in.ncell + 127) / 128), 128, 0, st>>>(fa);
     count_launch();
     DK_CUDA(cudaGetLastError());
+    if (K > fa.big_threshold) {
+        dk_final_kernel<true><<<BIG_BLOCKS, 128, 0, st>>>(fa);
+        count_launch();
+        DK_CUDA(cudaGetLastError());
+    }
     unsigned long long h_cnt[8] = {0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
@@ -960,19 +1083,30 @@ static int dk_get_weights(DkHandle* h, const std::vector<uint8_t>& nanmask, DkWe
     in.n = (int)cx.size();
     in.cx = cx.data(); in.cy = cy.data(); in.elev = cz.data(); in.ad = nullptr; in.d_dgrid = nullptr;
     in.orig = orig.data(); in.ncell = h->g.ncell; in.g = h->g;
-    DkWeights* W = new DkWeights();
-    int rc = dk_build(in, h->stream, W, &h->fallback_cells);
-    if (rc != SMRFB_OK) {
-        delete W;
-        return rc;
-    }
-    h->masks_built++;
-    h->max_active = std::max(h->max_active, W->K);
-    while (!h->cache.empty() && h->cache_bytes + W->bytes > h->cache_budget) {
+    auto evict_lru = [&]() {
         h->cache_bytes -= h->cache.back().second->bytes;
         delete h->cache.back().second;
         h->cache.pop_back();
+    };
+    // make room BEFORE building (one mask is 9-10 GB at 1e8 cells): estimate the new table with the largest active
+    // set seen so far (12 until a mask has been built), then evict least-recently-used masks and retry if an
+    // allocation still fails
+    const size_t est = (size_t)std::max(h->max_active, 12) * (size_t)h->g.ncell * (sizeof(double) + 1);
+    while (!h->cache.empty() && h->cache_bytes + est > h->cache_budget) evict_lru();
+    DkWeights* W = nullptr;
+    int rc;
+    for (;;) {
+        W = new DkWeights();
+        rc = dk_build(in, h->stream, W, &h->fallback_cells);
+        if (rc == SMRFB_OK) break;
+        delete W;
+        if (rc != SMRFB_ERR_CUDA || h->cache.empty()) return rc;
+        cudaGetLastError();   // clear the (non-sticky) allocation failure; a sticky error fails again and ends the loop
+        evict_lru();
     }
+    h->masks_built++;
+    h->max_active = std::max(h->max_active, W->K);
+    while (!h->cache.empty() && h->cache_bytes + W->bytes > h->cache_budget) evict_lru();
     h->cache.emplace_front(nanmask, W);
     h->cache_bytes += W->bytes;
     *out = W;
@@ -1031,7 +1165,7 @@ static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T
         DkDistArgs a;
         a.ncell = h->g.ncell; a.cbase = cbase; a.ncw = ncw; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
         a.rec = h->d_rec; a.recp = h->d_recp; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
-        a.vmin = vmin; a.vmax = vmax; a.out = d_out;
+        a.vmin = vmin; a.vmax = vmax; a.out = d_out; a.out_f32 = h->out_f32;
         const unsigned nblk = (unsigned)((ncw + 255) / 256);
         const unsigned nblk_d = (unsigned)((ncw + DK_DT - 1) / DK_DT);
         const size_t dsm = (size_t)2 * (DK_TCH / 2) * PR * sizeof(double) + 2 * sizeof(uint64_t);

@@ -35,6 +35,12 @@ struct GridHandle : HandleBase {
     size_t l4_cap = 0;
     double* d_l3 = nullptr;            // grid_local: staging of the caller's [T][3][S] block
     size_t l3_cap = 0;
+    double* d_ctgeo = nullptr;         // cubic: [nsimp][9] edge vectors e12, e23, e31 and cross-edge coefficients g
+    double* d_ctw = nullptr;           // cubic: [9][ncell] Clough-Tocher patch weights of every cell
+    double* d_cf = nullptr;            // cubic: staging of the caller's [T][nf][3][S] block (+ [T][2] coefficients)
+    size_t cf_cap = 0;
+    double* d_cvt = nullptr;           // cubic: [S][T][4 nf] (value, d/dx, d/dy, 0) per point, step and field
+    size_t cvt_cap = 0;
     GridHandle() : HandleBase(HK_GRID) {}
     ~GridHandle() override {
         cudaSetDevice(device);
@@ -46,6 +52,10 @@ struct GridHandle : HandleBase {
         cudaFree(d_pvt);
         cudaFree(d_l4);
         cudaFree(d_l3);
+        cudaFree(d_ctgeo);
+        cudaFree(d_ctw);
+        cudaFree(d_cf);
+        cudaFree(d_cvt);
     }
 };
 
@@ -83,13 +93,14 @@ struct GridArgs {
     int T, T_pad, detrend;
     double vmin, vmax;
     double* out;
+    int out_f32;                   // 1: out is float32 [T][ncell]
 };
 
 __global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs a) {
     const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
     if (c >= a.g.ncell) return;
-    double* op = a.out + c;
     const size_t ncell = (size_t)a.g.ncell;
+    const int f32 = a.out_f32;
     if (a.cell_nearest) {   // grid_method 'nearest': the value of the nearest source point, no hull, no arithmetic on it
         const double* vn = a.vt + (size_t)__ldg(a.cell_nearest + c) * a.T_pad;
         const double Zn = (a.detrend && a.g.dem) ? __ldg(a.g.dem + c) : 0.0;
@@ -102,15 +113,15 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs 
                 v0 = __dadd_rn(__dadd_rn(v0, __dmul_rn(pa.x, Zn)), pa.y);
                 v1 = __dadd_rn(__dadd_rn(v1, __dmul_rn(pb.x, Zn)), pb.y);
             }
-            __stcs(op + (size_t)t0 * ncell, clamp_nan_keep(v0, a.vmin, a.vmax));
-            if (t0 + 1 < a.T) __stcs(op + (size_t)(t0 + 1) * ncell, clamp_nan_keep(v1, a.vmin, a.vmax));
+            store_out(a.out, (size_t)t0 * ncell + c, clamp_nan_keep(v0, a.vmin, a.vmax), f32);
+            if (t0 + 1 < a.T) store_out(a.out, (size_t)(t0 + 1) * ncell + c, clamp_nan_keep(v1, a.vmin, a.vmax), f32);
         }
         return;
     }
     const int sx = __ldg(a.cell_simplex + c);
     if (sx < 0) {
         const double qnan = nan("");
-        for (int t = 0; t < a.T; t++) __stcs(op + (size_t)t * ncell, qnan);
+        for (int t = 0; t < a.T; t++) store_out(a.out, (size_t)t * ncell + c, qnan, f32);
         return;
     }
     double X, Y;
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute_kernel(GridArgs 
                 v = __dadd_rn(v, __dmul_rn(c1, xb[u]));
                 v = __dadd_rn(v, __dmul_rn(c2, xc[u]));
                 if (a.detrend) v = __dadd_rn(__dadd_rn(v, __dmul_rn(pv[2 * u], Z)), pv[2 * u + 1]);  // grid.py:210
-                __stcs(op + (size_t)(t0 + u) * ncell, clamp_nan_keep(v, a.vmin, a.vmax));
+                store_out(a.out, (size_t)(t0 + u) * ncell + c, clamp_nan_keep(v, a.vmin, a.vmax), f32);
             }
         }
     }
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute2_kernel(GridArgs
     if (c >= a.g.ncell) return;                       // ncell is even: c + 1 is a valid cell too
     const GridCell g0 = grid_cell_setup(a, c), g1 = grid_cell_setup(a, c + 1);
     const size_t ncell = (size_t)a.g.ncell;
-    double* op = a.out + c;
+    const int f32 = a.out_f32;
     const double qnan = nan("");
 #pragma unroll 1
     for (int t0 = 0; t0 < a.T; t0 += 2) {             // T_pad is even: vector loads stay in bounds
@@ -213,8 +224,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_distribute2_kernel(GridArgs
         v01 = g0.inside ? clamp_nan_keep(v01, a.vmin, a.vmax) : qnan;
         v10 = g1.inside ? clamp_nan_keep(v10, a.vmin, a.vmax) : qnan;
         v11 = g1.inside ? clamp_nan_keep(v11, a.vmin, a.vmax) : qnan;
-        __stcs(reinterpret_cast<double2*>(op + (size_t)t0 * ncell), make_double2(v00, v10));
-        if (t0 + 1 < a.T) __stcs(reinterpret_cast<double2*>(op + (size_t)(t0 + 1) * ncell), make_double2(v01, v11));
+        store_out2(a.out, (size_t)t0 * ncell + c, v00, v10, f32);
+        if (t0 + 1 < a.T) store_out2(a.out, (size_t)(t0 + 1) * ncell + c, v01, v11, f32);
     }
 }
 
@@ -266,8 +277,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_local_kernel(GridArgs a) { 
     if (c >= a.g.ncell) return;
     const GridLocalCell g = grid_local_setup(a, c);
     const size_t ncell = (size_t)a.g.ncell;
-    double* op = a.out + c;
-    for (int t = 0; t < a.T; t++) __stcs(op + (size_t)t * ncell, grid_local_value(g, t, a.vmin, a.vmax));
+    for (int t = 0; t < a.T; t++) store_out(a.out, (size_t)t * ncell + c, grid_local_value(g, t, a.vmin, a.vmax), a.out_f32);
 }
 
 __global__ void __launch_bounds__(GRID_THREADS) grid_local2_kernel(GridArgs a) {         // two adjacent cells, 128-bit stores
@@ -275,11 +285,10 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_local2_kernel(GridArgs a) {
     if (c >= a.g.ncell) return;                       // ncell is even: c + 1 is a valid cell too
     const GridLocalCell g0 = grid_local_setup(a, c), g1 = grid_local_setup(a, c + 1);
     const size_t ncell = (size_t)a.g.ncell;
-    double* op = a.out + c;
+    const int f32 = a.out_f32;
 #pragma unroll 2
     for (int t = 0; t < a.T; t++)
-        __stcs(reinterpret_cast<double2*>(op + (size_t)t * ncell),
-               make_double2(grid_local_value(g0, t, a.vmin, a.vmax), grid_local_value(g1, t, a.vmin, a.vmax)));
+        store_out2(a.out, (size_t)t * ncell + c, grid_local_value(g0, t, a.vmin, a.vmax), grid_local_value(g1, t, a.vmin, a.vmax), f32);
 }
 
 // d_f3: [T][3][S] on the device (residual, slope, intercept rows per step)
@@ -315,6 +324,7 @@ static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin,
     a.vmin = vmin;
     a.vmax = vmax;
     a.out = d_out;
+    a.out_f32 = h->out_f32;
     const long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     if ((h->g.ncell & 1) == 0 && !getenv("SMRFB_GRID_ONE_CELL")) {
@@ -322,6 +332,195 @@ static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin,
         grid_local2_kernel<<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
     } else
         grid_local_kernel<<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ grid_method 'cubic'
+// scipy.interpolate.CloughTocher2DInterpolator (reached from grid.py:204-207, :226-229 through griddata(method='cubic')
+// and from utils.py:447 on the cached triangulation): a C1 piecewise-cubic Bezier patch per Delaunay triangle, built
+// from the three vertex values and three vertex gradients.  The vertex gradients are estimated on the host by SciPy's
+// own iteration (its stopping point decides the low digits, so both sides must run the same code); the patch itself
+// is LINEAR in those nine data, so a cell needs nine weights -- formed once per launch by evaluating the patch on
+// the nine unit data, exactly SciPy's `_clough_tocher_2d_single` -- and a timestep costs nine multiply-adds:
+//   out = sum_v ( wf[v] f_v + wx[v] df_v/dx + wy[v] df_v/dy )                     v = the simplex's three vertices
+// nf = 1: out (+ p0 Z + p1: detrendedInterpolationMask, grid.py:210; the residuals and coefficients come from the host)
+// nf = 2: out = patch(field 0) + Z * patch(field 1)      (detrendedInterpolationLocal, grid.py:175, with field 0 =
+//         residual + intercept and field 1 = slope: the patch is linear, the three interpolations fold into two)
+struct CtData {
+    double f[3], d[6];
+};
+
+// SciPy `_clough_tocher_2d_single` for barycentrics b, geometry geo = {e12x, e12y, e23x, e23y, e31x, e31y, g0, g1, g2}
+__device__ __forceinline__ double ct_patch(const double* b, const double* geo, const CtData& v) {
+    const double e12x = geo[0], e12y = geo[1], e23x = geo[2], e23y = geo[3], e31x = geo[4], e31y = geo[5];
+    const double f1 = v.f[0], f2 = v.f[1], f3 = v.f[2];
+    const double df12 = +(v.d[0] * e12x + v.d[1] * e12y);
+    const double df21 = -(v.d[2] * e12x + v.d[3] * e12y);
+    const double df23 = +(v.d[2] * e23x + v.d[3] * e23y);
+    const double df32 = -(v.d[4] * e23x + v.d[5] * e23y);
+    const double df31 = +(v.d[4] * e31x + v.d[5] * e31y);
+    const double df13 = -(v.d[0] * e31x + v.d[1] * e31y);
+    const double c3000 = f1, c2100 = (df12 + 3 * c3000) / 3, c2010 = (df13 + 3 * c3000) / 3;
+    const double c0300 = f2, c1200 = (df21 + 3 * c0300) / 3, c0210 = (df23 + 3 * c0300) / 3;
+    const double c0030 = f3, c1020 = (df31 + 3 * c0030) / 3, c0120 = (df32 + 3 * c0030) / 3;
+    const double c2001 = (c2100 + c2010 + c3000) / 3;
+    const double c0201 = (c1200 + c0300 + c0210) / 3;
+    const double c0021 = (c1020 + c0120 + c0030) / 3;
+    const double c0111 = (geo[6] * (-c0300 + 3 * c0210 - 3 * c0120 + c0030) + (-c0300 + 2 * c0210 - c0120 + c0021 + c0201)) / 2;
+    const double c1011 = (geo[7] * (-c0030 + 3 * c1020 - 3 * c2010 + c3000) + (-c0030 + 2 * c1020 - c2010 + c2001 + c0021)) / 2;
+    const double c1101 = (geo[8] * (-c3000 + 3 * c2100 - 3 * c1200 + c0300) + (-c3000 + 2 * c2100 - c1200 + c2001 + c0201)) / 2;
+    const double c1002 = (c1101 + c1011 + c2001) / 3;
+    const double c0102 = (c1101 + c0111 + c0201) / 3;
+    const double c0012 = (c1011 + c0111 + c0021) / 3;
+    const double c0003 = (c1002 + c0102 + c0012) / 3;
+    const double minval = fmin(b[0], fmin(b[1], b[2]));
+    const double b1 = b[0] - minval, b2 = b[1] - minval, b3 = b[2] - minval, b4 = 3 * minval;
+    return b1 * b1 * b1 * c3000 + 3 * b1 * b1 * b2 * c2100 + 3 * b1 * b1 * b3 * c2010 + 3 * b1 * b1 * b4 * c2001 +
+           3 * b1 * b2 * b2 * c1200 + 6 * b1 * b2 * b4 * c1101 + 3 * b1 * b3 * b3 * c1020 + 6 * b1 * b3 * b4 * c1011 +
+           3 * b1 * b4 * b4 * c1002 + b2 * b2 * b2 * c0300 + 3 * b2 * b2 * b3 * c0210 + 3 * b2 * b2 * b4 * c0201 +
+           3 * b2 * b3 * b3 * c0120 + 6 * b2 * b3 * b4 * c0111 + 3 * b2 * b4 * b4 * c0102 + b3 * b3 * b3 * c0030 +
+           3 * b3 * b3 * b4 * c0021 + 3 * b3 * b4 * b4 * c0012 + b4 * b4 * b4 * c0003;
+}
+
+struct GridCubicArgs {
+    Geom g;
+    const int32_t* simplices;
+    const double* transform;
+    const int32_t* cell_simplex;
+    const double* ctgeo;     // [nsimp][9]
+    const double* ctw;       // [9][ncell] patch weights per cell
+    const double* cvt;       // [S][T][4 nf]
+    const double* pv;        // [T][2] or null
+    int T;
+    double vmin, vmax;
+    double* out;
+    int out_f32;
+};
+
+// fields[t][q][s] (q = 3 f + {value, d/dx, d/dy}) -> cvt[s][t][4 f + {0, 1, 2}], pad slot = 0
+__global__ void grid_cubic_pack_kernel(const double* __restrict__ fields, int T, int nf, int S, double* __restrict__ cvt) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (s >= S) return;
+    double* o = cvt + ((size_t)s * T + t) * (4 * nf);
+    for (int f = 0; f < nf; f++) {
+        const double* src = fields + ((size_t)t * nf + f) * 3 * S + s;
+        reinterpret_cast<double2*>(o)[2 * f] = make_double2(src[0], src[S]);
+        reinterpret_cast<double2*>(o)[2 * f + 1] = make_double2(src[2 * (size_t)S], 0.0);
+    }
+}
+
+// Once per handle (smrfb_grid_set_cubic): the nine patch weights of every cell, ctw[i][ncell] (zeros outside the hull).
+__global__ void __launch_bounds__(GRID_THREADS) grid_cubic_weights_kernel(GridCubicArgs a, double* __restrict__ ctw) {
+    const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (c >= a.g.ncell) return;
+    const size_t ncell = (size_t)a.g.ncell;
+    const int sx = __ldg(a.cell_simplex + c);
+    double w[9];       // weights of f_0..2, then (d/dx, d/dy) of vertex 0, 1, 2
+    if (sx < 0) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) w[i] = 0.0;
+    } else {
+        double X, Y;
+        cell_xy(a.g, c, X, Y);
+        const double* Tm = a.transform + (size_t)sx * 6;
+        const double dx = __dsub_rn(X, __ldg(Tm + 4)), dy = __dsub_rn(Y, __ldg(Tm + 5));
+        double b[3];
+        b[0] = __dadd_rn(__dmul_rn(__ldg(Tm + 0), dx), __dmul_rn(__ldg(Tm + 1), dy));
+        b[1] = __dadd_rn(__dmul_rn(__ldg(Tm + 2), dx), __dmul_rn(__ldg(Tm + 3), dy));
+        b[2] = __dsub_rn(__dsub_rn(1.0, b[0]), b[1]);
+        double geo[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) geo[i] = __ldg(a.ctgeo + (size_t)sx * 9 + i);
+#pragma unroll
+        for (int i = 0; i < 9; i++) {     // the patch is linear in its nine data: evaluate it on the unit data
+            CtData u;
+#pragma unroll
+            for (int j = 0; j < 3; j++) u.f[j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) u.d[j] = (i == 3 + j) ? 1.0 : 0.0;
+            w[i] = ct_patch(b, geo, u);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) ctw[(size_t)i * ncell + c] = w[i];
+}
+
+template <int NF>
+__global__ void __launch_bounds__(GRID_THREADS) grid_cubic_kernel(GridCubicArgs a) {
+    const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (c >= a.g.ncell) return;
+    const size_t ncell = (size_t)a.g.ncell;
+    const int f32 = a.out_f32;
+    const int sx = __ldg(a.cell_simplex + c);
+    if (sx < 0) {
+        const double qnan = nan("");
+        for (int t = 0; t < a.T; t++) store_out(a.out, (size_t)t * ncell + c, qnan, f32);
+        return;
+    }
+    double w[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) w[i] = __ldg(a.ctw + (size_t)i * ncell + c);
+    const size_t rowlen = (size_t)a.T * (4 * NF);
+    const double* vp[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) vp[v] = a.cvt + (size_t)__ldg(a.simplices + 3 * sx + v) * rowlen;
+    const double Z = a.g.dem ? __ldg(a.g.dem + c) : 0.0;
+#pragma unroll 2
+    for (int t = 0; t < a.T; t++) {
+        double val[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                const double2 x0 = __ldg(reinterpret_cast<const double2*>(vp[v] + (size_t)t * (4 * NF) + 4 * f));
+                const double2 x1 = __ldg(reinterpret_cast<const double2*>(vp[v] + (size_t)t * (4 * NF) + 4 * f + 2));
+                acc = fma(w[v], x0.x, acc);
+                acc = fma(w[3 + 2 * v], x0.y, acc);
+                acc = fma(w[4 + 2 * v], x1.x, acc);
+            }
+            val[f] = acc;
+        }
+        double r = val[0];
+        if (NF == 2) r = fma(Z, val[NF - 1], r);
+        else if (a.pv) r = __dadd_rn(__dadd_rn(r, __dmul_rn(__ldg(a.pv + 2 * t), Z)), __ldg(a.pv + 2 * t + 1));   // grid.py:210
+        store_out(a.out, (size_t)t * ncell + c, clamp_nan_keep(r, a.vmin, a.vmax), f32);
+    }
+}
+
+// d_fields: [T][nf][3][S] on the device; d_pv: [T][2] or null
+static int grid_cubic_run(GridHandle* h, const double* d_fields, int T, int nf, const double* d_pv, double vmin, double vmax,
+                          double* d_out, cudaStream_t st) {
+    SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
+    SMRFB_CHECK(nf == 1 || nf == 2, SMRFB_ERR_ARG, "cubic: nf must be 1 or 2");
+    SMRFB_CHECK(h->d_ctgeo && h->d_ctw, SMRFB_ERR_ARG, "grid method 'cubic' needs smrfb_grid_set_cubic() first");
+    SMRFB_CHECK((nf == 1 && !d_pv) || h->g.dem, SMRFB_ERR_ARG, "cubic with a trend needs GridZ");
+    const size_t S = (size_t)h->S;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_cvt, &h->cvt_cap, S * T * 4 * nf * sizeof(double)));
+    dim3 pg((unsigned)((S + 127) / 128), (unsigned)T);
+    grid_cubic_pack_kernel<<<pg, 128, 0, st>>>(d_fields, T, nf, (int)S, h->d_cvt);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    GridCubicArgs a;
+    a.g = h->g;
+    a.simplices = h->d_simplices;
+    a.transform = h->d_transform;
+    a.cell_simplex = h->d_cell_simplex;
+    a.ctgeo = h->d_ctgeo;
+    a.ctw = h->d_ctw;
+    a.cvt = h->d_cvt;
+    a.pv = d_pv;
+    a.T = T;
+    a.vmin = vmin;
+    a.vmax = vmax;
+    a.out = d_out;
+    a.out_f32 = h->out_f32;
+    const long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
+    SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+    if (nf == 1) grid_cubic_kernel<1><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    else grid_cubic_kernel<2><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
     return SMRFB_OK;
@@ -357,6 +556,7 @@ static int grid_run(GridHandle* h, const double* d_data, int T, int detrend, int
     a.vmin = vmin;
     a.vmax = vmax;
     a.out = d_out;
+    a.out_f32 = h->out_f32;
     long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     if (method == 0 && (h->g.ncell & 1) == 0 && !getenv("SMRFB_GRID_ONE_CELL")) {
@@ -428,6 +628,60 @@ int smrfb_grid_set_nearest(smrfb_handle_t hh, const int32_t* cell_nearest) {
     if (!h->d_cell_nearest) SMRFB_CUDA(cudaMalloc((void**)&h->d_cell_nearest, ncell * sizeof(int32_t)));
     SMRFB_CUDA(cudaMemcpy(h->d_cell_nearest, cell_nearest, ncell * sizeof(int32_t), cudaMemcpyHostToDevice));
     return SMRFB_OK;
+}
+
+int smrfb_grid_set_cubic(smrfb_handle_t hh, const double* ct_geom) {
+    SMRFB_CHECK(hh && ct_geom, SMRFB_ERR_ARG, "NULL handle / array");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    if (!h->d_ctgeo) SMRFB_CUDA(cudaMalloc((void**)&h->d_ctgeo, (size_t)h->nsimp * 9 * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpy(h->d_ctgeo, ct_geom, (size_t)h->nsimp * 9 * sizeof(double), cudaMemcpyHostToDevice));
+    if (!h->d_ctw) SMRFB_CUDA(cudaMalloc((void**)&h->d_ctw, (size_t)h->g.ncell * 9 * sizeof(double)));
+    GridCubicArgs a = {};
+    a.g = h->g;
+    a.simplices = h->d_simplices;
+    a.transform = h->d_transform;
+    a.cell_simplex = h->d_cell_simplex;
+    a.ctgeo = h->d_ctgeo;
+    const long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
+    SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
+    grid_cubic_weights_kernel<<<(unsigned)nblk, GRID_THREADS, 0, h->stream>>>(a, h->d_ctw);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    SMRFB_CUDA(cudaStreamSynchronize(h->stream));
+    return SMRFB_OK;
+}
+
+int smrfb_grid_distribute_cubic_dev(smrfb_handle_t hh, const double* d_fields, int T, int nf, const double* d_pv, double vmin,
+                                    double vmax, double* d_out, void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CHECK(d_fields && d_out, SMRFB_ERR_ARG, "NULL fields/out");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return grid_cubic_run(h, d_fields, T, nf, d_pv, vmin, vmax, d_out, st);
+}
+
+int smrfb_grid_distribute_cubic(smrfb_handle_t hh, const double* fields, int T, int nf, const double* pv, double vmin,
+                                double vmax, double* out) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    SMRFB_CHECK(fields && out && T > 0 && (nf == 1 || nf == 2), SMRFB_ERR_ARG, "NULL fields/out, T <= 0 or nf not 1 / 2");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S, per = (size_t)nf * 3 * S;
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_cf, &h->cf_cap, ((size_t)T * per + 2 * (size_t)T) * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpyAsync(h->d_cf, fields, (size_t)T * per * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double* d_pv = nullptr;
+    if (pv) {
+        d_pv = h->d_cf + (size_t)T * per;
+        SMRFB_CUDA(cudaMemcpyAsync(d_pv, pv, (size_t)T * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    return run_host_batches(h, T, 32, out, [&](int t0, int tn, double* d_out, cudaStream_t st) {
+        return grid_cubic_run(h, h->d_cf + (size_t)t0 * per, tn, nf, d_pv ? d_pv + 2 * (size_t)t0 : nullptr, vmin, vmax, d_out, st);
+    });
 }
 
 int smrfb_grid_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, int detrend, int slope_flag, int method,

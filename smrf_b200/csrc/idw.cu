@@ -67,6 +67,7 @@ struct IdwArgs {
     int clamp;            // 0 when both bounds are infinite: the compare / select instructions are skipped
     double vmin, vmax;
     double* out;          // [T][ncw]
+    int out_f32;          // 1: out is float32
     long long cbase;      // first cell of the window this launch distributes
     long long ncw;        // cells in the window
 };
@@ -352,12 +353,12 @@ __global__ void __launch_bounds__(IDW_THREADS, 1) idw_distribute_kernel(IdwArgs 
             }
             if (t < a.T) {
                 const long long c = cell0 + 2 * lane;
-                double* op = a.out + (size_t)t * (size_t)a.ncw + c;
+                const size_t oi = (size_t)t * (size_t)a.ncw + c;
                 if (c + 1 < a.ncw && even_pairs) {
-                    __stcs(reinterpret_cast<double2*>(op), make_double2(v[0], v[1]));
+                    store_out2(a.out, oi, v[0], v[1], a.out_f32);
                 } else {
-                    if (c < a.ncw) __stcs(op, v[0]);
-                    if (c + 1 < a.ncw) __stcs(op + 1, v[1]);
+                    if (c < a.ncw) store_out(a.out, oi, v[0], a.out_f32);
+                    if (c + 1 < a.ncw) store_out(a.out, oi + 1, v[1], a.out_f32);
                 }
             }
         }
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(IDWS_THREADS) idw_small_kernel(IdwArgs a) {
                 }
                 if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, Z)), pp.y);   // idw.py:144, left to right
                 if (a.clamp) val = clamp_nan_keep(val, a.vmin, a.vmax);
-                __stcs(a.out + (size_t)t * (size_t)a.ncw + c, val);
+                store_out(a.out, (size_t)t * (size_t)a.ncw + c, val, a.out_f32);
             }
         }
         __syncthreads();   // everyone is done with rb before the TMA engine overwrites it
@@ -534,6 +535,7 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     a.vmax = vmax;
     a.clamp = !(std::isinf(vmin) && vmin < 0 && std::isinf(vmax) && vmax > 0);
     a.out = d_out;
+    a.out_f32 = h->out_f32;
     a.cbase = cbase;
     a.ncw = ncw;
     // few stations: register-weight kernel.  Measured on B200 (4000 x 4000 cells, T = 512): S = 2: 348 G cell-steps/s;
@@ -558,7 +560,7 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     // steps, so short batches stay on the fp64 tensor-core kernel below
     if (h->i8_mode == 2 || (h->i8_mode == 1 && T >= 32))
         return idw_i8_run(st, &h->i8, h->g, h->d_mx, h->d_my, h->S, h->power, h->d_rec, h->L.RS, h->L.S_pad, h->d_valid, T,
-                          detrend, vmin, vmax, d_out, cbase, ncw, h->device);
+                          detrend, vmin, vmax, d_out, h->out_f32, cbase, ncw, h->device);
     long long nblk = (ncw + IDW_CT - 1) / IDW_CT;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     if (detrend) {
@@ -587,6 +589,7 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
     IdwHandle* h = new IdwHandle();
     h->device = device;
     h->power = power;
+    int smem_max = 0;
     int rc = upload_geom(h, nsta, mx, my, mz, ny, nx, grid_kind, gx, gy, dem);
     if (rc == SMRFB_OK) {
         h->L = make_layout(nsta, 8, IDW_MAXM, true);
@@ -604,7 +607,6 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
             if (h->i8_mode) rc = idw_i8_prepare(device);
         }
         h->smem_bytes = idw_smem_bytes(h->L);
-        int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         if (h->smem_bytes > (size_t)smem_max) {   // S_pad*68*8 B weight tile + 2*32*RS*8 B record ring <= 227 KB: S <= 200
             if (rc == SMRFB_OK && h->i8_mode) {   // 201..224 stations: only the int8 tensor-core kernel holds them
@@ -617,16 +619,17 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
         }
     }
     if (rc == SMRFB_OK && h->smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(idw_distribute_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)h->smem_bytes);
+        // the attribute is per function and device, not per handle: opt in to the device maximum so that a later
+        // handle with fewer stations cannot lower the limit under an earlier one
+        cudaError_t e = cudaFuncSetAttribute(idw_distribute_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(idw_distribute_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+            e = cudaFuncSetAttribute(idw_distribute_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(idw_distribute_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+            e = cudaFuncSetAttribute(idw_distribute_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(idw_distribute_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+            e = cudaFuncSetAttribute(idw_distribute_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(%zu B smem): %s", h->smem_bytes, cudaGetErrorString(e));
+            set_error("cudaFuncSetAttribute(%d B smem): %s", smem_max, cudaGetErrorString(e));
             rc = SMRFB_ERR_CUDA;
         }
     }

@@ -79,6 +79,7 @@ struct I8Args {
     int detrend;
     double vmin, vmax;
     double* out;
+    int out_f32;
     long long cbase, ncw;
     int ntiles;
     const int* maskhdr;     // [0] = distinct NaN masks among the T steps (idw_i8_mask_kernel)
@@ -793,6 +794,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                 double x[k1 - k0];
 #pragma unroll
                 for (int k = k0; k < k1; k++) x[k - k0] = CLAMP ? clamp_nan_keep_fast(xp[k], a.vmin, a.vmax, kmin, kmax) : xp[k];
+                if (a.out_f32) {              // float32 output (the reference's NetCDF type): 128 B per warp and step
+                    float* q = reinterpret_cast<float*>(a.out) + (size_t)pt0 * ostride + c;
+#pragma unroll
+                    for (int k = k0; k < k1; k++, q += ostride)
+                        if ((pok >> k) & 1u) __stcs(q, (float)x[k - k0]);
+                } else {
                 double* q = pop + (size_t)k0 * ostride;
                 if (pok == 0xffffu) {
 #pragma unroll
@@ -801,6 +808,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
 #pragma unroll
                     for (int k = k0; k < k1; k++, q += ostride)
                         if ((pok >> k) & 1u) __stcs(q, x[k - k0]);
+                }
                 }
 #ifdef I8_PROFILE
                 w_st += clock64() - tr0;
@@ -822,7 +830,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) idw_i8_kernel(I8Args a) {
                             double y = x;
                             if (DETREND) y = __dadd_rn(__dadd_rn(y, __dmul_rn(meta[4 * k], Z)), meta[4 * k + 1]);
                             if (CLAMP) y = clamp_nan_keep(y, a.vmin, a.vmax);
-                            __stcs(a.out + (size_t)(pt0 + k) * (size_t)a.ncw + c, y);
+                            store_out(a.out, (size_t)(pt0 + k) * (size_t)a.ncw + c, y, a.out_f32);
                         }
                     }
                 }
@@ -956,12 +964,14 @@ int idw_i8_prepare(int device) {
     SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    // per device (the caller has made `device` current): batches of more than 4096 steps need > 48 KB in the mask kernel
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return SMRFB_OK;
 }
 
 int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const double* d_mx, const double* d_my, int S,
                double power, const double* d_rec, int RS, int S_pad, const uint8_t* d_valid, int T, int detrend,
-               double vmin, double vmax, double* d_out, long long cbase, long long ncw, int device) {
+               double vmin, double vmax, double* d_out, int out_f32, long long cbase, long long ncw, int device) {
     SMRFB_CHECK(S <= IDW_I8_MAX_STATIONS, SMRFB_ERR_LIMIT, "the int8 tensor-core IDW kernel takes at most %d stations", IDW_I8_MAX_STATIONS);
     const int KB = (S + 31) / 32;
     const int nchunk = (T + I8_N - 1) / I8_N;
@@ -976,13 +986,6 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
     uint8_t* d_vu = scratch->d_blob + blob_bytes + ids_bytes;
     const size_t mask_smem = (size_t)T * (sizeof(unsigned long long) + sizeof(int));
     SMRFB_CHECK(mask_smem <= 200 * 1024, SMRFB_ERR_LIMIT, "the int8 IDW kernel takes at most %d steps per call", (int)(200 * 1024 / 12));
-    if (mask_smem > 48 * 1024) {
-        static size_t opted = 0;
-        if (mask_smem > opted) {
-            SMRFB_CUDA(cudaFuncSetAttribute(idw_i8_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            opted = 200 * 1024;
-        }
-    }
     idw_i8_mask_kernel<<<1, 1024, mask_smem, st>>>(d_valid, T, S, KB, d_hdr, d_ids, d_vu);
     idw_i8_slice_kernel<<<nchunk, 256, 0, st>>>(d_rec, RS, S, S_pad, d_valid, T, KB, d_ids, scratch->d_blob, chunk_bytes);
     count_launch(2);
@@ -1005,6 +1008,7 @@ int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const doub
     a.vmin = vmin;
     a.vmax = vmax;
     a.out = d_out;
+    a.out_f32 = out_f32;
     a.cbase = cbase;
     a.ncw = ncw;
     const long long ntiles = (ncw + I8_M - 1) / I8_M;

@@ -19,6 +19,6 @@ int idw_i8_prepare(int device);
 // (rec[t][RS]: residuals, p0, p1 at S_pad; valid[t][S]).
 int idw_i8_run(cudaStream_t st, IdwI8Scratch* scratch, const Geom& g, const double* d_mx, const double* d_my, int S,
                double power, const double* d_rec, int RS, int S_pad, const uint8_t* d_valid, int T, int detrend,
-               double vmin, double vmax, double* d_out, long long cbase, long long ncw, int device);
+               double vmin, double vmax, double* d_out, int out_f32, long long cbase, long long ncw, int device);
 
 }  // namespace smrfb

@@ -15,7 +15,7 @@ import numpy as np
 from .. import _lib
 
 
-class DK:
+class DK(_lib.HandleMixin):
     def __init__(self, mx, my, mz, GridX, GridY, GridZ, config, device=None):
         self.mx = _lib.as_f64(mx)
         self.my = _lib.as_f64(my)
@@ -39,17 +39,8 @@ class DK:
             self.shape[0], self.shape[1], kind, _lib.dptr(gx), _lib.dptr(gy), _lib.dptr(dem),
             int(config.get("detrend_slope", 0) or 0), self.device, self._h))
 
-    def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            try:
-                _lib.lib().smrfb_destroy(h)
-            except Exception:
-                pass
-            self._h = None
-
     # ------------------------------------------------------------------ batched extension
-    def distribute_block(self, data, vmin=None, vmax=None, pv=None, out=None):
+    def distribute_block(self, data, vmin=None, vmax=None, pv=None, out=None, out_dtype=None):
         """[T, nsta] (NaN = missing) -> float64 [T, ny, nx]. Always detrends (image_data.py:242-243)."""
         data = _lib.as_f64(data)
         if data.ndim == 1:
@@ -57,14 +48,14 @@ class DK:
         T, S = data.shape
         if S != self.nsta:
             raise ValueError("data has %d stations, DK was built for %d" % (S, self.nsta))
-        if out is None:
-            out = np.empty((T,) + self.shape, dtype=np.float64)
+        f32 = self._select_dtype(out_dtype, out)
+        out = _lib.out_array(T, self.shape, out, f32)
         pv_in = None if pv is None else _lib.as_f64(pv).reshape(T, 2)
         pv_out = np.empty((T, 2), dtype=np.float64)
         lo = -np.inf if vmin is None else float(vmin)
         hi = np.inf if vmax is None else float(vmax)
         _lib.check(_lib.lib().smrfb_dk_distribute(self._h, _lib.dptr(data), T, lo, hi, _lib.dptr(pv_in),
-                                                  _lib.dptr(pv_out), _lib.dptr(out)))
+                                                  _lib.dptr(pv_out), _lib.vptr(out)))
         self.pv_block = pv_out
         return out
 

@@ -13,7 +13,7 @@ import numpy as np
 from .. import _lib
 
 
-class IDW:
+class IDW(_lib.HandleMixin):
     def __init__(self, mx, my, GridX, GridY, mz=None, GridZ=None, power=2, zeroVal=-1, device=None):
         self.mx = _lib.as_f64(mx)
         self.my = _lib.as_f64(my)
@@ -36,22 +36,15 @@ class IDW:
             self.shape[0], self.shape[1], kind, _lib.dptr(gx), _lib.dptr(gy), _lib.dptr(dem),
             float(power), self.device, self._h))
 
-    def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            try:
-                _lib.lib().smrfb_destroy(h)
-            except Exception:
-                pass
-            self._h = None
-
     # ------------------------------------------------------------------ batched extension
-    def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None):
+    def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None, out_dtype=None):
         """Distribute T timesteps at once. data: [T, nsta] (NaN = missing station).
 
-        Returns float64 [T, ny, nx]; the elevation trend coefficients used land in ``self.pv_block``.
+        Returns float64 [T, ny, nx] (page-locked memory from the library's pool unless ``out`` is given); the
+        elevation trend coefficients used land in ``self.pv_block``.
         ``pv`` ([T, 2], optional) bypasses the device regression (e.g. np.polyfit coefficients).
-        ``out`` may be a preallocated (ideally pinned) C-contiguous [T, ny, nx] float64 array.
+        ``out`` may be a preallocated (ideally pinned) C-contiguous [T, ny, nx] array.
+        ``out_dtype=np.float32`` stores float32 (the reference's output-file type, contract 1e-5); default float64.
         """
         data = _lib.as_f64(data)
         if data.ndim == 1:
@@ -59,17 +52,15 @@ class IDW:
         T, S = data.shape
         if S != self.npoints:
             raise ValueError("data has %d stations, IDW was built for %d" % (S, self.npoints))
-        if out is None:
-            out = np.empty((T,) + self.shape, dtype=np.float64)
-        else:
-            assert out.shape == (T,) + self.shape
+        f32 = self._select_dtype(out_dtype, out)
+        out = _lib.out_array(T, self.shape, out, f32)
         pv_in = None if pv is None else _lib.as_f64(pv).reshape(T, 2)
         pv_out = np.empty((T, 2), dtype=np.float64)
         lo = -np.inf if vmin is None else float(vmin)
         hi = np.inf if vmax is None else float(vmax)
         _lib.check(_lib.lib().smrfb_idw_distribute(
             self._h, _lib.dptr(data), T, int(bool(detrend)), int(flag), lo, hi,
-            _lib.dptr(pv_in), _lib.dptr(pv_out), _lib.dptr(out)))
+            _lib.dptr(pv_in), _lib.dptr(pv_out), _lib.vptr(out)))
         self.pv_block = pv_out
         return out
 

@@ -114,8 +114,8 @@ def test_grid_local_golden(sp, golden, monkeypatch):
     np.testing.assert_array_equal(clamped, np.where(np.isnan(g["out_f0"]), np.nan, np.clip(g["out_f0"], lo, hi)))
     monkeypatch.setenv("SMRFB_GRID_ONE_CELL", "1")
     np.testing.assert_array_equal(grid.distribute_block_local(g["fields"], flag=-1, exact=True), g["out_f-1"])
-    with pytest.raises(NotImplementedError):
-        grid.detrendedInterpolation(g["fields"][0], 0, "cubic")
+    with pytest.raises(ValueError):
+        grid.distribute_block(g["fields"], grid_method="quintic")
 
 
 def test_grid_local_vs_oracle_larger(sp):
@@ -135,3 +135,75 @@ def test_grid_local_vs_oracle_larger(sp):
     out = grid.distribute_block_local(f, flag=-1)
     for t in (0, 17, 36):
         assert parity(out[t], o.detrendedInterpolation(f[t].copy(), -1, "linear"), step_scale(f[t])) <= TOL
+
+
+def _md(g):
+    import pandas as pd
+    return pd.DataFrame({"utm_x": g["px"], "utm_y": g["py"], "elevation": g["pz"], "latitude": g["lat"], "longitude": g["lon"]})
+
+
+def test_grid_cubic_golden(sp, golden):
+    """grid_method='cubic' (scipy CloughTocher2DInterpolator; the reference's default) against vectors produced by
+    executing the reference (tests/golden/make_golden_cubic.py): local detrend (grid.py:115-177 + utils.py:447), mask
+    detrend (grid.py:179-212) and plain interpolation (grid.py:214-231).  1e-9 relative, identical NaN pattern."""
+    import pandas as pd
+    g = golden("grid_cubic")
+    X, Y = np.meshgrid(g["x"], g["y"])
+    md = _md(g)
+    cfg = {"grid_local": True, "grid_local_n": int(g["k"]), "grid_mask": False}
+    grid = sp.GRID(cfg, g["px"], g["py"], X, Y, mz=g["pz"], GridZ=g["dem"], metadata=md)
+    for flag in (-1, 0, 1):
+        ref = g["local_f%d" % flag]
+        for t, row in enumerate(g["fields"]):
+            v = grid.detrendedInterpolation(pd.Series(row.copy(), index=md.index), flag, "cubic")
+            assert parity(v, ref[t], step_scale(row)) <= TOL, (flag, t)
+        blk = grid.distribute_block_local(g["fields"], flag=flag, grid_method="cubic")          # closed-form fits, one launch
+        for t in range(len(ref)):
+            assert parity(blk[t], ref[t], step_scale(g["fields"][t])) <= TOL, (flag, t)
+    grid2 = sp.GRID({"grid_local": False, "grid_mask": True}, g["px"], g["py"], X, Y, mz=g["pz"], GridZ=g["dem"], mask=g["mask"])
+    np.testing.assert_array_equal(grid2.mask, g["point_mask"])
+    for t, row in enumerate(g["fields"]):
+        v = grid2.detrendedInterpolation(pd.Series(row.copy()), -1, "cubic")
+        np.testing.assert_array_equal(grid2.pv, g["mask_pv"][t])                   # np.polyfit on the host, as the reference
+        assert parity(v, g["mask_out"][t], step_scale(row)) <= TOL, t
+        assert parity(grid2.calculateInterpolation(row.copy(), "cubic"), g["plain_out"][t], step_scale(row)) <= TOL, t
+    blk = grid2.distribute_block(g["fields"], detrend=True, flag=-1, grid_method="cubic")
+    for t in range(len(g["fields"])):
+        assert parity(blk[t], g["mask_out"][t], step_scale(g["fields"][t])) <= TOL
+    # clamp fused, float32 output mode (contract 1e-5)
+    lo, hi = float(np.nanpercentile(g["plain_out"], 20)), float(np.nanpercentile(g["plain_out"], 80))
+    cl = grid2.distribute_block(g["fields"], grid_method="cubic", vmin=lo, vmax=hi)
+    want = np.where(np.isnan(g["plain_out"]), np.nan, np.clip(g["plain_out"], lo, hi))
+    for t in range(len(want)):
+        assert parity(cl[t], want[t], step_scale(g["fields"][t])) <= TOL
+    f32 = grid2.distribute_block(g["fields"], grid_method="cubic", out_dtype=np.float32)
+    assert f32.dtype == np.float32
+    for t in range(len(want)):
+        assert parity(f32[t], g["plain_out"][t], step_scale(g["fields"][t])) <= 1e-5
+
+
+def test_grid_cubic_vs_oracle_larger(sp):
+    """Larger synthetic basin, 37 steps (several gradient-estimation threads), against the oracle (SciPy called where
+    the reference calls it)."""
+    import pandas as pd
+    from oracle import oracle as orc
+    from smrf_b200 import synthetic as syn
+    x, y, dem = syn.make_dem(90, 131, dx=60.0, seed=4)
+    X, Y = np.meshgrid(x, y)
+    px, py, pz = syn.make_source_lattice(x, y, dem, spacing=700.0, jitter=80.0, seed=8)
+    md = pd.DataFrame({"utm_x": px, "utm_y": py, "elevation": pz, "latitude": 43.0 + (py - py.min()) / 111000.0,
+                       "longitude": -116.0 + (px - px.min()) / 82000.0})
+    f = syn.make_source_fields(px, py, pz, 37, seed=2)
+    cfg = {"grid_local": True, "grid_local_n": 12, "grid_mask": False}
+    grid = sp.GRID(cfg, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+    o = orc.GRID(cfg, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+    out = grid.distribute_block_local(f, flag=-1, grid_method="cubic")
+    for t in (0, 17, 36):
+        assert parity(out[t], o.detrendedInterpolation(f[t].copy(), -1, "cubic"), step_scale(f[t])) <= TOL
+    cfg2 = {"grid_local": False, "grid_mask": False}
+    g2 = sp.GRID(cfg2, px, py, X, Y, mz=pz, GridZ=dem)
+    o2 = orc.GRID(cfg2, px, py, X, Y, mz=pz, GridZ=dem)
+    out = g2.distribute_block(f, detrend=True, flag=-1, grid_method="cubic", vmin=-5.0, vmax=5.0)
+    for t in (0, 20, 36):
+        ref = orc.set_min_max(o2.detrendedInterpolation(f[t].copy(), -1, "cubic"), -5.0, 5.0)
+        assert parity(out[t], ref, step_scale(f[t])) <= TOL

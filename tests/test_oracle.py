@@ -166,3 +166,34 @@ def test_grid_local_bitwise(golden):
     res0, slope0, _ = orc.local_fit(g["fields"][0], g["pz"], g["nbr"], 0)
     assert (slope0 < 0).any() and not (slope < 0).any() and np.all(icpt[slope0 < 0] == 0.0)
     assert not np.array_equal(g["out_f1"], g["out_f0"])
+
+
+def test_grid_cubic_golden(golden):
+    """grid_method='cubic' (Clough-Tocher), executed by the reference (tests/golden/make_golden_cubic.py): the oracle's
+    GRID calls SciPy exactly where grid.py / utils.py do -> bit-identical; the decomposed restatement the CUDA path
+    uses (nine weights per cell, SciPy's own gradient estimator) agrees to rounding."""
+    g = golden("grid_cubic")
+    X, Y = np.meshgrid(g["x"], g["y"])
+    md = _local_metadata(g)
+    cfg = {"grid_local": True, "grid_local_n": int(g["k"]), "grid_mask": False}
+    o = orc.GRID(cfg, g["px"], g["py"], X, Y, mz=g["pz"], GridZ=g["dem"], metadata=md)
+    for flag in (-1, 0, 1):
+        for t, row in enumerate(g["fields"]):
+            np.testing.assert_array_equal(o.detrendedInterpolation(row.copy(), flag, "cubic"), g["local_f%d" % flag][t])
+    assert not np.array_equal(g["local_f0"], golden("grid_local")["out_f0"])          # cubic differs from linear
+    o2 = orc.GRID({"grid_local": False, "grid_mask": True}, g["px"], g["py"], X, Y, mz=g["pz"], GridZ=g["dem"], mask=g["mask"])
+    np.testing.assert_array_equal(o2.mask, g["point_mask"])
+    plan = orc.cubic_plan(g["px"], g["py"], X, Y)
+    assert (plan["simplex"] < 0).sum() == np.isnan(g["plain_out"][0]).sum() > 0
+    for t, row in enumerate(g["fields"]):
+        np.testing.assert_array_equal(o2.detrendedInterpolation(row.copy(), -1, "cubic"), g["mask_out"][t])
+        np.testing.assert_array_equal(o2.pv, g["mask_pv"][t])
+        np.testing.assert_array_equal(o2.calculateInterpolation(row.copy(), "cubic"), g["plain_out"][t])
+        grad = orc.estimate_gradients(plan["tri"], row)[:, 0, :]
+        v = orc.cubic_apply(plan, row, grad, X.shape)
+        assert orc.parity_error(v, g["plain_out"][t], float(np.max(np.abs(row)))) < 1e-13
+        # detrended: residuals on the host with the reference's coefficients, the patch is evaluated on them
+        dtrend = row - (g["pz"] * o2.pv[0] + o2.pv[1])
+        grad = orc.estimate_gradients(plan["tri"], dtrend)[:, 0, :]
+        v = orc.cubic_apply(plan, dtrend, grad, X.shape) + o2.pv[0] * g["dem"] + o2.pv[1]
+        assert orc.parity_error(v, g["mask_out"][t], float(np.max(np.abs(row)))) < 1e-13
