@@ -139,6 +139,9 @@ int run_host_batches(HandleBase* h, int T, int step_align, double* out_, RunFn r
     if (const char* e = getenv("SMRFB_RING_BYTES")) budget = (size_t)strtoull(e, nullptr, 10);
     int tb = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / (ncell * sizeof(double))));
     if (tb > step_align) tb = tb / step_align * step_align;
+    // a batch that fits one slot whole would run kernel, then copy: cut it in two (>= 32 steps each, so long batches
+    // stay on the tensor-core IDW kernel) and the copy of the first half overlaps the kernels of the second
+    if (tb >= T && T >= 64) tb = ((T + 1) / 2 + step_align - 1) / step_align * step_align;
     const int nslots = tb >= T ? 1 : 2;
     const size_t slot_bytes = (size_t)tb * ncell * sizeof(double);
     if (h->ring_cap < slot_bytes * nslots) {

@@ -83,7 +83,8 @@ class image_data:
         elif dist == "dk":
             blk = self.dk.distribute_block(vals, vmin=self.min, vmax=self.max)
         elif self.config.get("grid_local") and self.config["detrend"]:     # grid.py:96-113 dispatches on grid_local
-            blk = self.grid.distribute_block_local(vals, flag=self.config.get("detrend_slope", 0), vmin=self.min, vmax=self.max)
+            blk = self.grid.distribute_block_local(vals, flag=self.config.get("detrend_slope", 0), vmin=self.min, vmax=self.max,
+                                                   grid_method=self.config.get("grid_method", "linear"))
         else:
             blk = self.grid.distribute_block(vals, detrend=bool(self.config["detrend"]), flag=self.config.get("detrend_slope", 0),
                                              vmin=self.min, vmax=self.max, grid_method=self.config.get("grid_method", "linear"))
@@ -92,7 +93,9 @@ class image_data:
         return blk
 
     def _distribute(self, data, other_attribute=None, zeros=None):
-        # image_data.py:210-263
+        # image_data.py:210-263.  The variable classes clamp right after this call (utils.set_min_max(v, self.min,
+        # self.max), e.g. air_temp.py:84); here the same NaN-preserving clamp is fused into the kernel's store, so the
+        # later set_min_max finds nothing left to do (it is idempotent) and the grid crosses PCIe once.
         key = getattr(data, "name", None)
         if self._block is not None and key in self._block_index:
             v = self._block[self._block_index[key]]
@@ -101,18 +104,31 @@ class image_data:
             if np.sum(data.isnull()) == data.shape[0]:
                 raise Exception("{}: All data values are NaN".format(self.variable))
             dist = self.config["distribution"]
+            lo, hi = self.min, self.max
             if dist == "idw":
-                if self.config["detrend"]:
+                if zeros is not None:          # rarely used branch of idw.py:96-110 (clips negatives itself)
                     v = self.idw.detrendedIDW(data.values, self.config["detrend_slope"], zeros=zeros)
                 else:
-                    v = self.idw.calculateIDW(data.values)
+                    v = self.idw.distribute_block(np.asarray(data.values, dtype=np.float64)[None, :],
+                                                  detrend=bool(self.config["detrend"]),
+                                                  flag=self.config.get("detrend_slope", 0), vmin=lo, vmax=hi)[0]
             elif dist == "dk":
-                v = self.dk.calculate(data.values)
+                v = self.dk.distribute_block(np.asarray(data.values, dtype=np.float64)[None, :], vmin=lo, vmax=hi)[0]
             elif dist == "grid":
+                method = self.config["grid_method"]
                 if self.config["detrend"]:
-                    v = self.grid.detrendedInterpolation(data, self.config["detrend_slope"], self.config["grid_method"])
+                    if self.config.get("grid_local"):
+                        vals = data.loc[self.metadata.index].values if hasattr(data, "loc") else np.asarray(data)
+                        v = self.grid.distribute_block_local(np.asarray(vals, dtype=np.float64)[None, :],
+                                                             flag=self.config["detrend_slope"], vmin=lo, vmax=hi, exact=True,
+                                                             grid_method=method)[0]
+                    else:
+                        v = self.grid.distribute_block(np.asarray(data.values, dtype=np.float64)[None, :], detrend=True,
+                                                       flag=self.config["detrend_slope"], vmin=lo, vmax=hi,
+                                                       grid_method=method)[0]
                 else:
-                    v = self.grid.calculateInterpolation(data.values, self.config["grid_method"])
+                    v = self.grid.distribute_block(np.asarray(data.values, dtype=np.float64)[None, :], detrend=False,
+                                                   vmin=lo, vmax=hi, grid_method=method)[0]
             else:
                 raise Exception("unknown distribution")
         if other_attribute is not None:

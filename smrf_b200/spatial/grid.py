@@ -123,8 +123,13 @@ class GRID(_lib.HandleMixin):
 
     def _ensure_cubic(self):
         if not getattr(self, "_cubic_ready", False):
+            from scipy.interpolate import CloughTocher2DInterpolator
             geo = self._cubic_geometry()
             _lib.check(_lib.lib().smrfb_grid_set_cubic(self._h, _lib.dptr(geo.reshape(-1))))
+            # scipy.spatial.Delaunay fills several attributes lazily (vertex_neighbor_vertices, transform, ...) and
+            # not thread-safely: touch them once here, single-threaded, before _gradients fans out over threads
+            # (measured: 8 threads on a fresh triangulation segfault, after this warm-up they are bit-identical)
+            CloughTocher2DInterpolator(self.tri, np.zeros(self.npoints))
             self._cubic_ready = True
 
     def _gradients(self, values):

@@ -40,8 +40,8 @@ def test_grid_golden(sp, golden):
     import pandas as pd
     v = grid.detrendedInterpolation(pd.Series(g["fields"][1]), -1, "linear")
     np.testing.assert_array_equal(np.isnan(v), np.isnan(g["out_m0_f-1"][1]))
-    with pytest.raises(NotImplementedError):
-        grid.calculateInterpolation(g["fields"][0], "cubic")
+    with pytest.raises(ValueError):
+        grid.calculateInterpolation(g["fields"][0], "quintic")
     # grid_method 'nearest' (NearestNDInterpolator): bit-exact copy of the nearest source value, detrended form within 1e-9
     out = grid.distribute_block(g["fields"], detrend=False, grid_method="nearest")
     np.testing.assert_array_equal(out, g["out_plain_nearest"])

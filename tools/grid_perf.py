@@ -54,3 +54,35 @@ e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 cs = ny * nx * T / (ms * 1e-3)
 print("GRID local %dx%d P=%d T=%d: %.2f ms  %.1f G cell-steps/s  write %.0f GB/s" % (ny, nx, len(px), T, ms, cs / 1e9, cs * 8 / 1e9))
+
+# grid_method='cubic' (Clough-Tocher): host gradient estimation (scipy) + the nine-weight kernel
+for name, obj, nf in (("cubic mask-detrended", g, 1), ("cubic local", gl, 2)):
+    t0 = time.perf_counter()
+    obj._ensure_cubic()
+    t_w = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    grad = obj._gradients(f if nf == 1 else np.concatenate([res, icpt, slope], axis=0))
+    t_g = time.perf_counter() - t0
+    fields = np.zeros((T, nf, 3, len(px)))
+    if nf == 1:
+        fields[:, 0, 0], fields[:, 0, 1], fields[:, 0, 2] = f, grad[:, :, 0], grad[:, :, 1]
+        pvs = torch.from_numpy(np.tile(np.array([-0.0065, 20.0]), (T, 1))).cuda()
+    else:
+        fields[:, 0, 0] = res + icpt
+        fields[:, 0, 1], fields[:, 0, 2] = grad[:T, :, 0] + grad[T:2 * T, :, 0], grad[:T, :, 1] + grad[T:2 * T, :, 1]
+        fields[:, 1, 0], fields[:, 1, 1], fields[:, 1, 2] = slope, grad[2 * T:, :, 0], grad[2 * T:, :, 1]
+        pvs = None
+    d_fc = torch.from_numpy(fields).cuda()
+    pvp = pvs.data_ptr() if pvs is not None else None
+    for _ in range(2):
+        _lib.check(L.smrfb_grid_distribute_cubic_dev(obj._h, d_fc.data_ptr(), T, nf, pvp, -50.0, 50.0, d_out.data_ptr(), st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        _lib.check(L.smrfb_grid_distribute_cubic_dev(obj._h, d_fc.data_ptr(), T, nf, pvp, -50.0, 50.0, d_out.data_ptr(), st))
+    e1.record(stream); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    cs = ny * nx * T / (ms * 1e-3)
+    print("GRID %s %dx%d P=%d T=%d: %.2f ms  %.1f G cell-steps/s  write %.0f GB/s   (weights once %.2f s, host gradients of %d columns %.2f s)"
+          % (name, ny, nx, len(px), T, ms, cs / 1e9, cs * 8 / 1e9, t_w, grad.shape[0], t_g))
