@@ -94,6 +94,13 @@ int smrfb_idw_distribute_window_dev(smrfb_handle_t h, const double* d_data, int 
                                     double vmin, double vmax, const double* d_pv_in, double* d_pv_out,
                                     int64_t cell_begin, int64_t cell_count, double* d_out, void* stream);
 
+/* Which kernel a whole-row call on this handle takes, and the plan of the near / far-field path (csrc/idw_far.cu):
+ * info[0] = 1 if the near field + interpolated far field kernels apply (uniform mesh, power <= 4, > 16 stations), [1] =
+ * Chebyshev nodes per direction, [2] = longest near-station list of a patch, [3] = patches, [4] = near-field radius in
+ * patch half widths x 1000, [5] = 1 if the int8 tensor-core kernel serves the other calls, [6] = 1 if the register-weight
+ * kernel does (<= 16 stations), [7] = reserved. */
+int smrfb_idw_info(smrfb_handle_t h, int info[8]);
+
 /* ------------------------------------------------------------------ DK (dk.py, krige.c, lusolv.c) */
 int smrfb_dk_create(int nsta, const double* mx, const double* my, const double* mz,
                     int ny, int nx, int grid_kind, const double* gx, const double* gy, const double* dem,

@@ -25,6 +25,7 @@
 //   * epilogue: reciprocal (rcp.approx + 2 Newton steps), retrend against the DEM, NaN-preserving
 //     clamp, 128-bit streaming stores.
 #include "common.cuh"
+#include "idw_far.cuh"
 #include "idw_i8.cuh"
 
 namespace smrfb {
@@ -43,14 +44,17 @@ struct IdwHandle : HandleBase {
     double power = 2.0;
     RecLayout L;
     size_t smem_bytes = 0;
+    bool far_only = false;      // more stations than the tensor-core kernels hold: only idw_far.cu applies
     bool use_small = false;     // register-weight kernel (few stations); decided at create time
     int i8_mode = 0;            // int8-sliced tcgen05 kernel: 0 = never (SMRFB_IDW_KERNEL=dmma or > 224 stations),
                                 // 1 = batches of >= 32 steps (default), 2 = always (SMRFB_IDW_KERNEL=i8)
     IdwI8Scratch i8;
+    IdwFarPlan far;             // uniform meshes: near field + interpolated far field (idw_far.cu), the default there
     IdwHandle() : HandleBase(HK_IDW) {}
     ~IdwHandle() override {
         cudaSetDevice(device);
         if (i8.d_blob) cudaFree(i8.d_blob);
+        far.release();
     }
 };
 
@@ -538,6 +542,11 @@ static int idw_run(IdwHandle* h, const double* d_data, int T, int detrend, int s
     a.out_f32 = h->out_f32;
     a.cbase = cbase;
     a.ncw = ncw;
+    // uniform mesh, whole rows: near field + interpolated far field (idw_far.cu), any number of stations
+    if (h->far.enabled && cbase % h->g.nx == 0 && ncw % h->g.nx == 0)
+        return idw_far_run(st, &h->far, h->g, h->d_mx, h->d_my, h->S, h->power, h->d_rec, h->L.RS, h->L.S_pad, h->d_valid, T,
+                           detrend, a.clamp, vmin, vmax, d_out, h->out_f32, (int)(cbase / h->g.nx), (int)(ncw / h->g.nx), h->device);
+    SMRFB_CHECK(!h->far_only, SMRFB_ERR_LIMIT, "IDW: %d stations are only supported on whole-row windows of a uniform mesh", h->S);
     // few stations: register-weight kernel.  Measured on B200 (4000 x 4000 cells, T = 512): S = 2: 348 G cell-steps/s;
     // S = 20: 178 G with either kernel; S = 32: 148 G here vs 163 G on the tensor-core kernel => switch at 16.
     if (h->use_small) {
@@ -591,6 +600,7 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
     h->power = power;
     int smem_max = 0;
     int rc = upload_geom(h, nsta, mx, my, mz, ny, nx, grid_kind, gx, gy, dem);
+    if (rc == SMRFB_OK) rc = idw_far_plan(&h->far, nsta, mx, my, ny, nx, grid_kind, gx, gy, power, device);
     if (rc == SMRFB_OK) {
         h->L = make_layout(nsta, 8, IDW_MAXM, true);
         h->use_small = (h->L.S_pad <= 16) && !getenv("SMRFB_IDW_FORCE_MMA");
@@ -611,6 +621,9 @@ int smrfb_idw_create(int nsta, const double* mx, const double* my, const double*
         if (h->smem_bytes > (size_t)smem_max) {   // S_pad*68*8 B weight tile + 2*32*RS*8 B record ring <= 227 KB: S <= 200
             if (rc == SMRFB_OK && h->i8_mode) {   // 201..224 stations: only the int8 tensor-core kernel holds them
                 h->i8_mode = 2;
+                h->smem_bytes = 0;
+            } else if (rc == SMRFB_OK && h->far.enabled) {   // beyond: near / far field only
+                h->far_only = true;
                 h->smem_bytes = 0;
             } else {
                 set_error("IDW: %d stations need %zu B of shared memory per CTA, device allows %d", nsta, h->smem_bytes, smem_max);
@@ -662,6 +675,21 @@ int smrfb_idw_distribute_window_dev(smrfb_handle_t hh, const double* d_data, int
     SMRFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return idw_run(h, d_data, T, detrend, slope_flag, vmin, vmax, d_pv_in, d_pv_out, d_out, st, cell_begin, cell_count);
+}
+
+int smrfb_idw_info(smrfb_handle_t hh, int info[8]) {
+    SMRFB_CHECK(hh && info, SMRFB_ERR_ARG, "NULL handle / info");
+    IdwHandle* h = reinterpret_cast<IdwHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_IDW, SMRFB_ERR_ARG, "not an IDW handle");
+    info[0] = h->far.enabled ? 1 : 0;
+    info[1] = h->far.nn;
+    info[2] = h->far.max_near;
+    info[3] = h->far.npx * h->far.npy;
+    info[4] = (int)(h->far.theta * 1000.0);
+    info[5] = h->i8_mode ? 1 : 0;
+    info[6] = h->use_small ? 1 : 0;
+    info[7] = 0;
+    return SMRFB_OK;
 }
 
 // Host-buffer entry: the batch is cut into sub-batches of steps so that a double-buffered device

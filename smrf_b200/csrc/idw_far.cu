@@ -1,0 +1,562 @@
+// idw_far.cu -- IDW (smrf/spatial/idw.py:53-110) on a uniform mesh as near field + interpolated far field.
+//
+// The reference evaluates  v(c, t) = sum_s w(c, s) r(s, t) / sum_s w(c, s) valid(s, t),  w = 1 / dist(c, s)^power, over ALL
+// stations for every cell: 2 S flop per output and term (400 + 400 at 200 stations), which puts the fp64 pipe, not HBM,
+// in charge.  For the stations that are far from a patch of cells, w(., s) is an analytic function of the
+// cell position with its singularity at the station, so over a 128 x 128-cell patch it is reproduced to ~1e-11 by its
+// tensor-product Chebyshev interpolant on nn x nn nodes once the station is further than theta patch half widths from
+// the patch (error per station <= eps(theta, nn, power) RELATIVE to its own weight, all weights positive, hence
+// |error of v| <= 2 eps max|r|; eps(6, 10, 2) = 1.0e-10, eps(8, 12, 4) = 1.1e-12, measured over all positions on the
+// boundary of the near region).  Interpolation is linear, so the far field of all far stations together is
+//     F(c, t) = sum_ky sum_kx Ly[row][ky] Lx[col][kx] G[ky][kx][t],     G[node][t] = sum_{s far} w(node, s) r(s, t)
+// (and the same with validity instead of residuals for the masked denominator -- no missing-station lists, no
+// cancellation).  Per launch:
+//   idw_far_pack_kernel   residual / validity pairs per (step, station) and their station-major transpose;
+//   idw_far_node_kernel   G for every patch the row window touches: a [nn^2 x S] x [S x 2T] product per patch, the node
+//                         weights generated in shared memory (near stations get weight 0 there);
+//   idw_far_kernel        one CTA per 8 rows x 128 columns: the patch's G streams through shared memory in 16-step chunks
+//                         (1-D TMA bulk copies, double buffered); each warp owns one row: it contracts the chunk with its
+//                         row's Ly (phase A), then every lane finishes 4 cells per step (phase B): the column basis is
+//                         folded into even / odd parts so that the mirror cells c and 127 - c share their products
+//                         (nn FMA per pair and term instead of 2 nn), adds the patch's near stations directly, divides,
+//                         retrends against the DEM, clamps and streams the row segment out with 256-byte stores.
+// Per output: ~12 FMA of interpolation + 2 per near station (1.5 on average at 200 stations over 300 km) + the epilogue,
+// against 800: the kernel is bound by the fp64 pipe at ~28 instructions per output.
+#include "idw_far.cuh"
+
+namespace smrfb {
+
+constexpr int FAR_RB = 8;            // mesh rows per CTA (one warp each)
+constexpr int FAR_TC = 16;           // timesteps per staged chunk
+constexpr int FAR_THREADS = FAR_RB * 32;
+constexpr int FAR_NQR = 2;           // near stations whose cell weights stay in registers; the rest go through global scratch
+constexpr int FAR_NODE_THREADS = 256;
+constexpr int FAR_NODE_COLS = 128;   // (step, term) columns per node-kernel tile
+
+void IdwFarPlan::release() {
+    cudaFree(d_near_off);
+    cudaFree(d_near_idx);
+    cudaFree(d_tab);
+    cudaFree(d_G);
+    cudaFree(d_rv);
+    cudaFree(d_wn);
+    d_near_off = d_near_idx = nullptr;
+    d_tab = d_G = d_rv = d_wn = nullptr;
+    G_cap = rv_cap = wn_cap = 0;
+    enabled = false;
+}
+
+struct FarXi {
+    double xi[12];
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// rv[t][s] = (residual, validity) and rvt[s][col], col = (t / 16) * 32 + term * 16 + t % 16
+__global__ void idw_far_pack_kernel(const double* __restrict__ rec, int RS, const uint8_t* __restrict__ valid, int T, int S,
+                                    int N, double2* __restrict__ rv, double* __restrict__ rvt) {
+    const int t = blockIdx.x;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        double r = 0.0, v = 0.0;
+        if (t < T) {
+            r = rec[(size_t)t * RS + s];
+            v = valid[(size_t)t * S + s] ? 1.0 : 0.0;
+        }
+        rv[(size_t)t * S + s] = make_double2(r, v);
+        const size_t col = (size_t)(t / FAR_TC) * (2 * FAR_TC) + (t % FAR_TC);
+        rvt[(size_t)s * N + col] = r;
+        rvt[(size_t)s * N + col + FAR_TC] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct FarNodeArgs {
+    const int* near_off;
+    const int* near_idx;
+    const double* mx;
+    const double* my;
+    const double* rvt;   // [S][N]
+    double* G;           // [patch][chunk][node][32]
+    double x0, dx, y0, dy, power;
+    int S, N, npx, pi0, SB;
+    FarXi xi;
+};
+
+template <int NN>
+__global__ void __launch_bounds__(FAR_NODE_THREADS, 1) idw_far_node_kernel(FarNodeArgs a) {
+    constexpr int NNODE = NN * NN;
+    constexpr int NPT = NNODE / 4;      // nodes per thread
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Wn = reinterpret_cast<double*>(smem_raw);                          // [SB][NNODE]
+    uint8_t* isnear = reinterpret_cast<uint8_t*>(Wn + (size_t)a.SB * NNODE);   // [S]
+    const int tid = threadIdx.x;
+    const int lp = blockIdx.x;
+    const int pj = lp % a.npx, pi = a.pi0 + lp / a.npx;
+    const int gp = pi * a.npx + pj;
+    for (int s = tid; s < a.S; s += FAR_NODE_THREADS) isnear[s] = 0;
+    __syncthreads();
+    for (int i = a.near_off[gp] + tid; i < a.near_off[gp + 1]; i += FAR_NODE_THREADS) isnear[a.near_idx[i]] = 1;
+    const double hx = 0.5 * (FAR_P - 1) * a.dx, hy = 0.5 * (FAR_P - 1) * a.dy;
+    const double xc = a.x0 + ((double)pj * FAR_P + 0.5 * (FAR_P - 1)) * a.dx;
+    const double yc = a.y0 + ((double)pi * FAR_P + 0.5 * (FAR_P - 1)) * a.dy;
+    const bool p2 = (a.power == 2.0);
+    const int ng = tid >> 6, cp = tid & 63;
+    const int nchunk = a.N / (2 * FAR_TC);
+    double* Gp = a.G + (size_t)lp * nchunk * NNODE * (2 * FAR_TC);
+
+    for (int sb0 = 0; sb0 < a.S; sb0 += a.SB) {
+        const int sbn = min(a.SB, a.S - sb0);
+        __syncthreads();
+        for (int i = tid; i < sbn * NNODE; i += FAR_NODE_THREADS) {
+            const int sl = i / NNODE, nd = i - sl * NNODE;
+            const int s = sb0 + sl;
+            double w = 0.0;
+            if (!isnear[s]) {
+                const double X = xc + hx * a.xi.xi[nd % NN], Y = yc + hy * a.xi.xi[nd / NN];
+                const double ddx = X - a.mx[s], ddy = Y - a.my[s];
+                const double q = ddx * ddx + ddy * ddy;
+                w = p2 ? 1.0 / q : 1.0 / pow(sqrt(q), a.power);
+            }
+            Wn[i] = w;
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < a.N; c0 += FAR_NODE_COLS) {
+            const int ca = c0 + cp, cb = c0 + 64 + cp;
+            const bool la = ca < a.N, lb = cb < a.N;
+            double acc0[NPT], acc1[NPT];
+#pragma unroll
+            for (int j = 0; j < NPT; j++) acc0[j] = acc1[j] = 0.0;
+            const double* wrow = Wn + ng * NPT;
+            const double* ba = a.rvt + (size_t)sb0 * a.N + (la ? ca : 0);
+            const double* bb = a.rvt + (size_t)sb0 * a.N + (lb ? cb : 0);
+#pragma unroll 2
+            for (int sl = 0; sl < sbn; sl++) {
+                const double b0 = __ldg(ba + (size_t)sl * a.N), b1 = __ldg(bb + (size_t)sl * a.N);
+#pragma unroll
+                for (int j = 0; j < NPT; j++) {
+                    const double w = wrow[(size_t)sl * NNODE + j];
+                    acc0[j] = fma(w, b0, acc0[j]);
+                    acc1[j] = fma(w, b1, acc1[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NPT; j++) {
+                const int node = ng * NPT + j;
+                if (la) {
+                    double* p = Gp + ((size_t)(ca >> 5) * NNODE + node) * 32 + (ca & 31);
+                    *p = sb0 ? *p + acc0[j] : acc0[j];
+                }
+                if (lb) {
+                    double* p = Gp + ((size_t)(cb >> 5) * NNODE + node) * 32 + (cb & 31);
+                    *p = sb0 ? *p + acc1[j] : acc1[j];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct FarArgs {
+    Geom g;
+    const double* mx;
+    const double* my;
+    const int* near_off;
+    const int* near_idx;
+    const double* tab;      // [128][NN] basis, then [64][NN] folded halves
+    const double* G;
+    const double2* rv;      // [T_pad][S]
+    const double* rec;
+    double* wn;             // near-weight scratch
+    double* out;
+    double power, vmin, vmax;
+    int S, RS, S_pad, T, nchunk, detrend, clamp, out_f32;
+    int row0, nrows, npx, pi0, qx;
+};
+
+template <int NN>
+__global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
+    constexpr int NNODE = NN * NN;
+    constexpr int NH = NN / 2;
+    constexpr int EOS = NH * 4 + 2;      // doubles per (row, step) in EO: NH x {E_num, O_num, E_den, O_den}, padded
+    constexpr uint32_t CHUNK_BYTES = NNODE * 2 * FAR_TC * sizeof(double);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Gs = reinterpret_cast<double*>(smem_raw);                    // [2][NNODE][32]
+    double* EO = Gs + 2 * NNODE * 2 * FAR_TC;                            // [RB][TC][EOS]
+    double* Lys = EO + FAR_RB * FAR_TC * EOS;                            // [RB][NN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Lys + FAR_RB * NN);     // [2]
+    int* nearl = reinterpret_cast<int*>(bars + 2);                       // [nq]
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int pj = blockIdx.x;
+    const int grow0 = (a.row0 / FAR_RB + (int)blockIdx.y) * FAR_RB;
+    const int pi = grow0 / FAR_P;
+    const int gp = pi * a.npx + pj;
+    const int lp = (pi - a.pi0) * a.npx + pj;
+    const int grow = grow0 + w;
+    const bool rowlive = grow >= a.row0 && grow < a.row0 + a.nrows;
+    const int rp = grow - pi * FAR_P;                                     // row within the patch
+    const int nq = a.near_off[gp + 1] - a.near_off[gp];
+    const double* Gp = a.G + (size_t)lp * a.nchunk * NNODE * (2 * FAR_TC);
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < nq; i += FAR_THREADS) nearl[i] = a.near_idx[a.near_off[gp] + i];
+    for (int i = tid; i < FAR_RB * NN; i += FAR_THREADS) {
+        const int r = min(grow0 - pi * FAR_P + i / NN, FAR_P - 1);
+        Lys[i] = a.tab[r * NN + i % NN];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int b = 0; b < 2 && b < a.nchunk; b++) {
+            mbar_arrive_expect_tx(&bars[b], CHUNK_BYTES);
+            bulk_g2s(Gs + b * NNODE * 2 * FAR_TC, Gp + (size_t)b * NNODE * 2 * FAR_TC, CHUNK_BYTES, &bars[b]);
+        }
+    }
+
+    // the lane's four cells: columns lane, 127 - lane (pair A) and 32 + lane, 95 - lane (pair B) of the patch
+    const int cb = pj * FAR_P;
+    int col[4] = {cb + lane, cb + FAR_P - 1 - lane, cb + 32 + lane, cb + FAR_P - 33 - lane};
+    bool live[4];
+    double Z[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        live[j] = rowlive && col[j] < a.g.nx;
+        Z[j] = (live[j] && a.g.dem) ? __ldg(a.g.dem + (size_t)grow * a.g.nx + col[j]) : 0.0;
+    }
+    double cA[NN], cB[NN];   // folded column basis: [0, NH) even part, [NH, NN) odd part
+    {
+        const double* f = a.tab + FAR_P * NN;
+#pragma unroll
+        for (int k = 0; k < NN; k++) {
+            cA[k] = __ldg(f + lane * NN + k);
+            cB[k] = __ldg(f + (32 + lane) * NN + k);
+        }
+    }
+    // near-station weights of the four cells
+    double wr[FAR_NQR][4];
+    unsigned coin = 0;       // bit j: a near station sits exactly on cell j (idw.py:69 leaves the distance 0)
+    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    double* wn = a.wn + blk * (size_t)a.qx * (FAR_RB * FAR_P) + (size_t)w * FAR_P + lane;
+    {
+        const bool p2 = (a.power == 2.0);
+        const double Y = rowlive ? __ldg(a.g.gy + grow) : 0.0;
+        double X[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) X[j] = live[j] ? __ldg(a.g.gx + col[j]) : 0.0;
+#pragma unroll
+        for (int qi = 0; qi < FAR_NQR; qi++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) wr[qi][j] = 0.0;
+        for (int qi = 0; qi < nq; qi++) {
+            const int s = nearl[qi];
+            const double sx = __ldg(a.mx + s), sy = __ldg(a.my + s);
+            double ws[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double ddx = __dsub_rn(X[j], sx), ddy = __dsub_rn(Y, sy);
+                const double q = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                const bool zero = (q == 0.0);
+                if (zero && live[j]) coin |= 1u << j;
+                double v = p2 ? fast_rcp<2>(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
+                ws[j] = (live[j] && !zero) ? v : 0.0;
+            }
+            if (qi == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wr[0][j] = ws[j];
+            } else if (qi == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wr[1][j] = ws[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wn[(size_t)(qi - FAR_NQR) * (FAR_RB * FAR_P) + 32 * j] = ws[j];
+            }
+        }
+    }
+    const size_t ncw = (size_t)a.nrows * a.g.nx;
+    size_t obase[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) obase[j] = (size_t)(grow - a.row0) * a.g.nx + col[j];
+    const int tcl = lane & (FAR_TC - 1), term = lane >> 4;
+
+    for (int ch = 0; ch < a.nchunk; ch++) {
+        const int buf = ch & 1;
+        const double* gs = Gs + buf * NNODE * 2 * FAR_TC;
+        mbar_wait(&bars[buf], (ch >> 1) & 1);
+        // ---- phase A: this warp's row of the chunk, E/O-folded over the mirrored column nodes
+        if (rowlive) {
+            double ly[NN];
+#pragma unroll
+            for (int ky = 0; ky < NN; ky++) ly[ky] = Lys[w * NN + ky];
+            double* eo = EO + ((size_t)w * FAR_TC + tcl) * EOS + term * 2;
+#pragma unroll
+            for (int k = 0; k < NH; k++) {
+                double g1 = 0.0, g2 = 0.0;
+#pragma unroll
+                for (int ky = 0; ky < NN; ky++) {
+                    g1 = fma(ly[ky], gs[(ky * NN + k) * 32 + lane], g1);
+                    g2 = fma(ly[ky], gs[(ky * NN + NN - 1 - k) * 32 + lane], g2);
+                }
+                eo[k * 4] = g1 + g2;
+                eo[k * 4 + 1] = g1 - g2;
+            }
+        }
+        __syncthreads();   // every warp is done with gs: refill it; EO is private to the warp
+        if (tid == 0 && ch + 2 < a.nchunk) {
+            mbar_arrive_expect_tx(&bars[buf], CHUNK_BYTES);
+            bulk_g2s(Gs + buf * NNODE * 2 * FAR_TC, Gp + (size_t)(ch + 2) * NNODE * 2 * FAR_TC, CHUNK_BYTES, &bars[buf]);
+        }
+        if (!rowlive) continue;
+        // ---- phase B
+        const int tend = min(FAR_TC, a.T - ch * FAR_TC);
+        for (int tl = 0; tl < tend; tl++) {
+            const int t = ch * FAR_TC + tl;
+            const double2* eo = reinterpret_cast<const double2*>(EO + ((size_t)w * FAR_TC + tl) * EOS);
+            double enA = 0.0, onA = 0.0, edA = 0.0, odA = 0.0, enB = 0.0, onB = 0.0, edB = 0.0, odB = 0.0;
+#pragma unroll
+            for (int k = 0; k < NH; k++) {
+                const double2 n2 = eo[2 * k], d2 = eo[2 * k + 1];     // (E_num, O_num), (E_den, O_den)
+                enA = fma(cA[k], n2.x, enA);
+                onA = fma(cA[NH + k], n2.y, onA);
+                edA = fma(cA[k], d2.x, edA);
+                odA = fma(cA[NH + k], d2.y, odA);
+                enB = fma(cB[k], n2.x, enB);
+                onB = fma(cB[NH + k], n2.y, onB);
+                edB = fma(cB[k], d2.x, edB);
+                odB = fma(cB[NH + k], d2.y, odB);
+            }
+            double num[4] = {enA + onA, enA - onA, enB + onB, enB - onB};
+            double den[4] = {edA + odA, edA - odA, edB + odB, edB - odB};
+            const double2* rvt = a.rv + (size_t)t * a.S;
+            if (nq > 0) {
+                const double2 x = __ldg(rvt + nearl[0]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    num[j] = fma(wr[0][j], x.x, num[j]);
+                    den[j] = fma(wr[0][j], x.y, den[j]);
+                }
+            }
+            if (nq > 1) {
+                const double2 x = __ldg(rvt + nearl[1]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    num[j] = fma(wr[1][j], x.x, num[j]);
+                    den[j] = fma(wr[1][j], x.y, den[j]);
+                }
+            }
+            for (int qi = FAR_NQR; qi < nq; qi++) {
+                const double2 x = __ldg(rvt + nearl[qi]);
+                const double* wq = wn + (size_t)(qi - FAR_NQR) * (FAR_RB * FAR_P);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double wv = wq[32 * j];
+                    num[j] = fma(wv, x.x, num[j]);
+                    den[j] = fma(wv, x.y, den[j]);
+                }
+            }
+            const double2 pp = *reinterpret_cast<const double2*>(a.rec + (size_t)t * a.RS + a.S_pad);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double r = fast_rcp<2>(den[j]);
+                const double q = num[j] * r;
+                double val = fma(fma(-den[j], q, num[j]), r, q);
+                if (coin & (1u << j)) {   // rare: a station sits exactly on this cell: inf weight => NaN, or 0 if its residual is 0
+                    const double X = __ldg(a.g.gx + col[j]), Y = __ldg(a.g.gy + grow);
+                    bool hit = false, bad = false;
+                    for (int qi = 0; qi < nq; qi++) {
+                        const int s = nearl[qi];
+                        const double ddx = __dsub_rn(X, a.mx[s]), ddy = __dsub_rn(Y, a.my[s]);
+                        const double2 x = rvt[s];
+                        if (__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) == 0.0 && x.y != 0.0) {
+                            hit = true;
+                            if (x.x != 0.0) bad = true;
+                        }
+                    }
+                    if (hit) val = bad ? nan("") : 0.0;
+                }
+                if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, Z[j])), pp.y);   // idw.py:144, left to right
+                if (a.clamp) val = clamp_nan_keep(val, a.vmin, a.vmax);
+                if (live[j]) store_out(a.out, (size_t)t * ncw + obase[j], val, a.out_f32);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+static void cheb_nodes(int nn, long double* xi) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int k = 0; k < nn; k++) xi[k] = cosl(pi * (2 * k + 1) / (2 * nn));
+    for (int k = 0; k < nn / 2; k++) xi[nn - 1 - k] = -xi[k];      // exactly symmetric
+}
+
+int idw_far_plan(IdwFarPlan* plan, int S, const double* mx, const double* my, int ny, int nx, int grid_kind,
+                 const double* gx, const double* gy, double power, int device) {
+    plan->enabled = false;
+    const char* k = getenv("SMRFB_IDW_KERNEL");
+    const bool forced = k && !strcmp(k, "far");
+    if (k && !forced && *k) return SMRFB_OK;                      // another kernel was asked for
+    if (grid_kind != 0 || nx < 2 || ny < 2 || !(power > 0.0 && power <= 4.0)) return SMRFB_OK;
+    if (S <= 16 && !forced) return SMRFB_OK;                      // the register-weight kernel is faster there
+    const double dx = (gx[nx - 1] - gx[0]) / (nx - 1), dy = (gy[ny - 1] - gy[0]) / (ny - 1);
+    if (dx == 0.0 || dy == 0.0 || !std::isfinite(dx) || !std::isfinite(dy)) return SMRFB_OK;
+    for (int j = 0; j < nx; j++)
+        if (fabs(gx[j] - (gx[0] + j * dx)) > 1e-7 * fabs(dx)) return SMRFB_OK;
+    for (int i = 0; i < ny; i++)
+        if (fabs(gy[i] - (gy[0] + i * dy)) > 1e-7 * fabs(dy)) return SMRFB_OK;
+    plan->nn = power <= 2.0 ? 10 : 12;
+    plan->theta = power <= 2.0 ? 6.0 : 8.0;
+    if (const char* e = getenv("SMRFB_IDW_FAR_THETA")) plan->theta = std::max(plan->theta, atof(e));   // only ever wider
+    plan->x0 = gx[0];
+    plan->dx = dx;
+    plan->y0 = gy[0];
+    plan->dy = dy;
+    plan->npx = (nx + FAR_P - 1) / FAR_P;
+    plan->npy = (ny + FAR_P - 1) / FAR_P;
+    const int np = plan->npx * plan->npy;
+    const double hx = 0.5 * (FAR_P - 1) * fabs(dx), hy = 0.5 * (FAR_P - 1) * fabs(dy);
+    const double rnear = plan->theta * std::max(hx, hy);
+    std::vector<int> idx;
+    plan->near_off.assign(np + 1, 0);
+    plan->max_near = 0;
+    for (int pi = 0; pi < plan->npy; pi++)
+        for (int pj = 0; pj < plan->npx; pj++) {
+            const double xc = gx[0] + (pj * (double)FAR_P + 0.5 * (FAR_P - 1)) * dx;
+            const double yc = gy[0] + (pi * (double)FAR_P + 0.5 * (FAR_P - 1)) * dy;
+            const int p = pi * plan->npx + pj;
+            for (int s = 0; s < S; s++) {
+                const double ex = std::max(0.0, fabs(mx[s] - xc) - hx), ey = std::max(0.0, fabs(my[s] - yc) - hy);
+                if (!(ex * ex + ey * ey >= rnear * rnear)) idx.push_back(s);   // NaN coordinates count as near
+            }
+            plan->near_off[p + 1] = (int)idx.size();
+            plan->max_near = std::max(plan->max_near, plan->near_off[p + 1] - plan->near_off[p]);
+        }
+    // Lagrange basis at the cell positions u_c = (c - 63.5) / 63.5 on the Chebyshev nodes, and its even / odd folding
+    const int nn = plan->nn;
+    long double xi[12];
+    cheb_nodes(nn, xi);
+    std::vector<double> tab((size_t)(FAR_P + FAR_P / 2) * nn);
+    std::vector<long double> L((size_t)FAR_P * nn);
+    for (int c = 0; c < FAR_P; c++) {
+        const long double u = ((long double)c - 0.5L * (FAR_P - 1)) / (0.5L * (FAR_P - 1));
+        for (int a = 0; a < nn; a++) {
+            long double v = 1.0L;
+            for (int m = 0; m < nn; m++)
+                if (m != a) v *= (u - xi[m]) / (xi[a] - xi[m]);
+            L[(size_t)c * nn + a] = v;
+            tab[(size_t)c * nn + a] = (double)v;
+        }
+    }
+    for (int c = 0; c < FAR_P / 2; c++)
+        for (int a = 0; a < nn / 2; a++) {
+            tab[(size_t)(FAR_P + c) * nn + a] = (double)(0.5L * (L[(size_t)c * nn + a] + L[(size_t)c * nn + nn - 1 - a]));
+            tab[(size_t)(FAR_P + c) * nn + nn / 2 + a] = (double)(0.5L * (L[(size_t)c * nn + a] - L[(size_t)c * nn + nn - 1 - a]));
+        }
+    SMRFB_CUDA(cudaSetDevice(device));
+    SMRFB_CUDA(cudaMalloc((void**)&plan->d_near_off, (np + 1) * sizeof(int)));
+    SMRFB_CUDA(cudaMalloc((void**)&plan->d_near_idx, std::max<size_t>(1, idx.size()) * sizeof(int)));
+    SMRFB_CUDA(cudaMalloc((void**)&plan->d_tab, tab.size() * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpy(plan->d_near_off, plan->near_off.data(), (np + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (!idx.empty()) SMRFB_CUDA(cudaMemcpy(plan->d_near_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SMRFB_CUDA(cudaMemcpy(plan->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    plan->enabled = true;
+    return SMRFB_OK;
+}
+
+template <int NN>
+static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArgs& fa, int npl, int nbands, int smem_max) {
+    constexpr int NNODE = NN * NN;
+    const size_t node_smem = (size_t)na.SB * NNODE * sizeof(double) + (size_t)na.S;
+    SMRFB_CHECK(node_smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: node kernel needs %zu B of shared memory", node_smem);
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_far_node_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    idw_far_node_kernel<NN><<<npl, FAR_NODE_THREADS, node_smem, st>>>(na);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    const size_t smem = (size_t)(2 * NNODE * 2 * FAR_TC + FAR_RB * FAR_TC * (NN / 2 * 4 + 2) + FAR_RB * NN) * sizeof(double) +
+                        2 * sizeof(uint64_t) + (size_t)std::max(1, plan->max_near) * sizeof(int);
+    SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: %zu B of shared memory per CTA", smem);
+    SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    idw_far_kernel<NN><<<dim3(plan->npx, nbands), FAR_THREADS, smem, st>>>(fa);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* d_mx, const double* d_my, int S,
+                double power, const double* d_rec, int RS, int S_pad, const uint8_t* d_valid, int T, int detrend,
+                int clamp, double vmin, double vmax, double* d_out, int out_f32, int row0, int nrows, int device) {
+    const int nn = plan->nn, nnode = nn * nn;
+    const int T_pad = (T + FAR_TC - 1) / FAR_TC * FAR_TC, nchunk = T_pad / FAR_TC, N = 2 * T_pad;
+    const int pi0 = row0 / FAR_P, pi1 = (row0 + nrows - 1) / FAR_P;
+    const int npl = (pi1 - pi0 + 1) * plan->npx;
+    const int nbands = (row0 + nrows - 1) / FAR_RB - row0 / FAR_RB + 1;
+    SMRFB_CHECK(nbands <= 65535, SMRFB_ERR_LIMIT, "IDW far field: too many rows for one launch");
+    int qmax = 0;
+    for (int p = pi0 * plan->npx; p < (pi1 + 1) * plan->npx; p++) qmax = std::max(qmax, plan->near_off[p + 1] - plan->near_off[p]);
+    const int qx = std::max(0, qmax - FAR_NQR);
+    SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_G, &plan->G_cap, (size_t)npl * nchunk * nnode * 2 * FAR_TC * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_rv, &plan->rv_cap, ((size_t)T_pad * S * 2 + (size_t)S * N) * sizeof(double)));
+    SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_wn, &plan->wn_cap,
+                               std::max<size_t>(16, (size_t)plan->npx * nbands * qx * FAR_RB * FAR_P * sizeof(double))));
+    double2* d_rv = reinterpret_cast<double2*>(plan->d_rv);
+    double* d_rvt = plan->d_rv + (size_t)T_pad * S * 2;
+    idw_far_pack_kernel<<<T_pad, 128, 0, st>>>(d_rec, RS, d_valid, T, S, N, d_rv, d_rvt);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    int smem_max = 0;
+    SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+
+    FarNodeArgs na;
+    na.near_off = plan->d_near_off;
+    na.near_idx = plan->d_near_idx;
+    na.mx = d_mx;
+    na.my = d_my;
+    na.rvt = d_rvt;
+    na.G = plan->d_G;
+    na.x0 = plan->x0;
+    na.dx = plan->dx;
+    na.y0 = plan->y0;
+    na.dy = plan->dy;
+    na.power = power;
+    na.S = S;
+    na.N = N;
+    na.npx = plan->npx;
+    na.pi0 = pi0;
+    na.SB = std::min(S, (int)((size_t)(200 * 1024) / (nnode * sizeof(double))));
+    long double xi[12];
+    cheb_nodes(nn, xi);
+    for (int k2 = 0; k2 < 12; k2++) na.xi.xi[k2] = k2 < nn ? (double)xi[k2] : 0.0;
+
+    FarArgs fa;
+    fa.g = g;
+    fa.mx = d_mx;
+    fa.my = d_my;
+    fa.near_off = plan->d_near_off;
+    fa.near_idx = plan->d_near_idx;
+    fa.tab = plan->d_tab;
+    fa.G = plan->d_G;
+    fa.rv = d_rv;
+    fa.rec = d_rec;
+    fa.wn = plan->d_wn;
+    fa.out = d_out;
+    fa.power = power;
+    fa.vmin = vmin;
+    fa.vmax = vmax;
+    fa.S = S;
+    fa.RS = RS;
+    fa.S_pad = S_pad;
+    fa.T = T;
+    fa.nchunk = nchunk;
+    fa.detrend = detrend;
+    fa.clamp = clamp;
+    fa.out_f32 = out_f32;
+    fa.row0 = row0;
+    fa.nrows = nrows;
+    fa.npx = plan->npx;
+    fa.pi0 = pi0;
+    fa.qx = qx;
+    return nn == 10 ? far_launch<10>(st, plan, na, fa, npl, nbands, smem_max) : far_launch<12>(st, plan, na, fa, npl, nbands, smem_max);
+}
+
+}  // namespace smrfb

@@ -36,6 +36,13 @@ class IDW(_lib.HandleMixin):
             self.shape[0], self.shape[1], kind, _lib.dptr(gx), _lib.dptr(gy), _lib.dptr(dem),
             float(power), self.device, self._h))
 
+    def kernel_info(self):
+        """Which device path serves this handle (smrfb_idw_info)."""
+        info = np.zeros(8, dtype=np.int32)
+        _lib.check(_lib.lib().smrfb_idw_info(self._h, info.ctypes.data_as(_lib.c_i32_p)))
+        return {"far_field": bool(info[0]), "nodes": int(info[1]), "max_near": int(info[2]), "patches": int(info[3]),
+                "theta": info[4] / 1000.0, "int8": bool(info[5]), "small": bool(info[6])}
+
     # ------------------------------------------------------------------ batched extension
     def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None, out_dtype=None):
         """Distribute T timesteps at once. data: [T, nsta] (NaN = missing station).

@@ -11,10 +11,16 @@ from util import TOL, parity, step_scale
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def sp():
+@pytest.fixture(params=["default", "dmma"])
+def sp(request, monkeypatch):
+    """default: near field + interpolated far field on uniform meshes (idw_far.cu), else the tensor-core kernels;
+    dmma: the dense fp64 tensor-core kernel for every call (SMRFB_IDW_KERNEL is read when a handle is created)."""
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if request.param == "dmma":
+        monkeypatch.setenv("SMRFB_IDW_KERNEL", "dmma")
+    else:
+        monkeypatch.delenv("SMRFB_IDW_KERNEL", raising=False)
     import smrf_b200.spatial as sp
     return sp
 
