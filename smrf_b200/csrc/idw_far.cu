@@ -27,11 +27,15 @@
 namespace smrfb {
 
 constexpr int FAR_RB = 8;            // mesh rows per CTA (one warp each)
-constexpr int FAR_TC = 16;           // timesteps per staged chunk
+constexpr int FAR_TC = 8;            // timesteps per staged chunk
+constexpr int FAR_CW = 2 * FAR_TC;   // columns per chunk: numerator steps, then denominator steps
 constexpr int FAR_THREADS = FAR_RB * 32;
 constexpr int FAR_NQR = 2;           // near stations whose cell weights stay in registers; the rest go through global scratch
+constexpr int FAR_NQM = 2;           // further near stations whose cell weights sit in shared memory
+constexpr int FAR_NQS = 7;           // near stations whose (residual, validity) pairs are staged in shared memory per chunk
 constexpr int FAR_NODE_THREADS = 256;
 constexpr int FAR_NODE_COLS = 128;   // (step, term) columns per node-kernel tile
+constexpr int FAR_NODE_KB = 8;       // stations per staged block of the node kernel
 
 void IdwFarPlan::release() {
     cudaFree(d_near_off);
@@ -51,7 +55,7 @@ struct FarXi {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// rv[t][s] = (residual, validity) and rvt[s][col], col = (t / 16) * 32 + term * 16 + t % 16
+// rv[t][s] = (residual, validity) and rvt[s][col], col = (t / TC) * 2 TC + term * TC + t % TC
 __global__ void idw_far_pack_kernel(const double* __restrict__ rec, int RS, const uint8_t* __restrict__ valid, int T, int S,
                                     int N, double2* __restrict__ rv, double* __restrict__ rvt) {
     const int t = blockIdx.x;
@@ -75,7 +79,7 @@ struct FarNodeArgs {
     const double* mx;
     const double* my;
     const double* rvt;   // [S][N]
-    double* G;           // [patch][chunk][node][32]
+    double* G;           // [patch][chunk][node][FAR_CW]
     double x0, dx, y0, dy, power;
     int S, N, npx, pi0, SB;
     FarXi xi;
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(FAR_NODE_THREADS, 1) idw_far_node_kernel(FarNo
     constexpr int NPT = NNODE / 4;      // nodes per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Wn = reinterpret_cast<double*>(smem_raw);                          // [SB][NNODE]
-    uint8_t* isnear = reinterpret_cast<uint8_t*>(Wn + (size_t)a.SB * NNODE);   // [S]
+    double* Bs = Wn + (size_t)a.SB * NNODE;                                     // [2][8][128] staged (residual | validity) columns
+    uint8_t* isnear = reinterpret_cast<uint8_t*>(Bs + 2 * FAR_NODE_KB * FAR_NODE_COLS);   // [S]
     const int tid = threadIdx.x;
     const int lp = blockIdx.x;
     const int pj = lp % a.npx, pi = a.pi0 + lp / a.npx;
@@ -126,27 +131,46 @@ __global__ void __launch_bounds__(FAR_NODE_THREADS, 1) idw_far_node_kernel(FarNo
 #pragma unroll
             for (int j = 0; j < NPT; j++) acc0[j] = acc1[j] = 0.0;
             const double* wrow = Wn + ng * NPT;
-            const double* ba = a.rvt + (size_t)sb0 * a.N + (la ? ca : 0);
-            const double* bb = a.rvt + (size_t)sb0 * a.N + (lb ? cb : 0);
-#pragma unroll 2
-            for (int sl = 0; sl < sbn; sl++) {
-                const double b0 = __ldg(ba + (size_t)sl * a.N), b1 = __ldg(bb + (size_t)sl * a.N);
+            // the (residual | validity) tile [8 stations][128 columns] goes through a double-buffered shared stage: the loads
+            // of block i + 1 are in flight while block i is consumed
+            double pre[4];
+            auto fetch = [&](int s0) {
 #pragma unroll
-                for (int j = 0; j < NPT; j++) {
-                    const double w = wrow[(size_t)sl * NNODE + j];
-                    acc0[j] = fma(w, b0, acc0[j]);
-                    acc1[j] = fma(w, b1, acc1[j]);
+                for (int i = 0; i < 4; i++) {
+                    const int e = tid + FAR_NODE_THREADS * i, sr = e >> 7, col = c0 + (e & 127);
+                    pre[i] = (s0 + sr < sbn && col < a.N) ? __ldg(a.rvt + (size_t)(sb0 + s0 + sr) * a.N + col) : 0.0;
+                }
+            };
+            fetch(0);
+            int buf = 0;
+            for (int s0 = 0; s0 < sbn; s0 += FAR_NODE_KB, buf ^= 1) {
+                double* bs = Bs + buf * FAR_NODE_KB * FAR_NODE_COLS;
+#pragma unroll
+                for (int i = 0; i < 4; i++) bs[tid + FAR_NODE_THREADS * i] = pre[i];
+                __syncthreads();
+                if (s0 + FAR_NODE_KB < sbn) fetch(s0 + FAR_NODE_KB);
+                const int kn = min(FAR_NODE_KB, sbn - s0);
+                for (int sr = 0; sr < kn; sr++) {
+                    const double b0 = bs[sr * FAR_NODE_COLS + cp], b1 = bs[sr * FAR_NODE_COLS + 64 + cp];
+                    const double* wr = wrow + (size_t)(s0 + sr) * NNODE;
+#pragma unroll
+                    for (int j = 0; j < NPT; j++) {
+                        const double w = wr[j];
+                        acc0[j] = fma(w, b0, acc0[j]);
+                        acc1[j] = fma(w, b1, acc1[j]);
+                    }
                 }
             }
+            __syncthreads();   // the stage is rewritten by the next tile's first block
 #pragma unroll
             for (int j = 0; j < NPT; j++) {
                 const int node = ng * NPT + j;
                 if (la) {
-                    double* p = Gp + ((size_t)(ca >> 5) * NNODE + node) * 32 + (ca & 31);
+                    double* p = Gp + ((size_t)(ca / FAR_CW) * NNODE + node) * FAR_CW + (ca % FAR_CW);
                     *p = sb0 ? *p + acc0[j] : acc0[j];
                 }
                 if (lb) {
-                    double* p = Gp + ((size_t)(cb >> 5) * NNODE + node) * 32 + (cb & 31);
+                    double* p = Gp + ((size_t)(cb / FAR_CW) * NNODE + node) * FAR_CW + (cb % FAR_CW);
                     *p = sb0 ? *p + acc1[j] : acc1[j];
                 }
             }
@@ -168,33 +192,58 @@ struct FarArgs {
     double* wn;             // near-weight scratch
     double* out;
     double power, vmin, vmax;
-    int S, RS, S_pad, T, nchunk, detrend, clamp, out_f32;
+    int S, RS, S_pad, T, nchunk, clamp, out_f32;
     int row0, nrows, npx, pi0, qx;
 };
 
-template <int NN>
+// A valid station exactly on the cell: the reference's weight is inf, the cell becomes NaN (inf / inf), or 0 when that
+// station's residual is exactly 0 (nansum drops inf * 0).  Returns true when `val` was replaced.
+__device__ __noinline__ double far_coincident(const double* gx, const double* gy, const double* mx, const double* my,
+                                              const int* nearl, int nq, const double2* rvt, int col, int grow, double val) {
+    const double X = __ldg(gx + col), Y = __ldg(gy + grow);
+    bool hit = false, bad = false;
+    for (int qi = 0; qi < nq; qi++) {
+        const int s = nearl[qi];
+        const double ddx = __dsub_rn(X, mx[s]), ddy = __dsub_rn(Y, my[s]);
+        const double2 x = rvt[s];
+        if (__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) == 0.0 && x.y != 0.0) {
+            hit = true;
+            if (x.x != 0.0) bad = true;
+        }
+    }
+    if (hit) val = bad ? nan("") : 0.0;
+    return val;
+}
+
+template <int NN, typename OutT, bool CLAMP>
 __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
     constexpr int NNODE = NN * NN;
     constexpr int NH = NN / 2;
     constexpr int EOS = NH * 4 + 2;      // doubles per (row, step) in EO: NH x {E_num, O_num, E_den, O_den}, padded
+    constexpr int SGS = 1 + FAR_NQS;     // double2 per step in the stage: (p0, p1), then (residual, validity) of the near stations
     constexpr uint32_t CHUNK_BYTES = NNODE * 2 * FAR_TC * sizeof(double);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Gs = reinterpret_cast<double*>(smem_raw);                    // [2][NNODE][32]
-    double* EO = Gs + 2 * NNODE * 2 * FAR_TC;                            // [RB][TC][EOS]
-    double* Lys = EO + FAR_RB * FAR_TC * EOS;                            // [RB][NN]
+    double* Gs = reinterpret_cast<double*>(smem_raw);                    // [2][NNODE][FAR_CW]
+    double* EO = Gs + 2 * NNODE * 2 * FAR_TC;                            // [2][RB][TC][EOS]
+    double2* stg = reinterpret_cast<double2*>(EO + 2 * FAR_RB * FAR_TC * EOS);   // [2][TC][SGS]
+    double* Lys = reinterpret_cast<double*>(stg + 2 * FAR_TC * SGS);     // [RB][NN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Lys + FAR_RB * NN);     // [2]
-    int* nearl = reinterpret_cast<int*>(bars + 2);                       // [nq]
+    double* wns = reinterpret_cast<double*>(bars + 2);                   // [NQM][RB][128] near weights 2, 3 of the cells
+    int* nearl = reinterpret_cast<int*>(wns + FAR_NQM * FAR_RB * FAR_P);   // [nq]
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int pj = blockIdx.x;
-    const int grow0 = (a.row0 / FAR_RB + (int)blockIdx.y) * FAR_RB;
-    const int pi = grow0 / FAR_P;
+    // grid: x = 8-row band within the 128-row patch (the 16 CTAs that share a patch's node sums launch together and
+    // meet in L2), y = patch column, z = patch row of the window
+    const int pj = blockIdx.y;
+    const int pi = a.pi0 + blockIdx.z;
+    const int grow0 = pi * FAR_P + blockIdx.x * FAR_RB;
+    if (grow0 + FAR_RB <= a.row0 || grow0 >= a.row0 + a.nrows) return;   // band outside the row window
     const int gp = pi * a.npx + pj;
-    const int lp = (pi - a.pi0) * a.npx + pj;
+    const int lp = blockIdx.z * a.npx + pj;
     const int grow = grow0 + w;
     const bool rowlive = grow >= a.row0 && grow < a.row0 + a.nrows;
-    const int rp = grow - pi * FAR_P;                                     // row within the patch
     const int nq = a.near_off[gp + 1] - a.near_off[gp];
+    const int nqs = min(nq, FAR_NQS);
     const double* Gp = a.G + (size_t)lp * a.nchunk * NNODE * (2 * FAR_TC);
 
     if (tid == 0) {
@@ -203,10 +252,7 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
         fence_mbar_init();
     }
     for (int i = tid; i < nq; i += FAR_THREADS) nearl[i] = a.near_idx[a.near_off[gp] + i];
-    for (int i = tid; i < FAR_RB * NN; i += FAR_THREADS) {
-        const int r = min(grow0 - pi * FAR_P + i / NN, FAR_P - 1);
-        Lys[i] = a.tab[r * NN + i % NN];
-    }
+    for (int i = tid; i < FAR_RB * NN; i += FAR_THREADS) Lys[i] = a.tab[(blockIdx.x * FAR_RB + i / NN) * NN + i % NN];
     __syncthreads();
     if (tid == 0) {
         for (int b = 0; b < 2 && b < a.nchunk; b++) {
@@ -217,13 +263,13 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
 
     // the lane's four cells: columns lane, 127 - lane (pair A) and 32 + lane, 95 - lane (pair B) of the patch
     const int cb = pj * FAR_P;
-    int col[4] = {cb + lane, cb + FAR_P - 1 - lane, cb + 32 + lane, cb + FAR_P - 33 - lane};
+    const int coff[4] = {lane, FAR_P - 1 - lane, 32 + lane, FAR_P - 33 - lane};
     bool live[4];
     double Z[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        live[j] = rowlive && col[j] < a.g.nx;
-        Z[j] = (live[j] && a.g.dem) ? __ldg(a.g.dem + (size_t)grow * a.g.nx + col[j]) : 0.0;
+        live[j] = rowlive && cb + coff[j] < a.g.nx;
+        Z[j] = (live[j] && a.g.dem) ? __ldg(a.g.dem + (size_t)grow * a.g.nx + cb + coff[j]) : 0.0;
     }
     double cA[NN], cB[NN];   // folded column basis: [0, NH) even part, [NH, NN) odd part
     {
@@ -237,14 +283,14 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
     // near-station weights of the four cells
     double wr[FAR_NQR][4];
     unsigned coin = 0;       // bit j: a near station sits exactly on cell j (idw.py:69 leaves the distance 0)
-    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const size_t blk = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     double* wn = a.wn + blk * (size_t)a.qx * (FAR_RB * FAR_P) + (size_t)w * FAR_P + lane;
     {
         const bool p2 = (a.power == 2.0);
         const double Y = rowlive ? __ldg(a.g.gy + grow) : 0.0;
         double X[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) X[j] = live[j] ? __ldg(a.g.gx + col[j]) : 0.0;
+        for (int j = 0; j < 4; j++) X[j] = live[j] ? __ldg(a.g.gx + cb + coff[j]) : 0.0;
 #pragma unroll
         for (int qi = 0; qi < FAR_NQR; qi++)
 #pragma unroll
@@ -255,12 +301,13 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             double ws[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                const bool lv = live[j];
                 const double ddx = __dsub_rn(X[j], sx), ddy = __dsub_rn(Y, sy);
                 const double q = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                 const bool zero = (q == 0.0);
-                if (zero && live[j]) coin |= 1u << j;
+                if (zero && lv) coin |= 1u << j;
                 double v = p2 ? fast_rcp<2>(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
-                ws[j] = (live[j] && !zero) ? v : 0.0;
+                ws[j] = (lv && !zero) ? v : 0.0;
             }
             if (qi == 0) {
 #pragma unroll
@@ -268,41 +315,63 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             } else if (qi == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) wr[1][j] = ws[j];
+            } else if (qi < FAR_NQR + FAR_NQM) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wns[(qi - FAR_NQR) * (FAR_RB * FAR_P) + w * FAR_P + lane + 32 * j] = ws[j];
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) wn[(size_t)(qi - FAR_NQR) * (FAR_RB * FAR_P) + 32 * j] = ws[j];
+                for (int j = 0; j < 4; j++) wn[(size_t)(qi - FAR_NQR - FAR_NQM) * (FAR_RB * FAR_P) + 32 * j] = ws[j];
             }
         }
     }
     const size_t ncw = (size_t)a.nrows * a.g.nx;
-    size_t obase[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) obase[j] = (size_t)(grow - a.row0) * a.g.nx + col[j];
-    const int tcl = lane & (FAR_TC - 1), term = lane >> 4;
+    OutT* orow = reinterpret_cast<OutT*>(a.out) + (size_t)(rowlive ? grow - a.row0 : 0) * a.g.nx + cb;
+    // the stage item this thread fetches per chunk: step tid / SGS, slot tid % SGS
+    const int sg_t = tid / SGS, sg_s = tid - sg_t * SGS;
+    const bool sg_on = sg_t < FAR_TC && sg_s <= nqs;
+    const int sg_sta = (sg_on && sg_s > 0) ? nearl[sg_s - 1] : 0;
 
     for (int ch = 0; ch < a.nchunk; ch++) {
         const int buf = ch & 1;
         const double* gs = Gs + buf * NNODE * 2 * FAR_TC;
+        double2 sgv = make_double2(0.0, 0.0);
+        if (sg_on) {
+            const int t = ch * FAR_TC + sg_t;
+            sgv = sg_s ? __ldg(a.rv + (size_t)t * a.S + sg_sta)
+                       : *reinterpret_cast<const double2*>(a.rec + (size_t)t * a.RS + a.S_pad);
+        }
         mbar_wait(&bars[buf], (ch >> 1) & 1);
-        // ---- phase A: this warp's row of the chunk, E/O-folded over the mirrored column nodes
-        if (rowlive) {
+        // ---- phase A: rows x node columns of the chunk, E/O-folded over the mirrored column nodes.  Warps 2p and 2p + 1
+        // share rows 2p, 2p + 1 and split the column-node pairs; a half warp owns one row and the chunk's 16 (term, step)
+        // columns, so the two halves read the same 128 bytes of gs per load
+        {
+            const int arow = (w & ~1) + (lane >> 4), gl = lane & (FAR_CW - 1);
+            constexpr int KH = (NH + 1) / 2;
+            const int k0 = (w & 1) ? KH : 0, k1 = (w & 1) ? NH : KH;
             double ly[NN];
 #pragma unroll
-            for (int ky = 0; ky < NN; ky++) ly[ky] = Lys[w * NN + ky];
-            double* eo = EO + ((size_t)w * FAR_TC + tcl) * EOS + term * 2;
+            for (int ky = 0; ky < NN; ky++) ly[ky] = Lys[arow * NN + ky];
+            double* eo = EO + (((size_t)buf * FAR_RB + arow) * FAR_TC + (gl & (FAR_TC - 1))) * EOS + (gl >> 3) * 2;
+            static_assert(FAR_TC == 8, "the (term, step) split of gl assumes 8 steps per chunk");
 #pragma unroll
-            for (int k = 0; k < NH; k++) {
-                double g1 = 0.0, g2 = 0.0;
+            for (int kk = 0; kk < KH; kk++) {
+                const int k = k0 + kk;
+                if (k < k1) {
+                    double g1 = 0.0, g2 = 0.0;
+                    const double* ga = gs + k * FAR_CW + gl;
+                    const double* gb = gs + (NN - 1 - k) * FAR_CW + gl;
 #pragma unroll
-                for (int ky = 0; ky < NN; ky++) {
-                    g1 = fma(ly[ky], gs[(ky * NN + k) * 32 + lane], g1);
-                    g2 = fma(ly[ky], gs[(ky * NN + NN - 1 - k) * 32 + lane], g2);
+                    for (int ky = 0; ky < NN; ky++) {
+                        g1 = fma(ly[ky], ga[ky * NN * FAR_CW], g1);
+                        g2 = fma(ly[ky], gb[ky * NN * FAR_CW], g2);
+                    }
+                    eo[k * 4] = g1 + g2;
+                    eo[k * 4 + 1] = g1 - g2;
                 }
-                eo[k * 4] = g1 + g2;
-                eo[k * 4 + 1] = g1 - g2;
             }
         }
-        __syncthreads();   // every warp is done with gs: refill it; EO is private to the warp
+        if (sg_on) stg[(buf * FAR_TC + sg_t) * SGS + sg_s] = sgv;
+        __syncthreads();   // every warp is done with gs: refill it; EO and the stage of this chunk are complete
         if (tid == 0 && ch + 2 < a.nchunk) {
             mbar_arrive_expect_tx(&bars[buf], CHUNK_BYTES);
             bulk_g2s(Gs + buf * NNODE * 2 * FAR_TC, Gp + (size_t)(ch + 2) * NNODE * 2 * FAR_TC, CHUNK_BYTES, &bars[buf]);
@@ -310,9 +379,10 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
         if (!rowlive) continue;
         // ---- phase B
         const int tend = min(FAR_TC, a.T - ch * FAR_TC);
-        for (int tl = 0; tl < tend; tl++) {
-            const int t = ch * FAR_TC + tl;
-            const double2* eo = reinterpret_cast<const double2*>(EO + ((size_t)w * FAR_TC + tl) * EOS);
+        const double2* eo = reinterpret_cast<const double2*>(EO + ((size_t)buf * FAR_RB + w) * FAR_TC * EOS);
+        const double2* sg = stg + buf * FAR_TC * SGS;
+        OutT* op = orow + (size_t)ch * FAR_TC * ncw;
+        for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, op += ncw) {
             double enA = 0.0, onA = 0.0, edA = 0.0, odA = 0.0, enB = 0.0, onB = 0.0, edB = 0.0, odB = 0.0;
 #pragma unroll
             for (int k = 0; k < NH; k++) {
@@ -328,9 +398,8 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             }
             double num[4] = {enA + onA, enA - onA, enB + onB, enB - onB};
             double den[4] = {edA + odA, edA - odA, edB + odB, edB - odB};
-            const double2* rvt = a.rv + (size_t)t * a.S;
             if (nq > 0) {
-                const double2 x = __ldg(rvt + nearl[0]);
+                const double2 x = sg[1];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     num[j] = fma(wr[0][j], x.x, num[j]);
@@ -338,7 +407,7 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 }
             }
             if (nq > 1) {
-                const double2 x = __ldg(rvt + nearl[1]);
+                const double2 x = sg[2];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     num[j] = fma(wr[1][j], x.x, num[j]);
@@ -346,8 +415,9 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 }
             }
             for (int qi = FAR_NQR; qi < nq; qi++) {
-                const double2 x = __ldg(rvt + nearl[qi]);
-                const double* wq = wn + (size_t)(qi - FAR_NQR) * (FAR_RB * FAR_P);
+                const double2 x = qi < FAR_NQS ? sg[1 + qi] : __ldg(a.rv + (size_t)(ch * FAR_TC + tl) * a.S + nearl[qi]);
+                const double* wq = qi < FAR_NQR + FAR_NQM ? wns + (qi - FAR_NQR) * (FAR_RB * FAR_P) + w * FAR_P + lane
+                                                          : wn + (size_t)(qi - FAR_NQR - FAR_NQM) * (FAR_RB * FAR_P);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const double wv = wq[32 * j];
@@ -355,32 +425,25 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                     den[j] = fma(wv, x.y, den[j]);
                 }
             }
-            const double2 pp = *reinterpret_cast<const double2*>(a.rec + (size_t)t * a.RS + a.S_pad);
+            const double2 pp = sg[0];
+            double val[4];
+            // quotient to ~4e-13 relative (reciprocal seed + two Newton steps) with the retrend fused in (idw.py:144)
+#pragma unroll
+            for (int j = 0; j < 4; j++) val[j] = fma(num[j], fast_rcp<2>(den[j]), fma(pp.x, Z[j], pp.y));
+            if (coin) {   // rare: a near station sits exactly on one of the lane's cells
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (coin & (1u << j))
+                        val[j] = far_coincident(a.g.gx, a.g.gy, a.mx, a.my, nearl, nq, a.rv + (size_t)(ch * FAR_TC + tl) * a.S,
+                                                cb + coff[j], grow, num[j] * fast_rcp<2>(den[j])) + fma(pp.x, Z[j], pp.y);
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const double r = fast_rcp<2>(den[j]);
-                const double q = num[j] * r;
-                double val = fma(fma(-den[j], q, num[j]), r, q);
-                if (coin & (1u << j)) {   // rare: a station sits exactly on this cell: inf weight => NaN, or 0 if its residual is 0
-                    const double X = __ldg(a.g.gx + col[j]), Y = __ldg(a.g.gy + grow);
-                    bool hit = false, bad = false;
-                    for (int qi = 0; qi < nq; qi++) {
-                        const int s = nearl[qi];
-                        const double ddx = __dsub_rn(X, a.mx[s]), ddy = __dsub_rn(Y, a.my[s]);
-                        const double2 x = rvt[s];
-                        if (__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) == 0.0 && x.y != 0.0) {
-                            hit = true;
-                            if (x.x != 0.0) bad = true;
-                        }
-                    }
-                    if (hit) val = bad ? nan("") : 0.0;
-                }
-                if (a.detrend) val = __dadd_rn(__dadd_rn(val, __dmul_rn(pp.x, Z[j])), pp.y);   // idw.py:144, left to right
-                if (a.clamp) val = clamp_nan_keep(val, a.vmin, a.vmax);
-                if (live[j]) store_out(a.out, (size_t)t * ncw + obase[j], val, a.out_f32);
+                double v = val[j];
+                if (CLAMP) v = clamp_nan_keep(v, a.vmin, a.vmax);
+                if (live[j]) __stcs(op + coff[j], (OutT)v);
             }
         }
-        __syncwarp();
     }
 }
 
@@ -467,17 +530,31 @@ int idw_far_plan(IdwFarPlan* plan, int S, const double* mx, const double* my, in
 template <int NN>
 static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArgs& fa, int npl, int nbands, int smem_max) {
     constexpr int NNODE = NN * NN;
-    const size_t node_smem = (size_t)na.SB * NNODE * sizeof(double) + (size_t)na.S;
+    const size_t node_smem = ((size_t)na.SB * NNODE + 2 * FAR_NODE_KB * FAR_NODE_COLS) * sizeof(double) + (size_t)na.S;
     SMRFB_CHECK(node_smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: node kernel needs %zu B of shared memory", node_smem);
     SMRFB_CUDA(cudaFuncSetAttribute(idw_far_node_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     idw_far_node_kernel<NN><<<npl, FAR_NODE_THREADS, node_smem, st>>>(na);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
-    const size_t smem = (size_t)(2 * NNODE * 2 * FAR_TC + FAR_RB * FAR_TC * (NN / 2 * 4 + 2) + FAR_RB * NN) * sizeof(double) +
-                        2 * sizeof(uint64_t) + (size_t)std::max(1, plan->max_near) * sizeof(int);
+    const size_t smem = (size_t)(2 * NNODE * 2 * FAR_TC + 2 * FAR_RB * FAR_TC * (NN / 2 * 4 + 2) + FAR_RB * NN) * sizeof(double) +
+                        (size_t)2 * FAR_TC * (1 + FAR_NQS) * sizeof(double2) + 2 * sizeof(uint64_t) +
+                        (size_t)FAR_NQM * FAR_RB * FAR_P * sizeof(double) +
+                        (size_t)std::max(1, plan->max_near) * sizeof(int);
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: %zu B of shared memory per CTA", smem);
-    SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    idw_far_kernel<NN><<<dim3(plan->npx, nbands), FAR_THREADS, smem, st>>>(fa);
+    const dim3 grid(FAR_P / FAR_RB, plan->npx, nbands);
+#define FAR_LAUNCH(OT, CL)                                                                                              \
+    do {                                                                                                                \
+        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN, OT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); \
+        idw_far_kernel<NN, OT, CL><<<grid, FAR_THREADS, smem, st>>>(fa);                                                 \
+    } while (0)
+    if (fa.out_f32) {
+        if (fa.clamp) FAR_LAUNCH(float, true);
+        else FAR_LAUNCH(float, false);
+    } else {
+        if (fa.clamp) FAR_LAUNCH(double, true);
+        else FAR_LAUNCH(double, false);
+    }
+#undef FAR_LAUNCH
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
     return SMRFB_OK;
@@ -490,15 +567,15 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
     const int T_pad = (T + FAR_TC - 1) / FAR_TC * FAR_TC, nchunk = T_pad / FAR_TC, N = 2 * T_pad;
     const int pi0 = row0 / FAR_P, pi1 = (row0 + nrows - 1) / FAR_P;
     const int npl = (pi1 - pi0 + 1) * plan->npx;
-    const int nbands = (row0 + nrows - 1) / FAR_RB - row0 / FAR_RB + 1;
-    SMRFB_CHECK(nbands <= 65535, SMRFB_ERR_LIMIT, "IDW far field: too many rows for one launch");
+    const int nbands = pi1 - pi0 + 1;          // grid z: patch rows of the window (x: the 16 bands of a patch row)
+    SMRFB_CHECK(nbands <= 65535 && plan->npx <= 65535, SMRFB_ERR_LIMIT, "IDW far field: too many patches for one launch");
     int qmax = 0;
     for (int p = pi0 * plan->npx; p < (pi1 + 1) * plan->npx; p++) qmax = std::max(qmax, plan->near_off[p + 1] - plan->near_off[p]);
-    const int qx = std::max(0, qmax - FAR_NQR);
+    const int qx = std::max(0, qmax - FAR_NQR - FAR_NQM);
     SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_G, &plan->G_cap, (size_t)npl * nchunk * nnode * 2 * FAR_TC * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_rv, &plan->rv_cap, ((size_t)T_pad * S * 2 + (size_t)S * N) * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_wn, &plan->wn_cap,
-                               std::max<size_t>(16, (size_t)plan->npx * nbands * qx * FAR_RB * FAR_P * sizeof(double))));
+                               std::max<size_t>(16, (size_t)plan->npx * nbands * (FAR_P / FAR_RB) * qx * FAR_RB * FAR_P * sizeof(double))));
     double2* d_rv = reinterpret_cast<double2*>(plan->d_rv);
     double* d_rvt = plan->d_rv + (size_t)T_pad * S * 2;
     idw_far_pack_kernel<<<T_pad, 128, 0, st>>>(d_rec, RS, d_valid, T, S, N, d_rv, d_rvt);
@@ -548,7 +625,6 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
     fa.S_pad = S_pad;
     fa.T = T;
     fa.nchunk = nchunk;
-    fa.detrend = detrend;
     fa.clamp = clamp;
     fa.out_f32 = out_f32;
     fa.row0 = row0;

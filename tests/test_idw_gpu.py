@@ -109,7 +109,8 @@ def test_idw_200_stations_vs_oracle(sp):
     idw_pts = sp.IDW(mx, my, X.T.copy(), Y.T.copy(), mz=mz, GridZ=dem.T.copy(), power=2.0)
     out_pts = idw_pts.distribute_block(data[:3], detrend=True, flag=-1, vmin=-73.0, vmax=47.0)
     out_3 = idw.distribute_block(data[:3], detrend=True, flag=-1, vmin=-73.0, vmax=47.0)   # same batch length: same kernel
-    np.testing.assert_array_equal(out_pts.transpose(0, 2, 1), out_3)
+    # (bit-identical when both take the same kernel; the mesh form may take the near / far-field kernels instead)
+    assert max(parity(out_pts[t].T, out_3[t], step_scale(data[t])) for t in range(3)) <= 1e-11
     for t in range(3):                                                                    # short and long batches agree
         assert parity(out_3[t], out[t], step_scale(data[t])) <= TOL
 
@@ -148,7 +149,9 @@ def test_idw_properties_large(sp):
     r0, r1 = 123, 391
     slab = sp.IDW(mx, my, X[r0:r1], Y[r0:r1], mz=mz, GridZ=dem[r0:r1], power=2.0)
     out_slab = slab.distribute_block(data, detrend=True, flag=-1, vmin=-73.0, vmax=47.0)
-    np.testing.assert_array_equal(out_slab, full[:, r0:r1])
+    # bit-identical on the dense kernels; the near / far-field kernels cut a sub-grid into different patches (row windows of
+    # ONE handle are bit-identical there: test_idw_far_gpu.py::test_far_row_windows_and_float32)
+    assert np.max(np.abs(out_slab - full[:, r0:r1])) <= 1e-10 * np.nanmax(np.abs(data))
     # linearity in the data for a fixed mask (no detrend, no clamp): IDW(a*d1 + d2) = a*IDW(d1) + IDW(d2)
     d1, d2 = data[:4].copy(), data[4:8].copy()
     m = np.isnan(d1) | np.isnan(d2)
