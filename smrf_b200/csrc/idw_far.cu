@@ -24,6 +24,8 @@
 // against 800: the kernel is bound by the fp64 pipe at ~28 instructions per output.
 #include "idw_far.cuh"
 
+#include <array>
+
 namespace smrfb {
 
 constexpr int FAR_RB = 8;            // mesh rows per CTA (one warp each)
@@ -44,6 +46,9 @@ void IdwFarPlan::release() {
     cudaFree(d_G);
     cudaFree(d_rv);
     cudaFree(d_wn);
+    cudaFree(d_coin);
+    d_coin = nullptr;
+    ncoin = 0;
     d_near_off = d_near_idx = nullptr;
     d_tab = d_G = d_rv = d_wn = nullptr;
     G_cap = rv_cap = wn_cap = 0;
@@ -196,23 +201,45 @@ struct FarArgs {
     int row0, nrows, npx, pi0, qx;
 };
 
-// A valid station exactly on the cell: the reference's weight is inf, the cell becomes NaN (inf / inf), or 0 when that
-// station's residual is exactly 0 (nansum drops inf * 0).  Returns true when `val` was replaced.
-__device__ __noinline__ double far_coincident(const double* gx, const double* gy, const double* mx, const double* my,
-                                              const int* nearl, int nq, const double2* rvt, int col, int grow, double val) {
-    const double X = __ldg(gx + col), Y = __ldg(gy + grow);
+// A valid station exactly on a cell centre: the reference's weight there is inf and the cell becomes NaN (inf / inf), or 0
+// when that station's residual is exactly 0 (nansum drops inf * 0) -- idw.py:69-94.  The main kernel gives such a station
+// weight 0 on that cell (right whenever the station is missing); this fix-up pass, over the at most S such cells, rewrites
+// the steps at which the station reports.  One thread per (pair, step); pairs are sorted by cell.
+struct FarCoinArgs {
+    const int* crow;
+    const int* ccol;
+    const int* csta;
+    const double2* rv;
+    const double* rec;
+    const double* dem;
+    void* out;
+    double vmin, vmax;
+    int npair, S, RS, S_pad, nx, row0, nrows, T, clamp, out_f32;
+};
+
+__global__ void idw_far_coin_kernel(FarCoinArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (int)(idx / a.T), t = (int)(idx % a.T);
+    if (p >= a.npair) return;
+    const int row = a.crow[p], col = a.ccol[p];
+    if (p > 0 && a.crow[p - 1] == row && a.ccol[p - 1] == col) return;   // the first pair of a cell speaks for all of them
+    if (row < a.row0 || row >= a.row0 + a.nrows) return;
     bool hit = false, bad = false;
-    for (int qi = 0; qi < nq; qi++) {
-        const int s = nearl[qi];
-        const double ddx = __dsub_rn(X, mx[s]), ddy = __dsub_rn(Y, my[s]);
-        const double2 x = rvt[s];
-        if (__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) == 0.0 && x.y != 0.0) {
+    for (int q = p; q < a.npair && a.crow[q] == row && a.ccol[q] == col; q++) {
+        const double2 x = a.rv[(size_t)t * a.S + a.csta[q]];
+        if (x.y != 0.0) {
             hit = true;
             if (x.x != 0.0) bad = true;
         }
     }
-    if (hit) val = bad ? nan("") : 0.0;
-    return val;
+    if (!hit) return;
+    const double2 pp = *reinterpret_cast<const double2*>(a.rec + (size_t)t * a.RS + a.S_pad);
+    const double Z = a.dem ? a.dem[(size_t)row * a.nx + col] : 0.0;
+    double val = (bad ? nan("") : 0.0) + fma(pp.x, Z, pp.y);
+    if (a.clamp) val = clamp_nan_keep(val, a.vmin, a.vmax);
+    const size_t o = ((size_t)t * a.nrows + (row - a.row0)) * a.nx + col;
+    if (a.out_f32) reinterpret_cast<float*>(a.out)[o] = (float)val;
+    else reinterpret_cast<double*>(a.out)[o] = val;
 }
 
 template <int NN, typename OutT, bool CLAMP>
@@ -282,7 +309,6 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
     }
     // near-station weights of the four cells
     double wr[FAR_NQR][4];
-    unsigned coin = 0;       // bit j: a near station sits exactly on cell j (idw.py:69 leaves the distance 0)
     const size_t blk = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     double* wn = a.wn + blk * (size_t)a.qx * (FAR_RB * FAR_P) + (size_t)w * FAR_P + lane;
     {
@@ -305,7 +331,6 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 const double ddx = __dsub_rn(X[j], sx), ddy = __dsub_rn(Y, sy);
                 const double q = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                 const bool zero = (q == 0.0);
-                if (zero && lv) coin |= 1u << j;
                 double v = p2 ? fast_rcp<2>(zero ? 1.0 : q) : 1.0 / pow(sqrt(zero ? 1.0 : q), a.power);   // idw.py:77
                 ws[j] = (lv && !zero) ? v : 0.0;
             }
@@ -348,27 +373,31 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             const int arow = (w & ~1) + (lane >> 4), gl = lane & (FAR_CW - 1);
             constexpr int KH = (NH + 1) / 2;
             const int k0 = (w & 1) ? KH : 0, k1 = (w & 1) ? NH : KH;
-            double ly[NN];
-#pragma unroll
-            for (int ky = 0; ky < NN; ky++) ly[ky] = Lys[arow * NN + ky];
             double* eo = EO + (((size_t)buf * FAR_RB + arow) * FAR_TC + (gl & (FAR_TC - 1))) * EOS + (gl >> 3) * 2;
             static_assert(FAR_TC == 8, "the (term, step) split of gl assumes 8 steps per chunk");
+            const double* ga = gs + k0 * FAR_CW + gl;               // node column k0 + kk
+            const double* gb = gs + (NN - 1 - k0) * FAR_CW + gl;    // its mirror NN - 1 - k0 - kk
+            const double* lyp = Lys + arow * NN;
+            double g1[KH], g2[KH];
 #pragma unroll
-            for (int kk = 0; kk < KH; kk++) {
-                const int k = k0 + kk;
-                if (k < k1) {
-                    double g1 = 0.0, g2 = 0.0;
-                    const double* ga = gs + k * FAR_CW + gl;
-                    const double* gb = gs + (NN - 1 - k) * FAR_CW + gl;
+            for (int kk = 0; kk < KH; kk++) g1[kk] = g2[kk] = 0.0;
 #pragma unroll
-                    for (int ky = 0; ky < NN; ky++) {
-                        g1 = fma(ly[ky], ga[ky * NN * FAR_CW], g1);
-                        g2 = fma(ly[ky], gb[ky * NN * FAR_CW], g2);
+            for (int ky = 0; ky < NN; ky++) {
+                const double ly = lyp[ky];
+#pragma unroll
+                for (int kk = 0; kk < KH; kk++) {
+                    if (k0 + kk < k1) {
+                        g1[kk] = fma(ly, ga[ky * NN * FAR_CW + kk * FAR_CW], g1[kk]);
+                        g2[kk] = fma(ly, gb[ky * NN * FAR_CW - kk * FAR_CW], g2[kk]);
                     }
-                    eo[k * 4] = g1 + g2;
-                    eo[k * 4 + 1] = g1 - g2;
                 }
             }
+#pragma unroll
+            for (int kk = 0; kk < KH; kk++)
+                if (k0 + kk < k1) {
+                    eo[(k0 + kk) * 4] = g1[kk] + g2[kk];
+                    eo[(k0 + kk) * 4 + 1] = g1[kk] - g2[kk];
+                }
         }
         if (sg_on) stg[(buf * FAR_TC + sg_t) * SGS + sg_s] = sgv;
         __syncthreads();   // every warp is done with gs: refill it; EO and the stage of this chunk are complete
@@ -430,13 +459,6 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             // quotient to ~4e-13 relative (reciprocal seed + two Newton steps) with the retrend fused in (idw.py:144)
 #pragma unroll
             for (int j = 0; j < 4; j++) val[j] = fma(num[j], fast_rcp<2>(den[j]), fma(pp.x, Z[j], pp.y));
-            if (coin) {   // rare: a near station sits exactly on one of the lane's cells
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (coin & (1u << j))
-                        val[j] = far_coincident(a.g.gx, a.g.gy, a.mx, a.my, nearl, nq, a.rv + (size_t)(ch * FAR_TC + tl) * a.S,
-                                                cb + coff[j], grow, num[j] * fast_rcp<2>(den[j])) + fma(pp.x, Z[j], pp.y);
-            }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 double v = val[j];
@@ -516,7 +538,24 @@ int idw_far_plan(IdwFarPlan* plan, int S, const double* mx, const double* my, in
             tab[(size_t)(FAR_P + c) * nn + a] = (double)(0.5L * (L[(size_t)c * nn + a] + L[(size_t)c * nn + nn - 1 - a]));
             tab[(size_t)(FAR_P + c) * nn + nn / 2 + a] = (double)(0.5L * (L[(size_t)c * nn + a] - L[(size_t)c * nn + nn - 1 - a]));
         }
+    // stations exactly on a cell centre (the device tests (X - mx)^2 + (Y - my)^2 == 0, i.e. equality of the doubles)
+    std::vector<std::array<int, 3>> coin;
+    for (int sidx = 0; sidx < S; sidx++) {
+        const long long j = llround((mx[sidx] - gx[0]) / dx), i = llround((my[sidx] - gy[0]) / dy);
+        for (long long jj = std::max(0LL, j - 1); jj <= std::min<long long>(nx - 1, j + 1); jj++)
+            for (long long ii = std::max(0LL, i - 1); ii <= std::min<long long>(ny - 1, i + 1); ii++)
+                if (gx[jj] == mx[sidx] && gy[ii] == my[sidx]) coin.push_back({(int)ii, (int)jj, sidx});
+    }
+    std::sort(coin.begin(), coin.end());
+    plan->ncoin = (int)coin.size();
     SMRFB_CUDA(cudaSetDevice(device));
+    if (plan->ncoin) {
+        std::vector<int> flat(3 * coin.size());
+        for (size_t q = 0; q < coin.size(); q++)
+            for (int c = 0; c < 3; c++) flat[c * coin.size() + q] = coin[q][c];
+        SMRFB_CUDA(cudaMalloc((void**)&plan->d_coin, flat.size() * sizeof(int)));
+        SMRFB_CUDA(cudaMemcpy(plan->d_coin, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     SMRFB_CUDA(cudaMalloc((void**)&plan->d_near_off, (np + 1) * sizeof(int)));
     SMRFB_CUDA(cudaMalloc((void**)&plan->d_near_idx, std::max<size_t>(1, idx.size()) * sizeof(int)));
     SMRFB_CUDA(cudaMalloc((void**)&plan->d_tab, tab.size() * sizeof(double)));
@@ -632,7 +671,35 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
     fa.npx = plan->npx;
     fa.pi0 = pi0;
     fa.qx = qx;
-    return nn == 10 ? far_launch<10>(st, plan, na, fa, npl, nbands, smem_max) : far_launch<12>(st, plan, na, fa, npl, nbands, smem_max);
+    SMRFB_PROPAGATE(nn == 10 ? far_launch<10>(st, plan, na, fa, npl, nbands, smem_max)
+                             : far_launch<12>(st, plan, na, fa, npl, nbands, smem_max));
+    if (plan->ncoin) {
+        FarCoinArgs ca;
+        ca.crow = plan->d_coin;
+        ca.ccol = plan->d_coin + plan->ncoin;
+        ca.csta = plan->d_coin + 2 * plan->ncoin;
+        ca.rv = d_rv;
+        ca.rec = d_rec;
+        ca.dem = g.dem;
+        ca.out = d_out;
+        ca.vmin = vmin;
+        ca.vmax = vmax;
+        ca.npair = plan->ncoin;
+        ca.S = S;
+        ca.RS = RS;
+        ca.S_pad = S_pad;
+        ca.nx = g.nx;
+        ca.row0 = row0;
+        ca.nrows = nrows;
+        ca.T = T;
+        ca.clamp = clamp;
+        ca.out_f32 = out_f32;
+        const long long n = (long long)plan->ncoin * T;
+        idw_far_coin_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ca);
+        count_launch();
+        SMRFB_CUDA(cudaGetLastError());
+    }
+    return SMRFB_OK;
 }
 
 }  // namespace smrfb

@@ -22,6 +22,8 @@ struct IdwFarPlan {
     int* d_near_idx = nullptr;   // [near_off[last]] station indices, ascending per patch
     double* d_tab = nullptr;     // [128][nn] Lagrange basis at the 128 cell positions, then [64][nn] folded (even | odd) halves
     std::vector<int> near_off;   // host copy (window maxima)
+    int ncoin = 0;               // (cell, station) pairs with the station exactly on the cell centre, sorted by cell
+    int* d_coin = nullptr;       // [3][ncoin]: row, column, station
     // scratch (grown on demand)
     double* d_G = nullptr;  size_t G_cap = 0;      // node sums [patch][chunk][ky][kx][num|den][16]
     double* d_rv = nullptr; size_t rv_cap = 0;     // [T_pad][S_pad][2] (residual, validity) and its station-major transpose
