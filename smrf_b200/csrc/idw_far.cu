@@ -197,6 +197,8 @@ struct FarArgs {
     double* wn;             // near-weight scratch
     double* out;
     double power, vmin, vmax;
+    long long ostride;      // bytes between consecutive steps of the output window
+    unsigned klo, kspan;    // clamp screen on the high word (see hi_key)
     int S, RS, S_pad, T, nchunk, clamp, out_f32;
     int row0, nrows, npx, pi0, qx;
 };
@@ -241,6 +243,35 @@ __global__ void idw_far_coin_kernel(FarCoinArgs a) {
     if (a.out_f32) reinterpret_cast<float*>(a.out)[o] = (float)val;
     else reinterpret_cast<double*>(a.out)[o] = val;
 }
+
+// Phase A of idw_far_kernel for KN node-column pairs k0 .. k0 + KN - 1: g1 = sum_ky ly[ky] G[ky][k], g2 the same for the mirror
+// column NN - 1 - k; stores E = g1 + g2, O = g1 - g2.
+template <int NN, int KN>
+__device__ __forceinline__ void far_phase_a(const double* __restrict__ gsl, const double* __restrict__ lyp, double* __restrict__ eo,
+                                            int k0) {
+    const double* ga = gsl + k0 * FAR_CW;
+    const double* gb = gsl + (NN - 1 - k0) * FAR_CW;
+    double g1[KN], g2[KN];
+#pragma unroll
+    for (int kk = 0; kk < KN; kk++) g1[kk] = g2[kk] = 0.0;
+#pragma unroll
+    for (int ky = 0; ky < NN; ky++) {
+        const double ly = lyp[ky];
+#pragma unroll
+        for (int kk = 0; kk < KN; kk++) {
+            g1[kk] = fma(ly, ga[ky * NN * FAR_CW + kk * FAR_CW], g1[kk]);
+            g2[kk] = fma(ly, gb[ky * NN * FAR_CW - kk * FAR_CW], g2[kk]);
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KN; kk++) {
+        eo[(k0 + kk) * 4] = g1[kk] + g2[kk];
+        eo[(k0 + kk) * 4 + 1] = g1[kk] - g2[kk];
+    }
+}
+
+// Monotone map of a double's high word to unsigned: key(a) < key(b) implies a < b for non-NaN a, b; NaNs map beyond +-inf.
+__host__ __device__ __forceinline__ unsigned hi_key(int hi) { return (unsigned)hi ^ ((unsigned)(hi >> 31) | 0x80000000u); }
 
 template <int NN, typename OutT, bool CLAMP>
 __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             }
         }
     }
-    const size_t ncw = (size_t)a.nrows * a.g.nx;
+    const bool full = rowlive && cb + FAR_P <= a.g.nx;     // all four cells of every lane exist
     OutT* orow = reinterpret_cast<OutT*>(a.out) + (size_t)(rowlive ? grow - a.row0 : 0) * a.g.nx + cb;
     // the stage item this thread fetches per chunk: step tid / SGS, slot tid % SGS
     const int sg_t = tid / SGS, sg_s = tid - sg_t * SGS;
@@ -371,33 +402,12 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
         // columns, so the two halves read the same 128 bytes of gs per load
         {
             const int arow = (w & ~1) + (lane >> 4), gl = lane & (FAR_CW - 1);
-            constexpr int KH = (NH + 1) / 2;
-            const int k0 = (w & 1) ? KH : 0, k1 = (w & 1) ? NH : KH;
             double* eo = EO + (((size_t)buf * FAR_RB + arow) * FAR_TC + (gl & (FAR_TC - 1))) * EOS + (gl >> 3) * 2;
             static_assert(FAR_TC == 8, "the (term, step) split of gl assumes 8 steps per chunk");
-            const double* ga = gs + k0 * FAR_CW + gl;               // node column k0 + kk
-            const double* gb = gs + (NN - 1 - k0) * FAR_CW + gl;    // its mirror NN - 1 - k0 - kk
             const double* lyp = Lys + arow * NN;
-            double g1[KH], g2[KH];
-#pragma unroll
-            for (int kk = 0; kk < KH; kk++) g1[kk] = g2[kk] = 0.0;
-#pragma unroll
-            for (int ky = 0; ky < NN; ky++) {
-                const double ly = lyp[ky];
-#pragma unroll
-                for (int kk = 0; kk < KH; kk++) {
-                    if (k0 + kk < k1) {
-                        g1[kk] = fma(ly, ga[ky * NN * FAR_CW + kk * FAR_CW], g1[kk]);
-                        g2[kk] = fma(ly, gb[ky * NN * FAR_CW - kk * FAR_CW], g2[kk]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int kk = 0; kk < KH; kk++)
-                if (k0 + kk < k1) {
-                    eo[(k0 + kk) * 4] = g1[kk] + g2[kk];
-                    eo[(k0 + kk) * 4 + 1] = g1[kk] - g2[kk];
-                }
+            constexpr int KA = (NH + 1) / 2, KB = NH - KA;      // node-column pairs of the even / odd warp of a row pair
+            if (w & 1) far_phase_a<NN, KB>(gs + gl, lyp, eo, KA);
+            else far_phase_a<NN, KA>(gs + gl, lyp, eo, 0);
         }
         if (sg_on) stg[(buf * FAR_TC + sg_t) * SGS + sg_s] = sgv;
         __syncthreads();   // every warp is done with gs: refill it; EO and the stage of this chunk are complete
@@ -410,8 +420,8 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
         const int tend = min(FAR_TC, a.T - ch * FAR_TC);
         const double2* eo = reinterpret_cast<const double2*>(EO + ((size_t)buf * FAR_RB + w) * FAR_TC * EOS);
         const double2* sg = stg + buf * FAR_TC * SGS;
-        OutT* op = orow + (size_t)ch * FAR_TC * ncw;
-        for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, op += ncw) {
+        OutT* op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(orow) + (long long)ch * FAR_TC * a.ostride);
+        for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(op) + a.ostride)) {
             double enA = 0.0, onA = 0.0, edA = 0.0, odA = 0.0, enB = 0.0, onB = 0.0, edB = 0.0, odB = 0.0;
 #pragma unroll
             for (int k = 0; k < NH; k++) {
@@ -459,11 +469,24 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             // quotient to ~4e-13 relative (reciprocal seed + two Newton steps) with the retrend fused in (idw.py:144)
 #pragma unroll
             for (int j = 0; j < 4; j++) val[j] = fma(num[j], fast_rcp<2>(den[j]), fma(pp.x, Z[j], pp.y));
+            if (CLAMP) {
+                // all four strictly inside (vmin, vmax) by their high words alone (integer pipe, one warp-wide vote); otherwise,
+                // NaNs included, the exact NaN-preserving clamp of utils.py:137-161
+                bool out = false;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                double v = val[j];
-                if (CLAMP) v = clamp_nan_keep(v, a.vmin, a.vmax);
-                if (live[j]) __stcs(op + coff[j], (OutT)v);
+                for (int j = 0; j < 4; j++) out |= hi_key(__double2hiint(val[j])) - a.klo >= a.kspan;
+                if (__any_sync(0xffffffffu, out)) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) val[j] = clamp_nan_keep(val[j], a.vmin, a.vmax);
+                }
+            }
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) __stcs(op + coff[j], (OutT)val[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (live[j]) __stcs(op + coff[j], (OutT)val[j]);
             }
         }
     }
@@ -671,6 +694,15 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
     fa.npx = plan->npx;
     fa.pi0 = pi0;
     fa.qx = qx;
+    fa.ostride = (long long)nrows * g.nx * (out_f32 ? 4 : 8);
+    {   // fast screen: key(vmin) < key(v) < key(vmax) on the high words proves vmin < v < vmax
+        long long blo, bhi;
+        memcpy(&blo, &vmin, 8);
+        memcpy(&bhi, &vmax, 8);
+        const unsigned klo = hi_key((int)(blo >> 32)), khi = hi_key((int)(bhi >> 32));
+        fa.klo = klo + 1;
+        fa.kspan = khi > klo + 1 ? khi - (klo + 1) : 0;
+    }
     SMRFB_PROPAGATE(nn == 10 ? far_launch<10>(st, plan, na, fa, npl, nbands, smem_max)
                              : far_launch<12>(st, plan, na, fa, npl, nbands, smem_max));
     if (plan->ncoin) {
