@@ -98,8 +98,12 @@ int smrfb_idw_distribute_window_dev(smrfb_handle_t h, const double* d_data, int 
  * info[0] = 1 if the near field + interpolated far field kernels apply (uniform mesh, power <= 4, > 16 stations), [1] =
  * Chebyshev nodes per direction, [2] = longest near-station list of a patch, [3] = patches, [4] = near-field radius in
  * patch half widths x 1000, [5] = 1 if the int8 tensor-core kernel serves the other calls, [6] = 1 if the register-weight
- * kernel does (<= 16 stations), [7] = reserved. */
+ * kernel does (<= 16 stations), [7] = mean near-station count per patch x 1000. */
 int smrfb_idw_info(smrfb_handle_t h, int info[8]);
+/* Per-launch device timing of the near / far-field path (CUDA events on the launch stream, for bench.py's roofline line).
+ * enable = 1 starts collecting, 0 stops.  If ms_out is non-NULL the handle's stream(s) are synchronised and the events
+ * collected so far are summed and dropped: ms_out[0] = node kernel ms, ms_out[1] = main kernel ms, ms_out[2] = launches. */
+int smrfb_idw_far_timing(smrfb_handle_t h, int enable, double ms_out[3]);
 
 /* ------------------------------------------------------------------ DK (dk.py, krige.c, lusolv.c) */
 int smrfb_dk_create(int nsta, const double* mx, const double* my, const double* mz,

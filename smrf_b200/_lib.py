@@ -44,6 +44,7 @@ _SIGS = {
                                                        ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_idw_info": (ctypes.c_int, [handle_t, c_i32_p]),
+    "smrfb_idw_far_timing": (ctypes.c_int, [handle_t, ctypes.c_int, c_double_p]),
     "smrfb_dk_distribute_window_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, c_double_p, ctypes.c_int, ctypes.c_double,
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),

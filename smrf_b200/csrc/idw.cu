@@ -688,7 +688,31 @@ int smrfb_idw_info(smrfb_handle_t hh, int info[8]) {
     info[4] = (int)(h->far.theta * 1000.0);
     info[5] = h->i8_mode ? 1 : 0;
     info[6] = h->use_small ? 1 : 0;
-    info[7] = 0;
+    info[7] = h->far.enabled && h->far.npx * h->far.npy > 0 ? (int)(1000.0 * h->far.near_off.back() / (h->far.npx * h->far.npy)) : 0;
+    return SMRFB_OK;
+}
+
+int smrfb_idw_far_timing(smrfb_handle_t hh, int enable, double ms_out[3]) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    IdwHandle* h = reinterpret_cast<IdwHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_IDW, SMRFB_ERR_ARG, "not an IDW handle");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    if (ms_out) {
+        ms_out[0] = ms_out[1] = ms_out[2] = 0.0;
+        std::vector<cudaEvent_t>& ev = h->far.tev;
+        for (size_t i = 0; i + 2 < ev.size(); i += 3) {
+            float a = 0.f, b = 0.f;
+            SMRFB_CUDA(cudaEventSynchronize(ev[i + 2]));
+            SMRFB_CUDA(cudaEventElapsedTime(&a, ev[i], ev[i + 1]));
+            SMRFB_CUDA(cudaEventElapsedTime(&b, ev[i + 1], ev[i + 2]));
+            ms_out[0] += a;
+            ms_out[1] += b;
+            ms_out[2] += 1.0;
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+    h->far.timing = enable != 0;
     return SMRFB_OK;
 }
 

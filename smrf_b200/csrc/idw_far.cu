@@ -40,6 +40,8 @@ constexpr int FAR_NODE_COLS = 128;   // (step, term) columns per node-kernel til
 constexpr int FAR_NODE_KB = 8;       // stations per staged block of the node kernel
 
 void IdwFarPlan::release() {
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    tev.clear();
     cudaFree(d_near_off);
     cudaFree(d_near_idx);
     cudaFree(d_tab);
@@ -589,15 +591,25 @@ int idw_far_plan(IdwFarPlan* plan, int S, const double* mx, const double* my, in
     return SMRFB_OK;
 }
 
+static void far_mark(IdwFarPlan* plan, cudaStream_t st) {
+    if (!plan->timing) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    plan->tev.push_back(e);
+}
+
 template <int NN>
 static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArgs& fa, int npl, int nbands, int smem_max) {
     constexpr int NNODE = NN * NN;
+    far_mark(plan, st);
     const size_t node_smem = ((size_t)na.SB * NNODE + 2 * FAR_NODE_KB * FAR_NODE_COLS) * sizeof(double) + (size_t)na.S;
     SMRFB_CHECK(node_smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: node kernel needs %zu B of shared memory", node_smem);
     SMRFB_CUDA(cudaFuncSetAttribute(idw_far_node_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     idw_far_node_kernel<NN><<<npl, FAR_NODE_THREADS, node_smem, st>>>(na);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
+    far_mark(plan, st);
     const size_t smem = (size_t)(2 * NNODE * 2 * FAR_TC + 2 * FAR_RB * FAR_TC * (NN / 2 * 4 + 2) + FAR_RB * NN) * sizeof(double) +
                         (size_t)2 * FAR_TC * (1 + FAR_NQS) * sizeof(double2) + 2 * sizeof(uint64_t) +
                         (size_t)FAR_NQM * FAR_RB * FAR_P * sizeof(double) +
@@ -617,6 +629,7 @@ static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArg
         else FAR_LAUNCH(double, false);
     }
 #undef FAR_LAUNCH
+    far_mark(plan, st);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
     return SMRFB_OK;

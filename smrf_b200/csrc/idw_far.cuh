@@ -28,6 +28,10 @@ struct IdwFarPlan {
     double* d_G = nullptr;  size_t G_cap = 0;      // node sums [patch][chunk][ky][kx][num|den][16]
     double* d_rv = nullptr; size_t rv_cap = 0;     // [T_pad][S_pad][2] (residual, validity) and its station-major transpose
     double* d_wn = nullptr; size_t wn_cap = 0;     // near weights beyond the two kept in registers
+    // optional per-launch timing (smrfb_idw_far_timing): three events per launch -- before the node kernel, between the
+    // node and the main kernel, after the main kernel -- on the launch stream
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;
     void release();
 };
 

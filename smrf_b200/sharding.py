@@ -58,11 +58,11 @@ class BlockRunner:
     Either way the rank's cells are walked in row slabs of `slab_rows` rows, one interpolator handle per slab and
     variable, so the page-locked staging stays bounded: two rotating buffers of [block_steps, slab_rows, nx]
     (float64, or float32 with out_dtype=np.float32 -- the type the reference's output files hold).  The sink is called
-    as sink(field_name, (t0, t1), (r0, r1), block) with block = [t1-t0, r1-r0, nx]; the view is valid until the second
-    next call.  There is no collective on the data path: ranks share nothing but the input tables."""
+    as sink(field_name, (t0, t1), (r0, r1), block) with block = [t1-t0, r1-r0, nx]; the view is valid until the
+    nbuf-th next call.  There is no collective on the data path: ranks share nothing but the input tables."""
 
     def __init__(self, fields, x, y, dem, stations, rank=0, world=1, partition="time", block_steps=64, slab_rows=1000,
-                 device=None, out_dtype=None):
+                 device=None, out_dtype=None, handles=None, nbuf=2):
         import numpy as np
         from . import _lib
         self.fields = list(fields)
@@ -78,7 +78,12 @@ class BlockRunner:
         self.slabs = row_slabs(self.ny, self.world if partition == "rows" else 1, self.rank if partition == "rows" else 0,
                                rows_per_slab=self.slab_rows)
         self._handles = {}
+        if handles:          # interpolators the caller already holds for the WHOLE grid (one slab): {field name: IDW | DK | GRID}
+            if len(self.slabs) != 1 or self.slabs[0] != (0, self.ny):
+                raise ValueError("handles= needs a single whole-grid slab (slab_rows >= ny, partition='time')")
+            self._handles = {(name, self.slabs[0]): h for name, h in handles.items()}
         self._pinned = None
+        self._nbuf = max(1, int(nbuf))    # rotating page-locked blocks: 2 lets the sink keep one while the next fills
         self._turn = 0
 
     def blocks(self, T):
@@ -120,8 +125,8 @@ class BlockRunner:
         import numpy as np
         if self._pinned is None:
             cap = self.block_steps * max(b - a for a, b in self.slabs) * self.nx
-            self._pinned = [_lib.pinned_empty((cap,), self.out_dtype) for _ in range(2)]
-        buf = self._pinned[self._turn & 1]
+            self._pinned = [_lib.pinned_empty((cap,), self.out_dtype) for _ in range(self._nbuf)]
+        buf = self._pinned[self._turn % self._nbuf]
         self._turn += 1
         return buf[: nt * rows * self.nx].reshape(nt, rows, self.nx)
 

@@ -41,7 +41,7 @@ class IDW(_lib.HandleMixin):
         info = np.zeros(8, dtype=np.int32)
         _lib.check(_lib.lib().smrfb_idw_info(self._h, info.ctypes.data_as(_lib.c_i32_p)))
         return {"far_field": bool(info[0]), "nodes": int(info[1]), "max_near": int(info[2]), "patches": int(info[3]),
-                "theta": info[4] / 1000.0, "int8": bool(info[5]), "small": bool(info[6])}
+                "theta": info[4] / 1000.0, "int8": bool(info[5]), "small": bool(info[6]), "mean_near": info[7] / 1000.0}
 
     # ------------------------------------------------------------------ batched extension
     def distribute_block(self, data, detrend=False, flag=0, vmin=None, vmax=None, pv=None, out=None, out_dtype=None):
