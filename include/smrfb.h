@@ -180,6 +180,29 @@ int smrfb_grid_distribute_cubic_dev(smrfb_handle_t h, const double* d_fields, in
  * are clamped in place through their device mapping (no allocation, no staging copy); pageable arrays are staged. */
 int smrfb_set_min_max(double* data, int64_t n, double vmin, double vmax, int device);
 
+/* ------------------------------------------------------------------ consumers of a distributed grid (SURVEY.md 8f N-a), WindNinja-style weights (8a G5) */
+/* Dew point (degC) from vapor pressure (Pa): smrf/envphys/core/dewpt.c:14-229 (envphys_c.cdewpt(vp, dpt, tolerance, nthreads),
+ * called at smrf/distribute/vapor_pressure.py:136-141): Brent root of sati(T) = e, result truncated to float, K -> C. */
+int smrfb_dew_point(const double* vp, int64_t n, double tol, double* dpt, int device);
+int smrfb_dew_point_dev(const double* d_vp, int64_t n, double tol, double* d_dpt, void* stream);
+/* Hook a consumer onto the NEXT host-buffer distribute calls of a handle (any method): kind 1 = the dew point of every
+ * distributed value, computed while the sub-batch is still in the handle's device ring and copied to out2 ([T][ncell], same
+ * element type as the primary output) -- the vapor-pressure grid crosses PCIe once and is never re-read from host memory.
+ * kind 0 removes the hook. */
+int smrfb_set_consumer(smrfb_handle_t h, int kind, double tol, void* out2);
+/* Wind azimuth from the two distributed direction components: az = arctan2(u, v) * 180 / pi, negative values + 360
+ * (smrf/distribute/wind/wind.py:175-178). */
+int smrfb_wind_direction(const double* u, const double* v, int64_t n, double* az, int device);
+int smrfb_wind_direction_dev(const double* d_u, const double* d_v, int64_t n, double* d_az, void* stream);
+/* utils.interp_weights / utils.grid_interpolate (smrf/utils/utils.py:377-427, used by smrf/distribute/wind/wind_ninja.py:171,
+ * 212-235): vertices [n][3] (indices into the npts source values) and weights [n][3] as interp_weights returns them;
+ * apply: out[t][i] = sum_j values[t][vtx[i][j]] * wts[i][j]; with fill_negative = 1 cells with a negative weight take `fill`
+ * (grid_interpolate, utils.py:424); with 0 the weights alone decide (NaN weights mark cells outside the hull: the
+ * LinearNDInterpolator rule of grid_interpolate_deconstructed). */
+int smrfb_interp_create(int64_t n, const int32_t* vtx, const double* wts, int npts, int fill_negative, int device, smrfb_handle_t* out);
+int smrfb_interp_apply(smrfb_handle_t h, const double* values, int T, double fill, double* out);
+int smrfb_interp_apply_dev(smrfb_handle_t h, const double* d_values, int T, double fill, double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

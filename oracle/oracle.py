@@ -553,3 +553,66 @@ def parity_error(got, ref, scale):
         return 0.0
     den = np.maximum(np.abs(ref[ok]), scale)
     return float(np.max(np.abs(got[ok] - ref[ok]) / den))
+
+
+# --------------------------------------------------------------------------------------------
+# consumers of a distributed grid (SURVEY.md 8f N-a) and WindNinja-style weights (8a G5)
+# --------------------------------------------------------------------------------------------
+def dew_point(vp, tol=0.01, impl="oracle"):
+    """Dew point (degC) of vapor pressure (Pa): impl='oracle' -> oracle/envphys_oracle.c (restatement of dewpt.c:14-229),
+    impl='ref' -> the reference's own dewpt.c + topotherm.c compiled in place (oracle/_ref/libenvphys_ref.so)."""
+    vp = np.ascontiguousarray(vp, dtype=np.float64)
+    out = np.empty_like(vp)
+    if impl == "ref":
+        path = os.path.join(_HERE, "_ref", "libenvphys_ref.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libenvphys_ref.so is missing (python oracle/build.py in the build container)")
+        L = _load(path)
+        L.dewpt.restype = None
+        L.dewpt.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+        L.dewpt(int(vp.size), _dptr(vp.reshape(-1)), 1, float(tol), _dptr(out.reshape(-1)))     # dewpt.c:14-20
+        return out
+    path = os.path.join(_HERE, "libenvphys_oracle.so")
+    if not os.path.exists(path):
+        from . import build
+        build.build_oracle()
+    L = _load(path)
+    L.oracle_dew_point.restype = None
+    L.oracle_dew_point.argtypes = [ctypes.c_long, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    L.oracle_dew_point(int(vp.size), _dptr(vp.reshape(-1)), float(tol), _dptr(out.reshape(-1)))
+    return out
+
+
+def dew_point_adjust(dpt, ta):
+    """vapor_pressure.py:143-147: the dew point may not exceed the air temperature."""
+    dpt = dpt.copy()
+    ind = dpt >= ta
+    if np.sum(ind) > 0:
+        dpt[ind] = ta[ind] - 0.2
+    return dpt
+
+
+def wind_direction(u, v):
+    """wind.py:175-178."""
+    az = np.arctan2(u, v) * 180 / np.pi
+    az[az < 0] = az[az < 0] + 360
+    return az
+
+
+def interp_weights(xy, uv, d=2):
+    """utils.py:377-406."""
+    from scipy.spatial import Delaunay
+    tri = Delaunay(xy)
+    simplex = tri.find_simplex(uv)
+    vertices = np.take(tri.simplices, simplex, axis=0)
+    temp = np.take(tri.transform, simplex, axis=0)
+    delta = uv - temp[:, d]
+    bary = np.einsum('njk,nk->nj', temp[:, :d, :], delta)
+    return vertices, np.hstack((bary, 1 - bary.sum(axis=1, keepdims=True)))
+
+
+def grid_interpolate(values, vtx, wts, shp, fill_value=np.nan):
+    """utils.py:409-427."""
+    ret = np.einsum('nj,nj->n', np.take(values, vtx), wts)
+    ret[np.any(wts < 0, axis=1)] = fill_value
+    return ret.reshape(shp[0], shp[1])

@@ -79,6 +79,14 @@ _SIGS = {
                                                    ctypes.c_double, ctypes.c_double, c_double_p]),
     "smrfb_grid_distribute_cubic_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                        ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_dew_point": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, c_double_p, ctypes.c_int]),
+    "smrfb_dew_point_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_set_consumer": (ctypes.c_int, [handle_t, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
+    "smrfb_wind_direction": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int]),
+    "smrfb_wind_direction_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_interp_create": (ctypes.c_int, [ctypes.c_int64, c_i32_p, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(handle_t)]),
+    "smrfb_interp_apply": (ctypes.c_int, [handle_t, c_double_p, ctypes.c_int, ctypes.c_double, c_double_p]),
+    "smrfb_interp_apply_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_set_min_max": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
 }
 
@@ -208,6 +216,22 @@ class HandleMixin:
             check(lib().smrfb_set_output_dtype(self._h, int(f32)))
             self._f32 = f32
         return f32
+
+    def dew_point_of(self, call, T, tol=0.01, out_dtype=np.float64):
+        """Run ``call()`` -- one distribute_block / distribute_block_local call on THIS handle, T steps, element type
+        ``out_dtype`` -- with the dew-point consumer hooked on (smrfb_set_consumer): returns (distributed block, dew point
+        block), the second computed on the device from the first while it is still in the handle's output ring
+        (vapor_pressure.py:136-141 without re-reading the grid)."""
+        dt = np.dtype(out_dtype)
+        out2 = pinned_empty((T,) + tuple(self.shape), dt)
+        check(lib().smrfb_set_consumer(self._h, 1, float(tol), out2.ctypes.data_as(ctypes.c_void_p)))
+        try:
+            out = call()
+        finally:
+            check(lib().smrfb_set_consumer(self._h, 0, 0.0, None))
+        if out.dtype != dt:
+            raise ValueError("dew_point_of: the call produced %s, out_dtype says %s" % (out.dtype, dt))
+        return out, out2
 
     def __del__(self):
         h = getattr(self, "_h", None)

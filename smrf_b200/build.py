@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmrfb.so")
-SOURCES = ["common.cu", "idw.cu", "idw_i8.cu", "idw_far.cu", "grid.cu", "dk.cu"]
+SOURCES = ["common.cu", "idw.cu", "idw_i8.cu", "idw_far.cu", "grid.cu", "dk.cu", "consumers.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("SMRFB_NVCC_DEFS", "").split()

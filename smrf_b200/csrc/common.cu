@@ -34,6 +34,7 @@ HandleBase::~HandleBase() {
     cudaFree(d_pv);
     cudaFree(d_flags);
     cudaFree(d_ring);
+    cudaFree(d_ring2);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }

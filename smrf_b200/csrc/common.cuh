@@ -81,7 +81,7 @@ struct RecLayout {
 };
 RecLayout make_layout(int S, int k_align, int maxm, bool mma_stride);
 
-enum HandleKind { HK_IDW = 0x1d0, HK_DK = 0xd4, HK_GRID = 0x621d };
+enum HandleKind { HK_IDW = 0x1d0, HK_DK = 0xd4, HK_GRID = 0x621d, HK_INTERP = 0x17e4 };
 
 struct HandleBase {
     int kind;
@@ -105,6 +105,12 @@ struct HandleBase {
     double* d_ring = nullptr;    // host-API output ring (up to 2 slots), kept across calls
     size_t ring_cap = 0;
     int out_f32 = 0;             // smrfb_set_output_dtype: 1 = outputs are written as float32 (the reference's NetCDF type)
+    // smrfb_set_consumer: a second output computed from every distributed sub-batch while it is still in the device ring
+    int consumer = 0;            // 0 none, 1 dew point (dewpt.c) of the distributed vapor pressure
+    double consumer_tol = 0.01;
+    void* consumer_out = nullptr;   // host [T][ncell], element type as out
+    double* d_ring2 = nullptr;
+    size_t ring2_cap = 0;
     explicit HandleBase(int k) : kind(k) {}
     virtual ~HandleBase();
 };
@@ -112,6 +118,8 @@ struct HandleBase {
 int upload_geom(HandleBase* h, int nsta, const double* mx, const double* my, const double* mz, int ny, int nx,
                 int grid_kind, const double* gx, const double* gy, const double* dem);
 int ensure_cap(void** p, size_t* cap, size_t need_bytes);
+// consumers.cu: dew point (C) of n vapor pressures (Pa); element types float64 / float32 per flag
+int launch_dew_point(cudaStream_t st, const void* d_ea, int in_f32, long long n, double tol, void* d_out, int out_f32);
 
 // Launch the station-prep kernel: regression, residuals, missing lists for T steps.
 //   fit_mode 0: residuals for every non-NaN station (IDW, GRID);   fit over (valid & fitmask)
@@ -155,6 +163,22 @@ int run_host_batches(HandleBase* h, int T, int step_align, double* out_, RunFn r
         h->ring_cap = slot_bytes * nslots;
     }
     double* ring[2] = {h->d_ring, nslots > 1 ? h->d_ring + (size_t)tb * ncell : nullptr};
+    double* ring2[2] = {nullptr, nullptr};
+    char* out2 = reinterpret_cast<char*>(h->consumer_out);
+    if (h->consumer) {
+        if (h->ring2_cap < slot_bytes * nslots) {
+            if (h->d_ring2) cudaFree(h->d_ring2);
+            h->d_ring2 = nullptr;
+            h->ring2_cap = 0;
+            if (cudaMalloc((void**)&h->d_ring2, slot_bytes * nslots) != cudaSuccess) {
+                set_error("cudaMalloc of the %zu-byte consumer ring failed", slot_bytes * nslots);
+                return SMRFB_ERR_CUDA;
+            }
+            h->ring2_cap = slot_bytes * nslots;
+        }
+        ring2[0] = h->d_ring2;
+        ring2[1] = nslots > 1 ? h->d_ring2 + (size_t)tb * ncell : nullptr;
+    }
     cudaEvent_t done[2], copied[2];
     for (int i = 0; i < 2; i++) {
         SMRFB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
@@ -165,12 +189,20 @@ int run_host_batches(HandleBase* h, int T, int step_align, double* out_, RunFn r
         const int tn = std::min(tb, T - t0);
         if (t0 >= 2 * tb) cudaStreamWaitEvent(h->stream, copied[slot], 0);   // ring slot free again
         rc = run(t0, tn, ring[slot], h->stream);
+        if (rc == SMRFB_OK && h->consumer == 1)
+            rc = launch_dew_point(h->stream, ring[slot], h->out_f32, (long long)tn * h->g.ncell, h->consumer_tol, ring2[slot], h->out_f32);
         if (rc != SMRFB_OK) break;
         cudaEventRecord(done[slot], h->stream);
         cudaStreamWaitEvent(h->copy_stream, done[slot], 0);
         if (cudaMemcpyAsync(out + (size_t)t0 * (size_t)h->g.ncell * esz, ring[slot], (size_t)tn * (size_t)h->g.ncell * esz,
                             cudaMemcpyDeviceToHost, h->copy_stream) != cudaSuccess) {
             set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SMRFB_ERR_CUDA;
+            break;
+        }
+        if (h->consumer && cudaMemcpyAsync(out2 + (size_t)t0 * (size_t)h->g.ncell * esz, ring2[slot], (size_t)tn * (size_t)h->g.ncell * esz,
+                                           cudaMemcpyDeviceToHost, h->copy_stream) != cudaSuccess) {
+            set_error("D2H copy of the consumer output failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = SMRFB_ERR_CUDA;
             break;
         }

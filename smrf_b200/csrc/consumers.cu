@@ -1,0 +1,317 @@
+// consumers.cu -- the immediate per-cell consumers of a freshly distributed grid (SURVEY.md 8f N-a) and the WindNinja-style
+// precomputed-weights interpolation (8a G5):
+//   * dew point from vapor pressure: smrf/envphys/core/dewpt.c:14-229 (Brent root of sati(T) = e, float-truncated result,
+//     K -> C) with the saturation curves of topotherm.c:109-176 -- either as a consumer hooked onto a distribute call
+//     (the vapor-pressure block is still in the handle's device ring: no second trip through host memory) or stand-alone;
+//   * wind azimuth from the two distributed direction components: smrf/distribute/wind/wind.py:175-178;
+//   * grid_interpolate with the vertices / weights of interp_weights: smrf/utils/utils.py:377-427.
+#include "common.cuh"
+
+namespace smrfb {
+
+constexpr double ENV_FREEZE = 2.7316e2;      // envphys.h:31
+constexpr double ENV_BOIL = 3.7315e2;        // envphys.h:32
+constexpr double ENV_SEA_LEVEL = 1.013246e5; // envphys.h:74
+
+// topotherm.c:109-137
+__device__ __forceinline__ double env_satw(double tk) {
+    const double l10 = log(1.e1);
+    double x = -7.90298 * (ENV_BOIL / tk - 1.) + 5.02808 * log(ENV_BOIL / tk) / l10 -
+               1.3816e-7 * (pow(1.e1, 1.1344e1 * (1. - tk / ENV_BOIL)) - 1.) +
+               8.1328e-3 * (pow(1.e1, -3.49149 * (ENV_BOIL / tk - 1.)) - 1.) + log(ENV_SEA_LEVEL) / l10;
+    return pow(1.e1, x);
+}
+// topotherm.c:143-176
+__device__ __forceinline__ double env_sati(double tk) {
+    if (tk > ENV_FREEZE) return env_satw(tk);
+    const double l10 = log(1.e1);
+    const double x = pow(1.e1, -9.09718 * ((ENV_FREEZE / tk) - 1.) - 3.56654 * log(ENV_FREEZE / tk) / l10 +
+                                   8.76793e-1 * (1. - (tk / ENV_FREEZE)) + log(6.1071) / l10);
+    return x * 1.e2;
+}
+
+// dewpt.c:95-229 (zerobr: Brent's method on f(t) = e - sati(t)); returns 0 where the reference gives up
+__device__ double env_zerobr(double a, double b, double t, double e_pass) {
+    const double meps = 2.2204460492503131e-16;
+    double c = 0., d = 0., e = 0., fa, fb, fc, m, p, q, r, s, tol;
+    if (a == b) return a;
+    fb = (fabs(b) >= fabs(a)) ? fabs(b) : fabs(a);
+    tol = 5.e-1 * t + 2 * meps * fb;
+    s = log(fabs(b - a) / tol) / log(2.);
+    int maxfun = (int)(s * s + 1);
+    fa = e_pass - env_sati(a);
+    fc = fb = e_pass - env_sati(b);
+    if (fabs(fb) <= tol) return b;
+    if (fabs(fa) <= tol) return a;
+    if (fb * fa > 0) return 0.;
+    while (maxfun--) {
+        if ((fb > 0 && fc > 0) || (fb <= 0 && fc <= 0)) {
+            c = a;
+            fc = fa;
+            d = e = b - a;
+        }
+        if (fabs(fc) < fabs(fb)) {
+            a = b;
+            b = c;
+            c = a;
+            fa = fb;
+            fb = fc;
+            fc = fa;
+        }
+        tol = meps * fabs(b) + t;
+        m = (c - b) / 2;
+        if (fabs(m) < tol || fb == 0) return b;
+        if (fabs(e) < tol || fabs(fa) <= fabs(fb)) {
+            d = e = m;
+        } else {
+            s = fb / fa;
+            if (a == c) {
+                p = 2 * m * s;
+                q = 1 - s;
+            } else {
+                q = fa / fc;
+                r = fb / fc;
+                p = s * (2 * m * q * (q - r) - (b - a) * (r - 1));
+                q -= 1;
+                q *= (r - 1) * (s - 1);
+            }
+            if (p > 0) q = -q;
+            else p = -p;
+            s = e;
+            e = d;
+            if (2 * p < 3 * m * q - fabs(tol * q) && p < fabs(s * q / 2)) d = p / q;
+            else d = e = m;
+        }
+        a = b;
+        fa = fb;
+        if (fabs(d) > tol) b += d;
+        else if (m > 0) b += tol;
+        else b -= tol;
+        fb = e_pass - env_sati(b);
+    }
+    return 0.;
+}
+
+// dewpt.c:63-92 + :14-47: spanning guesses, root, float truncation, K -> C.  NaN in -> NaN out (the reference would loop).
+__device__ double env_dew_point_c(double ea, double tol) {
+    if (!(ea == ea)) return ea;
+    double a = ENV_FREEZE;
+    int guard = 0;
+    while (ea < env_sati(a) && guard++ < 64) a *= .75;
+    double b = ENV_FREEZE + 15;
+    guard = 0;
+    while (ea > env_sati(b) && guard++ < 64) b *= 1.25;
+    float dpt = (float)env_zerobr(a, b, tol, ea);
+    dpt -= (float)ENV_FREEZE;                 // `dpt_p -= FREEZE` on a float: the subtraction rounds to float
+    return (double)dpt;
+}
+
+__global__ void dew_point_kernel(const double* __restrict__ ea, const float* __restrict__ ea32, long long n, double tol,
+                                 double* __restrict__ out, float* __restrict__ out32) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double e = ea ? ea[i] : (double)ea32[i];
+        const double v = env_dew_point_c(e, tol);
+        if (out) __stcs(out + i, v);
+        else __stcs(out32 + i, (float)v);
+    }
+}
+
+int launch_dew_point(cudaStream_t st, const void* d_ea, int in_f32, long long n, double tol, void* d_out, int out_f32) {
+    if (n <= 0) return SMRFB_OK;
+    const int threads = 256;
+    const long long blocks = std::min<long long>((n + threads - 1) / threads, 148LL * 32);
+    dew_point_kernel<<<(unsigned)blocks, threads, 0, st>>>(in_f32 ? nullptr : (const double*)d_ea, in_f32 ? (const float*)d_ea : nullptr, n, tol,
+                                                           out_f32 ? nullptr : (double*)d_out, out_f32 ? (float*)d_out : nullptr);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+// wind.py:175-178: az = arctan2(u, v) * 180 / pi; az[az < 0] += 360
+__global__ void wind_direction_kernel(const double* __restrict__ u, const double* __restrict__ v, long long n, double* __restrict__ out) {
+    const double pi = 3.141592653589793;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double az = __ddiv_rn(__dmul_rn(atan2(u[i], v[i]), 180.0), pi);
+        if (az < 0) az = __dadd_rn(az, 360.0);
+        __stcs(out + i, az);
+    }
+}
+
+// utils.py:409-427: ret = einsum('nj,nj->n', take(values, vtx), wts); ret[any(wts < 0, axis=1)] = fill
+__global__ void interp_apply_kernel(const int32_t* __restrict__ vtx, const double* __restrict__ wts, long long n, const double* __restrict__ values,
+                                    int npts, int T, double fill, int fill_negative, double* __restrict__ out) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int v0 = vtx[3 * c], v1 = vtx[3 * c + 1], v2 = vtx[3 * c + 2];
+        const double w0 = wts[3 * c], w1 = wts[3 * c + 1], w2 = wts[3 * c + 2];
+        const bool outside = fill_negative && ((w0 < 0) || (w1 < 0) || (w2 < 0));
+        for (int t = 0; t < T; t++) {
+            const double* val = values + (size_t)t * npts;
+            double r = __dadd_rn(__dadd_rn(__dmul_rn(__ldg(val + v0), w0), __dmul_rn(__ldg(val + v1), w1)), __dmul_rn(__ldg(val + v2), w2));
+            if (outside) r = fill;
+            __stcs(out + (size_t)t * n + c, r);
+        }
+    }
+}
+
+struct InterpHandle : HandleBase {
+    int32_t* d_vtx = nullptr;
+    double* d_wts = nullptr;
+    int npts = 0;
+    int fill_negative = 1;   // utils.py:424: cells with a negative weight take the fill value
+    InterpHandle() : HandleBase(HK_INTERP) {}
+    ~InterpHandle() override {
+        cudaSetDevice(device);
+        cudaFree(d_vtx);
+        cudaFree(d_wts);
+    }
+};
+
+}  // namespace smrfb
+
+using namespace smrfb;
+
+extern "C" {
+
+int smrfb_dew_point(const double* vp, int64_t n, double tol, double* dpt, int device) {
+    SMRFB_CHECK(vp && dpt && n >= 0, SMRFB_ERR_ARG, "NULL vapor pressure / output");
+    SMRFB_CUDA(cudaSetDevice(device));
+    double *d_in = nullptr, *d_out = nullptr;
+    const size_t chunk = (size_t)1 << 26;        // 64 Mi cells per piece: 1 GiB of device scratch
+    const size_t cap = std::min<size_t>((size_t)n, chunk);
+    if (n == 0) return SMRFB_OK;
+    SMRFB_CUDA(cudaMalloc((void**)&d_in, cap * sizeof(double)));
+    if (cudaMalloc((void**)&d_out, cap * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_in);
+        set_error("cudaMalloc failed");
+        return SMRFB_ERR_CUDA;
+    }
+    int rc = SMRFB_OK;
+    for (size_t o = 0; o < (size_t)n && rc == SMRFB_OK; o += cap) {
+        const size_t m = std::min(cap, (size_t)n - o);
+        if (cudaMemcpy(d_in, vp + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = SMRFB_ERR_CUDA;
+        if (rc == SMRFB_OK) rc = launch_dew_point(nullptr, d_in, 0, (long long)m, tol, d_out, 0);
+        if (rc == SMRFB_OK && cudaMemcpy(dpt + o, d_out, m * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SMRFB_ERR_CUDA;
+    }
+    if (rc == SMRFB_ERR_CUDA) set_error("dew point: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int smrfb_dew_point_dev(const double* d_vp, int64_t n, double tol, double* d_dpt, void* stream) {
+    SMRFB_CHECK(d_vp && d_dpt && n >= 0, SMRFB_ERR_ARG, "NULL vapor pressure / output");
+    return launch_dew_point((cudaStream_t)stream, d_vp, 0, (long long)n, tol, d_dpt, 0);
+}
+
+int smrfb_set_consumer(smrfb_handle_t hh, int kind, double tol, void* out2) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    SMRFB_CHECK(kind == 0 || kind == 1, SMRFB_ERR_ARG, "consumer kind must be 0 (none) or 1 (dew point)");
+    SMRFB_CHECK(kind == 0 || out2, SMRFB_ERR_ARG, "the consumer needs an output buffer");
+    HandleBase* h = reinterpret_cast<HandleBase*>(hh);
+    h->consumer = kind;
+    h->consumer_tol = tol;
+    h->consumer_out = out2;
+    return SMRFB_OK;
+}
+
+int smrfb_wind_direction(const double* u, const double* v, int64_t n, double* az, int device) {
+    SMRFB_CHECK(u && v && az && n >= 0, SMRFB_ERR_ARG, "NULL u / v / output");
+    if (n == 0) return SMRFB_OK;
+    SMRFB_CUDA(cudaSetDevice(device));
+    double *d_u = nullptr, *d_v = nullptr;
+    const size_t cap = std::min<size_t>((size_t)n, (size_t)1 << 26);
+    SMRFB_CUDA(cudaMalloc((void**)&d_u, cap * sizeof(double)));
+    if (cudaMalloc((void**)&d_v, cap * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_u);
+        set_error("cudaMalloc failed");
+        return SMRFB_ERR_CUDA;
+    }
+    int rc = SMRFB_OK;
+    for (size_t o = 0; o < (size_t)n && rc == SMRFB_OK; o += cap) {
+        const size_t m = std::min(cap, (size_t)n - o);
+        if (cudaMemcpy(d_u, u + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d_v, v + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = SMRFB_ERR_CUDA;
+        if (rc == SMRFB_OK) {
+            wind_direction_kernel<<<(unsigned)std::min<size_t>((m + 255) / 256, 148 * 32), 256>>>(d_u, d_v, (long long)m, d_u);
+            count_launch();
+            if (cudaMemcpy(az + o, d_u, m * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SMRFB_ERR_CUDA;
+        }
+    }
+    if (rc == SMRFB_ERR_CUDA) set_error("wind direction: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_u);
+    cudaFree(d_v);
+    return rc;
+}
+
+int smrfb_wind_direction_dev(const double* d_u, const double* d_v, int64_t n, double* d_az, void* stream) {
+    SMRFB_CHECK(d_u && d_v && d_az && n >= 0, SMRFB_ERR_ARG, "NULL u / v / output");
+    if (n == 0) return SMRFB_OK;
+    wind_direction_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_u, d_v, n, d_az);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+int smrfb_interp_create(int64_t n, const int32_t* vtx, const double* wts, int npts, int fill_negative, int device, smrfb_handle_t* out) {
+    SMRFB_CHECK(out, SMRFB_ERR_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    SMRFB_CHECK(n > 0 && vtx && wts && npts > 0, SMRFB_ERR_ARG, "need n > 0 cells, vertices, weights and npts > 0");
+    for (int64_t i = 0; i < 3 * n; i++) SMRFB_CHECK(vtx[i] >= 0 && vtx[i] < npts, SMRFB_ERR_ARG, "vertex %d outside [0, %d)", vtx[i], npts);
+    int ndev = 0;
+    SMRFB_CUDA(cudaGetDeviceCount(&ndev));
+    SMRFB_CHECK(device >= 0 && device < ndev, SMRFB_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    InterpHandle* h = new InterpHandle();
+    h->device = device;
+    h->npts = npts;
+    h->fill_negative = fill_negative;
+    h->g.ncell = n;
+    h->g.ny = 1;
+    h->g.nx = (int)std::min<int64_t>(n, 2147483647);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_vtx, (size_t)3 * n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_wts, (size_t)3 * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_vtx, vtx, (size_t)3 * n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_wts, wts, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("interp create: %s", cudaGetErrorString(e));
+        delete h;
+        return SMRFB_ERR_CUDA;
+    }
+    *out = reinterpret_cast<smrfb_handle_t>(h);
+    return SMRFB_OK;
+}
+
+static int interp_run(InterpHandle* h, const double* d_values, int T, double fill, double* d_out, cudaStream_t st) {
+    const long long n = h->g.ncell;
+    interp_apply_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 32), 256, 0, st>>>(h->d_vtx, h->d_wts, n, d_values, h->npts, T, fill, h->fill_negative, d_out);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+int smrfb_interp_apply_dev(smrfb_handle_t hh, const double* d_values, int T, double fill, double* d_out, void* stream) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    InterpHandle* h = reinterpret_cast<InterpHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_INTERP, SMRFB_ERR_ARG, "not an interpolation-weights handle");
+    SMRFB_CHECK(d_values && d_out && T > 0, SMRFB_ERR_ARG, "NULL values/out or T <= 0");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    return interp_run(h, d_values, T, fill, d_out, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int smrfb_interp_apply(smrfb_handle_t hh, const double* values, int T, double fill, double* out) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    InterpHandle* h = reinterpret_cast<InterpHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_INTERP, SMRFB_ERR_ARG, "not an interpolation-weights handle");
+    SMRFB_CHECK(values && out && T > 0, SMRFB_ERR_ARG, "NULL values/out or T <= 0");
+    SMRFB_CUDA(cudaSetDevice(h->device));
+    SMRFB_PROPAGATE(ensure_cap((void**)&h->d_data, &h->data_cap, (size_t)T * h->npts * sizeof(double)));
+    SMRFB_CUDA(cudaMemcpyAsync(h->d_data, values, (size_t)T * h->npts * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return run_host_batches(h, T, 1, out, [&](int t0, int tn, double* d_out, cudaStream_t st) {
+        return interp_run(h, h->d_data + (size_t)t0 * h->npts, tn, fill, d_out, st);
+    });
+}
+
+}  // extern "C"

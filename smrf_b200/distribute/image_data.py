@@ -24,6 +24,7 @@ class image_data:
         self.gridded = False
         self._block = None
         self._block_index = None
+        self._blocks = {}
         self._logger = logging.getLogger(__name__)
 
     def getConfig(self, cfg):
@@ -70,8 +71,21 @@ class image_data:
             raise Exception("Could not determine the distribution method for {}".format(self.variable))
 
     # ------------------------------------------------------------------ block façade
-    def prefetch(self, frame):
-        """Distribute every row of ``frame`` ([time x station] DataFrame) now; clamp to min/max fused."""
+    def prefetch(self, frame, other_attribute=None, clamp=True):
+        """Distribute every row of ``frame`` ([time x station] DataFrame) now; clamp to min/max fused (clamp=False: not).
+        With ``other_attribute`` the block serves later ``_distribute(row, other_attribute=...)`` calls."""
+        if other_attribute is not None:
+            if not hasattr(self, "_blocks"):
+                self._blocks = {}
+            keep = (self._block, self._block_index, self.min, self.max)
+            try:
+                if not clamp:
+                    self.min, self.max = -np.inf, np.inf
+                blk = self.prefetch(frame)
+                self._blocks[other_attribute] = (blk, self._block_index)
+            finally:
+                self._block, self._block_index, self.min, self.max = keep
+            return blk
         rows = frame[self.stations]
         vals = np.ascontiguousarray(rows.values, dtype=np.float64)
         if np.isnan(vals).all(axis=1).any():
@@ -92,19 +106,26 @@ class image_data:
         self._block_index = {k: i for i, k in enumerate(rows.index)}
         return blk
 
-    def _distribute(self, data, other_attribute=None, zeros=None):
+    def _distribute(self, data, other_attribute=None, zeros=None, clamp=None):
         # image_data.py:210-263.  The variable classes clamp right after this call (utils.set_min_max(v, self.min,
         # self.max), e.g. air_temp.py:84); here the same NaN-preserving clamp is fused into the kernel's store, so the
         # later set_min_max finds nothing left to do (it is idempotent) and the grid crosses PCIe once.
+        # clamp=None fuses it for the variable itself and not for an ``other_attribute`` (wind's direction components,
+        # wind.py:168-172, must not be clamped to the wind-speed limits); True / False force it.
+        if clamp is None:
+            clamp = other_attribute is None
         key = getattr(data, "name", None)
-        if self._block is not None and key in self._block_index:
+        blk = self._blocks.get(other_attribute) if hasattr(self, "_blocks") else None
+        if blk is not None and key in blk[1]:
+            v = blk[0][blk[1][key]]
+        elif other_attribute is None and self._block is not None and key in self._block_index:
             v = self._block[self._block_index[key]]
         else:
             data = data[self.stations]
             if np.sum(data.isnull()) == data.shape[0]:
                 raise Exception("{}: All data values are NaN".format(self.variable))
             dist = self.config["distribution"]
-            lo, hi = self.min, self.max
+            lo, hi = (self.min, self.max) if clamp else (None, None)
             if dist == "idw":
                 if zeros is not None:          # rarely used branch of idw.py:96-110 (clips negatives itself)
                     v = self.idw.detrendedIDW(data.values, self.config["detrend_slope"], zeros=zeros)
