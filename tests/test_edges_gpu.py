@@ -145,6 +145,9 @@ def test_idw_zeros_branch_and_error_paths(sp):
     with pytest.raises(SmrfbError):                                # detrend without elevations
         sp.IDW(mx, my, X, Y).distribute_block(row[None, :], detrend=True)
     big = np.linspace(0, 1, 300)
-    with pytest.raises(SmrfbError) as e:                           # more stations than a tile's shared memory holds
-        sp.IDW(big, big, X, Y, mz=big, GridZ=dem)
+    # more stations than the tensor-core kernels hold (224): fine on a uniform mesh (near / far-field kernels, any count),
+    # refused with SMRFB_ERR_LIMIT on an arbitrary point grid
+    assert sp.IDW(big, big, X, Y, mz=big, GridZ=dem).kernel_info()["far_field"]
+    with pytest.raises(SmrfbError) as e:
+        sp.IDW(big, big, X.T.copy(), Y.T.copy(), mz=big, GridZ=dem.T.copy())
     assert e.value.code == 4
