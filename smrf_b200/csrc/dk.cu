@@ -391,6 +391,427 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
+// dk_chain_kernel -- the elimination walk, second design ("common chain + per-cell lead").
+//
+// Measured on the C4 geometry (tools/dk_path_sim.py, tools/dk_main_chain_sim.py): neighbouring cells drop the SAME
+// stations, only in slightly different ORDER -- a 32 x 32 block of cells visits 0.66 distinct active sets per cell
+// but 16 distinct path prefixes per cell in 8 x 4 tiles, and a walk keyed by path (dk_build_kernel: fork, snapshot,
+// restore) pays one rank-1 downdate of the 162 KB inverse for each of them.  The weights of a cell depend on its
+// active SET only, so here a tile keeps ONE inverse S, that of the set A_main = all stations minus those EVERY live
+// cell of the tile has dropped, and a cell that is ahead by the stations Q (dropped by it, not yet by all) takes its
+// weights from the Schur complement
+//         w = w_main - S[:, Q] (S[Q, Q])^-1 w_main[Q]            (|Q| <= DK2_QM, a Gauss-Jordan solve per step)
+// which is what |Q| further rank-1 downdates in the cell's own order would give.  Cells step on their own (one warp
+// each, no block barrier, DK2_RA drops per round); once per round the stations common to all leads move into the
+// chain: S is downdated once per station and TILE (one pass over the packed triangle for up to DK2_PEND stations),
+// every cell's w_main follows, the leads shrink.  No forks: ~48 rounds per tile instead of ~770 shared rank-1 steps.
+// Within ~30 cells of a station the orders differ by more than DK2_QM: when nobody can step and nothing is common,
+// the cells that have dropped the most popular station go on (progress guaranteed), the others wait on a job stack
+// with a snapshot of S.
+// ------------------------------------------------------------------------------------------
+constexpr int DK2_QM = 12;              // largest lead of a cell over the common chain
+constexpr int DK2_LD = DK2_QM + 1;      // row stride of the lead system [S_QQ | w_Q] (odd: conflict-free columns)
+constexpr int DK2_PEND = 8;             // stations moved into the chain per round at most
+constexpr int DK2_RA = 4;               // drops per cell and round
+constexpr int DK2_FL = 4;               // stations per pass over the packed inverse
+constexpr int DK2_SCR = DK2_QM * DK2_LD + DK2_QM;   // doubles of per-warp scratch: the system + its solution
+
+__host__ __device__ inline size_t dk2_union_doubles(int NN, int NNP) {
+    const size_t stage = (size_t)DK_TILE * NN;                                       // right-hand sides at tile start
+    const size_t work = (size_t)DK2_PEND * NNP + DK2_PEND + (size_t)DK_WARPS * DK2_SCR;   // columns, 1/mu, lead systems
+    return stage > work ? stage : work;
+}
+__host__ __device__ inline size_t dk2_smem_bytes(int NN, int NNP) {
+    const size_t npk = (size_t)NN * (NN + 1) / 2;
+    return (npk + dk2_union_doubles(NN, NNP)) * sizeof(double) +
+           ((size_t)NNP + (NN + 1) + DK_TILE * DK_WORDS + 2 * DK_TILE + DK2_PEND + DK_WORDS + 16 + 2 * DK_TILE) * sizeof(int) + NNP;
+}
+
+__global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, NN = a.NN, NNP = a.NNP;
+    const int npk = NN * (NN + 1) / 2;
+    double* Sp = reinterpret_cast<double*>(smem_raw);            // [npk] packed upper triangle of the chain's inverse
+    double* un = Sp + npk;                                       // union: rhs staging | pcol, prmu, lead systems
+    double* stage = un;                                          // [32][NN]
+    double* pcol = un;                                           // [DK2_PEND][NNP] columns moving into the chain (0 = inactive)
+    double* prmu = pcol + DK2_PEND * NNP;                        // [DK2_PEND] 1 / pivot
+    double* scr = prmu + DK2_PEND;                               // [warps][DK2_SCR]
+    int* rowoff = reinterpret_cast<int*>(un + dk2_union_doubles(NN, NNP));   // [NNP]
+    int* kstack = rowoff + NNP;                                  // [NN + 1] stations of the chain, in order
+    unsigned* qmask = reinterpret_cast<unsigned*>(kstack + NN + 1);   // [32][8] lead of every cell as a bit set
+    int* clive = reinterpret_cast<int*>(qmask + DK_TILE * DK_WORDS);  // [32] cell still walking
+    int* cstep = clive + DK_TILE;                                // [32] drops of the cell in the last round
+    int* clist = cstep + DK_TILE;                                // [DK2_PEND] stations moving into the chain
+    unsigned* takenw = reinterpret_cast<unsigned*>(clist + DK2_PEND);   // [8] the same as a bit set
+    int* ctrl = reinterpret_cast<int*>(takenw + DK_WORDS);       // [16]
+    int* jobs = ctrl + 16;                                       // [32][2] waiting groups: cell mask, chain length
+    unsigned char* mact = reinterpret_cast<unsigned char*>(jobs + 2 * DK_TILE);   // [NNP] station still in the chain's set
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* snap_g = a.snap + (size_t)blockIdx.x * DK_MAXSNAP * npk;
+    const DkTiling tiling = dk_tiling(a.g, a.ncell, a.dgrid != nullptr);
+    const long long ntiles = tiling.ntiles;
+
+    for (int i = tid; i < NNP; i += DK_THREADS) rowoff[i] = i * NN - (i * (i + 1)) / 2;   // idx(i, j >= i) = rowoff[i] + j
+    __syncthreads();
+    auto roj = [&](int j) { return j * NN - ((j * (j + 1)) >> 1); };   // row offset of one of this lane's stations
+    auto pick = [&](const double (&v)[DK_QMAX], int slot) {      // v[slot] for a warp-uniform slot, no local memory
+        double r = v[0];
+#pragma unroll
+        for (int s = 1; s < DK_QMAX; s++)
+            if (slot == s) r = v[s];
+        return r;
+    };
+    unsigned n_round = 0, n_pop = 0, n_split = 0, n_moved = 0;
+
+    for (;;) {
+        if (tid == 0) ctrl[0] = (int)atomicAdd(a.tile_counter, 1ULL);
+        __syncthreads();
+        const long long tile = (unsigned)ctrl[0];
+        if (tile >= ntiles) break;
+        for (int p = tid; p < npk; p += DK_THREADS) Sp[p] = a.B0p[p];
+        const long long cell = dk_tile_cell(tiling, a.g, a.ncell, tile, warp);   // this warp's cell
+        {   // right-hand side [dist to every station ; 1] in rank order
+            double X = 0.0, Y = 0.0;
+            if (cell >= 0 && !a.dgrid) cell_xy(a.g, cell, X, Y);
+            for (int j = lane; j < NN; j += 32) {
+                double v = 0.0;
+                if (cell >= 0) {
+                    if (j == n) v = 1.0;
+                    else if (a.dgrid) v = a.dgrid[(size_t)cell * n + a.perm[j]];
+                    else v = dist_rn(X, Y, a.sx[j], a.sy[j]);
+                }
+                stage[warp * NN + j] = v;
+            }
+        }
+        for (int i = tid; i < NNP; i += DK_THREADS) mact[i] = (i < NN) ? 1 : 0;
+        __syncthreads();
+        double wm[DK_QMAX];                                      // w_main of this warp's cell: station lane + 32 s in slot s
+#pragma unroll
+        for (int s = 0; s < DK_QMAX; s++) wm[s] = 0.0;
+        for (int i = 0; i < NN; i++) {                           // w_main = S rhs (S symmetric, packed)
+            const double r = stage[warp * NN + i];
+            const int ro = rowoff[i];
+#pragma unroll
+            for (int s = 0; s < DK_QMAX; s++) {
+                const int j = lane + 32 * s;
+                if (j < NN) wm[s] = fma((j >= i) ? Sp[ro + j] : Sp[roj(j) + i], r, wm[s]);
+            }
+        }
+        unsigned actbits = 0;                                    // bit s: station lane + 32 s is in this cell's active set
+#pragma unroll
+        for (int s = 0; s < DK_QMAX; s++)
+            if (lane + 32 * s < n) actbits |= 1u << s;
+        int m = 0, myq = 0;                                      // the lead: lane i < m holds its i-th station (drop order)
+        bool mylive = cell >= 0;
+        if (lane < DK_WORDS) qmask[warp * DK_WORDS + lane] = 0u;
+        if (lane == 0) {
+            clive[warp] = mylive ? 1 : 0;
+            cstep[warp] = 0;
+        }
+        unsigned jobmask;
+        {
+            const long long cl = dk_tile_cell(tiling, a.g, a.ncell, tile, lane);
+            jobmask = __ballot_sync(FULL, cl >= 0);
+        }
+        int nmain = 0, nstack = 0;
+        __syncthreads();                                         // staging is dead: the union now holds pcol / lead systems
+
+        for (;;) {   // ---- rounds
+            // ---- phase A: this warp's cell drops up to DK2_RA stations on its own
+            int steps = 0;
+            if (mylive && ((jobmask >> warp) & 1u)) {
+                double* G = scr + warp * DK2_SCR;
+                double* zb = G + DK2_QM * DK2_LD;
+                while (steps < DK2_RA) {
+                    double acc[DK_QMAX];
+#pragma unroll
+                    for (int s = 0; s < DK_QMAX; s++) acc[s] = wm[s];
+                    if (m > 0) {
+                        for (int e0 = 0; e0 < m * m; e0 += 32) {             // G = S[Q, Q]
+                            const int e = e0 + lane;
+                            const bool ok = e < m * m;
+                            const int i = ok ? e / m : 0, c = ok ? e - i * m : 0;
+                            const int qi = __shfl_sync(FULL, myq, i), qc = __shfl_sync(FULL, myq, c);
+                            if (ok) G[i * DK2_LD + c] = Sp[rowoff[min(qi, qc)] + max(qi, qc)];
+                        }
+                        for (int i = 0; i < m; i++) {                        // right-hand side w_main[Q]
+                            const int q = __shfl_sync(FULL, myq, i);
+                            const double v = __shfl_sync(FULL, pick(wm, q >> 5), q & 31);
+                            if (lane == i) G[i * DK2_LD + m] = v;
+                        }
+                        __syncwarp();
+                        for (int p = 0; p < m; p++) {                        // Gauss-Jordan in drop order, no pivoting (as the
+                            const double r = dk_rcp(G[p * DK2_LD + p]);      // rank-1 downdates in that order would do)
+                            const int wd = m - p;                            // columns p + 1 .. m
+                            for (int e = lane; e < m * wd; e += 32) {
+                                const int i = e / wd, c = p + 1 + (e - i * wd);
+                                if (i != p) G[i * DK2_LD + c] = fma(-(G[i * DK2_LD + p] * r), G[p * DK2_LD + c], G[i * DK2_LD + c]);
+                            }
+                            __syncwarp();
+                        }
+                        if (lane < m) zb[lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
+                        __syncwarp();
+                        for (int c = 0; c < m; c++) {                        // w = w_main - S[:, Q] z
+                            const int q = __shfl_sync(FULL, myq, c);
+                            const int roq = rowoff[q];
+                            const double z = zb[c];
+#pragma unroll
+                            for (int s = 0; s < DK_QMAX; s++) {
+                                const int j = lane + 32 * s;
+                                if ((actbits >> s) & 1u) acc[s] = fma(-((j <= q) ? Sp[roj(j) + q] : Sp[roq + j]), z, acc[s]);
+                            }
+                        }
+                        __syncwarp();                                        // G / zb are rewritten in the next step
+                    }
+                    int k = -1;                                              // first (= highest) active station with w < 0
+#pragma unroll
+                    for (int s = 0; s < DK_QMAX; s++) {
+                        if (k < 0) {
+                            const int j = lane + 32 * s;
+                            const unsigned bb = __ballot_sync(FULL, ((actbits >> s) & 1u) && (j < a.nsel) && (acc[s] < 0.0));
+                            if (bb) k = 32 * s + __ffs(bb) - 1;
+                        }
+                    }
+                    if (k < 0 || n - nmain - m <= a.handoff) {               // finished, or few enough left for the exact solver
+                        unsigned myword = 0;
+#pragma unroll
+                        for (int s = 0; s < DK_WORDS; s++) {
+                            const unsigned bb = __ballot_sync(FULL, s < DK_QMAX && ((actbits >> s) & 1u));
+                            if (lane == s) myword = bb;
+                        }
+                        if (k >= 0 && lane == DK_WORDS - 1) myword |= 0x80000000u;   // bit 255: handed off undecided
+                        if (lane < DK_WORDS) a.final_act[(size_t)cell * DK_WORDS + lane] = myword;
+                        mylive = false;
+                        break;
+                    }
+                    if (m >= DK2_QM) break;                                  // lead full: wait for the chain
+                    if (lane == m) myq = k;
+                    if (lane == (k & 31)) actbits &= ~(1u << (k >> 5));
+                    if (lane == 0) qmask[warp * DK_WORDS + (k >> 5)] |= 1u << (k & 31);
+                    m++;
+                    steps++;
+                }
+                if (lane == 0) clive[warp] = mylive ? 1 : 0;
+            }
+            if (lane == 0) cstep[warp] = steps;
+            __syncthreads();   // (1) leads published
+
+            // ---- phase B1 (warp 0): what is common, what to do, the columns that move into the chain
+            if (warp == 0) {
+                bool lv = clive[lane] && ((jobmask >> lane) & 1u);
+                unsigned livem = __ballot_sync(FULL, lv);
+                int action = 0, nc = 0, snap = 0, nmain_new = nmain;
+                if (!livem) {
+                    if (nstack == 0) {
+                        action = 2;                                          // tile finished
+                    } else {
+                        action = 1;                                          // next waiting group
+                        nstack--;
+                        jobmask = (unsigned)jobs[2 * nstack];
+                        nmain_new = jobs[2 * nstack + 1];
+                    }
+                } else {
+                    const bool any = __ballot_sync(FULL, lv && cstep[lane] > 0) != 0u;
+                    unsigned cw[DK_WORDS];
+                    int nco = 0;
+#pragma unroll
+                    for (int w = 0; w < DK_WORDS; w++) {
+                        cw[w] = __reduce_and_sync(FULL, lv ? qmask[lane * DK_WORDS + w] : FULL);
+                        nco += __popc(cw[w]);
+                    }
+                    if (nco == 0 && !any) {   // stuck: split by the station most cells have dropped
+                        int best = -1, bestc = 0;
+#pragma unroll
+                        for (int w = 0; w < DK_WORDS; w++) {
+                            const unsigned mine = lv ? qmask[lane * DK_WORDS + w] : 0u;
+                            unsigned bits = __reduce_or_sync(FULL, mine);
+                            while (bits) {
+                                const int b = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const int c = __popc(__ballot_sync(FULL, (mine >> b) & 1u));
+                                if (c > bestc) {
+                                    bestc = c;
+                                    best = 32 * w + b;
+                                }
+                            }
+                        }
+                        const unsigned g1 = __ballot_sync(FULL, lv && ((qmask[lane * DK_WORDS + (best >> 5)] >> (best & 31)) & 1u));
+                        if (lane == 0) {
+                            jobs[2 * nstack] = (int)(livem & ~g1);
+                            jobs[2 * nstack + 1] = nmain;
+                        }
+                        nstack++;
+                        snap = 1;
+                        jobmask = g1;
+                        lv = lv && ((g1 >> lane) & 1u);
+                        livem = g1;
+                        nco = 0;
+#pragma unroll
+                        for (int w = 0; w < DK_WORDS; w++) {
+                            cw[w] = __reduce_and_sync(FULL, lv ? qmask[lane * DK_WORDS + w] : FULL);
+                            nco += __popc(cw[w]);
+                        }
+                    }
+                    unsigned tw = 0;                                         // lane w < 8: word w of the stations taken
+#pragma unroll
+                    for (int w = 0; w < DK_WORDS; w++) {
+                        unsigned bits = cw[w], tk = 0;
+                        while (bits && nc < DK2_PEND) {
+                            const int b = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            tk |= 1u << b;
+                            if (lane == 0) clist[nc] = 32 * w + b;
+                            nc++;
+                        }
+                        if (lane == w) tw = tk;
+                    }
+                    if (lane < DK_WORDS) takenw[lane] = tw;
+                    __syncwarp();
+                    unsigned dropbits = 0;                                   // stations of this round already moved
+                    for (int d = 0; d < nc; d++) {   // current column q of the inverse = stored column corrected for the columns moved before it
+                        const int q = clist[d];
+                        const int roq = rowoff[q];
+                        double v[DK_QMAX];
+#pragma unroll
+                        for (int s = 0; s < DK_QMAX; s++) {
+                            const int j = lane + 32 * s;
+                            const bool on = (j < NN) && mact[j] && !((dropbits >> s) & 1u);
+                            double x = 0.0;
+                            if (on) {
+                                x = (j <= q) ? Sp[roj(j) + q] : Sp[roq + j];
+                                for (int e = 0; e < d; e++) x = fma(-(pcol[e * NNP + j] * prmu[e]), pcol[e * NNP + q], x);
+                            }
+                            v[s] = x;
+                        }
+                        const double mu = __shfl_sync(FULL, pick(v, q >> 5), q & 31);
+                        if (lane == (q & 31)) dropbits |= 1u << (q >> 5);
+#pragma unroll
+                        for (int s = 0; s < DK_QMAX; s++) {
+                            const int j = lane + 32 * s;
+                            if (j < NNP) pcol[d * NNP + j] = (j == q) ? 0.0 : v[s];
+                        }
+                        if (lane == 0) prmu[d] = dk_rcp(mu);
+                        __syncwarp();
+                    }
+                }
+                if (lane == 0) {
+                    ctrl[1] = action;
+                    ctrl[2] = nc;
+                    ctrl[3] = (int)jobmask;
+                    ctrl[4] = nstack;
+                    ctrl[5] = nmain_new;
+                    ctrl[6] = snap;
+                }
+            }
+            __syncthreads();   // (2) decision + columns published
+            const int action = ctrl[1], nc = ctrl[2];
+            jobmask = (unsigned)ctrl[3];
+            nstack = ctrl[4];
+            n_round++;
+            if (action == 2) break;
+            if (action == 1) {   // a waiting group: back to the inverse and chain it was split off from
+                const double* sg = snap_g + (size_t)nstack * npk;
+                for (int q = tid; q < npk; q += DK_THREADS) Sp[q] = sg[q];
+                nmain = ctrl[5];
+                for (int i = tid; i < NNP; i += DK_THREADS) mact[i] = (i < NN) ? 1 : 0;
+                __syncthreads();
+                for (int d = tid; d < nmain; d += DK_THREADS) mact[kstack[d]] = 0;
+                n_pop++;
+                __syncthreads();
+                continue;
+            }
+            if (ctrl[6]) {       // split: the group left behind restarts from this inverse
+                double* sg = snap_g + (size_t)(nstack - 1) * npk;
+                for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Sp[q];
+                n_split++;
+                __syncthreads();
+            }
+            if (nc > 0) {
+                if (mylive && ((jobmask >> warp) & 1u)) {   // w_main follows the chain; the lead loses the stations moved
+                    for (int d = 0; d < nc; d++) {
+                        const int q = clist[d];
+                        const double f = __shfl_sync(FULL, pick(wm, q >> 5), q & 31) * prmu[d];
+#pragma unroll
+                        for (int s = 0; s < DK_QMAX; s++)
+                            if (lane + 32 * s < NN) wm[s] = fma(-f, pcol[d * NNP + lane + 32 * s], wm[s]);
+                    }
+                    int newm = 0, mynew = 0;
+                    for (int i = 0; i < m; i++) {
+                        const int qi = __shfl_sync(FULL, myq, i);
+                        if (!((takenw[qi >> 5] >> (qi & 31)) & 1u)) {
+                            if (lane == newm) mynew = qi;
+                            newm++;
+                        }
+                    }
+                    myq = mynew;
+                    m = newm;
+                    if (lane < DK_WORDS) qmask[warp * DK_WORDS + lane] &= ~takenw[lane];
+                }
+                // S -= sum_d col_d col_d' / mu_d on the packed triangle, DK2_FL stations per pass; rows dealt round-robin
+                // to the warps, zero entries (inactive stations) are no-ops, whole zero rows skipped
+                for (int d0 = 0; d0 < nc; d0 += DK2_FL) {
+                    const int nd = min(DK2_FL, nc - d0);
+                    const double* pc = pcol + d0 * NNP;
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        constexpr int QH = (DK_QMAX + 1) / 2;
+                        const int qa = half * QH, qb = half ? DK_QMAX : QH;
+                        double bj[DK2_FL][QH];
+#pragma unroll
+                        for (int d = 0; d < DK2_FL; d++)
+#pragma unroll
+                            for (int q = 0; q < QH; q++) {
+                                const int j = lane + 32 * (qa + q);
+                                bj[d][q] = (d < nd && qa + q < qb && j < NN) ? pc[d * NNP + j] : 0.0;
+                            }
+                        for (int i = warp; i < NN; i += DK_WARPS) {
+                            if ((i >> 5) >= qb) continue;              // the row starts right of this half
+                            double bi[DK2_FL];
+                            bool any = false;
+#pragma unroll
+                            for (int d = 0; d < DK2_FL; d++) {
+                                bi[d] = d < nd ? pc[d * NNP + i] * prmu[d0 + d] : 0.0;
+                                any |= bi[d] != 0.0;
+                            }
+                            if (!any) continue;
+                            double* row = Sp + rowoff[i];
+                            const int q0 = i >> 5;
+#pragma unroll
+                            for (int q = 0; q < QH; q++) {
+                                const int j = lane + 32 * (qa + q);
+                                if (qa + q < qb && qa + q >= q0 && j >= i && j < NN) {
+                                    double v = row[j];
+#pragma unroll
+                                    for (int d = 0; d < DK2_FL; d++) v = fma(-bi[d], bj[d][q], v);
+                                    row[j] = v;
+                                }
+                            }
+                        }
+                    }
+                    // (no barrier between passes: every element is handled by the same thread in each of them)
+                }
+                if (tid < nc) {
+                    kstack[nmain + tid] = clist[tid];
+                    mact[clist[tid]] = 0;
+                }
+                nmain += nc;
+                n_moved += nc;
+            }
+            __syncthreads();   // (3) S, mact, leads in place
+        }
+    }
+    if (tid == 0) {
+        atomicAdd(a.tile_counter + 2, (unsigned long long)n_round);
+        atomicAdd(a.tile_counter + 3, (unsigned long long)n_pop);
+        atomicAdd(a.tile_counter + 4, (unsigned long long)n_split);
+        atomicAdd(a.tile_counter + 5, (unsigned long long)n_moved);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Exact reference solve on the final active set (krige.c:140-197 + lusolv.c), one thread per cell.
 // ------------------------------------------------------------------------------------------
 struct DkFinalArgs {
@@ -911,8 +1332,12 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const long long ntiles = dk_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles;
     const int grid = (int)std::min<long long>(ntiles, nsm);
-    size_t smem = ((size_t)npk + (size_t)DK_TILE * NN + 2 * DK_PEND * NNP) * sizeof(double) +
-                  ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
+    // SMRFB_DK_WALK=tree selects the first design (path-keyed walk with forks), kept for comparison
+    const char* walk_env = getenv("SMRFB_DK_WALK");
+    const bool chain = !(walk_env && strcmp(walk_env, "tree") == 0);
+    size_t smem = chain ? dk2_smem_bytes(NN, NNP)
+                        : ((size_t)npk + (size_t)DK_TILE * NN + 2 * DK_PEND * NNP) * sizeof(double) +
+                              ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
 
     double *d_sx = nullptr, *d_sy = nullptr, *d_cx = nullptr, *d_cy = nullptr, *d_elev = nullptr, *d_ad = nullptr,
@@ -979,8 +1404,13 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     }
     ba.handoff = 10;   // below ~10 active stations a per-thread exact solve is cheaper than a CTA-wide rank-1 step
     if (n > DK_NSMAX) {
-        DK_CUDA(cudaFuncSetAttribute(dk_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dk_build_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+        if (chain) {
+            DK_CUDA(cudaFuncSetAttribute(dk_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_chain_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+        } else {
+            DK_CUDA(cudaFuncSetAttribute(dk_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_build_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+        }
     } else {   // small station sets: the exact per-cell solver does the whole elimination (pure reference arithmetic)
         const long long nw = in.ncell * DK_WORDS;
         dk_fill_all_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(in.ncell, n, d_final);
@@ -1057,8 +1487,9 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CHECK(!(h_small[1] & 1), SMRFB_ERR_SINGULAR, "DK: singular kriging system in the final solve");
     if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
     if (verbose)
-        fprintf(stderr, "[smrfb] dk_build: n=%d cells=%lld tiles=%lld applies=%llu restores=%llu forks=%llu K=%d fallback=%llu "
-                "walk %.1f ms, exact finish %.1f ms\n", n, in.ncell, ntiles, h_cnt[2], h_cnt[3], h_cnt[4], K, h_cnt[1], ms_walk, ms_final);
+        fprintf(stderr, "[smrfb] dk_build (%s): n=%d cells=%lld tiles=%lld %s=%llu restores=%llu %s=%llu moved=%llu K=%d fallback=%llu "
+                "walk %.1f ms, exact finish %.1f ms\n", chain ? "chain" : "tree", n, in.ncell, ntiles, chain ? "rounds" : "applies", h_cnt[2],
+                h_cnt[3], chain ? "splits" : "forks", h_cnt[4], h_cnt[5], K, h_cnt[1], ms_walk, ms_final);
 
     return SMRFB_OK;
 }

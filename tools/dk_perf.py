@@ -10,7 +10,8 @@ nx = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 x, y, dem = syn.make_dem(10000, 10000, dx=30.0, noise=False)
 mx, my, mz = syn.make_stations(S, x, y, dem, seed=7)
-r0, c0 = 3000, 4000
+r0 = int(sys.argv[4]) if len(sys.argv) > 4 else 3000
+c0 = int(sys.argv[5]) if len(sys.argv) > 5 else 4000
 xs, ys, ds = x[c0:c0 + nx], y[r0:r0 + ny], np.ascontiguousarray(dem[r0:r0 + ny, c0:c0 + nx])
 X = np.broadcast_to(xs[None, :], (ny, nx)); Y = np.broadcast_to(ys[:, None], (ny, nx))
 dk = DK(mx, my, mz, X, Y, ds, {"detrend_slope": 1})
