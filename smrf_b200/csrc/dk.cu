@@ -391,62 +391,92 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_build_kernel(DkBuildArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
-// dk_chain_kernel -- the elimination walk, second design ("common chain + per-cell lead").
+// dk_chain_kernel -- the elimination walk, second design ("one chain per tile, shared by active SET").
 //
 // Measured on the C4 geometry (tools/dk_path_sim.py, tools/dk_main_chain_sim.py): neighbouring cells drop the SAME
 // stations, only in slightly different ORDER -- a 32 x 32 block of cells visits 0.66 distinct active sets per cell
 // but 16 distinct path prefixes per cell in 8 x 4 tiles, and a walk keyed by path (dk_build_kernel: fork, snapshot,
 // restore) pays one rank-1 downdate of the 162 KB inverse for each of them.  The weights of a cell depend on its
-// active SET only, so here a tile keeps ONE inverse S, that of the set A_main = all stations minus those EVERY live
-// cell of the tile has dropped, and a cell that is ahead by the stations Q (dropped by it, not yet by all) takes its
-// weights from the Schur complement
-//         w = w_main - S[:, Q] (S[Q, Q])^-1 w_main[Q]            (|Q| <= DK2_QM, a Gauss-Jordan solve per step)
-// which is what |Q| further rank-1 downdates in the cell's own order would give.  Cells step on their own (one warp
-// each, no block barrier, DK2_RA drops per round); once per round the stations common to all leads move into the
-// chain: S is downdated once per station and TILE (one pass over the packed triangle for up to DK2_PEND stations),
-// every cell's w_main follows, the leads shrink.  No forks: ~48 rounds per tile instead of ~770 shared rank-1 steps.
-// Within ~30 cells of a station the orders differ by more than DK2_QM: when nobody can step and nothing is common,
-// the cells that have dropped the most popular station go on (progress guaranteed), the others wait on a job stack
-// with a snapshot of S.
+// active SET only.  Here a tile keeps ONE stored inverse S, that of the set A_chain = all stations minus those that
+// EVERY live cell of the tile has dropped (and that have been folded in); a cell is ahead of it by its LEAD Q (the
+// stations it has dropped since, |Q| <= DK2_QM).  Column k of the inverse of the cell's own set is the Schur complement
+//         col = S[:, k] - S[:, Q] (S[Q, Q])^-1 S[Q, k]
+// -- what |Q| rank-1 downdates would give -- and it is the SAME for all cells with the same (lead set, k): the
+// "combos" of a step.  One step, in lock step for the tile: every cell (one warp each, weights in registers) picks its
+// station; one warp per combo solves the small lead system; the CTA builds the combo columns; every cell applies its
+// combo's column (7 FMAs per lane).  Cells that swap the order of two drops are in different combos for a step or two
+// and then share again; nothing forks.  When the leads have >= DK2_FLMIN stations in common (or a lead is full) those
+// stations are folded into S: one pass over the packed triangle for up to DK2_FL of them, once per station and TILE.
+// Within ~30 cells of a station the orders differ by more than DK2_QM: when every live cell is full and nothing is
+// common, the cells that have dropped the most popular station go on (progress guaranteed), the others wait on a job
+// stack with a snapshot of S.
 // ------------------------------------------------------------------------------------------
-constexpr int DK2_QM = 12;              // largest lead of a cell over the common chain
-constexpr int DK2_LD = DK2_QM + 1;      // row stride of the lead system [S_QQ | w_Q] (odd: conflict-free columns)
-constexpr int DK2_PEND = 8;             // stations moved into the chain per round at most
-constexpr int DK2_RA = 4;               // drops per cell and round
+constexpr int DK2_QM = 12;              // largest lead of a cell over the chain
+constexpr int DK2_LD = DK2_QM + 1;      // row stride of the lead system [S_QQ | S_Qk] (odd: conflict-free columns)
+constexpr int DK2_PEND = 8;             // stations folded into the chain at once at most
+constexpr int DK2_FLMIN = 4;            // fold when the leads have at least this many stations in common
 constexpr int DK2_FL = 4;               // stations per pass over the packed inverse
-constexpr int DK2_SCR = DK2_QM * DK2_LD + DK2_QM;   // doubles of per-warp scratch: the system + its solution
+constexpr int DK2_CB = 8;               // combo columns built per pass
+constexpr int DK2_SCR = DK2_QM * DK2_LD;   // doubles of per-warp scratch: the lead system
 
+constexpr int DK2_NNP_MAX = (DK_MAXN + 1 + 31) / 32 * 32;
+// small arrays first, at compile-time offsets (the kernel runs at the 64-register cap: every pointer derived from n at
+// run time was being recomputed at each use)
+struct Dk2Small {
+    int rowoff[DK2_NNP_MAX];               // idx(i, j >= i) = rowoff[i] + j
+    int kstack[DK2_NNP_MAX];               // stations of the chain, in order
+    unsigned qmask[DK_TILE * DK_WORDS];    // lead of every cell as a bit set
+    int qlist[DK_TILE * DK2_QM];           // the same in drop order
+    int qcnt[DK_TILE];                     // lead length
+    int kc[DK_TILE];                       // station the cell wants to drop in this step
+    int clive[DK_TILE];                    // cell still walking
+    int clist[DK2_PEND];                   // stations being folded in
+    unsigned taken[DK_WORDS];              // the same as a bit set
+    int ctrl[8];                           // [0] tile, [1] some lead is full
+    int jobs[2 * DK_TILE];                 // waiting groups: cell mask, chain length
+    int kcb[DK2_CB], mcb[DK2_CB], lcb[DK2_CB];   // station, lead length, leader cell of the pass's combos
+    unsigned char mact[DK2_NNP_MAX];       // station still in the chain's set
+    double prmu[DK2_PEND];                 // 1 / pivot of the folded columns
+    double cbeta[DK2_CB];                  // pivot of the combo columns
+    double ycb[DK2_CB * DK2_QM];           // solutions of the lead systems
+};
 __host__ __device__ inline size_t dk2_union_doubles(int NN, int NNP) {
     const size_t stage = (size_t)DK_TILE * NN;                                       // right-hand sides at tile start
-    const size_t work = (size_t)DK2_PEND * NNP + DK2_PEND + (size_t)DK_WARPS * DK2_SCR;   // columns, 1/mu, lead systems
+    const size_t work = (size_t)DK2_PEND * NNP + (size_t)DK_WARPS * DK2_SCR;         // columns, lead systems
     return stage > work ? stage : work;
 }
 __host__ __device__ inline size_t dk2_smem_bytes(int NN, int NNP) {
     const size_t npk = (size_t)NN * (NN + 1) / 2;
-    return (npk + dk2_union_doubles(NN, NNP)) * sizeof(double) +
-           ((size_t)NNP + (NN + 1) + DK_TILE * DK_WORDS + 2 * DK_TILE + DK2_PEND + DK_WORDS + 16 + 2 * DK_TILE) * sizeof(int) + NNP;
+    return sizeof(Dk2Small) + (npk + dk2_union_doubles(NN, NNP)) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, NN = a.NN, NNP = a.NNP;
     const int npk = NN * (NN + 1) / 2;
-    double* Sp = reinterpret_cast<double*>(smem_raw);            // [npk] packed upper triangle of the chain's inverse
-    double* un = Sp + npk;                                       // union: rhs staging | pcol, prmu, lead systems
+    Dk2Small& sm = *reinterpret_cast<Dk2Small*>(smem_raw);
+    double* Sp = reinterpret_cast<double*>(smem_raw + sizeof(Dk2Small));   // [npk] packed upper triangle of the chain's inverse
+    double* un = Sp + npk;                                       // union: rhs staging | columns, lead systems
     double* stage = un;                                          // [32][NN]
-    double* pcol = un;                                           // [DK2_PEND][NNP] columns moving into the chain (0 = inactive)
-    double* prmu = pcol + DK2_PEND * NNP;                        // [DK2_PEND] 1 / pivot
-    double* scr = prmu + DK2_PEND;                               // [warps][DK2_SCR]
-    int* rowoff = reinterpret_cast<int*>(un + dk2_union_doubles(NN, NNP));   // [NNP]
-    int* kstack = rowoff + NNP;                                  // [NN + 1] stations of the chain, in order
-    unsigned* qmask = reinterpret_cast<unsigned*>(kstack + NN + 1);   // [32][8] lead of every cell as a bit set
-    int* clive = reinterpret_cast<int*>(qmask + DK_TILE * DK_WORDS);  // [32] cell still walking
-    int* cstep = clive + DK_TILE;                                // [32] drops of the cell in the last round
-    int* clist = cstep + DK_TILE;                                // [DK2_PEND] stations moving into the chain
-    unsigned* takenw = reinterpret_cast<unsigned*>(clist + DK2_PEND);   // [8] the same as a bit set
-    int* ctrl = reinterpret_cast<int*>(takenw + DK_WORDS);       // [16]
-    int* jobs = ctrl + 16;                                       // [32][2] waiting groups: cell mask, chain length
-    unsigned char* mact = reinterpret_cast<unsigned char*>(jobs + 2 * DK_TILE);   // [NNP] station still in the chain's set
+    double* pcol = un;                                           // [DK2_PEND][NNP] columns being folded in / combo columns
+    double* scr = pcol + DK2_PEND * NNP;                         // [warps][DK2_SCR]
+    int* const rowoff = sm.rowoff;
+    int* const kstack = sm.kstack;
+    unsigned* const qmask = sm.qmask;
+    int* const qlist = sm.qlist;
+    int* const qcnt = sm.qcnt;
+    int* const kc = sm.kc;
+    int* const clive = sm.clive;
+    int* const clist = sm.clist;
+    int* const ctrl = sm.ctrl;
+    int* const jobs = sm.jobs;
+    int* const kcb = sm.kcb;
+    int* const mcb = sm.mcb;
+    int* const lcb = sm.lcb;
+    unsigned char* const mact = sm.mact;
+    double* const prmu = sm.prmu;
+    double* const cbeta = sm.cbeta;
+    double* const ycb = sm.ycb;
 
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -456,7 +486,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
 
     for (int i = tid; i < NNP; i += DK_THREADS) rowoff[i] = i * NN - (i * (i + 1)) / 2;   // idx(i, j >= i) = rowoff[i] + j
     __syncthreads();
-    auto roj = [&](int j) { return j * NN - ((j * (j + 1)) >> 1); };   // row offset of one of this lane's stations
+    auto Sat = [&](int i, int j) { return Sp[rowoff[min(i, j)] + max(i, j)]; };
     auto pick = [&](const double (&v)[DK_QMAX], int slot) {      // v[slot] for a warp-uniform slot, no local memory
         double r = v[0];
 #pragma unroll
@@ -464,7 +494,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
             if (slot == s) r = v[s];
         return r;
     };
-    unsigned n_round = 0, n_pop = 0, n_split = 0, n_moved = 0;
+    unsigned n_step = 0, n_pop = 0, n_split = 0, n_moved = 0, n_combo = 0;
 
     for (;;) {
         if (tid == 0) ctrl[0] = (int)atomicAdd(a.tile_counter, 1ULL);
@@ -488,94 +518,51 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
         }
         for (int i = tid; i < NNP; i += DK_THREADS) mact[i] = (i < NN) ? 1 : 0;
         __syncthreads();
-        double wm[DK_QMAX];                                      // w_main of this warp's cell: station lane + 32 s in slot s
+        double w[DK_QMAX];                                       // weights of this warp's cell on ITS active set: station lane + 32 s in slot s
 #pragma unroll
-        for (int s = 0; s < DK_QMAX; s++) wm[s] = 0.0;
-        for (int i = 0; i < NN; i++) {                           // w_main = S rhs (S symmetric, packed)
+        for (int s = 0; s < DK_QMAX; s++) w[s] = 0.0;
+        for (int i = 0; i < NN; i++) {                           // w = S rhs (S symmetric, packed)
             const double r = stage[warp * NN + i];
             const int ro = rowoff[i];
 #pragma unroll
             for (int s = 0; s < DK_QMAX; s++) {
                 const int j = lane + 32 * s;
-                if (j < NN) wm[s] = fma((j >= i) ? Sp[ro + j] : Sp[roj(j) + i], r, wm[s]);
+                if (j < NN) w[s] = fma((j >= i) ? Sp[ro + j] : Sp[rowoff[j] + i], r, w[s]);
             }
         }
         unsigned actbits = 0;                                    // bit s: station lane + 32 s is in this cell's active set
 #pragma unroll
         for (int s = 0; s < DK_QMAX; s++)
             if (lane + 32 * s < n) actbits |= 1u << s;
-        int m = 0, myq = 0;                                      // the lead: lane i < m holds its i-th station (drop order)
         bool mylive = cell >= 0;
         if (lane < DK_WORDS) qmask[warp * DK_WORDS + lane] = 0u;
         if (lane == 0) {
             clive[warp] = mylive ? 1 : 0;
-            cstep[warp] = 0;
+            qcnt[warp] = 0;
         }
         unsigned jobmask;
         {
             const long long cl = dk_tile_cell(tiling, a.g, a.ncell, tile, lane);
             jobmask = __ballot_sync(FULL, cl >= 0);
         }
-        int nmain = 0, nstack = 0;
-        __syncthreads();                                         // staging is dead: the union now holds pcol / lead systems
+        int nmain = 0, nstack = 0, since = 0;
+        __syncthreads();                                         // staging is dead: the union now holds columns / lead systems
 
-        for (;;) {   // ---- rounds
-            // ---- phase A: this warp's cell drops up to DK2_RA stations on its own
-            int steps = 0;
-            if (mylive && ((jobmask >> warp) & 1u)) {
-                double* G = scr + warp * DK2_SCR;
-                double* zb = G + DK2_QM * DK2_LD;
-                while (steps < DK2_RA) {
-                    double acc[DK_QMAX];
-#pragma unroll
-                    for (int s = 0; s < DK_QMAX; s++) acc[s] = wm[s];
-                    if (m > 0) {
-                        for (int e0 = 0; e0 < m * m; e0 += 32) {             // G = S[Q, Q]
-                            const int e = e0 + lane;
-                            const bool ok = e < m * m;
-                            const int i = ok ? e / m : 0, c = ok ? e - i * m : 0;
-                            const int qi = __shfl_sync(FULL, myq, i), qc = __shfl_sync(FULL, myq, c);
-                            if (ok) G[i * DK2_LD + c] = Sp[rowoff[min(qi, qc)] + max(qi, qc)];
-                        }
-                        for (int i = 0; i < m; i++) {                        // right-hand side w_main[Q]
-                            const int q = __shfl_sync(FULL, myq, i);
-                            const double v = __shfl_sync(FULL, pick(wm, q >> 5), q & 31);
-                            if (lane == i) G[i * DK2_LD + m] = v;
-                        }
-                        __syncwarp();
-                        for (int p = 0; p < m; p++) {                        // Gauss-Jordan in drop order, no pivoting (as the
-                            const double r = dk_rcp(G[p * DK2_LD + p]);      // rank-1 downdates in that order would do)
-                            const int wd = m - p;                            // columns p + 1 .. m
-                            for (int e = lane; e < m * wd; e += 32) {
-                                const int i = e / wd, c = p + 1 + (e - i * wd);
-                                if (i != p) G[i * DK2_LD + c] = fma(-(G[i * DK2_LD + p] * r), G[p * DK2_LD + c], G[i * DK2_LD + c]);
-                            }
-                            __syncwarp();
-                        }
-                        if (lane < m) zb[lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
-                        __syncwarp();
-                        for (int c = 0; c < m; c++) {                        // w = w_main - S[:, Q] z
-                            const int q = __shfl_sync(FULL, myq, c);
-                            const int roq = rowoff[q];
-                            const double z = zb[c];
-#pragma unroll
-                            for (int s = 0; s < DK_QMAX; s++) {
-                                const int j = lane + 32 * s;
-                                if ((actbits >> s) & 1u) acc[s] = fma(-((j <= q) ? Sp[roj(j) + q] : Sp[roq + j]), z, acc[s]);
-                            }
-                        }
-                        __syncwarp();                                        // G / zb are rewritten in the next step
-                    }
-                    int k = -1;                                              // first (= highest) active station with w < 0
+        for (;;) {   // ---- steps
+            // ---- A: this warp's cell picks the first (= highest) active station with a negative weight
+            {
+                int k = -1;
+                __syncwarp();                                                // lane 0's lead bookkeeping of the last step
+                if (mylive && ((jobmask >> warp) & 1u)) {
 #pragma unroll
                     for (int s = 0; s < DK_QMAX; s++) {
                         if (k < 0) {
                             const int j = lane + 32 * s;
-                            const unsigned bb = __ballot_sync(FULL, ((actbits >> s) & 1u) && (j < a.nsel) && (acc[s] < 0.0));
+                            const unsigned bb = __ballot_sync(FULL, ((actbits >> s) & 1u) && (j < a.nsel) && (w[s] < 0.0));
                             if (bb) k = 32 * s + __ffs(bb) - 1;
                         }
                     }
-                    if (k < 0 || n - nmain - m <= a.handoff) {               // finished, or few enough left for the exact solver
+                    if (k < 0 || n - nmain - qcnt[warp] <= a.handoff) {      // finished, or few enough left for the exact solver
                         unsigned myword = 0;
 #pragma unroll
                         for (int s = 0; s < DK_WORDS; s++) {
@@ -585,95 +572,103 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
                         if (k >= 0 && lane == DK_WORDS - 1) myword |= 0x80000000u;   // bit 255: handed off undecided
                         if (lane < DK_WORDS) a.final_act[(size_t)cell * DK_WORDS + lane] = myword;
                         mylive = false;
-                        break;
+                        k = -1;
+                        if (lane == 0) clive[warp] = 0;
                     }
-                    if (m >= DK2_QM) break;                                  // lead full: wait for the chain
-                    if (lane == m) myq = k;
-                    if (lane == (k & 31)) actbits &= ~(1u << (k >> 5));
-                    if (lane == 0) qmask[warp * DK_WORDS + (k >> 5)] |= 1u << (k & 31);
-                    m++;
-                    steps++;
                 }
-                if (lane == 0) clive[warp] = mylive ? 1 : 0;
+                if (lane == 0) kc[warp] = k;
             }
-            if (lane == 0) cstep[warp] = steps;
-            __syncthreads();   // (1) leads published
+            __syncthreads();   // (1) choices published
+            n_step++;
 
-            // ---- phase B1 (warp 0): what is common, what to do, the columns that move into the chain
-            if (warp == 0) {
-                bool lv = clive[lane] && ((jobmask >> lane) & 1u);
-                unsigned livem = __ballot_sync(FULL, lv);
-                int action = 0, nc = 0, snap = 0, nmain_new = nmain;
-                if (!livem) {
-                    if (nstack == 0) {
-                        action = 2;                                          // tile finished
-                    } else {
-                        action = 1;                                          // next waiting group
-                        nstack--;
-                        jobmask = (unsigned)jobs[2 * nstack];
-                        nmain_new = jobs[2 * nstack + 1];
-                    }
-                } else {
-                    const bool any = __ballot_sync(FULL, lv && cstep[lane] > 0) != 0u;
-                    unsigned cw[DK_WORDS];
-                    int nco = 0;
+            // ---- B0 (every warp, identically): who is live, what the leads have in common, fold / split / next group
+            bool lv = clive[lane] && ((jobmask >> lane) & 1u);               // lane = cell from here on
+            unsigned livem = __ballot_sync(FULL, lv);
+            if (!livem) {
+                if (nstack == 0) break;                                      // tile finished
+                nstack--;                                                    // a waiting group: back to the inverse and chain it was split off from
+                jobmask = (unsigned)jobs[2 * nstack];
+                nmain = jobs[2 * nstack + 1];
+                const double* sg = snap_g + (size_t)nstack * npk;
+                for (int q = tid; q < npk; q += DK_THREADS) Sp[q] = sg[q];
+                for (int i = tid; i < NNP; i += DK_THREADS) mact[i] = (i < NN) ? 1 : 0;
+                __syncthreads();
+                for (int d = tid; d < nmain; d += DK_THREADS) mact[kstack[d]] = 0;
+                n_pop++;
+                __syncthreads();
+                continue;
+            }
+            const int kl = lv ? kc[lane] : -1;
+            const bool anyfull = __ballot_sync(FULL, lv && qcnt[lane] >= DK2_QM) != 0u;
+            const bool canstep = __ballot_sync(FULL, lv && kl >= 0 && qcnt[lane] < DK2_QM) != 0u;
+            unsigned cw[DK_WORDS];
+            int nco = 0;
+            since++;
+            if (since >= DK2_FLMIN || anyfull || !canstep) {   // DK2_FLMIN common stations take at least as many steps to appear
 #pragma unroll
-                    for (int w = 0; w < DK_WORDS; w++) {
-                        cw[w] = __reduce_and_sync(FULL, lv ? qmask[lane * DK_WORDS + w] : FULL);
-                        nco += __popc(cw[w]);
-                    }
-                    if (nco == 0 && !any) {   // stuck: split by the station most cells have dropped
-                        int best = -1, bestc = 0;
+                for (int q = 0; q < DK_WORDS; q++) {
+                    cw[q] = __reduce_and_sync(FULL, lv ? qmask[lane * DK_WORDS + q] : FULL);
+                    nco += __popc(cw[q]);
+                }
+            }
+            bool fold = nco >= DK2_FLMIN || (anyfull && nco > 0);
+            if (!fold && !canstep) {   // stuck: split by the station most cells have dropped
+                int best = -1, bestc = 0;
 #pragma unroll
-                        for (int w = 0; w < DK_WORDS; w++) {
-                            const unsigned mine = lv ? qmask[lane * DK_WORDS + w] : 0u;
-                            unsigned bits = __reduce_or_sync(FULL, mine);
-                            while (bits) {
-                                const int b = __ffs(bits) - 1;
-                                bits &= bits - 1;
-                                const int c = __popc(__ballot_sync(FULL, (mine >> b) & 1u));
-                                if (c > bestc) {
-                                    bestc = c;
-                                    best = 32 * w + b;
-                                }
-                            }
-                        }
-                        const unsigned g1 = __ballot_sync(FULL, lv && ((qmask[lane * DK_WORDS + (best >> 5)] >> (best & 31)) & 1u));
-                        if (lane == 0) {
-                            jobs[2 * nstack] = (int)(livem & ~g1);
-                            jobs[2 * nstack + 1] = nmain;
-                        }
-                        nstack++;
-                        snap = 1;
-                        jobmask = g1;
-                        lv = lv && ((g1 >> lane) & 1u);
-                        livem = g1;
-                        nco = 0;
-#pragma unroll
-                        for (int w = 0; w < DK_WORDS; w++) {
-                            cw[w] = __reduce_and_sync(FULL, lv ? qmask[lane * DK_WORDS + w] : FULL);
-                            nco += __popc(cw[w]);
+                for (int q = 0; q < DK_WORDS; q++) {
+                    const unsigned mine = lv ? qmask[lane * DK_WORDS + q] : 0u;
+                    unsigned bits = __reduce_or_sync(FULL, mine);
+                    while (bits) {
+                        const int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int c = __popc(__ballot_sync(FULL, (mine >> b) & 1u));
+                        if (c > bestc) {
+                            bestc = c;
+                            best = 32 * q + b;
                         }
                     }
-                    unsigned tw = 0;                                         // lane w < 8: word w of the stations taken
+                }
+                const unsigned g1 = __ballot_sync(FULL, lv && ((qmask[lane * DK_WORDS + (best >> 5)] >> (best & 31)) & 1u));
+                if (tid == 0) {
+                    jobs[2 * nstack] = (int)(livem & ~g1);
+                    jobs[2 * nstack + 1] = nmain;
+                }
+                double* sg = snap_g + (size_t)nstack * npk;                  // the group left behind restarts from this inverse
+                for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Sp[q];
+                nstack++;
+                n_split++;
+                jobmask = g1;
+                lv = lv && ((g1 >> lane) & 1u);
+                livem = g1;
+                nco = 0;
 #pragma unroll
-                    for (int w = 0; w < DK_WORDS; w++) {
-                        unsigned bits = cw[w], tk = 0;
-                        while (bits && nc < DK2_PEND) {
-                            const int b = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            tk |= 1u << b;
-                            if (lane == 0) clist[nc] = 32 * w + b;
-                            nc++;
-                        }
-                        if (lane == w) tw = tk;
+                for (int q = 0; q < DK_WORDS; q++) {
+                    cw[q] = __reduce_and_sync(FULL, lv ? qmask[lane * DK_WORDS + q] : FULL);
+                    nco += __popc(cw[q]);
+                }
+                fold = true;
+                __syncthreads();                                             // snapshot read of S done before the fold writes it
+            }
+            if (fold) {
+                // stations folded in: the first min(nco, DK2_PEND) common ones
+                int nc = 0;
+#pragma unroll
+                for (int q = 0; q < DK_WORDS; q++) {
+                    unsigned bits = cw[q], tk = 0;
+                    while (bits && nc < DK2_PEND) {
+                        const int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        tk |= 1u << b;
+                        if (tid == 0) clist[nc] = 32 * q + b;
+                        nc++;
                     }
-                    if (lane < DK_WORDS) takenw[lane] = tw;
+                    if (warp == 1 && lane == q) sm.taken[q] = tk;            // the stations taken, as a bit set
+                }
+                if (warp == 0) {   // current column q of the inverse = stored column corrected for the columns folded before it
                     __syncwarp();
-                    unsigned dropbits = 0;                                   // stations of this round already moved
-                    for (int d = 0; d < nc; d++) {   // current column q of the inverse = stored column corrected for the columns moved before it
+                    unsigned dropbits = 0;
+                    for (int d = 0; d < nc; d++) {
                         const int q = clist[d];
-                        const int roq = rowoff[q];
                         double v[DK_QMAX];
 #pragma unroll
                         for (int s = 0; s < DK_QMAX; s++) {
@@ -681,7 +676,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
                             const bool on = (j < NN) && mact[j] && !((dropbits >> s) & 1u);
                             double x = 0.0;
                             if (on) {
-                                x = (j <= q) ? Sp[roj(j) + q] : Sp[roq + j];
+                                x = Sat(j, q);
                                 for (int e = 0; e < d; e++) x = fma(-(pcol[e * NNP + j] * prmu[e]), pcol[e * NNP + q], x);
                             }
                             v[s] = x;
@@ -697,58 +692,16 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
                         __syncwarp();
                     }
                 }
-                if (lane == 0) {
-                    ctrl[1] = action;
-                    ctrl[2] = nc;
-                    ctrl[3] = (int)jobmask;
-                    ctrl[4] = nstack;
-                    ctrl[5] = nmain_new;
-                    ctrl[6] = snap;
-                }
-            }
-            __syncthreads();   // (2) decision + columns published
-            const int action = ctrl[1], nc = ctrl[2];
-            jobmask = (unsigned)ctrl[3];
-            nstack = ctrl[4];
-            n_round++;
-            if (action == 2) break;
-            if (action == 1) {   // a waiting group: back to the inverse and chain it was split off from
-                const double* sg = snap_g + (size_t)nstack * npk;
-                for (int q = tid; q < npk; q += DK_THREADS) Sp[q] = sg[q];
-                nmain = ctrl[5];
-                for (int i = tid; i < NNP; i += DK_THREADS) mact[i] = (i < NN) ? 1 : 0;
-                __syncthreads();
-                for (int d = tid; d < nmain; d += DK_THREADS) mact[kstack[d]] = 0;
-                n_pop++;
-                __syncthreads();
-                continue;
-            }
-            if (ctrl[6]) {       // split: the group left behind restarts from this inverse
-                double* sg = snap_g + (size_t)(nstack - 1) * npk;
-                for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Sp[q];
-                n_split++;
-                __syncthreads();
-            }
-            if (nc > 0) {
-                if (mylive && ((jobmask >> warp) & 1u)) {   // w_main follows the chain; the lead loses the stations moved
-                    for (int d = 0; d < nc; d++) {
-                        const int q = clist[d];
-                        const double f = __shfl_sync(FULL, pick(wm, q >> 5), q & 31) * prmu[d];
-#pragma unroll
-                        for (int s = 0; s < DK_QMAX; s++)
-                            if (lane + 32 * s < NN) wm[s] = fma(-f, pcol[d * NNP + lane + 32 * s], wm[s]);
-                    }
-                    int newm = 0, mynew = 0;
-                    for (int i = 0; i < m; i++) {
-                        const int qi = __shfl_sync(FULL, myq, i);
-                        if (!((takenw[qi >> 5] >> (qi & 31)) & 1u)) {
-                            if (lane == newm) mynew = qi;
-                            newm++;
-                        }
-                    }
-                    myq = mynew;
-                    m = newm;
-                    if (lane < DK_WORDS) qmask[warp * DK_WORDS + lane] &= ~takenw[lane];
+                __syncthreads();   // (F1) columns published
+                if (mylive && ((jobmask >> warp) & 1u)) {   // this warp's cell: the lead loses the stations folded in (its weights do not change)
+                    const int m = qcnt[warp];
+                    const int qi = lane < m ? qlist[warp * DK2_QM + lane] : 0;
+                    const bool keep = lane < m && !((sm.taken[qi >> 5] >> (qi & 31)) & 1u);
+                    const unsigned km = __ballot_sync(FULL, keep);
+                    __syncwarp();
+                    if (keep) qlist[warp * DK2_QM + __popc(km & ((1u << lane) - 1u))] = qi;
+                    if (lane == 0) qcnt[warp] = __popc(km);
+                    if (lane < DK_WORDS) qmask[warp * DK_WORDS + lane] &= ~sm.taken[lane];
                 }
                 // S -= sum_d col_d col_d' / mu_d on the packed triangle, DK2_FL stations per pass; rows dealt round-robin
                 // to the warps, zero entries (inactive stations) are no-ops, whole zero rows skipped
@@ -759,24 +712,20 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
                     for (int half = 0; half < 2; half++) {
                         constexpr int QH = (DK_QMAX + 1) / 2;
                         const int qa = half * QH, qb = half ? DK_QMAX : QH;
-                        double bj[DK2_FL][QH];
+                        double bj[DK2_FL][QH];                         // this lane's columns: col_d[j] / mu_d
 #pragma unroll
                         for (int d = 0; d < DK2_FL; d++)
 #pragma unroll
                             for (int q = 0; q < QH; q++) {
                                 const int j = lane + 32 * (qa + q);
-                                bj[d][q] = (d < nd && qa + q < qb && j < NN) ? pc[d * NNP + j] : 0.0;
+                                bj[d][q] = (d < nd && qa + q < qb && j < NN) ? pc[d * NNP + j] * prmu[d0 + d] : 0.0;
                             }
-                        for (int i = warp; i < NN; i += DK_WARPS) {
-                            if ((i >> 5) >= qb) continue;              // the row starts right of this half
+                        const int iend = min(NN, 32 * qb);             // rows further down start right of this half
+                        for (int i = warp; i < iend; i += DK_WARPS) {
+                            if (!mact[i]) continue;                    // a station that left the chain earlier
                             double bi[DK2_FL];
-                            bool any = false;
 #pragma unroll
-                            for (int d = 0; d < DK2_FL; d++) {
-                                bi[d] = d < nd ? pc[d * NNP + i] * prmu[d0 + d] : 0.0;
-                                any |= bi[d] != 0.0;
-                            }
-                            if (!any) continue;
+                            for (int d = 0; d < DK2_FL; d++) bi[d] = d < nd ? pc[d * NNP + i] : 0.0;
                             double* row = Sp + rowoff[i];
                             const int q0 = i >> 5;
 #pragma unroll
@@ -799,15 +748,95 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
                 }
                 nmain += nc;
                 n_moved += nc;
+                since = nco > nc ? DK2_FLMIN : 0;                            // more common stations are waiting
+                __syncthreads();   // (F2) S, mact, leads in place
             }
-            __syncthreads();   // (3) S, mact, leads in place
+
+            // ---- B: combos = distinct (lead set, station) pairs among the cells that step now (every warp, identically)
+            const int ml = qcnt[lane];
+            const bool stepping = lv && kl >= 0 && ml < DK2_QM;
+            unsigned grp = __ballot_sync(FULL, stepping) & __match_any_sync(FULL, kl);
+#pragma unroll
+            for (int q = 0; q < DK_WORDS; q++) grp &= __match_any_sync(FULL, qmask[lane * DK_WORDS + q]);
+            const int lead_lane = __ffs(grp) - 1;                            // defined for stepping cells
+            const unsigned leadm = __ballot_sync(FULL, stepping && lane == lead_lane);
+            const int ncombo = __popc(leadm);
+            const int combo_of_lane = stepping ? __popc(leadm & ((1u << lead_lane) - 1u)) : -1;
+            const int mycombo = __shfl_sync(FULL, combo_of_lane, warp);      // this warp's cell
+            const int myk = __shfl_sync(FULL, kl, warp);
+            n_combo += ncombo;
+            for (int g0 = 0; g0 < ncombo; g0 += DK2_CB) {
+                const int ncb = min(DK2_CB, ncombo - g0);
+                if (warp < ncb) {   // one warp per combo: y = (S[Q, Q])^-1 S[Q, k] by Gauss-Jordan in drop order, no pivoting
+                    const int L = __fns(leadm, 0, g0 + warp + 1);            // leader cell of the combo
+                    const int k = kc[L], m = qcnt[L];
+                    double* G = scr + warp * DK2_SCR;
+                    const int myq = lane < m ? qlist[L * DK2_QM + lane] : 0;
+                    for (int e0 = 0; e0 < m * (m + 1); e0 += 32) {
+                        const int e = e0 + lane;
+                        const bool ok = e < m * (m + 1);
+                        const int i = ok ? e / (m + 1) : 0, c = ok ? e - i * (m + 1) : 0;
+                        const int qi = __shfl_sync(FULL, myq, i), qc = __shfl_sync(FULL, myq, c < m ? c : 0);
+                        if (ok) G[i * DK2_LD + c] = Sat(qi, c < m ? qc : k);
+                    }
+                    __syncwarp();
+                    for (int p = 0; p < m; p++) {
+                        const double r = dk_rcp(G[p * DK2_LD + p]);
+                        const int wd = m - p;                                // columns p + 1 .. m
+                        for (int e = lane; e < m * wd; e += 32) {
+                            const int i = e / wd, c = p + 1 + (e - i * wd);
+                            if (i != p) G[i * DK2_LD + c] = fma(-(G[i * DK2_LD + p] * r), G[p * DK2_LD + c], G[i * DK2_LD + c]);
+                        }
+                        __syncwarp();
+                    }
+                    if (lane < m) ycb[warp * DK2_QM + lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
+                    if (lane == 0) {
+                        kcb[warp] = k;
+                        mcb[warp] = m;
+                        lcb[warp] = L;
+                    }
+                }
+                __syncthreads();   // (2) lead systems solved
+                for (int item = warp; item < ncb * DK_QMAX; item += DK_WARPS) {   // combo columns, 32 elements per item
+                    const int gw = item / DK_QMAX, s = item - gw * DK_QMAX;
+                    const int j = lane + 32 * s;
+                    const int k = kcb[gw], m = mcb[gw], L = lcb[gw];
+                    double x = 0.0;
+                    if (j < NN && mact[j] && !((qmask[L * DK_WORDS + (j >> 5)] >> (j & 31)) & 1u)) {
+                        x = Sat(j, k);
+                        for (int i = 0; i < m; i++) x = fma(-Sat(j, qlist[L * DK2_QM + i]), ycb[gw * DK2_QM + i], x);
+                    }
+                    if (j == k) {
+                        cbeta[gw] = x;
+                        x = 0.0;
+                    }
+                    if (j < NNP) pcol[gw * NNP + j] = x;
+                }
+                __syncthreads();   // (3) columns built
+                if (mycombo >= g0 && mycombo < g0 + ncb) {   // this warp's cell drops myk: w -= (w_k / beta) col
+                    const int gw = mycombo - g0;
+                    const double f = __shfl_sync(FULL, pick(w, myk >> 5), myk & 31) * dk_rcp(cbeta[gw]);
+#pragma unroll
+                    for (int s = 0; s < DK_QMAX; s++)
+                        if (lane + 32 * s < NN) w[s] = fma(-f, pcol[gw * NNP + lane + 32 * s], w[s]);
+                    if (lane == (myk & 31)) actbits &= ~(1u << (myk >> 5));
+                    if (lane == 0) {
+                        const int m = qcnt[warp];
+                        qlist[warp * DK2_QM + m] = myk;
+                        qcnt[warp] = m + 1;
+                        qmask[warp * DK_WORDS + (myk >> 5)] |= 1u << (myk & 31);
+                    }
+                }
+                if (g0 + DK2_CB < ncombo) __syncthreads();   // the next pass reuses the column buffer
+            }
         }
     }
     if (tid == 0) {
-        atomicAdd(a.tile_counter + 2, (unsigned long long)n_round);
+        atomicAdd(a.tile_counter + 2, (unsigned long long)n_step);
         atomicAdd(a.tile_counter + 3, (unsigned long long)n_pop);
         atomicAdd(a.tile_counter + 4, (unsigned long long)n_split);
         atomicAdd(a.tile_counter + 5, (unsigned long long)n_moved);
+        atomicAdd(a.tile_counter + 6, (unsigned long long)n_combo);
     }
 }
 
@@ -1487,9 +1516,9 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CHECK(!(h_small[1] & 1), SMRFB_ERR_SINGULAR, "DK: singular kriging system in the final solve");
     if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
     if (verbose)
-        fprintf(stderr, "[smrfb] dk_build (%s): n=%d cells=%lld tiles=%lld %s=%llu restores=%llu %s=%llu moved=%llu K=%d fallback=%llu "
-                "walk %.1f ms, exact finish %.1f ms\n", chain ? "chain" : "tree", n, in.ncell, ntiles, chain ? "rounds" : "applies", h_cnt[2],
-                h_cnt[3], chain ? "splits" : "forks", h_cnt[4], h_cnt[5], K, h_cnt[1], ms_walk, ms_final);
+        fprintf(stderr, "[smrfb] dk_build (%s): n=%d cells=%lld tiles=%lld %s=%llu restores=%llu %s=%llu folded=%llu combos=%llu K=%d "
+                "fallback=%llu walk %.1f ms, exact finish %.1f ms\n", chain ? "chain" : "tree", n, in.ncell, ntiles, chain ? "steps" : "applies",
+                h_cnt[2], h_cnt[3], chain ? "splits" : "forks", h_cnt[4], h_cnt[5], h_cnt[6], K, h_cnt[1], ms_walk, ms_final);
 
     return SMRFB_OK;
 }

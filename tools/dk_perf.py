@@ -20,7 +20,7 @@ t0 = time.perf_counter(); dk.distribute_block(data[:1]); t1 = time.perf_counter(
 print("build+1 step: %.2f s  (%.0f cells/s)" % (t1 - t0, ny * nx / (t1 - t0)), dk.stats())
 t0 = time.perf_counter(); dk.distribute_block(data); t1 = time.perf_counter()
 print("8 steps host API: %.3f s" % (t1 - t0))
-for rep in range(2):          # rebuild with other masks: kernel-time repeatability
+for rep in range(int(os.environ.get('DK_PERF_REBUILDS', '2'))):          # rebuild with other masks: kernel-time repeatability
     d2 = data[:1].copy(); d2[0, rep] = np.nan
     t0 = time.perf_counter(); dk.distribute_block(d2); t1 = time.perf_counter()
     print("rebuild %d: %.2f s" % (rep, t1 - t0))
