@@ -1193,6 +1193,149 @@ __global__ void __launch_bounds__(DK_DT) dk_distribute_kernel(DkDistArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// dk_distribute_mma_kernel -- the steady state as a small dense product per warp.
+// The 32 consecutive cells of a warp share almost all of their stations (union of the active sets over 32 cells of a
+// C4 row: 6.6 on average, 8 at most away from the stations), so  out[t][c] = sum_u R[t][u] W[u][c]  with u over the
+// union, plus two more columns for the trend (p0[t] * Z[c] + p1[t] * 1): an [8 steps x 4k] x [4k x 8 cells] product on
+// the fp64 tensor cores (DMMA.8x8x4).  W stays in registers as B fragments for the whole launch.  The ELL kernel
+// staged every step's WHOLE record (1.6 KB at 200 stations) in shared memory for 256 cells -- as many bytes from L2 as
+// it wrote to HBM -- and gathered 16 bytes per station, cell and step pair from there (ncu: L1 81 % busy, 0.55 of the
+// HBM peak).  Here the records of a mask group are first transposed to station-major rows (dk_transpose_kernel), and
+// a lane reads its A-fragment element straight from them: 8 consecutive steps of one union column are one 64-byte
+// run, shared through L1 by the warps around it; no staging, no block barrier in the step loop.  Warps whose union does
+// not fit DKM_KS k-steps (near stations, set boundaries) walk their ELL lists against the same rows.
+// ------------------------------------------------------------------------------------------
+constexpr int DKM_KS = 4;                // k-steps of four columns kept in registers: union + 2 trend columns <= 16
+constexpr int DKM_THREADS = 256;
+constexpr int DKM_WARPS = DKM_THREADS / 32;
+constexpr int DKM_WLD = 33;              // row stride of the per-warp dense weight scratch
+
+// recT[u][i] = record column u (station residual, or p0 / p1 at S_pad, S_pad + 1) of the group's i-th step; TP >= Tm, zero padded
+__global__ void dk_transpose_kernel(const double* __restrict__ rec, int RS, int ncol, const int* __restrict__ steps, int Tm, int TP,
+                                    double* __restrict__ recT) {
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, u = u0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < Tm && u < ncol) ? rec[(size_t)steps[i] * RS + u] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int u = u0 + r, i = i0 + threadIdx.x;
+        if (u < ncol && i < TP) recT[(size_t)u * TP + i] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void __launch_bounds__(DKM_THREADS) dk_distribute_mma_kernel(DkDistArgs a, const double* __restrict__ recT, int TP) {
+    __shared__ double Wd[DKM_WARPS * 4 * DKM_KS * DKM_WLD];                    // setup only: dense weights [warp][16][33]
+    __shared__ unsigned bm[DKM_WARPS * 8];                                     // stations of the warp's union
+    __shared__ int ulist[DKM_WARPS * 4 * DKM_KS];                              // the same as a list
+    const int SP = a.L.S_pad;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long c = (long long)blockIdx.x * DKM_THREADS + tid;             // cell within the window
+    const bool live = c < a.ncw;
+    const size_t gc = (size_t)(a.cbase + (live ? c : 0));
+
+    // ---- setup: union of the warp's stations, dense weights, B fragments
+    if (lane < 8) bm[warp * 8 + lane] = 0u;
+    for (int i = lane; i < 4 * DKM_KS * DKM_WLD; i += 32) Wd[warp * (4 * DKM_KS) * DKM_WLD + i] = 0.0;
+    __syncwarp();
+    for (int j = 0; j < a.K; j++) {
+        const double wv = live ? __ldg(a.wval + (size_t)j * a.ncell + gc) : 0.0;
+        if (wv != 0.0) {
+            const int s = __ldg(a.widx + (size_t)j * a.ncell + gc);
+            atomicOr(&bm[warp * 8 + (s >> 5)], 1u << (s & 31));
+        }
+    }
+    __syncwarp();
+    int nu = 0;
+    const unsigned mybm = lane < 8 ? bm[warp * 8 + lane] : 0u;
+    int mypre = 0;                                                             // lane w < 8: stations of the union below word w
+    {
+        const int cnt = __popc(mybm);
+        int run = cnt;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, run, o);
+            if (lane >= o) run += v;
+        }
+        mypre = run - cnt;
+        nu = __shfl_sync(FULL, run, 7);
+    }
+    const bool fast = nu + 2 <= 4 * DKM_KS;                                    // warp-uniform
+    const long long cw0 = (long long)blockIdx.x * DKM_THREADS + warp * 32;     // first cell of the warp
+    if (cw0 >= a.ncw) return;
+    if (fast) {
+        double Bf[DKM_KS][4];
+        const double* colA[DKM_KS];
+        double* wd = Wd + warp * (4 * DKM_KS) * DKM_WLD;
+        for (int j = 0; j < a.K; j++) {
+            const double wv = live ? __ldg(a.wval + (size_t)j * a.ncell + gc) : 0.0;
+            const int s = live ? __ldg(a.widx + (size_t)j * a.ncell + gc) : 0;
+            const unsigned word = __shfl_sync(FULL, mybm, s >> 5);
+            const int pre = __shfl_sync(FULL, mypre, s >> 5);
+            if (wv != 0.0) {
+                const int pos = pre + __popc(word & ((1u << (s & 31)) - 1u));
+                wd[pos * DKM_WLD + lane] = wv;
+                ulist[warp * 4 * DKM_KS + pos] = s;                            // same value from every cell that has the station
+            }
+        }
+        if (live) {
+            wd[nu * DKM_WLD + lane] = __ldg(a.dem + gc);                       // trend columns: p0[t] * Z + p1[t] * 1  (dk.py:168)
+            wd[(nu + 1) * DKM_WLD + lane] = 1.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < DKM_KS; s++) {
+            const int u = 4 * s + (lane & 3);
+            const int col = u < nu ? ulist[warp * 4 * DKM_KS + u] : (u == nu ? SP : (u == nu + 1 ? SP + 1 : 0));
+            colA[s] = recT + (size_t)col * TP + (lane >> 2);                   // padding columns: weight 0 against a finite value
+#pragma unroll
+            for (int b = 0; b < 4; b++) Bf[s][b] = wd[u * DKM_WLD + 8 * b + (lane >> 2)];
+        }
+        const int ks = (nu + 2 + 3) >> 2;
+        const bool vec = (a.ncw & 1) == 0;                                     // rows of the window stay 16-byte aligned
+        double af[DKM_KS], an[DKM_KS];
+#pragma unroll
+        for (int s = 0; s < DKM_KS; s++) af[s] = s < ks ? __ldg(colA[s]) : 0.0;
+        for (int t0 = 0; t0 < a.Tm; t0 += 8) {
+            const int tr = t0 + (lane >> 2);                                   // this lane's step (position within the group)
+            const bool rowok = tr < a.Tm;
+#pragma unroll
+            for (int s = 0; s < DKM_KS; s++) an[s] = (s < ks && t0 + 8 < TP) ? __ldg(colA[s] + t0 + 8) : 0.0;   // next row block
+            const size_t orow = rowok ? (size_t)__ldg(a.steps + tr) * a.ncw : 0;
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int s = 0; s < DKM_KS; s++)
+                    if (s < ks) dmma884(c0, c1, af[s], Bf[s][nb]);
+                const long long cc = cw0 + 8 * nb + 2 * (lane & 3);
+                c0 = clamp_nan_keep(c0, a.vmin, a.vmax);
+                c1 = clamp_nan_keep(c1, a.vmin, a.vmax);
+                if (rowok && cc + 1 < a.ncw && vec) store_out2(a.out, orow + cc, c0, c1, a.out_f32);
+                else if (rowok) {
+                    if (cc < a.ncw) store_out(a.out, orow + cc, c0, a.out_f32);
+                    if (cc + 1 < a.ncw) store_out(a.out, orow + cc + 1, c1, a.out_f32);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < DKM_KS; s++) af[s] = an[s];
+        }
+    } else if (live) {   // large union: this cell's ELL list against the same rows
+        const double Z = __ldg(a.dem + gc);
+        for (int t = 0; t < a.Tm; t++) {
+            double acc = 0.0;
+            for (int j = 0; j < a.K; j++)
+                acc = fma(__ldg(a.wval + (size_t)j * a.ncell + gc), __ldg(recT + (size_t)__ldg(a.widx + (size_t)j * a.ncell + gc) * TP + t), acc);
+            const double v = __dadd_rn(__dadd_rn(acc, __dmul_rn(__ldg(recT + (size_t)SP * TP + t), Z)), __ldg(recT + (size_t)(SP + 1) * TP + t));
+            store_out(a.out, (size_t)__ldg(a.steps + t) * a.ncw + c, clamp_nan_keep(v, a.vmin, a.vmax), a.out_f32);
+        }
+    }
+}
+
 // generic K (> DK_KREG): the ELL entries are re-read per step (L2)
 __global__ void __launch_bounds__(256) dk_distribute_generic_kernel(DkDistArgs a) {
     const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -1616,16 +1759,30 @@ static int dk_run(DkHandle* h, const double* d_data, const double* h_data, int T
         SMRFB_CUDA(cudaStreamSynchronize(st));
         SMRFB_PROPAGATE(ensure_cap((void**)&h->d_steps, &h->steps_cap, (size_t)Tm * sizeof(int)));
         SMRFB_CUDA(cudaMemcpyAsync(h->d_steps, groups[gi].data(), (size_t)Tm * sizeof(int), cudaMemcpyHostToDevice, st));
+        DkDistArgs a;
+        a.ncell = h->g.ncell; a.cbase = cbase; a.ncw = ncw; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
+        a.rec = h->d_rec; a.recp = nullptr; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
+        a.vmin = vmin; a.vmax = vmax; a.out = d_out; a.out_f32 = h->out_f32;
+        // meshes: neighbouring cells share their stations -> the tensor-core kernel; SMRFB_DK_STEADY=ell|mma overrides
+        const char* steady_env = getenv("SMRFB_DK_STEADY");
+        const bool use_mma = steady_env ? strcmp(steady_env, "mma") == 0 : h->g.kind == 0;
+        if (use_mma) {
+            const int ncol = h->L.S_pad + 2, TP = (Tm + 15) / 16 * 16;
+            SMRFB_PROPAGATE(ensure_cap((void**)&h->d_recp, &h->recp_cap, (size_t)ncol * TP * sizeof(double)));
+            dk_transpose_kernel<<<dim3((TP + 31) / 32, (ncol + 31) / 32), dim3(32, 8), 0, st>>>(h->d_rec, h->L.RS, ncol, h->d_steps, Tm, TP,
+                                                                                             h->d_recp);
+            dk_distribute_mma_kernel<<<(unsigned)((ncw + DKM_THREADS - 1) / DKM_THREADS), DKM_THREADS, 0, st>>>(a, h->d_recp, TP);
+            count_launch(2);
+            SMRFB_CUDA(cudaGetLastError());
+            continue;
+        }
         const int npair = (Tm + 1) / 2;
         const int PR = 2 * h->L.S_pad + 4;
         SMRFB_PROPAGATE(ensure_cap((void**)&h->d_recp, &h->recp_cap, (size_t)npair * PR * sizeof(double)));
         dk_pair_kernel<<<npair, 128, 0, st>>>(h->d_rec, h->L, h->d_steps, Tm, h->d_recp);
         count_launch();
         SMRFB_CUDA(cudaGetLastError());
-        DkDistArgs a;
-        a.ncell = h->g.ncell; a.cbase = cbase; a.ncw = ncw; a.dem = h->g.dem; a.K = W->K; a.widx = W->widx; a.wval = W->wval;
-        a.rec = h->d_rec; a.recp = h->d_recp; a.L = h->L; a.steps = h->d_steps; a.Tm = Tm;
-        a.vmin = vmin; a.vmax = vmax; a.out = d_out; a.out_f32 = h->out_f32;
+        a.recp = h->d_recp;
         const unsigned nblk = (unsigned)((ncw + 255) / 256);
         const unsigned nblk_d = (unsigned)((ncw + DK_DT - 1) / DK_DT);
         const size_t dsm = (size_t)2 * (DK_TCH / 2) * PR * sizeof(double) + 2 * sizeof(uint64_t);

@@ -123,7 +123,9 @@ def test_dk_properties(sp):
     data = syn.make_series("air_temp", mz, 6, seed=1)
     full = dk.distribute_block(data)
     slab = sp.DK(mx, my, mz, X[40:97], Y[40:97], dem[40:97], cfg)
-    np.testing.assert_array_equal(slab.distribute_block(data), full[:, 40:97])
+    # the tensor-core steady-state kernel sums a cell's terms in the order of its warp's station union, which depends on
+    # where the slab starts: equal to a few ulp, not bit for bit
+    np.testing.assert_allclose(slab.distribute_block(data), full[:, 40:97], rtol=1e-12, atol=1e-12)
     # exactness at a station: a cell coincident with station 5 reproduces its value
     mx2, my2 = mx.copy(), my.copy()
     mx2[5], my2[5] = x[33], y[21]
