@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--stations", type=int, default=200)
     ap.add_argument("--tb", type=int, default=0, help="timesteps per block (c4: 720 = 30 days of hourly steps; c5: 512)")
     ap.add_argument("--slab-rows", type=int, default=1024, help="DEM rows per cell slab (c4); the device-resident output block is [tb][slab]")
-    ap.add_argument("--te2e", type=int, default=0, help="timesteps per block on the host-buffer (e2e) leg; 0 = max(8, 32 // n_gpus)")
+    ap.add_argument("--te2e", type=int, default=0, help="timesteps per block on the host-buffer (e2e) leg; 0 = max(16, 32 // n_gpus)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the float32 and per-step-call measurements")
@@ -509,8 +509,8 @@ def main():
     del d_out
     torch.cuda.empty_cache()          # the host-buffer API keeps its own device ring per handle
     if not args.no_e2e:
-        # 0.8 GB of pinned host memory per step at 1e8 cells: 25.6 GB at one GPU, 6.4 GB per rank at 4-8 (the box has 196 GB)
-        Te = min(args.te2e if args.te2e > 0 else max(8, 32 // world), Tb)
+        # 0.8 GB of pinned host memory per step at 1e8 cells: 25.6 GB at one GPU, 12.8 GB per rank at 2-8 (the box has 196 GB)
+        Te = min(args.te2e if args.te2e > 0 else max(16, 32 // world), Tb)
         runner = BlockRunner(fields, x, y, dem, {"idw": sta, "dk": sta, "grid": pts}, rank=0, world=1, partition="time",
                              block_steps=Te, slab_rows=ny, device=local_rank, handles={f.name: objs[f.name] for f in fields},
                              nbuf=1)
@@ -537,6 +537,29 @@ def main():
                "api": "smrf_b200.sharding.BlockRunner.run(tables) over smrf_b200.spatial.IDW/DK/GRID.distribute_block -> pinned float64 "
                       "[T, rows, nx] blocks handed to a sink, slab by slab"}
         del runner
+        if not args.no_extras:
+            # secondary figure: the same leg with float32 blocks (the reference's output-file type, contract 1e-5) -- half the
+            # bytes over PCIe; never the headline
+            try:
+                r32 = BlockRunner(fields, x, y, dem, {"idw": sta, "dk": sta, "grid": pts}, rank=0, world=1, partition="time",
+                                  block_steps=Te, slab_rows=ny, device=local_rank, handles={f.name: objs[f.name] for f in fields},
+                                  nbuf=1, out_dtype=np.float32)
+                r32.run(tables)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(n_e2e):
+                    done32 = r32.run(tables)
+                barrier()
+                d32 = time.perf_counter() - t0
+                t32 = torch.tensor([d32], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+                d32 = float(t32.item())
+                e2e["f32_mode"] = {"value": world * done32 * n_e2e / d32, "unit": "cell-timesteps/s", "out_dtype": "f32", "contract": 1e-05,
+                                   "d2h_bytes_per_step": d2h_bytes // 2, "d2h_gbs_per_rank": d2h_bytes / 2 * n_e2e / d32 / 1e9}
+                del r32
+            except Exception as e:
+                e2e["f32_mode"] = {"error": repr(e)[:300]}
 
     # ---- the per-timestep drop-in call (what an unmodified run loop makes): T = 1 through image_data._distribute
     per_step = None
