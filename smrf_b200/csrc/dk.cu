@@ -841,6 +841,580 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
+// dk_sets_kernel -- the same walk as dk_chain_kernel (one stored inverse per tile, leads, combos, folds, splits) with the
+// cell weights TRANSPOSED: warp w owns the stations 7 w .. 7 w + 6 and lane l the cells l, l + 32 (a tile is 8 x 8 cells),
+// so a thread holds 7 x 2 weights.  In dk_chain_kernel a warp owned one cell and every per-cell operation was a
+// warp-wide instruction sequence (ncu: 5.3 M warp instructions per 32-cell tile, issue-bound); here picking the first
+// negative weight is 7 compares and one shared-memory atomicMin per thread, applying a combo column is 7 FMAs per cell
+// with the column read as a (mostly broadcast) gather, and twice as many cells share every fold of the inverse.
+// The per-cell bookkeeping (leads, live flags, combos) is done by warp 0 with lane = cell.
+// ------------------------------------------------------------------------------------------
+constexpr int DK3_NC = 2;                   // cell columns per lane: a tile is 32 * DK3_NC cells
+constexpr int DK3_C = 32 * DK3_NC;
+constexpr int DK3_TX = 8, DK3_TY = 8;       // tile shape on a mesh
+constexpr int DK3_SPW = 7;                  // stations per warp: 32 x 7 = 224 >= 201
+constexpr int DK3_MAXSNAP = DK3_C;          // a split leaves at least one cell behind
+constexpr int DK3_BIG = 0x7fffffff;
+static_assert(DK_WARPS * DK3_SPW >= DK_MAXN + 1, "every station needs an owner warp");
+
+struct Dk3Small {
+    int rowoff[DK2_NNP_MAX];
+    int kstack[DK2_NNP_MAX];
+    unsigned qmask[DK3_C * DK_WORDS];
+    int qlist[DK3_C * DK2_QM];
+    int qcnt[DK3_C];
+    int kc[2][DK3_C];                       // station picked by the cell in this step (atomicMin over the owner warps), double buffered
+    int clive[DK3_C];
+    int cid[DK3_C];                         // combo of the cell in this step, -1 = does not step
+    int clist[DK2_PEND];
+    unsigned taken[DK_WORDS];
+    unsigned chainw[DK_WORDS];              // stations still in the chain's set, as a bit set
+    int ctrl[16];
+    int jobs[(DK3_NC + 1) * DK3_MAXSNAP];
+    int kcb[DK3_C], mcb[DK3_C], lcb[DK3_C]; // station, lead length, leader cell of the step's combos
+    long long cellidx[DK3_C];               // flat grid index of the tile's cells (-1 outside)
+    unsigned char mact[DK2_NNP_MAX];
+    double wk[DK3_C];                       // weight of the picked station
+    double prmu[DK2_PEND];
+    double rbeta[DK2_CB];                   // 1 / pivot of the pass's combo columns
+    double ycb[DK2_CB * DK2_QM];
+    double cx[DK3_C], cy[DK3_C];
+};
+__host__ __device__ inline int dk3_stage_rows(int NN, int NNP) {   // rows of the right-hand-side stage that fit beside the work buffers
+    const size_t work = (size_t)2 * DK2_PEND * NNP + (size_t)DK2_CB * DK2_SCR;
+    const size_t rows = work / DK3_C;
+    return (int)(rows < 8 ? 8 : (rows > (size_t)NN ? (size_t)NN : rows));
+}
+__host__ __device__ inline size_t dk3_union_doubles(int NN, int NNP) {
+    const size_t work = (size_t)2 * DK2_PEND * NNP + (size_t)DK2_CB * DK2_SCR;
+    const size_t stage = (size_t)dk3_stage_rows(NN, NNP) * DK3_C;
+    return stage > work ? stage : work;
+}
+__host__ __device__ inline size_t dk3_smem_bytes(int NN, int NNP) {
+    const size_t npk = (size_t)NN * (NN + 1) / 2;
+    return sizeof(Dk3Small) + (npk + dk3_union_doubles(NN, NNP)) * sizeof(double);
+}
+struct Dk3Tiling {
+    int blocked, tiles_x;
+    long long ntiles;
+};
+__host__ __device__ inline Dk3Tiling dk3_tiling(const Geom& g, long long ncell, bool has_dgrid) {
+    Dk3Tiling t;
+    t.blocked = (!has_dgrid && g.kind == 0 && g.nx > 0 && (long long)g.ny * g.nx == ncell) ? 1 : 0;
+    t.tiles_x = t.blocked ? (g.nx + DK3_TX - 1) / DK3_TX : 0;
+    t.ntiles = t.blocked ? (long long)t.tiles_x * ((g.ny + DK3_TY - 1) / DK3_TY) : (ncell + DK3_C - 1) / DK3_C;
+    return t;
+}
+__device__ __forceinline__ long long dk3_tile_cell(const Dk3Tiling& tl, const Geom& g, long long ncell, long long tile, int ci) {
+    if (tl.blocked) {
+        const long long ty = tile / tl.tiles_x;
+        const int tx = (int)(tile - ty * tl.tiles_x);
+        const long long i = ty * DK3_TY + (ci / DK3_TX);
+        const int j = tx * DK3_TX + (ci % DK3_TX);
+        return (i < g.ny && j < g.nx) ? i * g.nx + j : -1;
+    }
+    const long long c = tile * DK3_C + ci;
+    return c < ncell ? c : -1;
+}
+
+__global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, NN = a.NN, NNP = a.NNP;
+    const int npk = NN * (NN + 1) / 2;
+    Dk3Small& sm = *reinterpret_cast<Dk3Small*>(smem_raw);
+    double* Sp = reinterpret_cast<double*>(smem_raw + sizeof(Dk3Small));   // [npk] packed upper triangle of the chain's inverse
+    double* un = Sp + npk;
+    double* stage = un;                                          // [SR][64] right-hand sides at tile start
+    double* pcol = un;                                           // [DK2_PEND][NNP] columns being folded in / combo columns
+    double* psm = pcol + DK2_PEND * NNP;                         // [DK2_PEND][NNP] the folded columns / pivot
+    double* scr = psm + DK2_PEND * NNP;                          // [DK2_CB][DK2_SCR] lead systems
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = warp * DK3_SPW;                               // this warp's stations j0 .. j0 + 6
+    double* snap_g = a.snap + (size_t)blockIdx.x * DK3_MAXSNAP * npk;
+    const Dk3Tiling tiling = dk3_tiling(a.g, a.ncell, a.dgrid != nullptr);
+    const long long ntiles = tiling.ntiles;
+    const int SR = dk3_stage_rows(NN, NNP);
+
+    for (int i = tid; i < DK2_NNP_MAX; i += DK_THREADS) sm.rowoff[i] = i * NN - (i * (i + 1)) / 2;
+    __syncthreads();
+    auto Sat = [&](int i, int j) { return Sp[sm.rowoff[min(i, j)] + max(i, j)]; };
+    unsigned n_step = 0, n_pop = 0, n_split = 0, n_moved = 0, n_combo = 0;
+
+    for (;;) {
+        if (tid == 0) sm.ctrl[0] = (int)atomicAdd(a.tile_counter, 1ULL);
+        __syncthreads();
+        const long long tile = (unsigned)sm.ctrl[0];
+        if (tile >= ntiles) break;
+        for (int p = tid; p < npk; p += DK_THREADS) Sp[p] = a.B0p[p];
+        if (tid < DK3_C) {
+            const long long cell = dk3_tile_cell(tiling, a.g, a.ncell, tile, tid);
+            sm.cellidx[tid] = cell;
+            double X = 0.0, Y = 0.0;
+            if (cell >= 0 && !a.dgrid) cell_xy(a.g, cell, X, Y);
+            sm.cx[tid] = X;
+            sm.cy[tid] = Y;
+            sm.clive[tid] = cell >= 0 ? 1 : 0;
+            sm.qcnt[tid] = 0;
+            sm.kc[0][tid] = DK3_BIG;
+            sm.kc[1][tid] = DK3_BIG;
+            sm.cid[tid] = -1;
+        }
+        for (int i = tid; i < DK3_C * DK_WORDS; i += DK_THREADS) sm.qmask[i] = 0u;
+        for (int i = tid; i < DK2_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
+        if (tid < DK_WORDS) {
+            const int lo = 32 * tid;
+            sm.chainw[tid] = n > lo ? (n - lo >= 32 ? FULL : ((1u << (n - lo)) - 1u)) : 0u;
+        }
+        __syncthreads();
+        // ---- weights on the full set: W = S rhs, the right-hand sides staged SR rows at a time
+        double W[DK3_NC][DK3_SPW];
+#pragma unroll
+        for (int c = 0; c < DK3_NC; c++)
+#pragma unroll
+            for (int s = 0; s < DK3_SPW; s++) W[c][s] = 0.0;
+        for (int i0 = 0; i0 < NN; i0 += SR) {
+            const int ni = min(SR, NN - i0);
+            for (int e = tid; e < ni * DK3_C; e += DK_THREADS) {
+                const int i = i0 + e / DK3_C, ci = e % DK3_C;
+                const long long cell = sm.cellidx[ci];
+                double v = 0.0;
+                if (cell >= 0) {
+                    if (i == n) v = 1.0;
+                    else if (a.dgrid) v = a.dgrid[(size_t)cell * n + a.perm[i]];
+                    else v = dist_rn(sm.cx[ci], sm.cy[ci], a.sx[i], a.sy[i]);
+                }
+                stage[e] = v;
+            }
+            __syncthreads();
+            for (int ii = 0; ii < ni; ii++) {
+                const int i = i0 + ii;
+                double r[DK3_NC];
+#pragma unroll
+                for (int c = 0; c < DK3_NC; c++) r[c] = stage[ii * DK3_C + lane + 32 * c];
+#pragma unroll
+                for (int s = 0; s < DK3_SPW; s++) {
+                    const int j = j0 + s;
+                    if (j < NN) {
+                        const double b = Sat(j, i);
+#pragma unroll
+                        for (int c = 0; c < DK3_NC; c++) W[c][s] = fma(b, r[c], W[c][s]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        unsigned act[DK3_NC];                                    // bit s: station j0 + s is in the cell's active set and may be dropped
+#pragma unroll
+        for (int c = 0; c < DK3_NC; c++) {
+            act[c] = 0u;
+#pragma unroll
+            for (int s = 0; s < DK3_SPW; s++)
+                if (j0 + s < a.nsel) act[c] |= 1u << s;                // stations at elevation <= 0 (rank >= nsel) are never dropped
+        }
+        unsigned jobmask[DK3_NC];
+#pragma unroll
+        for (int c = 0; c < DK3_NC; c++) jobmask[c] = __ballot_sync(FULL, sm.cellidx[lane + 32 * c] >= 0);
+        int nmain = 0, nstack = 0, since = 0, par = 0;
+
+        for (;;) {   // ---- steps
+            // ---- A: every cell's first (= highest) active station with a negative weight: the minimum over the owner warps
+#pragma unroll
+            for (int c = 0; c < DK3_NC; c++) {
+                const int ci = lane + 32 * c;
+                if (((jobmask[c] >> lane) & 1u) && sm.clive[ci]) {
+                    int best = DK3_BIG;
+#pragma unroll
+                    for (int s = DK3_SPW - 1; s >= 0; s--)
+                        if (((act[c] >> s) & 1u) && (W[c][s] < 0.0)) best = j0 + s;
+                    if (best != DK3_BIG) atomicMin(&sm.kc[par][ci], best);
+                }
+            }
+            __syncthreads();   // (1) choices in place
+            n_step++;
+
+            // ---- B (warp 0, lane = cell): finished cells, folds, splits, the step's combos
+            if (warp == 0) {
+                bool lv[DK3_NC];
+                int kl[DK3_NC];
+                unsigned livem[DK3_NC];
+                bool anyfull = false, canstep = false, anylive = false;
+#pragma unroll
+                for (int c = 0; c < DK3_NC; c++) {
+                    const int ci = lane + 32 * c;
+                    lv[c] = sm.clive[ci] && ((jobmask[c] >> lane) & 1u);
+                    const int k = sm.kc[par][ci], m = sm.qcnt[ci];
+                    sm.kc[par ^ 1][ci] = DK3_BIG;                            // the next step's slot
+                    if (lv[c] && (k == DK3_BIG || n - nmain - m <= a.handoff)) {   // finished, or few enough left for the exact solver
+                        const long long cell = sm.cellidx[ci];
+#pragma unroll
+                        for (int q = 0; q < DK_WORDS; q++) {
+                            unsigned word = sm.chainw[q] & ~sm.qmask[ci * DK_WORDS + q];
+                            if (q == DK_WORDS - 1 && k != DK3_BIG) word |= 0x80000000u;   // bit 255: handed off undecided
+                            a.final_act[(size_t)cell * DK_WORDS + q] = word;
+                        }
+                        sm.clive[ci] = 0;
+                        lv[c] = false;
+                    }
+                    kl[c] = lv[c] ? k : -1;
+                    livem[c] = __ballot_sync(FULL, lv[c]);
+                    anylive |= livem[c] != 0u;
+                    anyfull |= __ballot_sync(FULL, lv[c] && m >= DK2_QM) != 0u;
+                    canstep |= __ballot_sync(FULL, lv[c] && m < DK2_QM) != 0u;
+                    sm.cid[ci] = -1;
+                }
+                int action = 0, nc = 0, snap = 0, ncombo = 0;
+                if (!anylive) {
+                    action = nstack == 0 ? 2 : 1;
+                } else {
+                    unsigned cw[DK_WORDS];
+                    int nco = 0;
+                    since++;
+                    auto common = [&]() {
+                        nco = 0;
+#pragma unroll
+                        for (int q = 0; q < DK_WORDS; q++) {
+                            unsigned x = FULL;
+#pragma unroll
+                            for (int c = 0; c < DK3_NC; c++) x &= lv[c] ? sm.qmask[(lane + 32 * c) * DK_WORDS + q] : FULL;
+                            cw[q] = __reduce_and_sync(FULL, x);
+                            nco += __popc(cw[q]);
+                        }
+                    };
+#pragma unroll
+                    for (int q = 0; q < DK_WORDS; q++) cw[q] = 0u;
+                    if (since >= DK2_FLMIN || anyfull || !canstep) common();
+                    bool fold = nco >= DK2_FLMIN || (anyfull && nco > 0);
+                    if (!fold && !canstep) {   // stuck: split by the station most cells have dropped
+                        int best = -1, bestc = 0;
+#pragma unroll
+                        for (int q = 0; q < DK_WORDS; q++) {
+                            unsigned mine[DK3_NC], u = 0u;
+#pragma unroll
+                            for (int c = 0; c < DK3_NC; c++) {
+                                mine[c] = lv[c] ? sm.qmask[(lane + 32 * c) * DK_WORDS + q] : 0u;
+                                u |= mine[c];
+                            }
+                            unsigned bits = __reduce_or_sync(FULL, u);
+                            while (bits) {
+                                const int b = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                int cnt = 0;
+#pragma unroll
+                                for (int c = 0; c < DK3_NC; c++) cnt += __popc(__ballot_sync(FULL, (mine[c] >> b) & 1u));
+                                if (cnt > bestc) {
+                                    bestc = cnt;
+                                    best = 32 * q + b;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < DK3_NC; c++) {
+                            const unsigned g1 = __ballot_sync(FULL, lv[c] && ((sm.qmask[(lane + 32 * c) * DK_WORDS + (best >> 5)] >> (best & 31)) & 1u));
+                            if (lane == 0) sm.jobs[(DK3_NC + 1) * nstack + c] = (int)(livem[c] & ~g1);
+                            jobmask[c] = g1;
+                            lv[c] = lv[c] && ((g1 >> lane) & 1u);
+                            livem[c] = g1;
+                        }
+                        if (lane == 0) sm.jobs[(DK3_NC + 1) * nstack + DK3_NC] = nmain;
+                        nstack++;
+                        snap = 1;
+                        common();
+                        fold = true;
+                    }
+                    if (fold) {
+#pragma unroll
+                        for (int q = 0; q < DK_WORDS; q++) {
+                            unsigned bits = cw[q], tk = 0;
+                            while (bits && nc < DK2_PEND) {
+                                const int b = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                tk |= 1u << b;
+                                if (lane == 0) sm.clist[nc] = 32 * q + b;
+                                nc++;
+                            }
+                            if (lane == q) sm.taken[q] = tk;
+                        }
+                        since = nco > nc ? DK2_FLMIN : 0;
+                    }
+                    action = fold ? 3 : 0;
+                    if (lane == 0) {
+#pragma unroll
+                        for (int c = 0; c < DK3_NC; c++) sm.ctrl[8 + c] = (int)jobmask[c];
+                    }
+                    if (!fold) {   // combos right away: distinct (lead set, station) pairs among the stepping cells, per cell column
+#pragma unroll
+                        for (int c = 0; c < DK3_NC; c++) {
+                            const int ci = lane + 32 * c;
+                            const int m = sm.qcnt[ci];
+                            const bool stepping = lv[c] && m < DK2_QM;
+                            unsigned grp = __ballot_sync(FULL, stepping) & __match_any_sync(FULL, kl[c]);
+#pragma unroll
+                            for (int q = 0; q < DK_WORDS; q++) grp &= __match_any_sync(FULL, sm.qmask[ci * DK_WORDS + q]);
+                            const int lead_lane = __ffs(grp) - 1;
+                            const unsigned leadm = __ballot_sync(FULL, stepping && lane == lead_lane);
+                            if (stepping) {
+                                const int g = ncombo + __popc(leadm & ((1u << lead_lane) - 1u));
+                                sm.cid[ci] = g;
+                                if (lane == lead_lane) {
+                                    sm.kcb[g] = kl[c];
+                                    sm.mcb[g] = m;
+                                    sm.lcb[g] = ci;
+                                }
+                            }
+                            ncombo += __popc(leadm);
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    sm.ctrl[1] = action;
+                    sm.ctrl[2] = nc;
+                    sm.ctrl[3] = ncombo;
+                    sm.ctrl[4] = nstack;
+                    sm.ctrl[5] = snap;
+                    sm.ctrl[6] = since;
+                }
+            }
+            __syncthreads();   // (2) decisions published
+            const int action = sm.ctrl[1];
+            nstack = sm.ctrl[4];
+            if (action == 2) break;                                          // tile finished
+            if (action == 1) {   // a waiting group: back to the inverse and chain it was split off from
+                nstack--;
+#pragma unroll
+                for (int c = 0; c < DK3_NC; c++) jobmask[c] = (unsigned)sm.jobs[(DK3_NC + 1) * nstack + c];
+                nmain = sm.jobs[(DK3_NC + 1) * nstack + DK3_NC];
+                const double* sg = snap_g + (size_t)nstack * npk;
+                for (int q = tid; q < npk; q += DK_THREADS) Sp[q] = sg[q];
+                for (int i = tid; i < DK2_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
+                if (tid < DK_WORDS) {
+                    const int lo = 32 * tid;
+                    sm.chainw[tid] = n > lo ? (n - lo >= 32 ? FULL : ((1u << (n - lo)) - 1u)) : 0u;
+                }
+                if (tid < DK3_C) sm.kc[par][tid] = DK3_BIG;
+                __syncthreads();
+                for (int d = tid; d < nmain; d += DK_THREADS) {
+                    const int q = sm.kstack[d];
+                    sm.mact[q] = 0;
+                    atomicAnd(&sm.chainw[q >> 5], ~(1u << (q & 31)));
+                }
+                since = 0;
+                n_pop++;
+                __syncthreads();
+                continue;
+            }
+#pragma unroll
+            for (int c = 0; c < DK3_NC; c++) jobmask[c] = (unsigned)sm.ctrl[8 + c];
+            since = sm.ctrl[6];
+            if (sm.ctrl[5]) {   // split: the group left behind restarts from this inverse
+                double* sg = snap_g + (size_t)(nstack - 1) * npk;
+                for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Sp[q];
+                n_split++;
+                __syncthreads();
+            }
+            if (action == 3) {   // ---- fold the common stations into the chain; the cells pick again afterwards (no drop in this step)
+                const int nc = sm.ctrl[2];
+                if (warp == 0) {   // current column q of the inverse = stored column corrected for the columns folded before it
+                    unsigned dropbits = 0;
+                    for (int d = 0; d < nc; d++) {
+                        const int q = sm.clist[d];
+                        double v[DK_QMAX];
+#pragma unroll
+                        for (int s = 0; s < DK_QMAX; s++) {
+                            const int j = lane + 32 * s;
+                            const bool on = (j < NN) && sm.mact[j] && !((dropbits >> s) & 1u);
+                            double x = 0.0;
+                            if (on) {
+                                x = Sat(j, q);
+                                for (int e = 0; e < d; e++) x = fma(-psm[e * NNP + j], pcol[e * NNP + q], x);
+                            }
+                            v[s] = x;
+                        }
+                        double vq = v[0];
+#pragma unroll
+                        for (int s = 1; s < DK_QMAX; s++)
+                            if ((q >> 5) == s) vq = v[s];
+                        const double rmu = dk_rcp(__shfl_sync(FULL, vq, q & 31));
+                        if (lane == (q & 31)) dropbits |= 1u << (q >> 5);
+#pragma unroll
+                        for (int s = 0; s < DK_QMAX; s++) {
+                            const int j = lane + 32 * s;
+                            if (j < NNP) {
+                                const double x = (j == q) ? 0.0 : v[s];
+                                pcol[d * NNP + j] = x;
+                                psm[d * NNP + j] = x * rmu;
+                            }
+                        }
+                        if (lane == 0) sm.prmu[d] = rmu;
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();   // (F1) columns published
+                if (warp == 1) {   // leads lose the stations folded in (lane = cell)
+#pragma unroll
+                    for (int c = 0; c < DK3_NC; c++) {
+                        const int ci = lane + 32 * c;
+                        if (((jobmask[c] >> lane) & 1u) && sm.clive[ci]) {
+                            const int m = sm.qcnt[ci];
+                            int keep = 0;
+                            for (int i = 0; i < m; i++) {
+                                const int qi = sm.qlist[ci * DK2_QM + i];
+                                if (!((sm.taken[qi >> 5] >> (qi & 31)) & 1u)) sm.qlist[ci * DK2_QM + keep++] = qi;
+                            }
+                            sm.qcnt[ci] = keep;
+#pragma unroll
+                            for (int q = 0; q < DK_WORDS; q++) sm.qmask[ci * DK_WORDS + q] &= ~sm.taken[q];
+                        }
+                    }
+                }
+                // S -= sum_d col_d col_d' / mu_d on the packed triangle, DK2_FL stations per pass
+                for (int d0 = 0; d0 < nc; d0 += DK2_FL) {
+                    const int nd = min(DK2_FL, nc - d0);
+                    const double* pc = pcol + d0 * NNP;
+                    const double* ps = psm + d0 * NNP;
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        constexpr int QH = (DK_QMAX + 1) / 2;
+                        const int qa = half * QH, qb = half ? DK_QMAX : QH;
+                        double bj[DK2_FL][QH];                         // this lane's columns: col_d[j] / mu_d (zero beyond the set)
+#pragma unroll
+                        for (int d = 0; d < DK2_FL; d++)
+#pragma unroll
+                            for (int q = 0; q < QH; q++) bj[d][q] = (d < nd && qa + q < qb) ? ps[d * NNP + lane + 32 * (qa + q)] : 0.0;
+                        const int iend = min(NN, 32 * qb);
+                        for (int i = warp; i < iend; i += DK_WARPS) {
+                            if (!sm.mact[i]) continue;
+                            double bi[DK2_FL];
+#pragma unroll
+                            for (int d = 0; d < DK2_FL; d++) bi[d] = d < nd ? pc[d * NNP + i] : 0.0;
+                            double* row = Sp + sm.rowoff[i];
+                            const int q0 = i >> 5;
+#pragma unroll
+                            for (int q = 0; q < QH; q++) {
+                                const int j = lane + 32 * (qa + q);
+                                if (qa + q < qb && qa + q >= q0 && j >= i && j < NN) {
+                                    double v = row[j];
+#pragma unroll
+                                    for (int d = 0; d < DK2_FL; d++) v = fma(-bi[d], bj[d][q], v);
+                                    row[j] = v;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();   // every reader of mact in the pass is done
+                if (tid < nc) {
+                    const int q = sm.clist[tid];
+                    sm.kstack[nmain + tid] = q;
+                    sm.mact[q] = 0;
+                    atomicAnd(&sm.chainw[q >> 5], ~(1u << (q & 31)));
+                }
+                if (tid < DK3_C) sm.kc[par][tid] = DK3_BIG;                  // the cells pick again
+                nmain += nc;
+                n_moved += nc;
+                __syncthreads();   // (F2) S, chain set, leads in place
+                continue;
+            }
+            // ---- C: one warp per combo: y = (S[Q, Q])^-1 S[Q, k] (Gauss-Jordan in drop order, no pivoting), then the column
+            //         col = S[:, k] - S[:, Q] y over the combo's active set; meanwhile every owner publishes w_k of its cells
+            const int ncombo = sm.ctrl[3];
+            n_combo += ncombo;
+#pragma unroll
+            for (int c = 0; c < DK3_NC; c++) {
+                const int ci = lane + 32 * c;
+                const int k = sm.cid[ci] >= 0 ? sm.kc[par][ci] : -1;
+                const int s = k - j0;
+                if (s >= 0 && s < DK3_SPW) {
+                    double v = W[c][0];
+#pragma unroll
+                    for (int t = 1; t < DK3_SPW; t++)
+                        if (s == t) v = W[c][t];
+                    sm.wk[ci] = v;
+                    act[c] &= ~(1u << s);
+                }
+            }
+            for (int g0 = 0; g0 < ncombo; g0 += DK2_CB) {
+                const int ncb = min(DK2_CB, ncombo - g0);
+                if (warp < ncb) {
+                    const int L = sm.lcb[g0 + warp], k = sm.kcb[g0 + warp], m = sm.mcb[g0 + warp];
+                    double* G = scr + warp * DK2_SCR;
+                    const int myq = lane < m ? sm.qlist[L * DK2_QM + lane] : 0;
+                    for (int e0 = 0; e0 < m * (m + 1); e0 += 32) {
+                        const int e = e0 + lane;
+                        const bool ok = e < m * (m + 1);
+                        const int i = ok ? e / (m + 1) : 0, cc = ok ? e - i * (m + 1) : 0;
+                        const int qi = __shfl_sync(FULL, myq, i), qc = __shfl_sync(FULL, myq, cc < m ? cc : 0);
+                        if (ok) G[i * DK2_LD + cc] = Sat(qi, cc < m ? qc : k);
+                    }
+                    __syncwarp();
+                    for (int p = 0; p < m; p++) {
+                        const double r = dk_rcp(G[p * DK2_LD + p]);
+                        const int wd = m - p;
+                        for (int e = lane; e < m * wd; e += 32) {
+                            const int i = e / wd, cc = p + 1 + (e - i * wd);
+                            if (i != p) G[i * DK2_LD + cc] = fma(-(G[i * DK2_LD + p] * r), G[p * DK2_LD + cc], G[i * DK2_LD + cc]);
+                        }
+                        __syncwarp();
+                    }
+                    if (lane < m) sm.ycb[warp * DK2_QM + lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < DK_QMAX; s++) {
+                        const int j = lane + 32 * s;
+                        double x = 0.0;
+                        if (j < NN && sm.mact[j] && !((sm.qmask[L * DK_WORDS + (j >> 5)] >> (j & 31)) & 1u)) {
+                            x = Sat(j, k);
+                            for (int i = 0; i < m; i++) x = fma(-Sat(j, sm.qlist[L * DK2_QM + i]), sm.ycb[warp * DK2_QM + i], x);
+                        }
+                        if (j == k) {
+                            sm.rbeta[warp] = dk_rcp(x);
+                            x = 0.0;
+                        }
+                        if (j < NNP) pcol[warp * NNP + j] = x;
+                    }
+                }
+                __syncthreads();   // (3) columns built, w_k published
+                // ---- D: w -= (w_k / beta) col for every cell of the pass's combos
+#pragma unroll
+                for (int c = 0; c < DK3_NC; c++) {
+                    const int ci = lane + 32 * c;
+                    const int g = sm.cid[ci] - g0;
+                    if (g >= 0 && g < ncb) {
+                        const double f = sm.wk[ci] * sm.rbeta[g];
+                        const double* col = pcol + g * NNP + j0;
+#pragma unroll
+                        for (int s = 0; s < DK3_SPW; s++)
+                            if (j0 + s < NN) W[c][s] = fma(-f, col[s], W[c][s]);
+                    }
+                }
+                if (warp == 0) {   // the lead grows by the station dropped (lane = cell)
+#pragma unroll
+                    for (int c = 0; c < DK3_NC; c++) {
+                        const int ci = lane + 32 * c;
+                        const int g = sm.cid[ci] - g0;
+                        if (g >= 0 && g < ncb) {
+                            const int k = sm.kc[par][ci], m = sm.qcnt[ci];
+                            sm.qlist[ci * DK2_QM + m] = k;
+                            sm.qcnt[ci] = m + 1;
+                            sm.qmask[ci * DK_WORDS + (k >> 5)] |= 1u << (k & 31);
+                        }
+                    }
+                }
+                if (g0 + DK2_CB < ncombo) __syncthreads();   // the next pass reuses the column buffer
+            }
+            par ^= 1;
+        }
+    }
+    if (tid == 0) {
+        atomicAdd(a.tile_counter + 2, (unsigned long long)n_step);
+        atomicAdd(a.tile_counter + 3, (unsigned long long)n_pop);
+        atomicAdd(a.tile_counter + 4, (unsigned long long)n_split);
+        atomicAdd(a.tile_counter + 5, (unsigned long long)n_moved);
+        atomicAdd(a.tile_counter + 6, (unsigned long long)n_combo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Exact reference solve on the final active set (krige.c:140-197 + lusolv.c), one thread per cell.
 // ------------------------------------------------------------------------------------------
 struct DkFinalArgs {
@@ -1518,14 +2092,19 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     SMRFB_CUDA(cudaGetDevice(&dev));
     SMRFB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     SMRFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const long long ntiles = dk_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles;
-    const int grid = (int)std::min<long long>(ntiles, nsm);
-    // SMRFB_DK_WALK=tree selects the first design (path-keyed walk with forks), kept for comparison
+    // SMRFB_DK_WALK: sets (default; transposed weights, 64-cell tiles) | chain (one warp per cell, 32-cell tiles) | tree (round 1:
+    // path-keyed walk with forks) -- the older designs are kept for comparison
     const char* walk_env = getenv("SMRFB_DK_WALK");
-    const bool chain = !(walk_env && strcmp(walk_env, "tree") == 0);
-    size_t smem = chain ? dk2_smem_bytes(NN, NNP)
-                        : ((size_t)npk + (size_t)DK_TILE * NN + 2 * DK_PEND * NNP) * sizeof(double) +
-                              ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
+    const int walk = (walk_env && strcmp(walk_env, "tree") == 0) ? 0 : (walk_env && strcmp(walk_env, "chain") == 0) ? 1 : 2;
+    const bool chain = walk != 0;
+    const long long ntiles = walk == 2 ? dk3_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles
+                                       : dk_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles;
+    const int grid = (int)std::min<long long>(ntiles, nsm);
+    const int maxsnap = walk == 2 ? DK3_MAXSNAP : DK_MAXSNAP;
+    size_t smem = walk == 2 ? dk3_smem_bytes(NN, NNP)
+                  : walk == 1 ? dk2_smem_bytes(NN, NNP)
+                              : ((size_t)npk + (size_t)DK_TILE * NN + 2 * DK_PEND * NNP) * sizeof(double) +
+                                    ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
 
     double *d_sx = nullptr, *d_sy = nullptr, *d_cx = nullptr, *d_cy = nullptr, *d_elev = nullptr, *d_ad = nullptr,
@@ -1572,7 +2151,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
         DK_TRY(dev_upload(&d_rankof, rankof.data(), n));
     }
     DK_TRY(dev_upload(&d_orig, in.orig, n));
-    if (n > DK_NSMAX) DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * DK_MAXSNAP * npk * sizeof(double)));
+    if (n > DK_NSMAX) DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * maxsnap * npk * sizeof(double)));
     DK_CUDA(cudaMalloc((void**)&d_final, (size_t)in.ncell * DK_WORDS * sizeof(uint32_t)));
     DK_CUDA(cudaMalloc((void**)&d_cnt, 8 * sizeof(unsigned long long)));
     DK_CUDA(cudaMalloc((void**)&d_small, 4 * sizeof(int)));
@@ -1592,7 +2171,10 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     }
     ba.handoff = 10;   // below ~10 active stations a per-thread exact solve is cheaper than a CTA-wide rank-1 step
     if (n > DK_NSMAX) {
-        if (chain) {
+        if (walk == 2) {
+            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_sets_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+        } else if (walk == 1) {
             DK_CUDA(cudaFuncSetAttribute(dk_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dk_chain_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
         } else {
@@ -1676,7 +2258,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
     if (verbose)
         fprintf(stderr, "[smrfb] dk_build (%s): n=%d cells=%lld tiles=%lld %s=%llu restores=%llu %s=%llu folded=%llu combos=%llu K=%d "
-                "fallback=%llu walk %.1f ms, exact finish %.1f ms\n", chain ? "chain" : "tree", n, in.ncell, ntiles, chain ? "steps" : "applies",
+                "fallback=%llu walk %.1f ms, exact finish %.1f ms\n", walk == 2 ? "sets" : chain ? "chain" : "tree", n, in.ncell, ntiles, chain ? "steps" : "applies",
                 h_cnt[2], h_cnt[3], chain ? "splits" : "forks", h_cnt[4], h_cnt[5], h_cnt[6], K, h_cnt[1], ms_walk, ms_final);
 
     return SMRFB_OK;
