@@ -59,6 +59,7 @@ struct DkBuildArgs {
     const int* perm;       // [n] rank -> compressed station index
     const double* B0p;     // packed upper triangle of the inverse, rank order, NN*(NN+1)/2
     double* snap;          // [gridDim.x][DK_MAXSNAP][npk] fork snapshots of the packed inverse
+    double* sglob;         // dk_sets_kernel with more than DK_MAXN stations: [gridDim.x][npk] the packed inverse itself
     uint32_t* final_act;   // [ncell][DK_WORDS], bits over RANK index
     unsigned long long* tile_counter;
     int* maxcount;
@@ -852,14 +853,14 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
 constexpr int DK3_NC = 2;                   // cell columns per lane: a tile is 32 * DK3_NC cells
 constexpr int DK3_C = 32 * DK3_NC;
 constexpr int DK3_TX = 8, DK3_TY = 8;       // tile shape on a mesh
-constexpr int DK3_SPW = 7;                  // stations per warp: 32 x 7 = 224 >= 201
+constexpr int DK3_NMAX = 255;               // valid stations per mask: bit 255 of a cell's set flags a hand-off, station indices are uint8
+constexpr int DK3_NNP_MAX = 256;
 constexpr int DK3_MAXSNAP = DK3_C;          // a split leaves at least one cell behind
 constexpr int DK3_BIG = 0x7fffffff;
-static_assert(DK_WARPS * DK3_SPW >= DK_MAXN + 1, "every station needs an owner warp");
 
 struct Dk3Small {
-    int rowoff[DK2_NNP_MAX];
-    int kstack[DK2_NNP_MAX];
+    int rowoff[DK3_NNP_MAX];
+    int kstack[DK3_NNP_MAX];
     unsigned qmask[DK3_C * DK_WORDS];
     int qlist[DK3_C * DK2_QM];
     int qcnt[DK3_C];
@@ -873,7 +874,7 @@ struct Dk3Small {
     int jobs[(DK3_NC + 1) * DK3_MAXSNAP];
     int kcb[DK3_C], mcb[DK3_C], lcb[DK3_C]; // station, lead length, leader cell of the step's combos
     long long cellidx[DK3_C];               // flat grid index of the tile's cells (-1 outside)
-    unsigned char mact[DK2_NNP_MAX];
+    unsigned char mact[DK3_NNP_MAX];
     double wk[DK3_C];                       // weight of the picked station
     double prmu[DK2_PEND];
     double rbeta[DK2_CB];                   // 1 / pivot of the pass's combo columns
@@ -890,8 +891,8 @@ __host__ __device__ inline size_t dk3_union_doubles(int NN, int NNP) {
     const size_t stage = (size_t)dk3_stage_rows(NN, NNP) * DK3_C;
     return stage > work ? stage : work;
 }
-__host__ __device__ inline size_t dk3_smem_bytes(int NN, int NNP) {
-    const size_t npk = (size_t)NN * (NN + 1) / 2;
+__host__ __device__ inline size_t dk3_smem_bytes(int NN, int NNP, bool sglob) {
+    const size_t npk = sglob ? 0 : (size_t)NN * (NN + 1) / 2;     // more than 200 stations: the packed inverse lives in global memory (L2)
     return sizeof(Dk3Small) + (npk + dk3_union_doubles(NN, NNP)) * sizeof(double);
 }
 struct Dk3Tiling {
@@ -917,13 +918,18 @@ __device__ __forceinline__ long long dk3_tile_cell(const Dk3Tiling& tl, const Ge
     return c < ncell ? c : -1;
 }
 
+// SPW: stations per warp (32 x SPW >= n + 1); SGLOB: the packed inverse does not fit shared memory (n > 200) and is kept in
+// a per-CTA global buffer instead -- every access then costs an L2 round trip: correct, several times slower
+template <int SPW, bool SGLOB>
 __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
+    constexpr int DK3_SPW = SPW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, NN = a.NN, NNP = a.NNP;
     const int npk = NN * (NN + 1) / 2;
     Dk3Small& sm = *reinterpret_cast<Dk3Small*>(smem_raw);
-    double* Sp = reinterpret_cast<double*>(smem_raw + sizeof(Dk3Small));   // [npk] packed upper triangle of the chain's inverse
-    double* un = Sp + npk;
+    double* Sp = SGLOB ? a.sglob + (size_t)blockIdx.x * npk
+                       : reinterpret_cast<double*>(smem_raw + sizeof(Dk3Small));   // [npk] packed upper triangle of the chain's inverse
+    double* un = reinterpret_cast<double*>(smem_raw + sizeof(Dk3Small)) + (SGLOB ? 0 : npk);
     double* stage = un;                                          // [SR][64] right-hand sides at tile start
     double* pcol = un;                                           // [DK2_PEND][NNP] columns being folded in / combo columns
     double* psm = pcol + DK2_PEND * NNP;                         // [DK2_PEND][NNP] the folded columns / pivot
@@ -936,16 +942,25 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
     const long long ntiles = tiling.ntiles;
     const int SR = dk3_stage_rows(NN, NNP);
 
-    for (int i = tid; i < DK2_NNP_MAX; i += DK_THREADS) sm.rowoff[i] = i * NN - (i * (i + 1)) / 2;
+    for (int i = tid; i < DK3_NNP_MAX; i += DK_THREADS) sm.rowoff[i] = i * NN - (i * (i + 1)) / 2;
     __syncthreads();
     auto Sat = [&](int i, int j) { return Sp[sm.rowoff[min(i, j)] + max(i, j)]; };
     unsigned n_step = 0, n_pop = 0, n_split = 0, n_moved = 0, n_combo = 0;
+#ifdef DK3_PROFILE
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc0 = 0;   // thread 0: clocks per phase (init, pick, book, fold, solve, apply)
+#define DK3_T0() do { if (tid == 0) pc0 = clock64(); } while (0)
+#define DK3_T(i) do { if (tid == 0) { const long long c_ = clock64(); pt[i] += c_ - pc0; pc0 = c_; } } while (0)
+#else
+#define DK3_T0() do {} while (0)
+#define DK3_T(i) do {} while (0)
+#endif
 
     for (;;) {
         if (tid == 0) sm.ctrl[0] = (int)atomicAdd(a.tile_counter, 1ULL);
         __syncthreads();
         const long long tile = (unsigned)sm.ctrl[0];
         if (tile >= ntiles) break;
+        DK3_T0();
         for (int p = tid; p < npk; p += DK_THREADS) Sp[p] = a.B0p[p];
         if (tid < DK3_C) {
             const long long cell = dk3_tile_cell(tiling, a.g, a.ncell, tile, tid);
@@ -961,7 +976,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
             sm.cid[tid] = -1;
         }
         for (int i = tid; i < DK3_C * DK_WORDS; i += DK_THREADS) sm.qmask[i] = 0u;
-        for (int i = tid; i < DK2_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
+        for (int i = tid; i < DK3_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
         if (tid < DK_WORDS) {
             const int lo = 32 * tid;
             sm.chainw[tid] = n > lo ? (n - lo >= 32 ? FULL : ((1u << (n - lo)) - 1u)) : 0u;
@@ -1016,6 +1031,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
 #pragma unroll
         for (int c = 0; c < DK3_NC; c++) jobmask[c] = __ballot_sync(FULL, sm.cellidx[lane + 32 * c] >= 0);
         int nmain = 0, nstack = 0, since = 0, par = 0;
+        DK3_T(0);
 
         for (;;) {   // ---- steps
             // ---- A: every cell's first (= highest) active station with a negative weight: the minimum over the owner warps
@@ -1032,6 +1048,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
             }
             __syncthreads();   // (1) choices in place
             n_step++;
+            DK3_T(1);
 
             // ---- B (warp 0, lane = cell): finished cells, folds, splits, the step's combos
             if (warp == 0) {
@@ -1176,6 +1193,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 }
             }
             __syncthreads();   // (2) decisions published
+            DK3_T(2);
             const int action = sm.ctrl[1];
             nstack = sm.ctrl[4];
             if (action == 2) break;                                          // tile finished
@@ -1186,7 +1204,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 nmain = sm.jobs[(DK3_NC + 1) * nstack + DK3_NC];
                 const double* sg = snap_g + (size_t)nstack * npk;
                 for (int q = tid; q < npk; q += DK_THREADS) Sp[q] = sg[q];
-                for (int i = tid; i < DK2_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
+                for (int i = tid; i < DK3_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
                 if (tid < DK_WORDS) {
                     const int lo = 32 * tid;
                     sm.chainw[tid] = n > lo ? (n - lo >= 32 ? FULL : ((1u << (n - lo)) - 1u)) : 0u;
@@ -1218,9 +1236,9 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     unsigned dropbits = 0;
                     for (int d = 0; d < nc; d++) {
                         const int q = sm.clist[d];
-                        double v[DK_QMAX];
+                        double v[SPW];
 #pragma unroll
-                        for (int s = 0; s < DK_QMAX; s++) {
+                        for (int s = 0; s < SPW; s++) {
                             const int j = lane + 32 * s;
                             const bool on = (j < NN) && sm.mact[j] && !((dropbits >> s) & 1u);
                             double x = 0.0;
@@ -1232,12 +1250,12 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                         }
                         double vq = v[0];
 #pragma unroll
-                        for (int s = 1; s < DK_QMAX; s++)
+                        for (int s = 1; s < SPW; s++)
                             if ((q >> 5) == s) vq = v[s];
                         const double rmu = dk_rcp(__shfl_sync(FULL, vq, q & 31));
                         if (lane == (q & 31)) dropbits |= 1u << (q >> 5);
 #pragma unroll
-                        for (int s = 0; s < DK_QMAX; s++) {
+                        for (int s = 0; s < SPW; s++) {
                             const int j = lane + 32 * s;
                             if (j < NNP) {
                                 const double x = (j == q) ? 0.0 : v[s];
@@ -1250,6 +1268,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     }
                 }
                 __syncthreads();   // (F1) columns published
+                DK3_T(3);
                 if (warp == 1) {   // leads lose the stations folded in (lane = cell)
 #pragma unroll
                     for (int c = 0; c < DK3_NC; c++) {
@@ -1274,8 +1293,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     const double* ps = psm + d0 * NNP;
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
-                        constexpr int QH = (DK_QMAX + 1) / 2;
-                        const int qa = half * QH, qb = half ? DK_QMAX : QH;
+                        constexpr int QH = (SPW + 1) / 2;
+                        const int qa = half * QH, qb = half ? SPW : QH;
                         double bj[DK2_FL][QH];                         // this lane's columns: col_d[j] / mu_d (zero beyond the set)
 #pragma unroll
                         for (int d = 0; d < DK2_FL; d++)
@@ -1313,6 +1332,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 nmain += nc;
                 n_moved += nc;
                 __syncthreads();   // (F2) S, chain set, leads in place
+                DK3_T(4);
                 continue;
             }
             // ---- C: one warp per combo: y = (S[Q, Q])^-1 S[Q, k] (Gauss-Jordan in drop order, no pivoting), then the column
@@ -1359,7 +1379,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     if (lane < m) sm.ycb[warp * DK2_QM + lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
                     __syncwarp();
 #pragma unroll
-                    for (int s = 0; s < DK_QMAX; s++) {
+                    for (int s = 0; s < SPW; s++) {
                         const int j = lane + 32 * s;
                         double x = 0.0;
                         if (j < NN && sm.mact[j] && !((sm.qmask[L * DK_WORDS + (j >> 5)] >> (j & 31)) & 1u)) {
@@ -1374,6 +1394,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     }
                 }
                 __syncthreads();   // (3) columns built, w_k published
+                DK3_T(5);
                 // ---- D: w -= (w_k / beta) col for every cell of the pass's combos
 #pragma unroll
                 for (int c = 0; c < DK3_NC; c++) {
@@ -1403,8 +1424,13 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 if (g0 + DK2_CB < ncombo) __syncthreads();   // the next pass reuses the column buffer
             }
             par ^= 1;
+            DK3_T(6);
         }
     }
+#ifdef DK3_PROFILE
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) atomicAdd(a.tile_counter + 8 + i, (unsigned long long)pt[i]);
+#endif
     if (tid == 0) {
         atomicAdd(a.tile_counter + 2, (unsigned long long)n_step);
         atomicAdd(a.tile_counter + 3, (unsigned long long)n_pop);
@@ -2049,7 +2075,7 @@ static int dev_upload(T** dst, const T* src, size_t n) {
 static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long long* fallback_cells) {
     const int n = in.n, NN = n + 1, NNP = (NN + 31) / 32 * 32;
     SMRFB_CHECK(n >= 1, SMRFB_ERR_NODATA, "DK: no valid station");
-    SMRFB_CHECK(n <= DK_MAXN, SMRFB_ERR_LIMIT, "DK supports at most %d valid stations (got %d)", DK_MAXN, n);
+    SMRFB_CHECK(n <= DK3_NMAX, SMRFB_ERR_LIMIT, "DK supports at most %d valid stations (got %d)", DK3_NMAX, n);
     std::vector<double> ad((size_t)n * n, 0.0);
     if (in.ad) {
         std::copy(in.ad, in.ad + (size_t)n * n, ad.begin());
@@ -2096,19 +2122,21 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     // path-keyed walk with forks) -- the older designs are kept for comparison
     const char* walk_env = getenv("SMRFB_DK_WALK");
     const int walk = (walk_env && strcmp(walk_env, "tree") == 0) ? 0 : (walk_env && strcmp(walk_env, "chain") == 0) ? 1 : 2;
+    SMRFB_CHECK(walk == 2 || n <= DK_MAXN, SMRFB_ERR_LIMIT, "SMRFB_DK_WALK=%s supports at most %d valid stations (got %d)", walk_env, DK_MAXN, n);
+    const bool sglob = walk == 2 && n > DK_MAXN;   // the packed inverse (n + 1)(n + 2) / 2 doubles no longer fits shared memory
     const bool chain = walk != 0;
     const long long ntiles = walk == 2 ? dk3_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles
                                        : dk_tiling(in.g, in.ncell, in.d_dgrid != nullptr).ntiles;
     const int grid = (int)std::min<long long>(ntiles, nsm);
     const int maxsnap = walk == 2 ? DK3_MAXSNAP : DK_MAXSNAP;
-    size_t smem = walk == 2 ? dk3_smem_bytes(NN, NNP)
+    size_t smem = walk == 2 ? dk3_smem_bytes(NN, NNP, sglob)
                   : walk == 1 ? dk2_smem_bytes(NN, NNP)
                               : ((size_t)npk + (size_t)DK_TILE * NN + 2 * DK_PEND * NNP) * sizeof(double) +
                                     ((size_t)NNP + NN + DK_TILE + 8) * sizeof(int) + 64 * sizeof(DkPending) + NNP;
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "DK: %d stations need %zu B shared memory (max %d)", n, smem, smem_max);
 
     double *d_sx = nullptr, *d_sy = nullptr, *d_cx = nullptr, *d_cy = nullptr, *d_elev = nullptr, *d_ad = nullptr,
-           *d_B0p = nullptr, *d_undo = nullptr, *d_big = nullptr;
+           *d_B0p = nullptr, *d_undo = nullptr, *d_big = nullptr, *d_sglob = nullptr;
     int *d_perm = nullptr, *d_orig = nullptr, *d_small = nullptr, *d_rankof = nullptr, *d_ibig = nullptr;
     uint32_t* d_final = nullptr;
     unsigned long long* d_cnt = nullptr;
@@ -2116,7 +2144,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     auto cleanup = [&]() {
         cudaFree(d_sx); cudaFree(d_sy); cudaFree(d_cx); cudaFree(d_cy); cudaFree(d_elev); cudaFree(d_ad);
         cudaFree(d_B0p); cudaFree(d_undo); cudaFree(d_perm); cudaFree(d_rankof); cudaFree(d_orig); cudaFree(d_small); cudaFree(d_final);
-        cudaFree(d_cnt); cudaFree(d_big); cudaFree(d_ibig);
+        cudaFree(d_cnt); cudaFree(d_big); cudaFree(d_ibig); cudaFree(d_sglob);
     };
 #define DK_TRY(x)                 \
     do {                          \
@@ -2153,16 +2181,16 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     DK_TRY(dev_upload(&d_orig, in.orig, n));
     if (n > DK_NSMAX) DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * maxsnap * npk * sizeof(double)));
     DK_CUDA(cudaMalloc((void**)&d_final, (size_t)in.ncell * DK_WORDS * sizeof(uint32_t)));
-    DK_CUDA(cudaMalloc((void**)&d_cnt, 8 * sizeof(unsigned long long)));
+    DK_CUDA(cudaMalloc((void**)&d_cnt, 16 * sizeof(unsigned long long)));
     DK_CUDA(cudaMalloc((void**)&d_small, 4 * sizeof(int)));
-    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), st));
+    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
     DK_CUDA(cudaMemsetAsync(d_small, 0, 4 * sizeof(int), st));
 
     DkBuildArgs ba;
     ba.n = n; ba.NN = NN; ba.NNP = NNP; ba.nsel = nsel;
     ba.ncell = in.ncell; ba.g = in.g;
     ba.sx = d_sx; ba.sy = d_sy; ba.dgrid = in.d_dgrid; ba.perm = d_perm; ba.B0p = d_B0p; ba.snap = d_undo;
-    ba.final_act = d_final; ba.tile_counter = d_cnt; ba.maxcount = d_small;
+    ba.final_act = d_final; ba.tile_counter = d_cnt; ba.maxcount = d_small; ba.sglob = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     const bool verbose = getenv("SMRFB_DK_VERBOSE") != nullptr;
     if (verbose) {
@@ -2171,9 +2199,14 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     }
     ba.handoff = 10;   // below ~10 active stations a per-thread exact solve is cheaper than a CTA-wide rank-1 step
     if (n > DK_NSMAX) {
-        if (walk == 2) {
-            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dk_sets_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
+        if (walk == 2 && sglob) {
+            DK_CUDA(cudaMalloc((void**)&d_sglob, (size_t)grid * npk * sizeof(double)));
+            ba.sglob = d_sglob;
+            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_sets_kernel<8, true><<<grid, DK_THREADS, smem, st>>>(ba);
+        } else if (walk == 2) {
+            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_sets_kernel<7, false><<<grid, DK_THREADS, smem, st>>>(ba);
         } else if (walk == 1) {
             DK_CUDA(cudaFuncSetAttribute(dk_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dk_chain_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
@@ -2247,7 +2280,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
         count_launch();
         DK_CUDA(cudaGetLastError());
     }
-    unsigned long long h_cnt[8] = {0};
+    unsigned long long h_cnt[16] = {0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaStreamSynchronize(st));
@@ -2256,6 +2289,16 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
 #undef DK_CUDA
     SMRFB_CHECK(!(h_small[1] & 1), SMRFB_ERR_SINGULAR, "DK: singular kriging system in the final solve");
     if (fallback_cells) *fallback_cells += (long long)h_cnt[1];
+#ifdef DK3_PROFILE
+    if (verbose && walk == 2) {
+        double tot = 0;
+        for (int i = 0; i < 8; i++) tot += (double)h_cnt[8 + i];
+        fprintf(stderr, "[smrfb] dk_sets phases (share of thread 0's clocks): init %.1f%%  pick %.1f%%  book %.1f%%  fold-extract %.1f%%  "
+                "fold-flush %.1f%%  solve+column %.1f%%  apply %.1f%%;  clocks per step %.0f\n", 100 * h_cnt[8] / tot, 100 * h_cnt[9] / tot,
+                100 * h_cnt[10] / tot, 100 * h_cnt[11] / tot, 100 * h_cnt[12] / tot, 100 * h_cnt[13] / tot, 100 * h_cnt[14] / tot,
+                (tot - h_cnt[8]) / std::max(1.0, (double)h_cnt[2] / grid));
+    }
+#endif
     if (verbose)
         fprintf(stderr, "[smrfb] dk_build (%s): n=%d cells=%lld tiles=%lld %s=%llu restores=%llu %s=%llu folded=%llu combos=%llu K=%d "
                 "fallback=%llu walk %.1f ms, exact finish %.1f ms\n", walk == 2 ? "sets" : chain ? "chain" : "tree", n, in.ncell, ntiles, chain ? "steps" : "applies",
@@ -2541,7 +2584,7 @@ int smrfb_krige_grid(int nsta, int ngrid, const double* ad, const double* dgrid,
                      double* weights) {
     (void)nthreads;
     SMRFB_CHECK(nsta > 0 && ngrid > 0 && ad && dgrid && elevations && weights, SMRFB_ERR_ARG, "bad krige_grid arguments");
-    SMRFB_CHECK(nsta <= DK_MAXN, SMRFB_ERR_LIMIT, "krige_grid supports at most %d stations (got %d)", DK_MAXN, nsta);
+    SMRFB_CHECK(nsta <= DK3_NMAX, SMRFB_ERR_LIMIT, "krige_grid supports at most %d stations (got %d)", DK3_NMAX, nsta);
     int dev = 0;
     if (const char* e = getenv("SMRFB_DEVICE")) dev = atoi(e);
     SMRFB_CUDA(cudaSetDevice(dev));

@@ -27,7 +27,7 @@ def test_krige_kat_call_grid(sp, golden):
 
 
 @pytest.mark.parametrize("nsta,ncell,seed", [(1, 5, 9), (2, 40, 0), (5, 200, 1), (13, 333, 2), (40, 500, 3),
-                                             (100, 300, 4), (200, 96, 5)])
+                                             (100, 300, 4), (200, 96, 5), (231, 48, 6)])   # 231 > 200: the inverse leaves shared memory
 def test_krige_grid_vs_oracle(sp, nsta, ncell, seed):
     from oracle import oracle as orc
     rng = np.random.default_rng(seed)
