@@ -843,8 +843,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
 
 // ------------------------------------------------------------------------------------------
 // dk_sets_kernel -- the same walk as dk_chain_kernel (one stored inverse per tile, leads, combos, folds, splits) with the
-// cell weights TRANSPOSED: warp w owns the stations 7 w .. 7 w + 6 and lane l the cells l, l + 32 (a tile is 8 x 8 cells),
-// so a thread holds 7 x 2 weights.  In dk_chain_kernel a warp owned one cell and every per-cell operation was a
+// cell weights TRANSPOSED: warp w (of 16) owns the stations 14 w .. 14 w + 13 and lane l the cells l, l + 32 (a tile is 8 x 8
+// cells), so a thread holds 14 x 2 weights (512 threads: at 1024 the 64-register cap spilled them to local memory).  In dk_chain_kernel a warp owned one cell and every per-cell operation was a
 // warp-wide instruction sequence (ncu: 5.3 M warp instructions per 32-cell tile, issue-bound); here picking the first
 // negative weight is 7 compares and one shared-memory atomicMin per thread, applying a combo column is 7 FMAs per cell
 // with the column read as a (mostly broadcast) gather, and twice as many cells share every fold of the inverse.
@@ -853,6 +853,9 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
 constexpr int DK3_NC = 2;                   // cell columns per lane: a tile is 32 * DK3_NC cells
 constexpr int DK3_C = 32 * DK3_NC;
 constexpr int DK3_TX = 8, DK3_TY = 8;       // tile shape on a mesh
+constexpr int DK3_THREADS = 512;
+constexpr int DK3_FOLD = 4;                 // stations folded into the chain at once (their columns stay in warp 0's registers)
+constexpr int DK3_WARPS = DK3_THREADS / 32;
 constexpr int DK3_NMAX = 255;               // valid stations per mask: bit 255 of a cell's set flags a hand-off, station indices are uint8
 constexpr int DK3_NNP_MAX = 256;
 constexpr int DK3_MAXSNAP = DK3_C;          // a split leaves at least one cell behind
@@ -871,6 +874,7 @@ struct Dk3Small {
     unsigned taken[DK_WORDS];
     unsigned chainw[DK_WORDS];              // stations still in the chain's set, as a bit set
     int ctrl[16];
+    unsigned stats[8];                      // thread 0: steps, job pops, splits, stations folded, combos
     int jobs[(DK3_NC + 1) * DK3_MAXSNAP];
     int kcb[DK3_C], mcb[DK3_C], lcb[DK3_C]; // station, lead length, leader cell of the step's combos
     long long cellidx[DK3_C];               // flat grid index of the tile's cells (-1 outside)
@@ -879,6 +883,7 @@ struct Dk3Small {
     double prmu[DK2_PEND];
     double rbeta[DK2_CB];                   // 1 / pivot of the pass's combo columns
     double ycb[DK2_CB * DK2_QM];
+    int qcb[DK2_CB * DK2_QM];               // the lead of the pass's combos
     double cx[DK3_C], cy[DK3_C];
 };
 __host__ __device__ inline int dk3_stage_rows(int NN, int NNP) {   // rows of the right-hand-side stage that fit beside the work buffers
@@ -920,9 +925,10 @@ __device__ __forceinline__ long long dk3_tile_cell(const Dk3Tiling& tl, const Ge
 
 // SPW: stations per warp (32 x SPW >= n + 1); SGLOB: the packed inverse does not fit shared memory (n > 200) and is kept in
 // a per-CTA global buffer instead -- every access then costs an L2 round trip: correct, several times slower
-template <int SPW, bool SGLOB>
-__global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
-    constexpr int DK3_SPW = SPW;
+template <int SPW, int QS, bool SGLOB>
+__global__ void __launch_bounds__(DK3_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
+    constexpr int DK3_SPW = SPW;       // stations per warp; QS: 32-wide slots that cover the n + 1 rows of a column
+    static_assert(DK3_WARPS * SPW >= 32 * QS, "every station needs an owner warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, NN = a.NN, NNP = a.NNP;
     const int npk = NN * (NN + 1) / 2;
@@ -942,15 +948,19 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
     const long long ntiles = tiling.ntiles;
     const int SR = dk3_stage_rows(NN, NNP);
 
-    for (int i = tid; i < DK3_NNP_MAX; i += DK_THREADS) sm.rowoff[i] = i * NN - (i * (i + 1)) / 2;
+    for (int i = tid; i < DK3_NNP_MAX; i += DK3_THREADS) sm.rowoff[i] = i * NN - (i * (i + 1)) / 2;
     __syncthreads();
     auto Sat = [&](int i, int j) { return Sp[sm.rowoff[min(i, j)] + max(i, j)]; };
-    unsigned n_step = 0, n_pop = 0, n_split = 0, n_moved = 0, n_combo = 0;
+    if (tid < 8) sm.stats[tid] = 0u;
 #ifdef DK3_PROFILE
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc0 = 0;   // thread 0: clocks per phase (init, pick, book, fold, solve, apply)
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc0 = 0, qt[6] = {0, 0, 0, 0, 0, 0}, qc0 = 0;   // thread 0: clocks per phase (init, pick, book, fold, solve, apply)
 #define DK3_T0() do { if (tid == 0) pc0 = clock64(); } while (0)
 #define DK3_T(i) do { if (tid == 0) { const long long c_ = clock64(); pt[i] += c_ - pc0; pc0 = c_; } } while (0)
+#define DK3_Q0() do { if (tid == 0) qc0 = clock64(); } while (0)
+#define DK3_Q(i) do { if (tid == 0) { const long long c_ = clock64(); qt[i] += c_ - qc0; qc0 = c_; } } while (0)
 #else
+#define DK3_Q0() do {} while (0)
+#define DK3_Q(i) do {} while (0)
 #define DK3_T0() do {} while (0)
 #define DK3_T(i) do {} while (0)
 #endif
@@ -961,7 +971,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
         const long long tile = (unsigned)sm.ctrl[0];
         if (tile >= ntiles) break;
         DK3_T0();
-        for (int p = tid; p < npk; p += DK_THREADS) Sp[p] = a.B0p[p];
+        for (int p = tid; p < npk; p += DK3_THREADS) Sp[p] = a.B0p[p];
         if (tid < DK3_C) {
             const long long cell = dk3_tile_cell(tiling, a.g, a.ncell, tile, tid);
             sm.cellidx[tid] = cell;
@@ -975,8 +985,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
             sm.kc[1][tid] = DK3_BIG;
             sm.cid[tid] = -1;
         }
-        for (int i = tid; i < DK3_C * DK_WORDS; i += DK_THREADS) sm.qmask[i] = 0u;
-        for (int i = tid; i < DK3_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
+        for (int i = tid; i < DK3_C * DK_WORDS; i += DK3_THREADS) sm.qmask[i] = 0u;
+        for (int i = tid; i < DK3_NNP_MAX; i += DK3_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
         if (tid < DK_WORDS) {
             const int lo = 32 * tid;
             sm.chainw[tid] = n > lo ? (n - lo >= 32 ? FULL : ((1u << (n - lo)) - 1u)) : 0u;
@@ -990,7 +1000,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
             for (int s = 0; s < DK3_SPW; s++) W[c][s] = 0.0;
         for (int i0 = 0; i0 < NN; i0 += SR) {
             const int ni = min(SR, NN - i0);
-            for (int e = tid; e < ni * DK3_C; e += DK_THREADS) {
+            for (int e = tid; e < ni * DK3_C; e += DK3_THREADS) {
                 const int i = i0 + e / DK3_C, ci = e % DK3_C;
                 const long long cell = sm.cellidx[ci];
                 double v = 0.0;
@@ -1047,7 +1057,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 }
             }
             __syncthreads();   // (1) choices in place
-            n_step++;
+            if (tid == 0) sm.stats[0]++;
             DK3_T(1);
 
             // ---- B (warp 0, lane = cell): finished cells, folds, splits, the step's combos
@@ -1143,7 +1153,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
 #pragma unroll
                         for (int q = 0; q < DK_WORDS; q++) {
                             unsigned bits = cw[q], tk = 0;
-                            while (bits && nc < DK2_PEND) {
+                            while (bits && nc < DK3_FOLD) {
                                 const int b = __ffs(bits) - 1;
                                 bits &= bits - 1;
                                 tk |= 1u << b;
@@ -1203,21 +1213,21 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 for (int c = 0; c < DK3_NC; c++) jobmask[c] = (unsigned)sm.jobs[(DK3_NC + 1) * nstack + c];
                 nmain = sm.jobs[(DK3_NC + 1) * nstack + DK3_NC];
                 const double* sg = snap_g + (size_t)nstack * npk;
-                for (int q = tid; q < npk; q += DK_THREADS) Sp[q] = sg[q];
-                for (int i = tid; i < DK3_NNP_MAX; i += DK_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
+                for (int q = tid; q < npk; q += DK3_THREADS) Sp[q] = sg[q];
+                for (int i = tid; i < DK3_NNP_MAX; i += DK3_THREADS) sm.mact[i] = (i < NN) ? 1 : 0;
                 if (tid < DK_WORDS) {
                     const int lo = 32 * tid;
                     sm.chainw[tid] = n > lo ? (n - lo >= 32 ? FULL : ((1u << (n - lo)) - 1u)) : 0u;
                 }
                 if (tid < DK3_C) sm.kc[par][tid] = DK3_BIG;
                 __syncthreads();
-                for (int d = tid; d < nmain; d += DK_THREADS) {
+                for (int d = tid; d < nmain; d += DK3_THREADS) {
                     const int q = sm.kstack[d];
                     sm.mact[q] = 0;
                     atomicAnd(&sm.chainw[q >> 5], ~(1u << (q & 31)));
                 }
                 since = 0;
-                n_pop++;
+                if (tid == 0) sm.stats[1]++;
                 __syncthreads();
                 continue;
             }
@@ -1226,36 +1236,39 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
             since = sm.ctrl[6];
             if (sm.ctrl[5]) {   // split: the group left behind restarts from this inverse
                 double* sg = snap_g + (size_t)(nstack - 1) * npk;
-                for (int q = tid; q < npk; q += DK_THREADS) sg[q] = Sp[q];
-                n_split++;
+                for (int q = tid; q < npk; q += DK3_THREADS) sg[q] = Sp[q];
+                if (tid == 0) sm.stats[2]++;
                 __syncthreads();
             }
             if (action == 3) {   // ---- fold the common stations into the chain; the cells pick again afterwards (no drop in this step)
                 const int nc = sm.ctrl[2];
                 if (warp == 0) {   // current column q of the inverse = stored column corrected for the columns folded before it
+                    // (keeping the raw columns in registers and correcting them there was tried: the 56 extra registers spill the
+                    // weights around it and the kernel as a whole got slower)
                     unsigned dropbits = 0;
                     for (int d = 0; d < nc; d++) {
                         const int q = sm.clist[d];
-                        double v[SPW];
+                        const int roq = sm.rowoff[q];
+                        double v[QS];
 #pragma unroll
-                        for (int s = 0; s < SPW; s++) {
+                        for (int s = 0; s < QS; s++) {
                             const int j = lane + 32 * s;
                             const bool on = (j < NN) && sm.mact[j] && !((dropbits >> s) & 1u);
                             double x = 0.0;
                             if (on) {
-                                x = Sat(j, q);
+                                x = (j <= q) ? Sp[j * NN - ((j * (j + 1)) >> 1) + q] : Sp[roq + j];
                                 for (int e = 0; e < d; e++) x = fma(-psm[e * NNP + j], pcol[e * NNP + q], x);
                             }
                             v[s] = x;
                         }
                         double vq = v[0];
 #pragma unroll
-                        for (int s = 1; s < SPW; s++)
+                        for (int s = 1; s < QS; s++)
                             if ((q >> 5) == s) vq = v[s];
                         const double rmu = dk_rcp(__shfl_sync(FULL, vq, q & 31));
                         if (lane == (q & 31)) dropbits |= 1u << (q >> 5);
 #pragma unroll
-                        for (int s = 0; s < SPW; s++) {
+                        for (int s = 0; s < QS; s++) {
                             const int j = lane + 32 * s;
                             if (j < NNP) {
                                 const double x = (j == q) ? 0.0 : v[s];
@@ -1293,15 +1306,15 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     const double* ps = psm + d0 * NNP;
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
-                        constexpr int QH = (SPW + 1) / 2;
-                        const int qa = half * QH, qb = half ? SPW : QH;
+                        constexpr int QH = (QS + 1) / 2;
+                        const int qa = half * QH, qb = half ? QS : QH;
                         double bj[DK2_FL][QH];                         // this lane's columns: col_d[j] / mu_d (zero beyond the set)
 #pragma unroll
                         for (int d = 0; d < DK2_FL; d++)
 #pragma unroll
                             for (int q = 0; q < QH; q++) bj[d][q] = (d < nd && qa + q < qb) ? ps[d * NNP + lane + 32 * (qa + q)] : 0.0;
                         const int iend = min(NN, 32 * qb);
-                        for (int i = warp; i < iend; i += DK_WARPS) {
+                        for (int i = warp; i < iend; i += DK3_WARPS) {
                             if (!sm.mact[i]) continue;
                             double bi[DK2_FL];
 #pragma unroll
@@ -1330,7 +1343,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                 }
                 if (tid < DK3_C) sm.kc[par][tid] = DK3_BIG;                  // the cells pick again
                 nmain += nc;
-                n_moved += nc;
+                if (tid == 0) sm.stats[3] += nc;
                 __syncthreads();   // (F2) S, chain set, leads in place
                 DK3_T(4);
                 continue;
@@ -1338,7 +1351,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
             // ---- C: one warp per combo: y = (S[Q, Q])^-1 S[Q, k] (Gauss-Jordan in drop order, no pivoting), then the column
             //         col = S[:, k] - S[:, Q] y over the combo's active set; meanwhile every owner publishes w_k of its cells
             const int ncombo = sm.ctrl[3];
-            n_combo += ncombo;
+            DK3_Q0();
+            if (tid == 0) sm.stats[4] += ncombo;
 #pragma unroll
             for (int c = 0; c < DK3_NC; c++) {
                 const int ci = lane + 32 * c;
@@ -1353,8 +1367,10 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                     act[c] &= ~(1u << s);
                 }
             }
+            DK3_Q(0);
             for (int g0 = 0; g0 < ncombo; g0 += DK2_CB) {
                 const int ncb = min(DK2_CB, ncombo - g0);
+                DK3_Q0();
                 if (warp < ncb) {
                     const int L = sm.lcb[g0 + warp], k = sm.kcb[g0 + warp], m = sm.mcb[g0 + warp];
                     double* G = scr + warp * DK2_SCR;
@@ -1367,6 +1383,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                         if (ok) G[i * DK2_LD + cc] = Sat(qi, cc < m ? qc : k);
                     }
                     __syncwarp();
+                    DK3_Q(1);
                     for (int p = 0; p < m; p++) {
                         const double r = dk_rcp(G[p * DK2_LD + p]);
                         const int wd = m - p;
@@ -1376,24 +1393,36 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
                         }
                         __syncwarp();
                     }
-                    if (lane < m) sm.ycb[warp * DK2_QM + lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
-                    __syncwarp();
-#pragma unroll
-                    for (int s = 0; s < SPW; s++) {
-                        const int j = lane + 32 * s;
-                        double x = 0.0;
-                        if (j < NN && sm.mact[j] && !((sm.qmask[L * DK_WORDS + (j >> 5)] >> (j & 31)) & 1u)) {
-                            x = Sat(j, k);
-                            for (int i = 0; i < m; i++) x = fma(-Sat(j, sm.qlist[L * DK2_QM + i]), sm.ycb[warp * DK2_QM + i], x);
-                        }
-                        if (j == k) {
-                            sm.rbeta[warp] = dk_rcp(x);
-                            x = 0.0;
-                        }
-                        if (j < NNP) pcol[warp * NNP + j] = x;
+                    DK3_Q(2);
+                    if (lane < m) {
+                        sm.ycb[warp * DK2_QM + lane] = G[lane * DK2_LD + m] * dk_rcp(G[lane * DK2_LD + lane]);
+                        sm.qcb[warp * DK2_QM + lane] = myq;
                     }
+                    DK3_Q(3);
                 }
+                __syncthreads();   // (3a) lead systems solved
+                for (int item = warp; item < ncb * QS; item += DK3_WARPS) {   // col = S[:, k] - S[:, Q] y, 32 rows per item
+                    const int g = item / QS, sl = item - g * QS;
+                    const int j = lane + 32 * sl;
+                    const int L = sm.lcb[g0 + g], kk = sm.kcb[g0 + g], m = sm.mcb[g0 + g];
+                    const int roj = j * NN - ((j * (j + 1)) >> 1);
+                    double x = 0.0;
+                    if (j < NN && sm.mact[j] && !((sm.qmask[L * DK_WORDS + (j >> 5)] >> (j & 31)) & 1u)) {
+                        x = (j <= kk) ? Sp[roj + kk] : Sp[sm.rowoff[kk] + j];
+                        for (int i = 0; i < m; i++) {
+                            const int q = sm.qcb[g * DK2_QM + i];
+                            x = fma(-((j <= q) ? Sp[roj + q] : Sp[sm.rowoff[q] + j]), sm.ycb[g * DK2_QM + i], x);
+                        }
+                    }
+                    if (j == kk) {
+                        sm.rbeta[g] = dk_rcp(x);
+                        x = 0.0;
+                    }
+                    if (j < NNP) pcol[g * NNP + j] = x;
+                }
+                DK3_Q(4);
                 __syncthreads();   // (3) columns built, w_k published
+                DK3_Q(5);
                 DK3_T(5);
                 // ---- D: w -= (w_k / beta) col for every cell of the pass's combos
 #pragma unroll
@@ -1430,13 +1459,11 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_sets_kernel(DkBuildArgs a) {
 #ifdef DK3_PROFILE
     if (tid == 0)
         for (int i = 0; i < 8; i++) atomicAdd(a.tile_counter + 8 + i, (unsigned long long)pt[i]);
+    if (tid == 0)
+        for (int i = 0; i < 6; i++) atomicAdd(a.tile_counter + 16 + i, (unsigned long long)qt[i]);
 #endif
     if (tid == 0) {
-        atomicAdd(a.tile_counter + 2, (unsigned long long)n_step);
-        atomicAdd(a.tile_counter + 3, (unsigned long long)n_pop);
-        atomicAdd(a.tile_counter + 4, (unsigned long long)n_split);
-        atomicAdd(a.tile_counter + 5, (unsigned long long)n_moved);
-        atomicAdd(a.tile_counter + 6, (unsigned long long)n_combo);
+        for (int i = 0; i < 5; i++) atomicAdd(a.tile_counter + 2 + i, (unsigned long long)sm.stats[i]);
     }
 }
 
@@ -2181,9 +2208,9 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
     DK_TRY(dev_upload(&d_orig, in.orig, n));
     if (n > DK_NSMAX) DK_CUDA(cudaMalloc((void**)&d_undo, (size_t)grid * maxsnap * npk * sizeof(double)));
     DK_CUDA(cudaMalloc((void**)&d_final, (size_t)in.ncell * DK_WORDS * sizeof(uint32_t)));
-    DK_CUDA(cudaMalloc((void**)&d_cnt, 16 * sizeof(unsigned long long)));
+    DK_CUDA(cudaMalloc((void**)&d_cnt, 24 * sizeof(unsigned long long)));
     DK_CUDA(cudaMalloc((void**)&d_small, 4 * sizeof(int)));
-    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
+    DK_CUDA(cudaMemsetAsync(d_cnt, 0, 24 * sizeof(unsigned long long), st));
     DK_CUDA(cudaMemsetAsync(d_small, 0, 4 * sizeof(int), st));
 
     DkBuildArgs ba;
@@ -2202,11 +2229,11 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
         if (walk == 2 && sglob) {
             DK_CUDA(cudaMalloc((void**)&d_sglob, (size_t)grid * npk * sizeof(double)));
             ba.sglob = d_sglob;
-            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dk_sets_kernel<8, true><<<grid, DK_THREADS, smem, st>>>(ba);
+            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel<16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_sets_kernel<16, 8, true><<<grid, DK3_THREADS, smem, st>>>(ba);
         } else if (walk == 2) {
-            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dk_sets_kernel<7, false><<<grid, DK_THREADS, smem, st>>>(ba);
+            DK_CUDA(cudaFuncSetAttribute(dk_sets_kernel<14, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dk_sets_kernel<14, 7, false><<<grid, DK3_THREADS, smem, st>>>(ba);
         } else if (walk == 1) {
             DK_CUDA(cudaFuncSetAttribute(dk_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dk_chain_kernel<<<grid, DK_THREADS, smem, st>>>(ba);
@@ -2280,7 +2307,7 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
         count_launch();
         DK_CUDA(cudaGetLastError());
     }
-    unsigned long long h_cnt[16] = {0};
+    unsigned long long h_cnt[24] = {0};
     DK_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     DK_CUDA(cudaStreamSynchronize(st));
@@ -2296,7 +2323,11 @@ static int dk_build(const DkBuildInput& in, cudaStream_t st, DkWeights* W, long 
         fprintf(stderr, "[smrfb] dk_sets phases (share of thread 0's clocks): init %.1f%%  pick %.1f%%  book %.1f%%  fold-extract %.1f%%  "
                 "fold-flush %.1f%%  solve+column %.1f%%  apply %.1f%%;  clocks per step %.0f\n", 100 * h_cnt[8] / tot, 100 * h_cnt[9] / tot,
                 100 * h_cnt[10] / tot, 100 * h_cnt[11] / tot, 100 * h_cnt[12] / tot, 100 * h_cnt[13] / tot, 100 * h_cnt[14] / tot,
-                (tot - h_cnt[8]) / std::max(1.0, (double)h_cnt[2] / grid));
+                (tot - h_cnt[8]) / std::max(1.0, (double)h_cnt[2]));
+        double q = 0;
+        for (int i = 0; i < 6; i++) q += (double)h_cnt[16 + i];
+        fprintf(stderr, "[smrfb] dk_sets solve phase: publish w_k %.1f%%  fill %.1f%%  Gauss-Jordan %.1f%%  y %.1f%%  column %.1f%%  barrier %.1f%%\n",
+                100 * h_cnt[16] / q, 100 * h_cnt[17] / q, 100 * h_cnt[18] / q, 100 * h_cnt[19] / q, 100 * h_cnt[20] / q, 100 * h_cnt[21] / q);
     }
 #endif
     if (verbose)
