@@ -851,10 +851,10 @@ __global__ void __launch_bounds__(DK_THREADS, 1) dk_chain_kernel(DkBuildArgs a) 
 // The per-cell bookkeeping (leads, live flags, combos) is done by warp 0 with lane = cell.
 // ------------------------------------------------------------------------------------------
 constexpr int DK3_NC = 2;                   // cell columns per lane: a tile is 32 * DK3_NC cells
+constexpr int DK3_FOLD = 4;                 // stations folded into the chain at once
 constexpr int DK3_C = 32 * DK3_NC;
 constexpr int DK3_TX = 8, DK3_TY = 8;       // tile shape on a mesh
 constexpr int DK3_THREADS = 512;
-constexpr int DK3_FOLD = 4;                 // stations folded into the chain at once (their columns stay in warp 0's registers)
 constexpr int DK3_WARPS = DK3_THREADS / 32;
 constexpr int DK3_NMAX = 255;               // valid stations per mask: bit 255 of a cell's set flags a hand-off, station indices are uint8
 constexpr int DK3_NNP_MAX = 256;
@@ -881,6 +881,7 @@ struct Dk3Small {
     unsigned char mact[DK3_NNP_MAX];
     double wk[DK3_C];                       // weight of the picked station
     double prmu[DK2_PEND];
+    double piv[DK3_FOLD * DK3_FOLD];        // piv[e][d]: entry of folded column e at the station of column d > e
     double rbeta[DK2_CB];                   // 1 / pivot of the pass's combo columns
     double ycb[DK2_CB * DK2_QM];
     int qcb[DK2_CB * DK2_QM];               // the lead of the pass's combos
@@ -1242,43 +1243,47 @@ __global__ void __launch_bounds__(DK3_THREADS, 1) dk_sets_kernel(DkBuildArgs a) 
             }
             if (action == 3) {   // ---- fold the common stations into the chain; the cells pick again afterwards (no drop in this step)
                 const int nc = sm.ctrl[2];
-                if (warp == 0) {   // current column q of the inverse = stored column corrected for the columns folded before it
-                    // (keeping the raw columns in registers and correcting them there was tried: the 56 extra registers spill the
-                    // weights around it and the kernel as a whole got slower)
-                    unsigned dropbits = 0;
-                    for (int d = 0; d < nc; d++) {
-                        const int q = sm.clist[d];
-                        const int roq = sm.rowoff[q];
-                        double v[QS];
+                if (warp < QS) {   // current column q_d of the inverse = stored column corrected for the columns folded before it:
+                    // x_d[j] = S(j, q_d) - sum_{e < d} (c_e[j] / mu_e) c_e[q_d].  One warp per 32 rows, the row's corrected values
+                    // stay in registers; what the later columns need of column d -- its entries at their stations -- goes
+                    // through shared memory (piv), one named barrier among these warps per column.  (One warp doing all rows
+                    // column by column took 12 k clocks per fold; all columns in one warp's registers spilled the weights.)
+                    const int j = lane + 32 * warp;
+                    const int roj = j * NN - ((j * (j + 1)) >> 1);
+                    const bool rowon = j < NN && sm.mact[j];
+                    double c[DK3_FOLD];
 #pragma unroll
-                        for (int s = 0; s < QS; s++) {
-                            const int j = lane + 32 * s;
-                            const bool on = (j < NN) && sm.mact[j] && !((dropbits >> s) & 1u);
+                    for (int d = 0; d < DK3_FOLD; d++) {
+                        c[d] = 0.0;
+                        if (d < nc) {                                          // uniform
+                            const int q = sm.clist[d];
+                            bool on = rowon;
+#pragma unroll
+                            for (int e = 0; e < d; e++) on = on && (j != sm.clist[e]);
                             double x = 0.0;
                             if (on) {
-                                x = (j <= q) ? Sp[j * NN - ((j * (j + 1)) >> 1) + q] : Sp[roq + j];
-                                for (int e = 0; e < d; e++) x = fma(-psm[e * NNP + j], pcol[e * NNP + q], x);
-                            }
-                            v[s] = x;
-                        }
-                        double vq = v[0];
+                                x = (j <= q) ? Sp[roj + q] : Sp[sm.rowoff[q] + j];
 #pragma unroll
-                        for (int s = 1; s < QS; s++)
-                            if ((q >> 5) == s) vq = v[s];
-                        const double rmu = dk_rcp(__shfl_sync(FULL, vq, q & 31));
-                        if (lane == (q & 31)) dropbits |= 1u << (q >> 5);
-#pragma unroll
-                        for (int s = 0; s < QS; s++) {
-                            const int j = lane + 32 * s;
-                            if (j < NNP) {
-                                const double x = (j == q) ? 0.0 : v[s];
-                                pcol[d * NNP + j] = x;
-                                psm[d * NNP + j] = x * rmu;
+                                for (int e = 0; e < d; e++) x = fma(-(c[e] * sm.prmu[e]), sm.piv[e * DK3_FOLD + d], x);
                             }
+                            if (j == q) {
+                                sm.prmu[d] = dk_rcp(x);
+                                x = 0.0;
+                            } else {
+#pragma unroll
+                                for (int d2 = d + 1; d2 < DK3_FOLD; d2++)
+                                    if (d2 < nc && j == sm.clist[d2]) sm.piv[d * DK3_FOLD + d2] = x;
+                            }
+                            c[d] = x;
+                            named_bar_sync(1, 32 * QS);
                         }
-                        if (lane == 0) sm.prmu[d] = rmu;
-                        __syncwarp();
                     }
+#pragma unroll
+                    for (int d = 0; d < DK3_FOLD; d++)
+                        if (d < nc && j < NNP) {
+                            pcol[d * NNP + j] = c[d];
+                            psm[d * NNP + j] = c[d] * sm.prmu[d];
+                        }
                 }
                 __syncthreads();   // (F1) columns published
                 DK3_T(3);

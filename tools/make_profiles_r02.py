@@ -50,8 +50,8 @@ CAPTURES = [
      {"kernel": "dk_distribute_mma_kernel", "shape": "cells3000000_T720_S200"}),
     ("r02_dk_steady.ncu-rep", "dk_distribute_kernel (the ELL kernel the tensor-core kernel replaced on meshes), same launch",
      {"kernel": "dk_distribute_kernel", "shape": "cells3000000_T720_S200"}),
-    ("dk2_chain.ncu-rep", "dk_chain_kernel, the one-off DK weight build (64 x 1024 cells of the C4 basin, 200 stations) "
-                          "-- `python tools/dk_perf.py 64 1024 200`", None),
+    ("r02_dk_sets.ncu-rep", "dk_sets_kernel, the one-off DK weight build (64 x 1024 cells of the C4 basin, 200 stations) "
+                            "-- `python tools/dk_perf.py 64 1024 200`", None),
 ]
 
 
@@ -80,7 +80,7 @@ def launches(wl, md):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[mv].replace(",", ""))
-    steady = {k: v for k, v in agg.items() if not k.startswith(("dk_chain", "dk_build", "dk_final"))}
+    steady = {k: v for k, v in agg.items() if not k.startswith(("dk_chain", "dk_build", "dk_final", "dk_sets"))}
     tot = sum(v[1] for v in steady.values())
     md.append("\n### %s: `ncu --metrics gpu__time_duration.sum --clock-control none` around `python bench.py%s --steps 1 --warmup 3 "
               "--no-cpu-baseline --no-e2e --no-extras`\n" % (wl.upper(), "" if wl == "c4" else " --workload c5"))
