@@ -185,6 +185,14 @@ int smrfb_set_min_max(double* data, int64_t n, double vmin, double vmax, int dev
  * called at smrf/distribute/vapor_pressure.py:136-141): Brent root of sati(T) = e, result truncated to float, K -> C. */
 int smrfb_dew_point(const double* vp, int64_t n, double tol, double* dpt, int device);
 int smrfb_dew_point_dev(const double* d_vp, int64_t n, double tol, double* d_dpt, void* stream);
+
+/* Wet / ice bulb temperature (C) from air temperature (C), dew point (C) and elevation (m):
+ * replaces envphys_c.cwbt -> iwbt (smrf/envphys/core/envphys_c.pyx:103-139, iwbt.c:84-134).  Where the reference prints and calls
+ * exit(-1) -- a temperature below 0 K, no convergence within 10 Newton steps (iwbt.c:74-77, 123-126) -- the host form returns
+ * SMRFB_ERR_ARG / SMRFB_ERR_NODATA after filling tw; the device form ORs 2 / 1 into *d_flags (an int the caller zeroed). */
+int smrfb_wet_bulb(const double* ta, const double* td, const double* z, int64_t n, double tol, double* tw, int device);
+int smrfb_wet_bulb_dev(const double* d_ta, const double* d_td, const double* d_z, int64_t n, double tol, double* d_tw, int* d_flags,
+                       void* stream);
 /* Hook a consumer onto the NEXT host-buffer distribute calls of a handle (any method): kind 1 = the dew point of every
  * distributed value, computed while the sub-batch is still in the handle's device ring and copied to out2 ([T][ncell], same
  * element type as the primary output) -- the vapor-pressure grid crosses PCIe once and is never re-read from host memory.

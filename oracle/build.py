@@ -1,7 +1,7 @@
 """Build recipe for the CPU oracle (TEST INFRASTRUCTURE ONLY).
 
 * ``build_oracle()``  -> ``oracle/libkrige_oracle.so`` from ``oracle/krige_oracle.c`` (our restatement).
-* ``build_ref_envphys()`` -> ``oracle/_ref/libenvphys_ref.so`` from the reference's ``dewpt.c`` + ``topotherm.c`` in place.
+* ``build_ref_envphys()`` -> ``oracle/_ref/libenvphys_ref.so`` from the reference's ``dewpt.c`` + ``iwbt.c`` + ``topotherm.c`` in place.
 * ``build_ref()``     -> ``oracle/_ref/libkrige_ref.so`` compiled from the reference's own, unmodified
   ``krige.c / lusolv.c / array.c`` where they lie under ``/root/reference`` (never copied into the repo).
   Flags are the reference's (``setup.py:39-42``: ``-fopenmp -O3``).  Only possible in the build
@@ -58,8 +58,8 @@ def build_ref(force=False):
 
 
 def build_ref_envphys(force=False):
-    """Compile the reference's dewpt.c + topotherm.c (saturation curves) in place. Returns the .so path or None."""
-    srcs = [os.path.join(REF_ENV, f) for f in ("dewpt.c", "topotherm.c")]
+    """Compile the reference's dewpt.c + iwbt.c + topotherm.c (saturation curves) in place. Returns the .so path or None."""
+    srcs = [os.path.join(REF_ENV, f) for f in ("dewpt.c", "iwbt.c", "topotherm.c")]
     if not all(os.path.exists(s) for s in srcs):
         return REF_ENV_SO if os.path.exists(REF_ENV_SO) else None
     if not force and _newer(REF_ENV_SO, srcs):

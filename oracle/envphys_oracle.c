@@ -1,5 +1,5 @@
-/* envphys_oracle.c -- CPU restatement (TEST INFRASTRUCTURE ONLY) of the dew-point routine that consumes the distributed
- * vapor-pressure grid: smrf/envphys/core/dewpt.c:14-229 with the saturation curves of smrf/envphys/core/topotherm.c:109-176.
+/* envphys_oracle.c -- CPU restatement (TEST INFRASTRUCTURE ONLY) of the dew-point and wet-bulb routines that consume the
+ * distributed grids (wet bulb: smrf/envphys/core/iwbt.c:14-134, at the end of this file); dew point: smrf/envphys/core/dewpt.c:14-229 with the saturation curves of smrf/envphys/core/topotherm.c:109-176.
  * Restated, not copied: one state struct, iterative form; the arithmetic order of every expression follows the reference
  * so that the Brent iteration takes the same path.  Pinned against the reference C compiled in place
  * (oracle/_ref/libenvphys_ref.so, tests/test_oracle.py). */
@@ -102,4 +102,56 @@ void oracle_dew_point(long n, const double* ea, double tol, double* dpt) {
         v -= K_FREEZE;
         dpt[i] = v;
     }
+}
+
+/* iwbt.c:14-81: Newton iteration on the psychrometer equation, K in, K out; *bad where the reference calls exit(-1) */
+static double wet_bulb_k(double ta, double dpt, double press, double tol, int* bad) {
+    const double rh2o = 461.5, epsw = 18.0153 / 28.9644, cp_air = 1.005e3;
+    double xlh, xlhv, xlhf, ea, esat, psyc, step = 1.0, ti = ta, prev, dedt, pf, dpdt, mid = (ta + dpt) / 2.0;
+    int it = 0;
+    if (ta <= K_FREEZE) {
+        xlhv = 2.5e6 - 2.95573e3 * (mid - K_FREEZE);
+        xlhf = 3.336e5 + 1.6667e2 * (K_FREEZE - mid);
+        xlh = xlhv + xlhf;
+    } else if (dpt <= K_FREEZE) {
+        xlhv = 2.5e6 - 2.95573e3 * (mid - K_FREEZE);
+        xlhf = 3.336e5 + 1.6667e2 * (K_FREEZE - ((K_FREEZE + dpt) / 2.0));
+        xlh = xlhv + (((K_FREEZE - dpt) / (ta - dpt)) * xlhf);
+    } else {
+        xlh = 2.5e6 - 2.95573e3 * (((ta + dpt) / 2) - K_FREEZE);
+    }
+    ea = sat_ice(dpt);
+    esat = sat_ice(ta);
+    psyc = epsw * (xlh / (cp_air * press));
+    while (step > tol) {
+        prev = ti;
+        if (ti != ta) esat = sat_ice(ti);
+        dedt = xlh * (esat / (rh2o * (ti * ti)));
+        pf = (ti - ta) + (psyc * (esat - ea));
+        dpdt = 1.0 + (psyc * dedt);
+        ti = ti - (pf / dpdt);
+        step = prev - ti;
+        if (++it > 10) {
+            *bad |= 1;
+            break;
+        }
+    }
+    return ti;
+}
+
+/* iwbt.c:84-134; returns the flags (1: no convergence, 2: below 0 K) where the reference exits */
+int oracle_wet_bulb(long n, const double* ta, const double* td, const double* z, double tol, double* tw) {
+    long i;
+    int bad = 0;
+    for (i = 0; i < n; i++) {
+        double pa = P_SEA, tak = ta[i] + K_FREEZE, tdk = td[i] + K_FREEZE;
+        if (z[i] != 0.0) pa = P_SEA * pow(2.88e2 / (2.88e2 + -6.5 * (z[i] / 1000.0)), 9.80665 * 28.9644 / (8.31432e3 * -6.5 * 1.e-3));
+        if (tak < 0 || tdk < 0) {
+            bad |= 2;
+            tw[i] = NAN;
+            continue;
+        }
+        tw[i] = wet_bulb_k(tak, tdk, pa, tol, &bad) - K_FREEZE;
+    }
+    return bad;
 }

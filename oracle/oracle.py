@@ -583,6 +583,34 @@ def dew_point(vp, tol=0.01, impl="oracle"):
     return out
 
 
+def wet_bulb(ta, td, z, tol=0.01, impl="oracle"):
+    """Wet / ice bulb temperature (degC) from air temperature, dew point (degC) and elevation (m): impl='oracle' ->
+    oracle/envphys_oracle.c (restatement of iwbt.c:14-134), impl='ref' -> the reference's own iwbt.c compiled in place.  Inputs
+    for which the reference would exit(-1) (below 0 K, no convergence) must not be given to impl='ref'."""
+    ta, td, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (ta, td, z))
+    out = np.empty_like(ta)
+    dp = ctypes.POINTER(ctypes.c_double)
+    if impl == "ref":
+        path = os.path.join(_HERE, "_ref", "libenvphys_ref.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libenvphys_ref.so is missing (python oracle/build.py in the build container)")
+        L = _load(path)
+        L.iwbt.restype = None
+        L.iwbt.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_int, ctypes.c_double, dp]
+        L.iwbt(int(ta.size), _dptr(ta.reshape(-1)), _dptr(td.reshape(-1)), _dptr(z.reshape(-1)), 1, float(tol), _dptr(out.reshape(-1)))   # iwbt.c:84-91
+        return out
+    path = os.path.join(_HERE, "libenvphys_oracle.so")
+    from . import build
+    build.build_oracle()
+    L = _load(path)
+    L.oracle_wet_bulb.restype = ctypes.c_int
+    L.oracle_wet_bulb.argtypes = [ctypes.c_long, dp, dp, dp, ctypes.c_double, dp]
+    bad = L.oracle_wet_bulb(int(ta.size), _dptr(ta.reshape(-1)), _dptr(td.reshape(-1)), _dptr(z.reshape(-1)), float(tol), _dptr(out.reshape(-1)))
+    if bad:
+        raise RuntimeError("wet bulb: the reference would exit here (flags %d: 1 = no convergence in 10 steps, 2 = below 0 K)" % bad)
+    return out
+
+
 def dew_point_adjust(dpt, ta):
     """vapor_pressure.py:143-147: the dew point may not exceed the air temperature."""
     dpt = dpt.copy()

@@ -81,6 +81,9 @@ _SIGS = {
                                                        ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_dew_point": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, c_double_p, ctypes.c_int]),
     "smrfb_dew_point_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_wet_bulb": (ctypes.c_int, [c_double_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_double, c_double_p, ctypes.c_int]),
+    "smrfb_wet_bulb_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_set_consumer": (ctypes.c_int, [handle_t, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
     "smrfb_wind_direction": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int]),
     "smrfb_wind_direction_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),

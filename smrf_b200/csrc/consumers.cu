@@ -3,6 +3,8 @@
 //   * dew point from vapor pressure: smrf/envphys/core/dewpt.c:14-229 (Brent root of sati(T) = e, float-truncated result,
 //     K -> C) with the saturation curves of topotherm.c:109-176 -- either as a consumer hooked onto a distribute call
 //     (the vapor-pressure block is still in the handle's device ring: no second trip through host memory) or stand-alone;
+//   * wet / ice bulb temperature from air and dew point temperature: smrf/envphys/core/iwbt.c:14-134 (Newton iteration on the
+//     psychrometer equation, at most 10 steps), what precipitation.py uses as the precipitation temperature;
 //   * wind azimuth from the two distributed direction components: smrf/distribute/wind/wind.py:175-178;
 //   * grid_interpolate with the vertices / weights of interp_weights: smrf/utils/utils.py:377-427.
 #include "common.cuh"
@@ -127,6 +129,66 @@ int launch_dew_point(cudaStream_t st, const void* d_ea, int in_f32, long long n,
     return SMRFB_OK;
 }
 
+// iwbt.c:14-81 wetbulb(ta, dpt, press, tol), temperatures in K; *bad is set where the reference would exit(-1)
+__device__ double env_wetbulb(double ta, double dpt, double press, double tol, int* bad) {
+    const double RH2O = 461.5, EPSW = 18.0153 / 28.9644, CP_AIR = 1.005e3;      // iwbt.c:11-12, envphys.h:16,21,37
+    auto lh_vap = [](double t) { return 2.5e6 - 2.95573e3 * (t - ENV_FREEZE); };   // envphys.h:281
+    auto lh_fus = [](double t) { return 3.336e5 + 1.6667e2 * (ENV_FREEZE - t); };   // envphys.h:288
+    double xlh;
+    if (ta <= ENV_FREEZE) {
+        xlh = lh_vap((ta + dpt) / 2.0) + lh_fus((ta + dpt) / 2.0);
+    } else if (dpt <= ENV_FREEZE) {
+        const double xlhv = lh_vap((ta + dpt) / 2.0), xlhf = lh_fus((ENV_FREEZE + dpt) / 2.0);
+        const double fu_fac = (ENV_FREEZE - dpt) / (ta - dpt);
+        xlh = xlhv + (fu_fac * xlhf);
+    } else {
+        xlh = lh_vap((ta + dpt) / 2);
+    }
+    const double ea = env_sati(dpt);
+    double esat = env_sati(ta);
+    const double psyc = EPSW * (xlh / (CP_AIR * press));
+    double dti = 1.0, ti = ta;
+    int i = 0;
+    while (dti > tol) {
+        const double ti0 = ti;
+        if (ti != ta) esat = env_sati(ti);
+        const double dedt = xlh * (esat / (RH2O * (ti * ti)));
+        const double pf = (ti - ta) + (psyc * (esat - ea));
+        const double dpdt = 1.0 + (psyc * dedt);
+        ti = ti - (pf / dpdt);
+        dti = ti0 - ti;
+        i++;
+        if (i > 10) {          // iwbt.c:74-77: "failure to converge in 10 iterations", exit(-1)
+            *bad = 1;
+            break;
+        }
+    }
+    return ti;
+}
+
+// iwbt.c:84-134: per cell, pressure from the elevation (hydrostatic, standard atmosphere), C -> K, wetbulb, K -> C
+__global__ void wet_bulb_kernel(const double* __restrict__ ta, const double* __restrict__ td, const double* __restrict__ z, long long n,
+                                double tol, double* __restrict__ tw, int* __restrict__ flags) {
+    const double RGAS = 8.31432e3, STD_AIRTMP = 2.88e2, STD_LAPSE = -6.5, GRAVITY = 9.80665, MOL_AIR = 28.9644;   // envphys.h
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double zp = z[i];
+        double pa = ENV_SEA_LEVEL;
+        if (zp != 0.0)   // HYSTAT(SEA_LEVEL, STD_AIRTMP, STD_LAPSE, z / 1000, GRAVITY, MOL_AIR), envphys.h:205-207
+            pa = ENV_SEA_LEVEL * pow(STD_AIRTMP / (STD_AIRTMP + STD_LAPSE * (zp / 1000.0)), GRAVITY * MOL_AIR / (RGAS * STD_LAPSE * 1.e-3));
+        const double tak = ta[i] + ENV_FREEZE, tdk = td[i] + ENV_FREEZE;
+        int bad = 0;
+        double v;
+        if (tak < 0 || tdk < 0) {          // iwbt.c:123-126: "ta or td < 0", exit(-1)
+            bad = 2;
+            v = nan("");
+        } else {
+            v = env_wetbulb(tak, tdk, pa, tol, &bad) - ENV_FREEZE;
+        }
+        if (bad) atomicOr(flags, bad);
+        __stcs(tw + i, v);
+    }
+}
+
 // wind.py:175-178: az = arctan2(u, v) * 180 / pi; az[az < 0] += 360
 __global__ void wind_direction_kernel(const double* __restrict__ u, const double* __restrict__ v, long long n, double* __restrict__ out) {
     const double pi = 3.141592653589793;
@@ -201,6 +263,59 @@ int smrfb_dew_point(const double* vp, int64_t n, double tol, double* dpt, int de
 int smrfb_dew_point_dev(const double* d_vp, int64_t n, double tol, double* d_dpt, void* stream) {
     SMRFB_CHECK(d_vp && d_dpt && n >= 0, SMRFB_ERR_ARG, "NULL vapor pressure / output");
     return launch_dew_point((cudaStream_t)stream, d_vp, 0, (long long)n, tol, d_dpt, 0);
+}
+
+static int launch_wet_bulb(cudaStream_t st, const double* d_ta, const double* d_td, const double* d_z, long long n, double tol, double* d_tw,
+                           int* d_flags) {
+    if (n <= 0) return SMRFB_OK;
+    const int threads = 256;
+    const long long blocks = std::min<long long>((n + threads - 1) / threads, 148LL * 32);
+    wet_bulb_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_ta, d_td, d_z, n, tol, d_tw, d_flags);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
+int smrfb_wet_bulb(const double* ta, const double* td, const double* z, int64_t n, double tol, double* tw, int device) {
+    SMRFB_CHECK(ta && td && z && tw && n >= 0, SMRFB_ERR_ARG, "NULL air temperature / dew point / elevation / output");
+    SMRFB_CHECK(tol > 0, SMRFB_ERR_ARG, "wet bulb: the tolerance must be positive (the reference iterates while the step exceeds it)");
+    SMRFB_CUDA(cudaSetDevice(device));
+    if (n == 0) return SMRFB_OK;
+    const size_t cap = std::min<size_t>((size_t)n, (size_t)1 << 25);
+    double* d = nullptr;
+    int* d_flags = nullptr;
+    SMRFB_CUDA(cudaMalloc((void**)&d, 4 * cap * sizeof(double)));
+    if (cudaMalloc((void**)&d_flags, sizeof(int)) != cudaSuccess) {
+        cudaFree(d);
+        set_error("cudaMalloc failed");
+        return SMRFB_ERR_CUDA;
+    }
+    cudaMemset(d_flags, 0, sizeof(int));
+    int rc = SMRFB_OK, flags = 0;
+    for (size_t o = 0; o < (size_t)n && rc == SMRFB_OK; o += cap) {
+        const size_t m = std::min(cap, (size_t)n - o);
+        if (cudaMemcpy(d, ta + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d + cap, td + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d + 2 * cap, z + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = SMRFB_ERR_CUDA;
+        if (rc == SMRFB_OK) rc = launch_wet_bulb(nullptr, d, d + cap, d + 2 * cap, (long long)m, tol, d + 3 * cap, d_flags);
+        if (rc == SMRFB_OK && cudaMemcpy(tw + o, d + 3 * cap, m * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SMRFB_ERR_CUDA;
+    }
+    if (rc == SMRFB_OK && cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SMRFB_ERR_CUDA;
+    if (rc == SMRFB_ERR_CUDA) set_error("wet bulb: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    cudaFree(d_flags);
+    // where the reference prints and calls exit(-1) (iwbt.c:74-77, 123-126) this returns an error; tw is filled regardless
+    SMRFB_CHECK(rc != SMRFB_OK || !(flags & 2), SMRFB_ERR_ARG, "wet bulb: ta or td below 0 K at some cell");
+    SMRFB_CHECK(rc != SMRFB_OK || !(flags & 1), SMRFB_ERR_NODATA, "wet bulb: failure to converge in 10 iterations at some cell");
+    return rc;
+}
+
+int smrfb_wet_bulb_dev(const double* d_ta, const double* d_td, const double* d_z, int64_t n, double tol, double* d_tw, int* d_flags,
+                       void* stream) {
+    SMRFB_CHECK(d_ta && d_td && d_z && d_tw && d_flags && n >= 0, SMRFB_ERR_ARG, "NULL air temperature / dew point / elevation / output / flags");
+    SMRFB_CHECK(tol > 0, SMRFB_ERR_ARG, "wet bulb: the tolerance must be positive");
+    return launch_wet_bulb((cudaStream_t)stream, d_ta, d_td, d_z, (long long)n, tol, d_tw, d_flags);
 }
 
 int smrfb_set_consumer(smrfb_handle_t hh, int kind, double tol, void* out2) {

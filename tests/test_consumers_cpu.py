@@ -20,6 +20,25 @@ def test_dew_point_oracle_matches_reference_golden(golden):
     assert abs(d[0]) < 0.2                                    # ~0 degC at the triple-point pressure
 
 
+def test_wet_bulb_oracle_matches_reference_golden(golden):
+    """oracle/envphys_oracle.c (restatement of iwbt.c:14-134) against vectors produced by the reference's iwbt.c itself."""
+    from oracle import oracle as orc
+    g = golden("wetbulb")
+    for tol in (0.01, 0.05):
+        np.testing.assert_array_equal(orc.wet_bulb(g["ta"], g["td"], g["z"], tol), g["tw_tol%g" % tol])      # bit for bit
+    ref_so = os.path.join(os.path.dirname(orc.__file__), "_ref", "libenvphys_ref.so")
+    if os.path.exists(ref_so):
+        rng = np.random.default_rng(8)
+        ta = rng.uniform(-30.0, 30.0, 20000)
+        td = ta - rng.gamma(1.5, 4.0, 20000)
+        z = rng.uniform(0.0, 4000.0, 20000)
+        np.testing.assert_array_equal(orc.wet_bulb(ta, td, z, 0.01), orc.wet_bulb(ta, td, z, 0.01, impl="ref"))
+    tw = orc.wet_bulb(np.array([10.0, -5.0]), np.array([10.0, -9.0]), np.array([0.0, 2000.0]), 0.001)
+    assert abs(tw[0] - 10.0) < 1e-6 and -9.0 < tw[1] < -5.0         # saturated air: wet bulb = air temperature; else in between
+    with pytest.raises(RuntimeError):
+        orc.wet_bulb(np.array([-300.0]), np.array([-300.0]), np.array([0.0]), 0.01)     # below 0 K: the reference exits
+
+
 def test_wind_direction_and_weights_oracle():
     from oracle import oracle as orc
     az = orc.wind_direction(np.array([0.0, 1.0, 0.0, -1.0, -0.5]), np.array([1.0, 0.0, -1.0, 0.0, 0.5]))

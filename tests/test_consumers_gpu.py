@@ -46,6 +46,29 @@ def test_dew_point_standalone_and_golden(gpu, golden):
     _dew_close(dpt, orc.dew_point(vp, 0.01), 0.01)
 
 
+def test_wet_bulb_standalone_and_golden(gpu, golden):
+    """smrfb_wet_bulb (envphys_c.cwbt, iwbt.c:84-134) against the reference-generated vectors: the device's pow / log differ from
+    glibc's in the last bit, so the iterates agree to ~1e-12; a borderline `step > tol` test may add or drop one Newton step,
+    which moves the result by less than the routine's tolerance."""
+    from smrf_b200 import envphys_c
+    from smrf_b200._lib import SmrfbError
+    g = golden("wetbulb")
+    for tol in (0.01, 0.05):
+        tw = np.zeros_like(g["ta"])
+        envphys_c.cwbt(g["ta"], g["td"], g["z"], tw, tol, 4)
+        d = np.abs(tw - g["tw_tol%g" % tol])
+        assert np.mean(d <= 1e-9) >= 0.999, np.mean(d <= 1e-9)
+        assert d.max() <= tol, d.max()
+    ta = np.random.default_rng(2).uniform(-20.0, 25.0, (31, 47))
+    tw = np.empty_like(ta)
+    envphys_c.cwbt(ta, ta - 3.0, np.full_like(ta, 1800.0), tw, 0.01)
+    assert np.all(tw <= ta + 1e-9) and np.all(tw >= ta - 3.0 - 1e-9)
+    with pytest.raises(SmrfbError):                               # below 0 K: the reference prints and exits
+        envphys_c.cwbt(np.array([-300.0]), np.array([-300.0]), np.array([0.0]), np.empty(1), 0.01)
+    with pytest.raises(SmrfbError):                               # tolerance 0 can only end in the reference's exit(-1)
+        envphys_c.cwbt(np.array([5.0]), np.array([1.0]), np.array([0.0]), np.empty(1), 0.0)
+
+
 def test_dew_point_consumer_on_idw_dk_grid(gpu):
     from oracle import oracle as orc
     from smrf_b200 import synthetic as syn
