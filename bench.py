@@ -418,6 +418,7 @@ def main():
             _lib.check(L.smrfb_dk_distribute_window_dev(h, d_rows[f.name].data_ptr(), _lib.dptr(rows[f.name]), Tb, lo, hi,
                                                         None, None, cbeg, ccnt, d_out.data_ptr(), st))
         elif f.opts.get("grid_local"):
+            _lib.check(L.smrfb_grid_set_local_exact(h, 0))       # block path: closed-form fits, folded + fused interpolation
             _lib.check(L.smrfb_grid_distribute_local_dev(h, d_rows[f.name].data_ptr(), Tb, lo, hi, d_out.data_ptr(), st))
         else:
             _lib.check(L.smrfb_grid_distribute_dev(h, d_rows[f.name].data_ptr(), Tb, int(f.detrend), f.slope, 0, lo, hi,

@@ -153,6 +153,10 @@ int smrfb_grid_distribute_dev(smrfb_handle_t h, const double* d_data, int T, int
  * residual, the slope and the intercept of the per-point local fits (grid.py:125-141,164-166; computed by the
  * caller, smrf_b200/spatial/grid.py); out[t] = interp(residual) + interp(slope) * GridZ + interp(intercept), each
  * interpolation as griddata / LinearNDInterpolator evaluates it (utils.py:430-449), NaN outside the hull. */
+/* grid_local arithmetic: exact = 1 (default) evaluates the three interpolations in scipy.interpolate.griddata's operation order
+ * (bit-identical to grid.py:143-175 given the same per-point fits); exact = 0 folds residual + intercept into one field and uses
+ * fused multiply-adds -- a few ulp away, 1.7 x faster; what a block caller with its own (closed-form) fits wants. */
+int smrfb_grid_set_local_exact(smrfb_handle_t h, int exact);
 int smrfb_grid_distribute_local(smrfb_handle_t h, const double* fields3, int T, double vmin, double vmax, double* out);
 int smrfb_grid_distribute_local_dev(smrfb_handle_t h, const double* d_fields3, int T, double vmin, double vmax,
                                     double* d_out, void* stream);

@@ -70,6 +70,7 @@ _SIGS = {
     "smrfb_grid_distribute_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_grid_set_local_exact": (ctypes.c_int, [handle_t, ctypes.c_int]),
     "smrfb_grid_distribute_local": (ctypes.c_int, [handle_t, c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                                    c_double_p]),
     "smrfb_grid_distribute_local_dev": (ctypes.c_int, [handle_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,

@@ -34,6 +34,7 @@ struct GridHandle : HandleBase {
     double* d_l4 = nullptr;            // grid_local: [T][4][S] residual, slope, intercept, 0 per step
     size_t l4_cap = 0;
     double* d_l3 = nullptr;            // grid_local: staging of the caller's [T][3][S] block
+    int local_exact = 1;               // grid_local: 1 = griddata's operation order, bit for bit; 0 = folded + fused (smrfb_grid_set_local_exact)
     size_t l3_cap = 0;
     double* d_ctgeo = nullptr;         // cubic: [nsimp][9] edge vectors e12, e23, e31 and cross-edge coefficients g
     double* d_ctw = nullptr;           // cubic: [9][ncell] Clough-Tocher patch weights of every cell
@@ -291,19 +292,85 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_local2_kernel(GridArgs a) {
         store_out2(a.out, (size_t)t * ncell + c, grid_local_value(g0, t, a.vmin, a.vmax), grid_local_value(g1, t, a.vmin, a.vmax), f32);
 }
 
+// ---- grid_local, folded form (smrfb_grid_set_local_exact(h, 0); what the block path uses with its closed-form fits, which are
+// not the reference's bit for bit either).  ncu on grid_local2_kernel: L1 wavefronts 98 % of peak (nine 8-byte vertex values per
+// cell-step: 18 wavefronts per 32 outputs), fp64 pipe 41 %.  Interpolation is linear, so
+//     out = interp(residual) + interp(slope) Z + interp(intercept) = interp(residual + intercept) + Z interp(slope):
+// two fields per vertex (ONE 128-bit load) instead of three, and with fused multiply-adds 7 fp64 instructions per output
+// instead of 24.  The result differs from the three-interpolation order by a few ulp of the largest term (contract 1e-9).
+// l2[2 t + f][s]: f = 0 residual + intercept, f = 1 slope
+__global__ void grid_local_fold_kernel(const double* __restrict__ f3, int T, int S, double* __restrict__ l2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)T * S) return;
+    const int t = (int)(i / S), s = (int)(i - (long long)t * S);
+    const double* p = f3 + (size_t)t * 3 * S;
+    l2[(size_t)(2 * t) * S + s] = p[s] + p[2 * (size_t)S + s];
+    l2[(size_t)(2 * t + 1) * S + s] = p[(size_t)S + s];
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(GRID_THREADS) grid_local_fold2_kernel(GridArgs a) {    // two adjacent cells per thread
+    const long long c = ((long long)blockIdx.x * GRID_THREADS + threadIdx.x) * 2;
+    if (c >= a.g.ncell) return;                       // ncell is even: c + 1 is a valid cell too
+    const GridLocalCell g0 = grid_local_setup(a, c), g1 = grid_local_setup(a, c + 1);    // va / vb / vc: rows of vt, here [2 t + f]
+    const size_t ncell = (size_t)a.g.ncell;
+    OutT* op = reinterpret_cast<OutT*>(a.out) + c;
+    const double qnan = nan("");
+#pragma unroll 2
+    for (int t = 0; t < a.T; t++, op += ncell) {
+        const double2 a0 = __ldg(reinterpret_cast<const double2*>(g0.va + 2 * t));
+        const double2 b0 = __ldg(reinterpret_cast<const double2*>(g0.vb + 2 * t));
+        const double2 c0 = __ldg(reinterpret_cast<const double2*>(g0.vc + 2 * t));
+        const double2 a1 = __ldg(reinterpret_cast<const double2*>(g1.va + 2 * t));
+        const double2 b1 = __ldg(reinterpret_cast<const double2*>(g1.vb + 2 * t));
+        const double2 c1 = __ldg(reinterpret_cast<const double2*>(g1.vc + 2 * t));
+        const double r0 = fma(g0.c2, c0.x, fma(g0.c1, b0.x, g0.c0 * a0.x)), s0 = fma(g0.c2, c0.y, fma(g0.c1, b0.y, g0.c0 * a0.y));
+        const double r1 = fma(g1.c2, c1.x, fma(g1.c1, b1.x, g1.c0 * a1.x)), s1 = fma(g1.c2, c1.y, fma(g1.c1, b1.y, g1.c0 * a1.y));
+        const double v0 = g0.inside ? clamp_nan_keep(fma(s0, g0.Z, r0), a.vmin, a.vmax) : qnan;
+        const double v1 = g1.inside ? clamp_nan_keep(fma(s1, g1.Z, r1), a.vmin, a.vmax) : qnan;
+        if constexpr (sizeof(OutT) == 4) __stcs(reinterpret_cast<float2*>(op), make_float2((float)v0, (float)v1));
+        else __stcs(reinterpret_cast<double2*>(op), make_double2(v0, v1));
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(GRID_THREADS) grid_local_fold1_kernel(GridArgs a) {    // one cell per thread (odd cell counts)
+    const long long c = (long long)blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (c >= a.g.ncell) return;
+    const GridLocalCell g = grid_local_setup(a, c);
+    const size_t ncell = (size_t)a.g.ncell;
+    OutT* op = reinterpret_cast<OutT*>(a.out) + c;
+    for (int t = 0; t < a.T; t++, op += ncell) {
+        const double2 a0 = __ldg(reinterpret_cast<const double2*>(g.va + 2 * t));
+        const double2 b0 = __ldg(reinterpret_cast<const double2*>(g.vb + 2 * t));
+        const double2 c0 = __ldg(reinterpret_cast<const double2*>(g.vc + 2 * t));
+        const double r = fma(g.c2, c0.x, fma(g.c1, b0.x, g.c0 * a0.x)), sl = fma(g.c2, c0.y, fma(g.c1, b0.y, g.c0 * a0.y));
+        const double v = g.inside ? clamp_nan_keep(fma(sl, g.Z, r), a.vmin, a.vmax) : nan("");
+        __stcs(op, (OutT)v);
+    }
+}
+
 // d_f3: [T][3][S] on the device (residual, slope, intercept rows per step)
 static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin, double vmax, double* d_out, cudaStream_t st) {
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
     SMRFB_CHECK(h->g.dem, SMRFB_ERR_ARG, "grid_local needs GridZ");
     const size_t S = (size_t)h->S;
-    const int R = 4 * T, R_pad = (R + 31) / 32 * 32;
+    const bool fold = !h->local_exact;
+    const int R = (fold ? 2 : 4) * T, R_pad = (R + 31) / 32 * 32;
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_l4, &h->l4_cap, (size_t)R * S * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_rec, &h->rec_cap, (size_t)R_pad * h->L.RS * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_vt, &h->vt_cap, (size_t)R_pad * S * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&h->d_pvt, &h->pvt_cap, (size_t)R_pad * 2 * sizeof(double)));
-    SMRFB_CUDA(cudaMemsetAsync(h->d_l4, 0, (size_t)R * S * sizeof(double), st));
-    SMRFB_CUDA(cudaMemcpy2DAsync(h->d_l4, 4 * S * sizeof(double), d_f3, 3 * S * sizeof(double), 3 * S * sizeof(double), (size_t)T,
-                                 cudaMemcpyDeviceToDevice, st));
+    if (fold) {
+        const long long ne = (long long)T * (long long)S;
+        grid_local_fold_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(d_f3, T, (int)S, h->d_l4);
+        count_launch();
+        SMRFB_CUDA(cudaGetLastError());
+    } else {
+        SMRFB_CUDA(cudaMemsetAsync(h->d_l4, 0, (size_t)R * S * sizeof(double), st));
+        SMRFB_CUDA(cudaMemcpy2DAsync(h->d_l4, 4 * S * sizeof(double), d_f3, 3 * S * sizeof(double), 3 * S * sizeof(double), (size_t)T,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
     SMRFB_PROPAGATE(launch_prep(st, h->d_l4, R, R_pad, h->S, h->L, nullptr, nullptr, 0, 0, nullptr, nullptr, h->d_rec, nullptr,
                                 h->d_flags));
     dim3 tb(32, 8), tg((h->S + 31) / 32, R_pad / 32);
@@ -327,7 +394,16 @@ static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin,
     a.out_f32 = h->out_f32;
     const long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
-    if ((h->g.ncell & 1) == 0 && !getenv("SMRFB_GRID_ONE_CELL")) {
+    if (fold) {
+        const long long nb2 = (h->g.ncell / 2 + GRID_THREADS - 1) / GRID_THREADS;
+        if ((h->g.ncell & 1) == 0) {
+            if (h->out_f32) grid_local_fold2_kernel<float><<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
+            else grid_local_fold2_kernel<double><<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
+        } else {
+            if (h->out_f32) grid_local_fold1_kernel<float><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+            else grid_local_fold1_kernel<double><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+        }
+    } else if ((h->g.ncell & 1) == 0 && !getenv("SMRFB_GRID_ONE_CELL")) {
         const long long nb2 = (h->g.ncell / 2 + GRID_THREADS - 1) / GRID_THREADS;
         grid_local2_kernel<<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
     } else
@@ -694,6 +770,14 @@ int smrfb_grid_distribute_dev(smrfb_handle_t hh, const double* d_data, int T, in
     SMRFB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return grid_run(h, d_data, T, detrend, slope_flag, method, vmin, vmax, d_pv_in, d_pv_out, d_out, st);
+}
+
+int smrfb_grid_set_local_exact(smrfb_handle_t hh, int exact) {
+    SMRFB_CHECK(hh, SMRFB_ERR_ARG, "NULL handle");
+    GridHandle* h = reinterpret_cast<GridHandle*>(hh);
+    SMRFB_CHECK(h->kind == HK_GRID, SMRFB_ERR_ARG, "not a GRID handle");
+    h->local_exact = exact ? 1 : 0;
+    return SMRFB_OK;
 }
 
 int smrfb_grid_distribute_local_dev(smrfb_handle_t hh, const double* d_fields3, int T, double vmin, double vmax, double* d_out,

@@ -278,6 +278,9 @@ class GRID(_lib.HandleMixin):
         out = _lib.out_array(T, self.shape, out, f32)
         lo = -np.inf if vmin is None else float(vmin)
         hi = np.inf if vmax is None else float(vmax)
+        # exact fits (np.polyfit per point, the per-step reference path) keep griddata's operation order bit for bit; the
+        # vectorised closed-form fits of the block path differ from polyfit in the last digits anyway: folded, fused kernel
+        _lib.check(_lib.lib().smrfb_grid_set_local_exact(self._h, 1 if exact else 0))
         _lib.check(_lib.lib().smrfb_grid_distribute_local(self._h, _lib.dptr(f3), T, lo, hi, _lib.vptr(out)))
         return out
 

@@ -1,5 +1,5 @@
 """Device-resident timing of the GRID-linear kernel on the C5 shape (development aid)."""
-import sys, time
+import os, sys, time
 import numpy as np
 import torch
 sys.path.insert(0, ".")
@@ -43,6 +43,7 @@ t0 = time.perf_counter()
 res, slope, icpt = gl.local_fit(f, flag=-1, exact=False)
 print("local fits of %d steps x %d points (closed form, host): %.3f s" % (T, len(px), time.perf_counter() - t0))
 d_f3 = torch.from_numpy(np.ascontiguousarray(np.stack([res, slope, icpt], axis=1))).cuda()
+_lib.check(L.smrfb_grid_set_local_exact(gl._h, int(os.environ.get('GRID_LOCAL_EXACT', '0'))))
 for _ in range(2):
     _lib.check(L.smrfb_grid_distribute_local_dev(gl._h, d_f3.data_ptr(), T, -50.0, 50.0, d_out.data_ptr(), st))
 torch.cuda.synchronize()
