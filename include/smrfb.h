@@ -197,6 +197,15 @@ int smrfb_dew_point_dev(const double* d_vp, int64_t n, double tol, double* d_dpt
 int smrfb_wet_bulb(const double* ta, const double* td, const double* z, int64_t n, double tol, double* tw, int device);
 int smrfb_wet_bulb_dev(const double* d_ta, const double* d_td, const double* d_z, int64_t n, double tol, double* d_tw, int* d_flags,
                        void* stream);
+/* Precipitation phase and new-snow density from the precipitation temperature (the distributed dew point, C) and the distributed
+ * precipitation (mm; the storm total for marks2017): replaces Snow.phase_and_density (smrf/envphys/snow.py:37-75, called at
+ * smrf/distribute/precipitation.py:376-379, 428-431) with the models of smrf/envphys/nasde_model/: model 0 = susong1999
+ * (susong_1999.py:29-116), 1 = piecewise_susong1999 (piecewise_suosong_1999.py:42-87), 2 = marks2017 (marks_2017.py:73-207).
+ * pcs = fraction of the precipitation that is snow (0..1), rho_s = density of the new snow (kg/m^3).  The device form takes an int
+ * of scratch the caller zeroed (marks2017 first asks whether any cell has precipitation). */
+int smrfb_snow_phase(const double* tpp, const double* pp, int64_t n, int model, double* pcs, double* rho_s, int device);
+int smrfb_snow_phase_dev(const double* d_tpp, const double* d_pp, int64_t n, int model, double* d_pcs, double* d_rho_s, int* d_any,
+                         void* stream);
 /* Hook a consumer onto the NEXT host-buffer distribute calls of a handle (any method): kind 1 = the dew point of every
  * distributed value, computed while the sub-batch is still in the handle's device ring and copied to out2 ([T][ncell], same
  * element type as the primary output) -- the vapor-pressure grid crosses PCIe once and is never re-read from host memory.

@@ -620,6 +620,71 @@ def dew_point_adjust(dpt, ta):
     return dpt
 
 
+def snow_phase_and_density(temperature, precipitation, nasde_model):
+    """envphys/snow.py:37-75 Snow.phase_and_density -> (snow_density, percent_snow) of the three new-accumulated-snow-density
+    models: 'susong1999' (nasde_model/susong_1999.py:29-116, a 7-row table of the precipitation temperature),
+    'piecewise_susong1999' (piecewise_suosong_1999.py:42-87 with utils.py:12-71) and 'marks2017' (marks_2017.py:73-207:
+    compaction by overburden and metamorphism where there is snow water equivalent).  The inputs are copied, as the
+    reference's np.array() does (the models clip the temperature in place)."""
+    pp = np.array(precipitation, dtype=float)
+    t = np.array(temperature, dtype=float)
+    if nasde_model == "susong1999":
+        ps = np.zeros(pp.shape)
+        sd = np.zeros(pp.shape)
+        if np.sum(pp) == 0:                                         # susong_1999.py:96-97
+            return sd, ps
+        rows = [(-np.inf, -5, 1, 75), (-5, -3, 1, 100), (-3, -1.5, 1, 150), (-1.5, -0.5, 1, 175), (-0.5, 0.0, 0.75, 200),
+                (0.0, 0.5, 0.25, 250), (0.5, np.inf, 0, 0)]          # susong_1999.py:29-72; 1e309 is inf
+        for lo, hi, snow, den in rows:
+            ind = (t >= lo) & (t < hi)
+            ps[ind] = snow
+            sd[ind] = den
+        ps[pp == 0] = 0                                             # susong_1999.py:111-112
+        sd[pp == 0] = 0
+        return sd, ps
+    if nasde_model not in ("piecewise_susong1999", "marks2017"):
+        raise ValueError("%s is not an implemented new accumulated snow density (NASDE) model" % nasde_model)
+
+    def piecewise(tpp):                                             # check_temperature + calc_percent_snow + density
+        tpp[tpp < -10.0] = -10.0                                    # utils.py:67-70 (t_min = -10, t_max = 0)
+        tsnow = tpp.copy()
+        tsnow[tpp > 0.0] = 0.0
+        pcs = np.zeros(tpp.shape)                                   # utils.py:25-37
+        pcs[tpp <= -0.5] = 1.0
+        ind = (tpp > -0.5) & (tpp <= 0.0)
+        pcs[ind] = (-tpp[ind] / 0.5) * 0.25 + 0.75
+        ind = (tpp > 0.0) & (tpp <= 0.0 + 1.0)
+        pcs[ind] = (-tpp[ind] / (0.0 + 1.0)) * 0.75 + 0.75
+        t_range = 0.0 - -10.0                                       # piecewise_suosong_1999.py:74-83
+        ex = 1.0 + (((t_range + (tsnow - 0.0)) / t_range) * 0.75)
+        ex[ex > 1.75] = 1.75
+        rho_ns = 50.0 + (1.7 * ((tpp - 0.0) + 15.0) ** ex)
+        return pcs, rho_ns, tsnow
+
+    if nasde_model == "piecewise_susong1999":
+        pcs, rho_ns, _ = piecewise(t)
+        return rho_ns, pcs
+    # marks2017: rho_ns, d_rho_m, d_rho_c, zs and rho_s are ONE array in the reference (the chained assignment of
+    # marks_2017.py:113-115), so the last write -- rho_s -- is what 'rho_s' returns: 0 where there is no snow water equivalent
+    rho_s = np.zeros(t.shape)
+    pcs = np.zeros(t.shape)
+    if np.any(pp > 0):                                              # marks_2017.py:118
+        pcs, rho_orig, tsnow = piecewise(t)
+        swe = pp * pcs
+        i = swe > 0.0
+        if np.any(i):
+            s_tsnow = tsnow[i]
+            s_swe = swe[i]
+            s_rho_ns = rho_orig[i] / 1000.0
+            d_rho_c = (0.026 * np.exp(-0.08 * (0.0 - s_tsnow)) * s_swe * np.exp(-21.0 * s_rho_ns))      # :149-150
+            ind = (s_rho_ns * 1000.0) >= 100.0
+            c11 = np.ones(s_rho_ns.shape)
+            c11[ind] = np.exp(-0.046 * (s_rho_ns[ind] * 1000.0 - 100.0))                                 # :155
+            d_rho_m = 0.01 * c11 * np.exp(-0.04 * (0.0 - s_tsnow))                                       # :157-159
+            rho_s[i] = s_rho_ns + ((d_rho_c + d_rho_m) * s_rho_ns)                                       # :162
+    return rho_s * 1000.0, pcs
+
+
 def wind_direction(u, v):
     """wind.py:175-178."""
     az = np.arctan2(u, v) * 180 / np.pi

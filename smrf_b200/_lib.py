@@ -82,6 +82,9 @@ _SIGS = {
                                                        ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_dew_point": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, c_double_p, ctypes.c_int]),
     "smrfb_dew_point_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "smrfb_snow_phase": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int]),
+    "smrfb_snow_phase_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "smrfb_wet_bulb": (ctypes.c_int, [c_double_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_double, c_double_p, ctypes.c_int]),
     "smrfb_wet_bulb_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),

@@ -6,6 +6,8 @@
 //   * wet / ice bulb temperature from air and dew point temperature: smrf/envphys/core/iwbt.c:14-134 (Newton iteration on the
 //     psychrometer equation, at most 10 steps), what precipitation.py uses as the precipitation temperature;
 //   * wind azimuth from the two distributed direction components: smrf/distribute/wind/wind.py:175-178;
+//   * precipitation phase and new-snow density from the precipitation temperature and the distributed precipitation:
+//     smrf/envphys/snow.py:37-75 with the three models of smrf/envphys/nasde_model/ (susong1999, piecewise_susong1999, marks2017);
 //   * grid_interpolate with the vertices / weights of interp_weights: smrf/utils/utils.py:377-427.
 #include "common.cuh"
 
@@ -199,6 +201,84 @@ __global__ void wind_direction_kernel(const double* __restrict__ u, const double
     }
 }
 
+// ---- precipitation phase / new-snow density (envphys/snow.py:37-75).  NumPy evaluates every expression below element by element
+// in fp64 without contraction: the _rn intrinsics keep that order; pow / exp are the device's (<= 2 ulp from glibc's).
+// nasde_model/utils.py:53-71 (check_temperature, t_min = -10, t_max = 0), :12-37 (calc_percent_snow), and
+// piecewise_suosong_1999.py:74-83 (density of uncompacted snow)
+__device__ __forceinline__ void snow_piecewise(double t, double* pcs, double* rho_ns, double* tsnow) {
+    const double tpp = (t < -10.0) ? -10.0 : t;                    // NaN stays NaN
+    const double ts = (tpp > 0.0) ? 0.0 : tpp;
+    double p = 0.0;
+    if (tpp <= -0.5) p = 1.0;
+    else if (tpp <= 0.0) p = __dadd_rn(__dmul_rn(-tpp / 0.5, 0.25), 0.75);          // (-0.5, 0]
+    else if (tpp <= 1.0) p = __dadd_rn(__dmul_rn(-tpp / 1.0, 0.75), 0.75);          // (0, t_max + 1]
+    double ex = __dadd_rn(1.0, __dmul_rn(__dadd_rn(10.0, __dsub_rn(ts, 0.0)) / 10.0, 0.75));
+    if (ex > 1.75) ex = 1.75;
+    *pcs = p;
+    *rho_ns = __dadd_rn(50.0, __dmul_rn(1.7, pow(__dadd_rn(__dsub_rn(tpp, 0.0), 15.0), ex)));
+    *tsnow = ts;
+}
+
+// model 0 susong1999 (susong_1999.py:29-116), 1 piecewise_susong1999, 2 marks2017 (marks_2017.py:73-207; any_pp: np.any(pp > 0))
+__global__ void snow_phase_kernel(const double* __restrict__ tpp, const double* __restrict__ pp, long long n, int model,
+                                  const int* __restrict__ any_pp, double* __restrict__ pcs_out, double* __restrict__ rho_out) {
+    const int any = *any_pp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double t = tpp[i], p = pp[i];
+        double pcs = 0.0, rho = 0.0;
+        if (model == 0) {
+            // rows [lo, hi): a NaN temperature matches none; cells without precipitation report nothing.  The reference's early
+            // return on np.sum(precipitation) == 0 gives the same zeros (precipitation is clamped to >= 0 upstream)
+            if (p != 0.0) {
+                if (t < -5.0) { pcs = 1.0; rho = 75.0; }
+                else if (t < -3.0) { pcs = 1.0; rho = 100.0; }
+                else if (t < -1.5) { pcs = 1.0; rho = 150.0; }
+                else if (t < -0.5) { pcs = 1.0; rho = 175.0; }
+                else if (t < 0.0) { pcs = 0.75; rho = 200.0; }
+                else if (t < 0.5) { pcs = 0.25; rho = 250.0; }
+            }
+        } else if (model == 1) {
+            double ts;
+            snow_piecewise(t, &pcs, &rho, &ts);
+        } else if (any) {
+            double ts, rho_orig;
+            snow_piecewise(t, &pcs, &rho_orig, &ts);
+            const double swe = __dmul_rn(p, pcs);
+            if (swe > 0.0) {
+                const double rns = rho_orig / 1000.0;
+                const double drc = __dmul_rn(__dmul_rn(__dmul_rn(0.026, exp(__dmul_rn(-0.08, __dsub_rn(0.0, ts)))), swe),
+                                             exp(__dmul_rn(-21.0, rns)));                                     // :149-150
+                const double r1000 = __dmul_rn(rns, 1000.0);
+                const double c11 = (r1000 >= 100.0) ? exp(__dmul_rn(-0.046, __dsub_rn(r1000, 100.0))) : 1.0;   // :152-155
+                const double drm = __dmul_rn(__dmul_rn(0.01, c11), exp(__dmul_rn(-0.04, __dsub_rn(0.0, ts))));  // :157-159
+                rho = __dmul_rn(__dadd_rn(rns, __dmul_rn(__dadd_rn(drc, drm), rns)), 1000.0);                  // :162, :195
+            }
+        }
+        __stcs(pcs_out + i, pcs);
+        __stcs(rho_out + i, rho);
+    }
+}
+
+__global__ void snow_any_kernel(const double* __restrict__ pp, long long n, int* __restrict__ any_pp) {
+    bool a = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a |= pp[i] > 0.0;
+    if (__any_sync(0xffffffffu, a) && (threadIdx.x & 31) == 0) atomicOr(any_pp, 1);
+}
+
+static int launch_snow_phase(cudaStream_t st, const double* d_t, const double* d_pp, long long n, int model, int* d_any, bool scan,
+                             double* d_pcs, double* d_rho) {
+    if (n <= 0) return SMRFB_OK;
+    const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32);
+    if (scan) {
+        snow_any_kernel<<<blocks, 256, 0, st>>>(d_pp, n, d_any);
+        count_launch();
+    }
+    snow_phase_kernel<<<blocks, 256, 0, st>>>(d_t, d_pp, n, model, d_any, d_pcs, d_rho);
+    count_launch();
+    SMRFB_CUDA(cudaGetLastError());
+    return SMRFB_OK;
+}
+
 // utils.py:409-427: ret = einsum('nj,nj->n', take(values, vtx), wts); ret[any(wts < 0, axis=1)] = fill
 __global__ void interp_apply_kernel(const int32_t* __restrict__ vtx, const double* __restrict__ wts, long long n, const double* __restrict__ values,
                                     int npts, int T, double fill, int fill_negative, double* __restrict__ out) {
@@ -316,6 +396,49 @@ int smrfb_wet_bulb_dev(const double* d_ta, const double* d_td, const double* d_z
     SMRFB_CHECK(d_ta && d_td && d_z && d_tw && d_flags && n >= 0, SMRFB_ERR_ARG, "NULL air temperature / dew point / elevation / output / flags");
     SMRFB_CHECK(tol > 0, SMRFB_ERR_ARG, "wet bulb: the tolerance must be positive");
     return launch_wet_bulb((cudaStream_t)stream, d_ta, d_td, d_z, (long long)n, tol, d_tw, d_flags);
+}
+
+int smrfb_snow_phase(const double* tpp, const double* pp, int64_t n, int model, double* pcs, double* rho_s, int device) {
+    SMRFB_CHECK(tpp && pp && pcs && rho_s && n >= 0, SMRFB_ERR_ARG, "NULL temperature / precipitation / outputs");
+    SMRFB_CHECK(model >= 0 && model <= 2, SMRFB_ERR_ARG, "model must be 0 (susong1999), 1 (piecewise_susong1999) or 2 (marks2017)");
+    if (n == 0) return SMRFB_OK;
+    SMRFB_CUDA(cudaSetDevice(device));
+    const size_t cap = std::min<size_t>((size_t)n, (size_t)1 << 25);
+    double* d = nullptr;
+    int* d_any = nullptr;
+    SMRFB_CUDA(cudaMalloc((void**)&d, 4 * cap * sizeof(double)));
+    if (cudaMalloc((void**)&d_any, sizeof(int)) != cudaSuccess) {
+        cudaFree(d);
+        set_error("cudaMalloc failed");
+        return SMRFB_ERR_CUDA;
+    }
+    int rc = SMRFB_OK;
+    // marks2017 looks at the WHOLE precipitation array first (np.any(pp > 0), marks_2017.py:118): decided on the host here
+    int any = 0;
+    if (model == 2)
+        for (int64_t i = 0; i < n && !any; i++) any = pp[i] > 0.0;
+    if (cudaMemcpy(d_any, &any, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) rc = SMRFB_ERR_CUDA;
+    for (size_t o = 0; o < (size_t)n && rc == SMRFB_OK; o += cap) {
+        const size_t m = std::min(cap, (size_t)n - o);
+        if (cudaMemcpy(d, tpp + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d + cap, pp + o, m * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = SMRFB_ERR_CUDA;
+        if (rc == SMRFB_OK) rc = launch_snow_phase(nullptr, d, d + cap, (long long)m, model, d_any, false, d + 2 * cap, d + 3 * cap);
+        if (rc == SMRFB_OK && (cudaMemcpy(pcs + o, d + 2 * cap, m * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                               cudaMemcpy(rho_s + o, d + 3 * cap, m * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess))
+            rc = SMRFB_ERR_CUDA;
+    }
+    if (rc == SMRFB_ERR_CUDA) set_error("snow phase: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    cudaFree(d_any);
+    return rc;
+}
+
+int smrfb_snow_phase_dev(const double* d_tpp, const double* d_pp, int64_t n, int model, double* d_pcs, double* d_rho_s, int* d_any,
+                         void* stream) {
+    SMRFB_CHECK(d_tpp && d_pp && d_pcs && d_rho_s && d_any && n >= 0, SMRFB_ERR_ARG, "NULL temperature / precipitation / outputs / scratch");
+    SMRFB_CHECK(model >= 0 && model <= 2, SMRFB_ERR_ARG, "model must be 0 (susong1999), 1 (piecewise_susong1999) or 2 (marks2017)");
+    return launch_snow_phase((cudaStream_t)stream, d_tpp, d_pp, (long long)n, model, d_any, model == 2, d_pcs, d_rho_s);
 }
 
 int smrfb_set_consumer(smrfb_handle_t hh, int kind, double tol, void* out2) {

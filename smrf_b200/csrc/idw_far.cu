@@ -275,8 +275,10 @@ __device__ __forceinline__ void far_phase_a(const double* __restrict__ gsl, cons
 // Monotone map of a double's high word to unsigned: key(a) < key(b) implies a < b for non-NaN a, b; NaNs map beyond +-inf.
 __host__ __device__ __forceinline__ unsigned hi_key(int hi) { return (unsigned)hi ^ ((unsigned)(hi >> 31) | 0x80000000u); }
 
-template <int NN, typename OutT, bool CLAMP>
-__global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
+// MINB: CTAs per SM the register allocation aims at: 2 (128 registers, no spills) or 3 (80 registers, ~9 local loads per step)
+// PIPE: phase B software-pipelined over the steps of a chunk
+template <int NN, typename OutT, bool CLAMP, int MINB, bool PIPE>
+__global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
     constexpr int NNODE = NN * NN;
     constexpr int NH = NN / 2;
     constexpr int EOS = NH * 4 + 2;      // doubles per (row, step) in EO: NH x {E_num, O_num, E_den, O_den}, padded
@@ -423,11 +425,13 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
         const double2* eo = reinterpret_cast<const double2*>(EO + ((size_t)buf * FAR_RB + w) * FAR_TC * EOS);
         const double2* sg = stg + buf * FAR_TC * SGS;
         OutT* op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(orow) + (long long)ch * FAR_TC * a.ostride);
-        for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(op) + a.ostride)) {
+        // one step in three parts: the interpolation sums (straight-line: 8 NH multiply-adds), the near stations (branches on the
+        // patch's station count), the finish (reciprocal, retrend, clamp, stores)
+        auto accumulate = [&](const double2* e, double (&num)[4], double (&den)[4]) {
             double enA = 0.0, onA = 0.0, edA = 0.0, odA = 0.0, enB = 0.0, onB = 0.0, edB = 0.0, odB = 0.0;
 #pragma unroll
             for (int k = 0; k < NH; k++) {
-                const double2 n2 = eo[2 * k], d2 = eo[2 * k + 1];     // (E_num, O_num), (E_den, O_den)
+                const double2 n2 = e[2 * k], d2 = e[2 * k + 1];     // (E_num, O_num), (E_den, O_den)
                 enA = fma(cA[k], n2.x, enA);
                 onA = fma(cA[NH + k], n2.y, onA);
                 edA = fma(cA[k], d2.x, edA);
@@ -437,10 +441,12 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 edB = fma(cB[k], d2.x, edB);
                 odB = fma(cB[NH + k], d2.y, odB);
             }
-            double num[4] = {enA + onA, enA - onA, enB + onB, enB - onB};
-            double den[4] = {edA + odA, edA - odA, edB + odB, edB - odB};
+            num[0] = enA + onA, num[1] = enA - onA, num[2] = enB + onB, num[3] = enB - onB;
+            den[0] = edA + odA, den[1] = edA - odA, den[2] = edB + odB, den[3] = edB - odB;
+        };
+        auto near_add = [&](const double2* g, int tl, double (&num)[4], double (&den)[4]) {
             if (nq > 0) {
-                const double2 x = sg[1];
+                const double2 x = g[1];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     num[j] = fma(wr[0][j], x.x, num[j]);
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 }
             }
             if (nq > 1) {
-                const double2 x = sg[2];
+                const double2 x = g[2];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     num[j] = fma(wr[1][j], x.x, num[j]);
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 }
             }
             for (int qi = FAR_NQR; qi < nq; qi++) {
-                const double2 x = qi < FAR_NQS ? sg[1 + qi] : __ldg(a.rv + (size_t)(ch * FAR_TC + tl) * a.S + nearl[qi]);
+                const double2 x = qi < FAR_NQS ? g[1 + qi] : __ldg(a.rv + (size_t)(ch * FAR_TC + tl) * a.S + nearl[qi]);
                 const double* wq = qi < FAR_NQR + FAR_NQM ? wns + (qi - FAR_NQR) * (FAR_RB * FAR_P) + w * FAR_P + lane
                                                           : wn + (size_t)(qi - FAR_NQR - FAR_NQM) * (FAR_RB * FAR_P);
 #pragma unroll
@@ -466,11 +472,13 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                     den[j] = fma(wv, x.y, den[j]);
                 }
             }
-            const double2 pp = sg[0];
-            double val[4];
-            // quotient to ~4e-13 relative (reciprocal seed + two Newton steps) with the retrend fused in (idw.py:144)
+        };
+        // quotient to ~4e-13 relative (reciprocal seed + two Newton steps) with the retrend fused in (idw.py:144)
+        auto quotient = [&](const double2 pp, const double (&num)[4], const double (&den)[4], double (&val)[4]) {
 #pragma unroll
             for (int j = 0; j < 4; j++) val[j] = fma(num[j], fast_rcp<2>(den[j]), fma(pp.x, Z[j], pp.y));
+        };
+        auto emit = [&](double (&val)[4], OutT* o) {
             if (CLAMP) {
                 // all four strictly inside (vmin, vmax) by their high words alone (integer pipe, one warp-wide vote); otherwise,
                 // NaNs included, the exact NaN-preserving clamp of utils.py:137-161
@@ -484,11 +492,41 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
             }
             if (full) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) __stcs(op + coff[j], (OutT)val[j]);
+                for (int j = 0; j < 4; j++) __stcs(o + coff[j], (OutT)val[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (live[j]) __stcs(op + coff[j], (OutT)val[j]);
+                    if (live[j]) __stcs(o + coff[j], (OutT)val[j]);
+            }
+        };
+        if constexpr (PIPE) {
+            // software pipeline: the sums of step t + 1 and the reciprocal / retrend chain of step t share one basic block, so the
+            // scheduler fills the chain's latencies with the multiply-adds
+            double num[4], den[4];
+            accumulate(eo, num, den);
+            near_add(sg, 0, num, den);
+            for (int tl = 0; tl + 1 < tend; tl++) {
+                double nnum[4], nden[4], val[4];
+                eo += EOS / 2;
+                accumulate(eo, nnum, nden);
+                quotient(sg[0], num, den, val);
+                sg += SGS;
+                emit(val, op);
+                op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(op) + a.ostride);
+                near_add(sg, tl + 1, nnum, nden);
+#pragma unroll
+                for (int j = 0; j < 4; j++) num[j] = nnum[j], den[j] = nden[j];
+            }
+            double val[4];
+            quotient(sg[0], num, den, val);
+            emit(val, op);
+        } else {
+            for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(op) + a.ostride)) {
+                double num[4], den[4], val[4];
+                accumulate(eo, num, den);
+                near_add(sg, tl, num, den);
+                quotient(sg[0], num, den, val);
+                emit(val, op);
             }
         }
     }
@@ -634,10 +672,19 @@ static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArg
                         (size_t)std::max(1, plan->max_near) * sizeof(int);
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: %zu B of shared memory per CTA", smem);
     const dim3 grid(FAR_P / FAR_RB, plan->npx, nbands);
+    static const int minb = getenv("SMRFB_FAR_MINB") ? atoi(getenv("SMRFB_FAR_MINB")) : 2;
+    static const int pipe = getenv("SMRFB_FAR_PIPE") ? atoi(getenv("SMRFB_FAR_PIPE")) : 0;
+#define FAR_LAUNCH1(OT, CL, MB, PP)                                                                                     \
+    do {                                                                                                                \
+        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN, OT, CL, MB, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); \
+        idw_far_kernel<NN, OT, CL, MB, PP><<<grid, FAR_THREADS, smem, st>>>(fa);                                         \
+    } while (0)
 #define FAR_LAUNCH(OT, CL)                                                                                              \
     do {                                                                                                                \
-        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN, OT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); \
-        idw_far_kernel<NN, OT, CL><<<grid, FAR_THREADS, smem, st>>>(fa);                                                 \
+        if (minb == 3 && pipe) FAR_LAUNCH1(OT, CL, 3, true);                                                            \
+        else if (minb == 3) FAR_LAUNCH1(OT, CL, 3, false);                                                              \
+        else if (pipe) FAR_LAUNCH1(OT, CL, 2, true);                                                                    \
+        else FAR_LAUNCH1(OT, CL, 2, false);                                                                             \
     } while (0)
     if (fa.out_f32) {
         if (fa.clamp) FAR_LAUNCH(float, true);
@@ -647,6 +694,7 @@ static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArg
         else FAR_LAUNCH(double, false);
     }
 #undef FAR_LAUNCH
+#undef FAR_LAUNCH1
     far_mark(plan, st);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());

@@ -1,9 +1,12 @@
 """The distribution calls of smrf.distribute.precipitation.ppt (smrf/distribute/precipitation.py:327-369, 405-425): the
 hourly field -- skipped when no station reports precipitation (``data.sum() == 0``) -- and, on the first step of a storm,
 the storm total distributed through the SAME interpolator (for DK a second station mask: the cached kriging weights of
-both masks stay resident).  Storm tracking, phase and new-snow density (envphys.snow) are outside the path."""
+both masks stay resident) -- followed, when the precipitation temperature is handed in, by the phase / new-snow density
+consumer (Snow.phase_and_density, precipitation.py:376-384, 428-431) on the device.  Storm tracking (envphys.storms) is outside
+the path."""
 import numpy as np
 
+from ..snow import Snow
 from .image_data import image_data as _image_data
 
 
@@ -21,15 +24,19 @@ class ppt(_image_data):
         self.storms = None                    # DataFrame with 'start', 'end' and one storm-total column per station
         self.storm_id = 0
         self.storming = False
+        self.nasde_model = pptConfig.get('new_snow_density_model', 'susong1999') if hasattr(pptConfig, 'get') else 'susong1999'
 
     def initialize(self, topo, data, date_time=None):
         self.date_time = date_time
         self._initialize(topo, data.metadata)
         self.precip = np.zeros((topo.dem.shape[0], topo.dem.shape[1]))
         self.storm_total = np.zeros((topo.dem.shape[0], topo.dem.shape[1]))
+        self.percent_snow = np.zeros(self.precip.shape)
+        self.snow_density = np.zeros(self.precip.shape)
 
-    def distribute(self, data, time=None):
-        # precipitation.py:335-369 (marks2017) / :420-421 (susong1999): the distribution part
+    def distribute(self, data, time=None, precip_temp=None):
+        # precipitation.py:335-369 (marks2017) / :420-421 (susong1999): the distribution part; with precip_temp (the dew point
+        # or wet bulb grid, precipitation.py:271-279) also percent_snow / snow_density (:371-384, :428-431, :394-401)
         if data.sum() > 0.0:
             storm_start = None
             if self.storms is not None:
@@ -42,8 +49,18 @@ class ppt(_image_data):
             if storm_start is not None and time == storm_start:
                 storm = self.storms.iloc[self.storm_id]
                 self._distribute(storm[self.stations].astype(float), other_attribute='storm_total', clamp=True)
+            if precip_temp is not None:
+                marks = self.nasde_model == 'marks2017'
+                if marks and not (self.storming and np.min(precip_temp) < 2.0):      # precipitation.py:371, 381-384
+                    self.snow_density = np.zeros(self.precip.shape)
+                    self.percent_snow = np.zeros(self.precip.shape)
+                else:
+                    self.snow_density, self.percent_snow = Snow.phase_and_density(precip_temp, self.precip, self.nasde_model)
         else:
             self.precip = np.zeros(self.precip.shape)
+            if precip_temp is not None:
+                self.percent_snow = np.zeros(self.precip.shape)
+                self.snow_density = np.zeros(self.precip.shape)
 
     def distribute_thread(self, smrf_queue, data_queue):
         for date_time in self.date_time:

@@ -39,6 +39,26 @@ def test_wet_bulb_oracle_matches_reference_golden(golden):
         orc.wet_bulb(np.array([-300.0]), np.array([-300.0]), np.array([0.0]), 0.01)     # below 0 K: the reference exits
 
 
+def test_snow_phase_oracle_matches_reference_golden(golden):
+    """oracle.snow_phase_and_density (restatement of envphys/snow.py + nasde_model/*.py) against vectors produced by executing
+    the reference's own Snow.phase_and_density (tests/golden/make_golden_snow.py): bit for bit, all three models, on the hourly
+    precipitation, on a storm total and on an all-dry hour."""
+    from oracle import oracle as orc
+    g = golden("snow")
+    for model in ("susong1999", "piecewise_susong1999", "marks2017"):
+        for tag in ("pp", "storm", "zero"):
+            t0 = g["t"].copy()
+            rho, pcs = orc.snow_phase_and_density(t0, g[tag], model)
+            np.testing.assert_array_equal(rho, g["%s_%s_rho" % (model, tag)])
+            np.testing.assert_array_equal(pcs, g["%s_%s_pcs" % (model, tag)])
+            np.testing.assert_array_equal(t0, g["t"])                  # the caller's temperature is not clipped
+    rho, pcs = orc.snow_phase_and_density(np.array([-7.0, -0.25, 0.25, 3.0]), np.array([1.0, 1.0, 1.0, 1.0]), "susong1999")
+    np.testing.assert_array_equal(rho, [75.0, 200.0, 250.0, 0.0])
+    np.testing.assert_array_equal(pcs, [1.0, 0.75, 0.25, 0.0])
+    with pytest.raises(ValueError):
+        orc.snow_phase_and_density(np.zeros(2), np.zeros(2), "nope")
+
+
 def test_wind_direction_and_weights_oracle():
     from oracle import oracle as orc
     az = orc.wind_direction(np.array([0.0, 1.0, 0.0, -1.0, -0.5]), np.array([1.0, 0.0, -1.0, 0.0, 0.5]))

@@ -232,15 +232,70 @@ def test_variable_wrappers_per_step_like_the_reference_loop(gpu):
         v["cloud_factor"].distribute(frames["cloud_factor"].loc[t])
         cfr = frames["cloud_factor"].loc[t].values
         assert parity(v["cloud_factor"].cloud_factor, orc.set_min_max(oidw.calculateIDW(cfr.copy()), 0.0, 1.0), 1.0) <= TOL
-        v["precip"].distribute(frames["precip"].loc[t], t)
+        v["precip"].nasde_model = ("susong1999", "marks2017", "piecewise_susong1999")[k % 3]
+        v["precip"].distribute(frames["precip"].loc[t], t, precip_temp=v["vapor_pressure"].precip_temp)
         pr = frames["precip"].loc[t].values
         if pr.sum() > 0:
             assert parity(v["precip"].precip, orc.set_min_max(odk.calculate(pr.copy()), 0.0, None), step_scale(pr)) <= TOL
+            # phase / density of the new snow from the precipitation temperature (precipitation.py:371-384, 428-431)
+            if v["precip"].nasde_model == "marks2017" and not (v["precip"].storming and v["vapor_pressure"].precip_temp.min() < 2.0):
+                assert not v["precip"].snow_density.any() and not v["precip"].percent_snow.any()
+            else:
+                rho_ref, pcs_ref = orc.snow_phase_and_density(v["vapor_pressure"].precip_temp, v["precip"].precip, v["precip"].nasde_model)
+                np.testing.assert_array_equal(v["precip"].percent_snow, pcs_ref)
+                _snow_close(v["precip"].snow_density, rho_ref)
         else:
-            assert not v["precip"].precip.any()
+            assert not v["precip"].precip.any() and not v["precip"].percent_snow.any() and not v["precip"].snow_density.any()
         if k == 2:                                                                  # first hour of the storm
             st = storm.values.astype(float)
             assert parity(v["precip"].storm_total, orc.set_min_max(odk.calculate(st.copy()), 0.0, None), step_scale(st)) <= TOL
+
+
+def _snow_close(got, ref):
+    """pcs is table / linear arithmetic in the reference's operation order: bit for bit.  The densities go through pow / exp,
+    where the device's routines differ from glibc's by <= 2 ulp: 1e-12 relative."""
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1.0), initial=0.0) <= 1e-12
+
+
+def test_snow_phase_and_density_golden_and_oracle(gpu, golden):
+    """smrfb_snow_phase (Snow.phase_and_density, envphys/snow.py:37-75) against the reference-generated vectors and the oracle."""
+    import torch
+    from oracle import oracle as orc
+    from smrf_b200 import _lib
+    from smrf_b200.snow import Snow
+    g = golden("snow")
+    for model in ("susong1999", "piecewise_susong1999", "marks2017"):
+        for tag in ("pp", "storm", "zero"):
+            t0 = g["t"].copy()
+            rho, pcs = Snow.phase_and_density(t0, g[tag], model)
+            np.testing.assert_array_equal(t0, g["t"])
+            np.testing.assert_array_equal(pcs, g["%s_%s_pcs" % (model, tag)])
+            _snow_close(rho, g["%s_%s_rho" % (model, tag)])
+            if model == "susong1999":
+                np.testing.assert_array_equal(rho, g["%s_%s_rho" % (model, tag)])
+    rng = np.random.default_rng(12)
+    t = rng.uniform(-14.0, 3.0, (301, 257))
+    pp = np.where(rng.random(t.shape) < 0.4, 0.0, rng.gamma(0.8, 3.0, t.shape))
+    t[5, 7] = np.nan
+    pp[9, 9] = np.nan
+    for model in ("susong1999", "piecewise_susong1999", "marks2017"):
+        rho, pcs = Snow.phase_and_density(t, pp, model)
+        rho_ref, pcs_ref = orc.snow_phase_and_density(t, pp, model)
+        np.testing.assert_array_equal(pcs, pcs_ref)
+        _snow_close(rho, rho_ref)
+        # device-resident form (what a fused caller uses): same kernels
+        d_t, d_pp = torch.from_numpy(t).cuda(), torch.from_numpy(pp).cuda()
+        d_pcs, d_rho = torch.empty_like(d_t), torch.empty_like(d_t)
+        d_any = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib().smrfb_snow_phase_dev(d_t.data_ptr(), d_pp.data_ptr(), t.size, Snow.MODELS[model], d_pcs.data_ptr(),
+                                                   d_rho.data_ptr(), d_any.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(d_pcs.cpu().numpy(), pcs)
+        np.testing.assert_array_equal(d_rho.cpu().numpy(), rho)
+    with pytest.raises(ValueError):
+        Snow.phase_and_density(t, pp, "nope")
 
 
 def test_threaded_run_loop_with_block_prefetch_and_sink(gpu, tmp_path):
