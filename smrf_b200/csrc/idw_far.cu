@@ -25,6 +25,7 @@
 #include "idw_far.cuh"
 
 #include <array>
+#include <type_traits>
 
 namespace smrfb {
 
@@ -33,7 +34,7 @@ constexpr int FAR_TC = 8;            // timesteps per staged chunk
 constexpr int FAR_CW = 2 * FAR_TC;   // columns per chunk: numerator steps, then denominator steps
 constexpr int FAR_THREADS = FAR_RB * 32;
 constexpr int FAR_NQR = 2;           // near stations whose cell weights stay in registers; the rest go through global scratch
-constexpr int FAR_NQM = 2;           // further near stations whose cell weights sit in shared memory
+constexpr int FAR_NQM = 2;           // further near stations whose cell weights sit in shared memory (default; FarArgs::nqm, as many as fit)
 constexpr int FAR_NQS = 7;           // near stations whose (residual, validity) pairs are staged in shared memory per chunk
 constexpr int FAR_NODE_THREADS = 256;
 constexpr int FAR_NODE_COLS = 128;   // (step, term) columns per node-kernel tile
@@ -202,7 +203,7 @@ struct FarArgs {
     long long ostride;      // bytes between consecutive steps of the output window
     unsigned klo, kspan;    // clamp screen on the high word (see hi_key)
     int S, RS, S_pad, T, nchunk, clamp, out_f32;
-    int row0, nrows, npx, pi0, qx;
+    int row0, nrows, npx, pi0, qx, nqm;
 };
 
 // A valid station exactly on a cell centre: the reference's weight there is inf and the cell becomes NaN (inf / inf), or 0
@@ -275,10 +276,8 @@ __device__ __forceinline__ void far_phase_a(const double* __restrict__ gsl, cons
 // Monotone map of a double's high word to unsigned: key(a) < key(b) implies a < b for non-NaN a, b; NaNs map beyond +-inf.
 __host__ __device__ __forceinline__ unsigned hi_key(int hi) { return (unsigned)hi ^ ((unsigned)(hi >> 31) | 0x80000000u); }
 
-// MINB: CTAs per SM the register allocation aims at: 2 (128 registers, no spills) or 3 (80 registers, ~9 local loads per step)
-// PIPE: phase B software-pipelined over the steps of a chunk
-template <int NN, typename OutT, bool CLAMP, int MINB, bool PIPE>
-__global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
+template <int NN, typename OutT, bool CLAMP>
+__global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
     constexpr int NNODE = NN * NN;
     constexpr int NH = NN / 2;
     constexpr int EOS = NH * 4 + 2;      // doubles per (row, step) in EO: NH x {E_num, O_num, E_den, O_den}, padded
@@ -291,7 +290,7 @@ __global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
     double* Lys = reinterpret_cast<double*>(stg + 2 * FAR_TC * SGS);     // [RB][NN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Lys + FAR_RB * NN);     // [2]
     double* wns = reinterpret_cast<double*>(bars + 2);                   // [NQM][RB][128] near weights 2, 3 of the cells
-    int* nearl = reinterpret_cast<int*>(wns + FAR_NQM * FAR_RB * FAR_P);   // [nq]
+    int* nearl = reinterpret_cast<int*>(wns + a.nqm * FAR_RB * FAR_P);   // [nq]
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     // grid: x = 8-row band within the 128-row patch (the 16 CTAs that share a patch's node sums launch together and
@@ -375,12 +374,12 @@ __global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
             } else if (qi == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) wr[1][j] = ws[j];
-            } else if (qi < FAR_NQR + FAR_NQM) {
+            } else if (qi < FAR_NQR + a.nqm) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) wns[(qi - FAR_NQR) * (FAR_RB * FAR_P) + w * FAR_P + lane + 32 * j] = ws[j];
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) wn[(size_t)(qi - FAR_NQR - FAR_NQM) * (FAR_RB * FAR_P) + 32 * j] = ws[j];
+                for (int j = 0; j < 4; j++) wn[(size_t)(qi - FAR_NQR - a.nqm) * (FAR_RB * FAR_P) + 32 * j] = ws[j];
             }
         }
     }
@@ -424,6 +423,7 @@ __global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
         const int tend = min(FAR_TC, a.T - ch * FAR_TC);
         const double2* eo = reinterpret_cast<const double2*>(EO + ((size_t)buf * FAR_RB + w) * FAR_TC * EOS);
         const double2* sg = stg + buf * FAR_TC * SGS;
+        const double* wsm = wns + w * FAR_P + lane;
         OutT* op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(orow) + (long long)ch * FAR_TC * a.ostride);
         // one step in three parts: the interpolation sums (straight-line: 8 NH multiply-adds), the near stations (branches on the
         // patch's station count), the finish (reciprocal, retrend, clamp, stores)
@@ -461,13 +461,26 @@ __global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
                     den[j] = fma(wr[1][j], x.y, den[j]);
                 }
             }
-            for (int qi = FAR_NQR; qi < nq; qi++) {
-                const double2 x = qi < FAR_NQS ? g[1 + qi] : __ldg(a.rv + (size_t)(ch * FAR_TC + tl) * a.S + nearl[qi]);
-                const double* wq = qi < FAR_NQR + FAR_NQM ? wns + (qi - FAR_NQR) * (FAR_RB * FAR_P) + w * FAR_P + lane
-                                                          : wn + (size_t)(qi - FAR_NQR - FAR_NQM) * (FAR_RB * FAR_P);
+            // further stations: weights from shared memory (the first nqm), then from the L1-resident global scratch; their
+            // (residual, validity) pairs from the stage (the first NQS), then from global memory
+            const int q1 = min(nq, FAR_NQR + a.nqm), q2 = min(nq, FAR_NQS);
+            int qi = FAR_NQR;
+            for (; qi < q1; qi++) {
+                const double2 x = g[1 + qi];
+                const double* wq = wsm + (qi - FAR_NQR) * (FAR_RB * FAR_P);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const double wv = wq[32 * j];
+                    num[j] = fma(wv, x.x, num[j]);
+                    den[j] = fma(wv, x.y, den[j]);
+                }
+            }
+            for (; qi < nq; qi++) {
+                const double2 x = qi < q2 ? g[1 + qi] : __ldg(a.rv + (size_t)(ch * FAR_TC + tl) * a.S + nearl[qi]);
+                const double* wq = wn + (size_t)(qi - FAR_NQR - a.nqm) * (FAR_RB * FAR_P);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double wv = wq[32 * j];      // written by this thread in the prologue: a plain (coherent) load
                     num[j] = fma(wv, x.x, num[j]);
                     den[j] = fma(wv, x.y, den[j]);
                 }
@@ -478,7 +491,8 @@ __global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; j++) val[j] = fma(num[j], fast_rcp<2>(den[j]), fma(pp.x, Z[j], pp.y));
         };
-        auto emit = [&](double (&val)[4], OutT* o) {
+        // pf / pm: the step's output row at the lane's forward (lane, 32 + lane) and mirror (127 - lane, 95 - lane) columns
+        auto emit = [&](double (&val)[4], OutT* pf, OutT* pm, auto fullc) {
             if (CLAMP) {
                 // all four strictly inside (vmin, vmax) by their high words alone (integer pipe, one warp-wide vote); otherwise,
                 // NaNs included, the exact NaN-preserving clamp of utils.py:137-161
@@ -490,45 +504,38 @@ __global__ void __launch_bounds__(FAR_THREADS, MINB) idw_far_kernel(FarArgs a) {
                     for (int j = 0; j < 4; j++) val[j] = clamp_nan_keep(val[j], a.vmin, a.vmax);
                 }
             }
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) __stcs(o + coff[j], (OutT)val[j]);
+            if constexpr (decltype(fullc)::value) {
+                __stcs(pf, (OutT)val[0]);
+                __stcs(pm, (OutT)val[1]);
+                __stcs(pf + 32, (OutT)val[2]);
+                __stcs(pm - 32, (OutT)val[3]);
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (live[j]) __stcs(o + coff[j], (OutT)val[j]);
+                if (live[0]) __stcs(pf, (OutT)val[0]);
+                if (live[1]) __stcs(pm, (OutT)val[1]);
+                if (live[2]) __stcs(pf + 32, (OutT)val[2]);
+                if (live[3]) __stcs(pm - 32, (OutT)val[3]);
             }
         };
-        if constexpr (PIPE) {
-            // software pipeline: the sums of step t + 1 and the reciprocal / retrend chain of step t share one basic block, so the
-            // scheduler fills the chain's latencies with the multiply-adds
-            double num[4], den[4];
-            accumulate(eo, num, den);
-            near_add(sg, 0, num, den);
-            for (int tl = 0; tl + 1 < tend; tl++) {
-                double nnum[4], nden[4], val[4];
-                eo += EOS / 2;
-                accumulate(eo, nnum, nden);
-                quotient(sg[0], num, den, val);
-                sg += SGS;
-                emit(val, op);
-                op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(op) + a.ostride);
-                near_add(sg, tl + 1, nnum, nden);
-#pragma unroll
-                for (int j = 0; j < 4; j++) num[j] = nnum[j], den[j] = nden[j];
-            }
-            double val[4];
-            quotient(sg[0], num, den, val);
-            emit(val, op);
-        } else {
-            for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, op = reinterpret_cast<OutT*>(reinterpret_cast<char*>(op) + a.ostride)) {
+        // Measured and dropped: a software pipeline over the steps (the sums of step t + 1 in one basic block with the reciprocal /
+        // retrend chain of step t): 19.62 against 19.64 ms per C4 slab field; 3 CTAs per SM at 80 registers (~9 local loads per
+        // step): 34.1 ms.  tools/dfma_issue_probe.cu shows why: a DFMA holds the sub-partition's issue port for both of its
+        // pipe cycles (2.07 clk alone, + ~1 clk per integer / load instruction beside it), so a warp-step of F fp64 and O other
+        // instructions costs 2 F + O issue cycles whatever the latency hiding: 2 x 91 + 94 = 276 here, 332 measured.
+        // the step loop, specialised on whether all four cells of every lane exist (uniform per warp), two running output pointers
+        auto steps = [&](auto fullc) {
+            char* pf = reinterpret_cast<char*>(op + lane);
+            char* pm = reinterpret_cast<char*>(op + (FAR_P - 1 - lane));
+#pragma unroll 2
+            for (int tl = 0; tl < tend; tl++, eo += EOS / 2, sg += SGS, pf += a.ostride, pm += a.ostride) {
                 double num[4], den[4], val[4];
                 accumulate(eo, num, den);
                 near_add(sg, tl, num, den);
                 quotient(sg[0], num, den, val);
-                emit(val, op);
+                emit(val, reinterpret_cast<OutT*>(pf), reinterpret_cast<OutT*>(pm), fullc);
             }
-        }
+        };
+        if (full) steps(std::true_type{});
+        else steps(std::false_type{});
     }
 }
 
@@ -668,23 +675,14 @@ static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArg
     far_mark(plan, st);
     const size_t smem = (size_t)(2 * NNODE * 2 * FAR_TC + 2 * FAR_RB * FAR_TC * (NN / 2 * 4 + 2) + FAR_RB * NN) * sizeof(double) +
                         (size_t)2 * FAR_TC * (1 + FAR_NQS) * sizeof(double2) + 2 * sizeof(uint64_t) +
-                        (size_t)FAR_NQM * FAR_RB * FAR_P * sizeof(double) +
+                        (size_t)fa.nqm * FAR_RB * FAR_P * sizeof(double) +
                         (size_t)std::max(1, plan->max_near) * sizeof(int);
     SMRFB_CHECK(smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: %zu B of shared memory per CTA", smem);
     const dim3 grid(FAR_P / FAR_RB, plan->npx, nbands);
-    static const int minb = getenv("SMRFB_FAR_MINB") ? atoi(getenv("SMRFB_FAR_MINB")) : 2;
-    static const int pipe = getenv("SMRFB_FAR_PIPE") ? atoi(getenv("SMRFB_FAR_PIPE")) : 0;
-#define FAR_LAUNCH1(OT, CL, MB, PP)                                                                                     \
-    do {                                                                                                                \
-        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN, OT, CL, MB, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); \
-        idw_far_kernel<NN, OT, CL, MB, PP><<<grid, FAR_THREADS, smem, st>>>(fa);                                         \
-    } while (0)
 #define FAR_LAUNCH(OT, CL)                                                                                              \
     do {                                                                                                                \
-        if (minb == 3 && pipe) FAR_LAUNCH1(OT, CL, 3, true);                                                            \
-        else if (minb == 3) FAR_LAUNCH1(OT, CL, 3, false);                                                              \
-        else if (pipe) FAR_LAUNCH1(OT, CL, 2, true);                                                                    \
-        else FAR_LAUNCH1(OT, CL, 2, false);                                                                             \
+        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_kernel<NN, OT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); \
+        idw_far_kernel<NN, OT, CL><<<grid, FAR_THREADS, smem, st>>>(fa);                                                 \
     } while (0)
     if (fa.out_f32) {
         if (fa.clamp) FAR_LAUNCH(float, true);
@@ -694,7 +692,6 @@ static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArg
         else FAR_LAUNCH(double, false);
     }
 #undef FAR_LAUNCH
-#undef FAR_LAUNCH1
     far_mark(plan, st);
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
@@ -712,7 +709,12 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
     SMRFB_CHECK(nbands <= 65535 && plan->npx <= 65535, SMRFB_ERR_LIMIT, "IDW far field: too many patches for one launch");
     int qmax = 0;
     for (int p = pi0 * plan->npx; p < (pi1 + 1) * plan->npx; p++) qmax = std::max(qmax, plan->near_off[p + 1] - plan->near_off[p]);
-    const int qx = std::max(0, qmax - FAR_NQR - FAR_NQM);
+    // near stations 2 .. 2 + nqm - 1 keep their cell weights in shared memory (8 KB each), the rest go through a global scratch
+    // that lives in L1.  More of them in shared memory was measured SLOWER on the dense C5 network (47.1 against 44.5 ms per
+    // 512-step field at nqm = 5): the larger carve-out leaves the scratch of the remaining stations no L1 to live in.
+    int nqm = FAR_NQM;
+    if (const char* e = getenv("SMRFB_FAR_NQM")) nqm = std::max(0, atoi(e));
+    const int qx = std::max(0, qmax - FAR_NQR - nqm);
     SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_G, &plan->G_cap, (size_t)npl * nchunk * nnode * 2 * FAR_TC * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_rv, &plan->rv_cap, ((size_t)T_pad * S * 2 + (size_t)S * N) * sizeof(double)));
     SMRFB_PROPAGATE(ensure_cap((void**)&plan->d_wn, &plan->wn_cap,
@@ -773,6 +775,7 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
     fa.npx = plan->npx;
     fa.pi0 = pi0;
     fa.qx = qx;
+    fa.nqm = nqm;
     fa.ostride = (long long)nrows * g.nx * (out_f32 ? 4 : 8);
     {   // fast screen: key(vmin) < key(v) < key(vmax) on the high words proves vmin < v < vmax
         long long blo, bhi;

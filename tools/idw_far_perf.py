@@ -1,6 +1,6 @@
 """Device-resident timing of the IDW kernels on a WINDOW of the C4 mesh (30 m cells inside a 300 km network of 200
 stations, i.e. the station density of BASELINE.json configs[3]) -- development aid, not the bench.
-usage: idw_far_perf.py [ny nx S T]   env: SMRFB_IDW_KERNEL (unset = default), DROP_MODE=block|iid, IDW_COMPARE=dmma|i8"""
+usage: idw_far_perf.py [ny nx S T dx domain_cells]   (C5 density: 4000 4000 200 512 10 4000)   env: SMRFB_IDW_KERNEL (unset = default), DROP_MODE=block|iid, IDW_COMPARE=dmma|i8"""
 import os
 import sys
 
@@ -17,14 +17,15 @@ def main():
     S = int(sys.argv[3]) if len(sys.argv) > 3 else 200
     T = int(sys.argv[4]) if len(sys.argv) > 4 else 720
     rng = np.random.default_rng(7)
-    dx = 30.0
+    dx = float(sys.argv[5]) if len(sys.argv) > 5 else 30.0
+    dom = int(sys.argv[6]) if len(sys.argv) > 6 else 10000
     x = 500000.0 + dx * np.arange(nx)
-    y = 4800000.0 - 97000.0 - dx * np.arange(ny)
+    y = 4800000.0 - (97000.0 if dom == 10000 else 0.0) - dx * np.arange(ny)
     X, Y = x[None, :], y[:, None]
     dem = (1800.0 + 700.0 * np.sin(2 * np.pi * X / 41000.0) * np.cos(2 * np.pi * Y / 57000.0)
            + 120.0 * np.sin(2 * np.pi * X / 3100.0 + 1.0) * np.sin(2 * np.pi * Y / 2300.0)).astype(np.float32).astype(np.float64)
-    mx = 500000.0 + dx * rng.integers(0, 10000, S) + 0.37 * dx
-    my = 4800000.0 - dx * rng.integers(0, 10000, S) + 0.37 * dx
+    mx = 500000.0 + dx * rng.integers(0, dom, S) + 0.37 * dx
+    my = 4800000.0 - dx * rng.integers(0, dom, S) + 0.37 * dx
     mz = 1800.0 + 700.0 * np.sin(2 * np.pi * mx / 41000.0) * np.cos(2 * np.pi * my / 57000.0) + rng.normal(0, 5.0, S)
     if os.environ.get("DROP_MODE") == "block":
         data, nm = syn.dropouts_block(syn.make_series("air_temp", mz, T), max_masks=12, per_year=40.0)
