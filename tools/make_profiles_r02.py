@@ -45,6 +45,12 @@ CAPTURES = [
     ("r02_far_c4slab.ncu-rep", "idw_far_kernel, one IDW field on a C4 slab (1024 x 10000 cells, 200 stations, 720 steps, i.i.d. dropouts) "
                                "-- `python tools/idw_far_perf.py 1024 10000 200 720`",
      {"kernel": "idw_far_kernel", "shape": "cells10240000_T720_S200"}),
+    ("r02_far_c5.ncu-rep", "idw_far_kernel on the dense C5 network (4000 x 4000 cells of 10 m, the same 200 stations over 40 km: 12 x 12 nodes "
+                           "from theta = 4, 4.8 near stations per patch, 512 steps) -- `python tools/idw_far_perf.py 4000 4000 200 512 10 4000`",
+     {"kernel": "idw_far_kernel", "shape": "cells16000000_T512_S200"}),
+    ("r02_grid_fold.ncu-rep", "grid_local_fold2_kernel, GRID grid_local (folded form) on the C5 grid (4000 x 4000 cells, 4900 source points, "
+                              "256 steps) -- `python tools/grid_perf.py 4000 4000 256`",
+     {"kernel": "grid_local_fold2_kernel", "shape": "cells16000000_T256_P4900"}),
     ("r02_dk_mma.ncu-rep", "dk_distribute_mma_kernel, DK steady state on a C4 row band (300 x 10000 cells, 720 steps) "
                            "-- `python tools/dk_steady_perf.py`",
      {"kernel": "dk_distribute_mma_kernel", "shape": "cells3000000_T720_S200"}),
