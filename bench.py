@@ -675,7 +675,8 @@ def roofline(wl, fields, objs, launch_ms, far, far_ms, steps, nslab, slab_cells,
                                       "outputs; a DFMA holds a sub-partition's fp64 pipe for 2 clk and the others do not hide under it at 16 warps "
                                       "per SM (tools/dfma_issue_probe.cu, profiles/r02_dfma_issue_probe.txt; ncu's per-instruction samples give "
                                       "DFMA 46 % of the time = exactly 2 clk each, the rest ~1.7 clk each); the fp64 peak is builder-measured "
-                                      "(DFMA issue loop, profiles/r01_peak_probe.json), "MEASURED_PEAKS.json holds no fp64 figure"},
+                                      "(DFMA issue loop, profiles/r01_peak_probe.json), "
+                                      "MEASURED_PEAKS.json holds no fp64 figure"},
                 "why": "the reference's dense sum is 4 S = 800 flop per 8-byte output (100 flop/B, far right of the fp64 ridge at 5.2 "
                        "flop/B); the near / far-field split brings it to ~%.0f flop per output so that the kernel comes within reach "
                        "of the HBM write roof" % (flops / (slab_cells * Tb))}
