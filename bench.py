@@ -530,11 +530,32 @@ def main():
         dt = float(tt.item())
         d2h_bytes = int(nf * Te * ncell * 8)
         ceiling = d2h_ceiling(torch) if rank == 0 else None
+        ceiling_all = None
+        if world > 1:
+            # what the box's host side takes when every rank copies at once (the GPUs share PCIe switches and one NUMA node):
+            # world x 4 GiB device -> pinned host, all ranks between two barriers, bytes / the slowest rank's time
+            try:
+                src = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+                dst = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+                dst.copy_(src)
+                barrier()
+                t1 = time.perf_counter()
+                for _ in range(4):
+                    dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                tc = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+                ceiling_all = world * 4 * float(1 << 30) / float(tc.item()) / 1e9
+                del src, dst
+            except Exception:
+                ceiling_all = None
         e2e = {"value": world * done * n_e2e / dt, "unit": "cell-timesteps/s",
                "h2d_bytes_per_step": int(nf * Te * rows[fields[0].name].shape[1] * 8), "d2h_bytes_per_step": d2h_bytes,
                "steps_per_block": Te, "blocks_timed": n_e2e, "d2h_gbs_per_rank": d2h_bytes * n_e2e / dt / 1e9,
                "d2h_ceiling_gbs_one_rank_alone": ceiling,
-               "frac_of_d2h_ceiling": (d2h_bytes * n_e2e / dt / 1e9 / ceiling) if ceiling else None,
+               "d2h_ceiling_gbs_all_ranks_at_once": ceiling_all,
+               "frac_of_d2h_ceiling": ((world * d2h_bytes * n_e2e / dt / 1e9 / ceiling_all) if ceiling_all else
+                                       (d2h_bytes * n_e2e / dt / 1e9 / ceiling) if ceiling else None),
                "api": "smrf_b200.sharding.BlockRunner.run(tables) over smrf_b200.spatial.IDW/DK/GRID.distribute_block -> pinned float64 "
                       "[T, rows, nx] blocks handed to a sink, slab by slab"}
         del runner

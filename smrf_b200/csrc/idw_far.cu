@@ -186,6 +186,107 @@ __global__ void __launch_bounds__(FAR_NODE_THREADS, 1) idw_far_node_kernel(FarNo
     }
 }
 
+// The same product on the fp64 tensor cores (default): G[node][col] = sum_s Wn[s][node] B[s][col] as DMMA.8x8x4 tiles.  16 warps;
+// a warp owns 8 of the tile's 128 columns and ALL node tiles (13 or 18 accumulator pairs in registers), so the B fragment of a
+// k-step is loaded once and every A fragment feeds one DMMA; the node stride NP is = 8 (mod 16) doubles, which makes an A
+// fragment load two wavefronts.  The DFMA kernel above (8 warps per SM, one shared load per two multiply-adds)
+// reached 41 % of the fp64 peak.
+constexpr int FAR_NODE_MMA_THREADS = 512;
+template <int NN>
+struct FarNodeMma {
+    static constexpr int NNODE = NN * NN;
+    static constexpr int MT = (NNODE + 7) / 8;                               // node tiles
+    static constexpr int NP = MT * 8 + ((MT * 8) % 16 == 8 ? 0 : 8);         // padded node stride: 104 (NN = 10), 152 (NN = 12)
+};
+
+template <int NN>
+__global__ void __launch_bounds__(FAR_NODE_MMA_THREADS, 1) idw_far_node_mma_kernel(FarNodeArgs a) {
+    constexpr int NNODE = FarNodeMma<NN>::NNODE, MT = FarNodeMma<NN>::MT, NP = FarNodeMma<NN>::NP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Wn = reinterpret_cast<double*>(smem_raw);                          // [SB][NP], SB a multiple of 8
+    uint8_t* isnear = reinterpret_cast<uint8_t*>(Wn + (size_t)a.SB * NP);      // [S]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lp = blockIdx.x;
+    const int pj = lp % a.npx, pi = a.pi0 + lp / a.npx;
+    const int gp = pi * a.npx + pj;
+    for (int s = tid; s < a.S; s += FAR_NODE_MMA_THREADS) isnear[s] = 0;
+    __syncthreads();
+    for (int i = a.near_off[gp] + tid; i < a.near_off[gp + 1]; i += FAR_NODE_MMA_THREADS) isnear[a.near_idx[i]] = 1;
+    const double hx = 0.5 * (FAR_P - 1) * a.dx, hy = 0.5 * (FAR_P - 1) * a.dy;
+    const double xc = a.x0 + ((double)pj * FAR_P + 0.5 * (FAR_P - 1)) * a.dx;
+    const double yc = a.y0 + ((double)pi * FAR_P + 0.5 * (FAR_P - 1)) * a.dy;
+    const bool p2 = (a.power == 2.0);
+    const int nchunk = a.N / (2 * FAR_TC);
+    double* Gp = a.G + (size_t)lp * nchunk * NNODE * (2 * FAR_TC);
+    const int fk = lane & 3, fr = lane >> 2;          // fragment coordinates: k / row of A, k / column of B
+
+    for (int sb0 = 0; sb0 < a.S; sb0 += a.SB) {
+        const int sbn = min(a.SB, a.S - sb0), sbn8 = (sbn + 7) & ~7;
+        __syncthreads();
+        for (int i = tid; i < sbn8 * NP; i += FAR_NODE_MMA_THREADS) {      // padded nodes and padded stations get weight 0
+            const int sl = i / NP, nd = i - sl * NP;
+            const int s = sb0 + sl;
+            double w = 0.0;
+            if (sl < sbn && nd < NNODE && !isnear[s]) {
+                const double X = xc + hx * a.xi.xi[nd % NN], Y = yc + hy * a.xi.xi[nd / NN];
+                const double ddx = X - a.mx[s], ddy = Y - a.my[s];
+                const double q = ddx * ddx + ddy * ddy;
+                w = p2 ? 1.0 / q : 1.0 / pow(sqrt(q), a.power);
+            }
+            Wn[i] = w;
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < a.N; c0 += FAR_NODE_COLS) {
+            double acc[MT][2];
+#pragma unroll
+            for (int m = 0; m < MT; m++) acc[m][0] = acc[m][1] = 0.0;
+            // A B element is used by exactly one warp of the CTA, so the B fragments come straight from global memory (the
+            // [S][N] table is L2-resident, a fragment load is four 64-byte runs) through a register queue PF k-steps deep:
+            // no staging, no block barrier inside a tile
+            constexpr int PF = 4;
+            const int bcol = c0 + warp * 8 + fr;
+            const double* bp = a.rvt + (size_t)(sb0 + fk) * a.N + bcol;
+            auto bload = [&](int k4) -> double {
+                return (k4 * 4 + fk < sbn && bcol < a.N) ? __ldg(bp + (size_t)k4 * 4 * a.N) : 0.0;
+            };
+            double bq[PF];
+#pragma unroll
+            for (int i = 0; i < PF; i++) bq[i] = bload(i);
+            const int nk = sbn8 / 4;
+            for (int k0 = 0; k0 < nk; k0 += PF) {
+#pragma unroll
+                for (int i = 0; i < PF; i++) {
+                    const int k4 = k0 + i;
+                    if (k4 < nk) {           // uniform
+                        const double b = bq[i];
+                        bq[i] = bload(k4 + PF);
+                        const double* wa = Wn + (size_t)(k4 * 4 + fk) * NP + fr;
+#pragma unroll
+                        for (int m = 0; m < MT; m++) dmma884(acc[m][0], acc[m][1], wa[m * 8], b);
+                    }
+                }
+            }
+            const int col = c0 + warp * 8 + 2 * fk;
+            if (col < a.N) {   // N is a multiple of 16: col + 1 exists too
+#pragma unroll
+                for (int m = 0; m < MT; m++) {
+                    const int node = m * 8 + fr;
+                    if (node < NNODE) {
+                        double2* p = reinterpret_cast<double2*>(Gp + ((size_t)(col / FAR_CW) * NNODE + node) * FAR_CW + (col % FAR_CW));
+                        double2 v = make_double2(acc[m][0], acc[m][1]);
+                        if (sb0) {
+                            const double2 o = *p;
+                            v.x += o.x;
+                            v.y += o.y;
+                        }
+                        *p = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 struct FarArgs {
     Geom g;
@@ -666,10 +767,22 @@ template <int NN>
 static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArgs& fa, int npl, int nbands, int smem_max) {
     constexpr int NNODE = NN * NN;
     far_mark(plan, st);
-    const size_t node_smem = ((size_t)na.SB * NNODE + 2 * FAR_NODE_KB * FAR_NODE_COLS) * sizeof(double) + (size_t)na.S;
-    SMRFB_CHECK(node_smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: node kernel needs %zu B of shared memory", node_smem);
-    SMRFB_CUDA(cudaFuncSetAttribute(idw_far_node_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    idw_far_node_kernel<NN><<<npl, FAR_NODE_THREADS, node_smem, st>>>(na);
+    static const bool node_fma = getenv("SMRFB_FAR_NODE") && !strcmp(getenv("SMRFB_FAR_NODE"), "fma");
+    if (node_fma) {
+        const size_t node_smem = ((size_t)na.SB * NNODE + 2 * FAR_NODE_KB * FAR_NODE_COLS) * sizeof(double) + (size_t)na.S;
+        SMRFB_CHECK(node_smem <= (size_t)smem_max, SMRFB_ERR_LIMIT, "IDW far field: node kernel needs %zu B of shared memory", node_smem);
+        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_node_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        idw_far_node_kernel<NN><<<npl, FAR_NODE_THREADS, node_smem, st>>>(na);
+    } else {
+        constexpr int NP = FarNodeMma<NN>::NP;
+        const size_t fixed = (size_t)na.S + 16;
+        const int sb_cap = (int)(((size_t)smem_max - fixed) / (NP * sizeof(double))) & ~7;      // stations per block, a multiple of 8
+        na.SB = std::min((na.S + 7) & ~7, sb_cap);
+        SMRFB_CHECK(na.SB >= 8, SMRFB_ERR_LIMIT, "IDW far field: no room for the node weights in shared memory");
+        const size_t node_smem = (size_t)na.SB * NP * sizeof(double) + fixed;
+        SMRFB_CUDA(cudaFuncSetAttribute(idw_far_node_mma_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        idw_far_node_mma_kernel<NN><<<npl, FAR_NODE_MMA_THREADS, node_smem, st>>>(na);
+    }
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
     far_mark(plan, st);
