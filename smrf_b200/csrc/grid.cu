@@ -350,6 +350,100 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_local_fold1_kernel(GridArgs
     }
 }
 
+// Staged form of the folded kernel (default).  ncu on grid_local_fold2_kernel: L1 wavefronts 97 % of peak -- every lane asks for
+// 96 bytes per step although the 64 cells of a warp sit in one to three triangles.  Along the linear cell index a CTA's 512
+// cells fall into a few RUNS of equal simplex; the CTA lists its runs (a block scan of "my simplex differs from my left
+// neighbour's"), stages the runs' vertex values for 16 steps at a time in shared memory (coalesced 256-byte reads per vertex), and
+// the step loop reads them with broadcast 128-bit shared loads: ~12 wavefronts per warp-step instead of ~38.  More than GLS_MAXR
+// runs in a CTA (a source lattice finer than ~13 cells): the direct loads of the kernel above.
+constexpr int GLS_TC = 16;
+constexpr int GLS_MAXR = 40;
+constexpr int GLS_RS = GLS_TC + 1;       // row stride in double2: distinct rows start in different banks
+
+template <typename OutT>
+__global__ void __launch_bounds__(GRID_THREADS, 4) grid_local_fold_staged_kernel(GridArgs a) {
+    __shared__ double2 vals[GLS_MAXR * 3 * GLS_RS];
+    __shared__ int vid[GLS_MAXR * 3];
+    __shared__ int wsum[GRID_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const long long c = ((long long)blockIdx.x * GRID_THREADS + tid) * 2;
+    const bool valid = c < a.g.ncell;                 // ncell is even: c + 1 is a valid cell too
+    const int sx0 = valid ? __ldg(a.cell_simplex + c) : -1, sx1 = valid ? __ldg(a.cell_simplex + c + 1) : -1;
+    const bool f0 = valid && (tid == 0 || sx0 != __ldg(a.cell_simplex + c - 1)), f1 = valid && sx1 != sx0;
+    // inclusive scan of the run starts over the CTA
+    int inc = (int)f0 + (int)f1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) wsum[wp] = inc;
+    __syncthreads();
+    int base = 0, nruns = 0;
+#pragma unroll
+    for (int i = 0; i < GRID_THREADS / 32; i++) {
+        const int v = wsum[i];
+        if (i < wp) base += v;
+        nruns += v;
+    }
+    const int r1 = base + inc - 1, r0 = r1 - (int)f1;       // run of cell c + 1, of cell c
+    const bool staged = nruns <= GLS_MAXR;                   // uniform
+    if (staged) {
+        if (f0) {
+#pragma unroll
+            for (int v = 0; v < 3; v++) vid[3 * r0 + v] = sx0 >= 0 ? __ldg(a.simplices + 3 * sx0 + v) : -1;
+        }
+        if (f1) {
+#pragma unroll
+            for (int v = 0; v < 3; v++) vid[3 * r1 + v] = sx1 >= 0 ? __ldg(a.simplices + 3 * sx1 + v) : -1;
+        }
+    }
+    GridLocalCell g0, g1;
+    if (valid) {
+        g0 = grid_local_setup(a, c);
+        g1 = grid_local_setup(a, c + 1);
+    }
+    const size_t ncell = (size_t)a.g.ncell;
+    OutT* op = reinterpret_cast<OutT*>(a.out) + c;
+    const double qnan = nan("");
+    auto finish = [&](const double2 a0, const double2 b0, const double2 c0, const double2 a1, const double2 b1, const double2 c1) {
+        const double r0v = fma(g0.c2, c0.x, fma(g0.c1, b0.x, g0.c0 * a0.x)), s0v = fma(g0.c2, c0.y, fma(g0.c1, b0.y, g0.c0 * a0.y));
+        const double r1v = fma(g1.c2, c1.x, fma(g1.c1, b1.x, g1.c0 * a1.x)), s1v = fma(g1.c2, c1.y, fma(g1.c1, b1.y, g1.c0 * a1.y));
+        const double v0 = g0.inside ? clamp_nan_keep(fma(s0v, g0.Z, r0v), a.vmin, a.vmax) : qnan;
+        const double v1 = g1.inside ? clamp_nan_keep(fma(s1v, g1.Z, r1v), a.vmin, a.vmax) : qnan;
+        if constexpr (sizeof(OutT) == 4) __stcs(reinterpret_cast<float2*>(op), make_float2((float)v0, (float)v1));
+        else __stcs(reinterpret_cast<double2*>(op), make_double2(v0, v1));
+    };
+    if (!staged) {
+        if (!valid) return;
+#pragma unroll 2
+        for (int t = 0; t < a.T; t++, op += ncell)
+            finish(__ldg(reinterpret_cast<const double2*>(g0.va + 2 * t)), __ldg(reinterpret_cast<const double2*>(g0.vb + 2 * t)),
+                   __ldg(reinterpret_cast<const double2*>(g0.vc + 2 * t)), __ldg(reinterpret_cast<const double2*>(g1.va + 2 * t)),
+                   __ldg(reinterpret_cast<const double2*>(g1.vb + 2 * t)), __ldg(reinterpret_cast<const double2*>(g1.vc + 2 * t)));
+        return;
+    }
+    const double2* p0 = vals + (size_t)(3 * r0) * GLS_RS;
+    const double2* p1 = vals + (size_t)(3 * r1) * GLS_RS;
+    const int nitem = nruns * 3 * GLS_TC;
+    for (int t0 = 0; t0 < a.T; t0 += GLS_TC) {
+        __syncthreads();          // the previous chunk has been consumed (first pass: vid is complete)
+        for (int i = tid; i < nitem; i += GRID_THREADS) {
+            const int row = i / GLS_TC, tc = i - row * GLS_TC;
+            const int v = vid[row];
+            vals[row * GLS_RS + tc] = (v >= 0 && t0 + tc < a.T) ? __ldg(reinterpret_cast<const double2*>(a.vt + (size_t)v * a.T_pad) + t0 + tc)
+                                                                 : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (valid) {
+            const int tn = min(GLS_TC, a.T - t0);
+#pragma unroll 2
+            for (int tc = 0; tc < tn; tc++, op += ncell)
+                finish(p0[tc], p0[GLS_RS + tc], p0[2 * GLS_RS + tc], p1[tc], p1[GLS_RS + tc], p1[2 * GLS_RS + tc]);
+        }
+    }
+}
+
 // d_f3: [T][3][S] on the device (residual, slope, intercept rows per step)
 static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin, double vmax, double* d_out, cudaStream_t st) {
     SMRFB_CHECK(T > 0, SMRFB_ERR_ARG, "T must be > 0");
@@ -396,7 +490,11 @@ static int grid_local_run(GridHandle* h, const double* d_f3, int T, double vmin,
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
     if (fold) {
         const long long nb2 = (h->g.ncell / 2 + GRID_THREADS - 1) / GRID_THREADS;
-        if ((h->g.ncell & 1) == 0) {
+        const bool direct = getenv("SMRFB_GRID_FOLD_DIRECT") != nullptr;      // the kernel without staging, for comparison
+        if ((h->g.ncell & 1) == 0 && !direct) {
+            if (h->out_f32) grid_local_fold_staged_kernel<float><<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
+            else grid_local_fold_staged_kernel<double><<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
+        } else if ((h->g.ncell & 1) == 0) {
             if (h->out_f32) grid_local_fold2_kernel<float><<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
             else grid_local_fold2_kernel<double><<<(unsigned)nb2, GRID_THREADS, 0, st>>>(a);
         } else {

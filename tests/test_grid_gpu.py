@@ -137,6 +137,38 @@ def test_grid_local_vs_oracle_larger(sp):
         assert parity(out[t], o.detrendedInterpolation(f[t].copy(), -1, "linear"), step_scale(f[t])) <= TOL
 
 
+def test_grid_local_staged_kernel_matches_direct_loads(sp, monkeypatch):
+    """The block path of grid_local runs the folded kernel with the vertex values staged per CTA in shared memory (runs of equal
+    simplex along the cell index); with more runs per CTA than fit it loads directly.  Both do the same arithmetic: bit-identical
+    to the un-staged kernel (SMRFB_GRID_FOLD_DIRECT) on a coarse source lattice (staged), a fine one (direct fallback inside the
+    staged kernel), an odd row length (runs wrap rows), 37 steps (two chunks and a ragged tail), float32 output -- and within
+    1e-9 of the oracle."""
+    import pandas as pd
+    from oracle import oracle as orc
+    from smrf_b200 import synthetic as syn
+    for (ny, nx, dx, spacing) in ((64, 130, 30.0, 1500.0), (40, 87, 60.0, 400.0), (33, 64, 10.0, 2500.0)):
+        x, y, dem = syn.make_dem(ny, nx, dx=dx, seed=6)
+        X, Y = np.meshgrid(x, y)
+        px, py, pz = syn.make_source_lattice(x, y, dem, spacing=spacing, jitter=spacing / 9.0, seed=3)
+        md = pd.DataFrame({"utm_x": px, "utm_y": py, "elevation": pz, "latitude": 43.0 + (py - py.min()) / 111000.0,
+                           "longitude": -116.0 + (px - px.min()) / 82000.0})
+        f = syn.make_source_fields(px, py, pz, 37, seed=5)
+        cfg = {"grid_local": True, "grid_local_n": min(12, len(px)), "grid_mask": False}
+        grid = sp.GRID(cfg, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+        monkeypatch.delenv("SMRFB_GRID_FOLD_DIRECT", raising=False)
+        staged = grid.distribute_block_local(f, flag=-1, vmin=-40.0, vmax=40.0)
+        staged32 = grid.distribute_block_local(f, flag=-1, vmin=-40.0, vmax=40.0, out_dtype=np.float32)
+        monkeypatch.setenv("SMRFB_GRID_FOLD_DIRECT", "1")
+        direct = grid.distribute_block_local(f, flag=-1, vmin=-40.0, vmax=40.0)
+        monkeypatch.delenv("SMRFB_GRID_FOLD_DIRECT", raising=False)
+        np.testing.assert_array_equal(staged, direct)
+        np.testing.assert_array_equal(staged32, direct.astype(np.float32))
+        o = orc.GRID(cfg, px, py, X, Y, mz=pz, GridZ=dem, metadata=md)
+        for t in (0, 15, 16, 36):
+            ref = orc.set_min_max(o.detrendedInterpolation(f[t].copy(), -1, "linear"), -40.0, 40.0)
+            assert parity(staged[t], ref, step_scale(f[t])) <= TOL
+
+
 def _md(g):
     import pandas as pd
     return pd.DataFrame({"utm_x": g["px"], "utm_y": g["py"], "elevation": g["pz"], "latitude": g["lat"], "longitude": g["lon"]})
