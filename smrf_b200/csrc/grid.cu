@@ -664,6 +664,164 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_cubic_kernel(GridCubicArgs 
     }
 }
 
+// Staged form (default), as for grid_local above: a CTA's 256 consecutive cells fall into a few runs of equal simplex; the runs'
+// vertex data (value and gradient, 4 NF doubles per vertex and step) are staged for 8 steps at a time in shared memory and read
+// back with broadcast 128-bit loads.  The direct kernel asks L1 for 96 NF bytes per cell-step.
+constexpr int GCS_TC = 8;
+constexpr int GCS_MAXR = 24;
+
+template <int NF, int CPT>      // CPT: adjacent cells per thread (2 when the cell count is even: they mostly share their simplex and its loads)
+__global__ void __launch_bounds__(GRID_THREADS) grid_cubic_staged_kernel(GridCubicArgs a) {
+    constexpr int Q = 2 * NF;                 // double2 per (vertex, step)
+    constexpr int RS = GCS_TC * Q + 1;        // row stride in double2
+    constexpr int MAXR = GCS_MAXR * CPT;
+    __shared__ double2 vals[GCS_MAXR * 3 * RS * (CPT == 2 && NF == 2 ? 1 : CPT)];
+    constexpr int MAXR_FIT = (int)(sizeof(vals) / sizeof(double2)) / (3 * RS);
+    static_assert(MAXR_FIT >= GCS_MAXR, "stage too small");
+    __shared__ int vid[MAXR * 3];
+    __shared__ int wsum[GRID_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const long long c = ((long long)blockIdx.x * GRID_THREADS + tid) * CPT;
+    const bool valid = c < a.g.ncell;         // CPT == 2: the cell count is even, c + 1 is a valid cell too
+    int sx[CPT];
+    bool fl[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) sx[j] = valid ? __ldg(a.cell_simplex + c + j) : -1;
+    fl[0] = valid && (tid == 0 || sx[0] != __ldg(a.cell_simplex + c - 1));
+    if (CPT == 2) fl[CPT - 1] = valid && sx[CPT - 1] != sx[0];
+    int inc = 0;
+#pragma unroll
+    for (int j = 0; j < CPT; j++) inc += (int)fl[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) wsum[wp] = inc;
+    __syncthreads();
+    int base = 0, nruns = 0;
+#pragma unroll
+    for (int i = 0; i < GRID_THREADS / 32; i++) {
+        const int v = wsum[i];
+        if (i < wp) base += v;
+        nruns += v;
+    }
+    int r[CPT];
+    r[CPT - 1] = base + inc - 1;
+    if (CPT == 2) r[0] = r[CPT - 1] - (int)fl[CPT - 1];
+    const bool staged = nruns <= MAXR_FIT;     // uniform
+    if (staged) {
+#pragma unroll
+        for (int j = 0; j < CPT; j++)
+            if (fl[j]) {
+#pragma unroll
+                for (int v = 0; v < 3; v++) vid[3 * r[j] + v] = sx[j] >= 0 ? __ldg(a.simplices + 3 * sx[j] + v) : -1;
+            }
+    }
+    const size_t ncell = (size_t)a.g.ncell;
+    const int f32 = a.out_f32;
+    bool inside[CPT];
+    double w[CPT][9], Z[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) {
+        inside[j] = valid && sx[j] >= 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) w[j][i] = inside[j] ? __ldg(a.ctw + (size_t)i * ncell + c + j) : 0.0;
+        Z[j] = (inside[j] && a.g.dem) ? __ldg(a.g.dem + c + j) : 0.0;
+    }
+    const double qnan = nan("");
+    auto patch = [&](int j, const double2 (&x)[3][Q], double (&val)[NF]) {
+#pragma unroll
+        for (int ff = 0; ff < NF; ff++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                acc = fma(w[j][v], x[v][2 * ff].x, acc);
+                acc = fma(w[j][3 + 2 * v], x[v][2 * ff].y, acc);
+                acc = fma(w[j][4 + 2 * v], x[v][2 * ff + 1].x, acc);
+            }
+            val[ff] = acc;
+        }
+    };
+    auto combine = [&](int j, const double (&val)[NF], int t) -> double {
+        double rr = val[0];
+        if (NF == 2) rr = fma(Z[j], val[NF - 1], rr);
+        else if (a.pv) rr = __dadd_rn(__dadd_rn(rr, __dmul_rn(__ldg(a.pv + 2 * t), Z[j])), __ldg(a.pv + 2 * t + 1));   // grid.py:210
+        return inside[j] ? clamp_nan_keep(rr, a.vmin, a.vmax) : qnan;
+    };
+    auto emit = [&](const double (&o)[CPT], int t) {
+        if (CPT == 2) store_out2(a.out, (size_t)t * ncell + c, o[0], o[CPT - 1], f32);
+        else store_out(a.out, (size_t)t * ncell + c, o[0], f32);
+    };
+    if (!staged) {
+        if (!valid) return;
+        const size_t rowlen = (size_t)a.T * (4 * NF);
+        const double2* vp[CPT][3];
+#pragma unroll
+        for (int j = 0; j < CPT; j++)
+#pragma unroll
+            for (int v = 0; v < 3; v++)
+                vp[j][v] = reinterpret_cast<const double2*>(a.cvt + (size_t)(inside[j] ? __ldg(a.simplices + 3 * sx[j] + v) : 0) * rowlen);
+        for (int t = 0; t < a.T; t++) {
+            double o[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                double2 x[3][Q];
+#pragma unroll
+                for (int v = 0; v < 3; v++)
+#pragma unroll
+                    for (int q = 0; q < Q; q++) x[v][q] = __ldg(vp[j][v] + (size_t)t * Q + q);
+                double val[NF];
+                patch(j, x, val);
+                o[j] = combine(j, val, t);
+            }
+            emit(o, t);
+        }
+        return;
+    }
+    const double2* pr[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) pr[j] = vals + (size_t)(3 * r[j]) * RS;
+    const bool same = CPT == 2 && r[0] == r[CPT - 1];
+    const int nitem = nruns * 3 * GCS_TC * Q;
+    for (int t0 = 0; t0 < a.T; t0 += GCS_TC) {
+        __syncthreads();          // the previous chunk has been consumed (first pass: vid is complete)
+        for (int i = tid; i < nitem; i += GRID_THREADS) {
+            const int row = i / (GCS_TC * Q), rem = i - row * (GCS_TC * Q), tc = rem / Q;
+            const int v = vid[row];
+            vals[row * RS + rem] = (v >= 0 && t0 + tc < a.T)
+                                       ? __ldg(reinterpret_cast<const double2*>(a.cvt + ((size_t)v * a.T + t0) * (4 * NF)) + rem)
+                                       : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (valid) {
+            const int tn = min(GCS_TC, a.T - t0);
+            for (int tc = 0; tc < tn; tc++) {
+                double o[CPT];
+                double2 x[3][Q];
+#pragma unroll
+                for (int v = 0; v < 3; v++)
+#pragma unroll
+                    for (int q = 0; q < Q; q++) x[v][q] = pr[0][v * RS + tc * Q + q];
+                double val[NF];
+                patch(0, x, val);
+                o[0] = combine(0, val, t0 + tc);
+                if (CPT == 2) {
+                    if (!same) {       // the second cell starts a new run: its own vertex rows
+#pragma unroll
+                        for (int v = 0; v < 3; v++)
+#pragma unroll
+                            for (int q = 0; q < Q; q++) x[v][q] = pr[CPT - 1][v * RS + tc * Q + q];
+                    }
+                    patch(CPT - 1, x, val);
+                    o[CPT - 1] = combine(CPT - 1, val, t0 + tc);
+                }
+                emit(o, t0 + tc);
+            }
+        }
+    }
+}
+
 // d_fields: [T][nf][3][S] on the device; d_pv: [T][2] or null
 static int grid_cubic_run(GridHandle* h, const double* d_fields, int T, int nf, const double* d_pv, double vmin, double vmax,
                           double* d_out, cudaStream_t st) {
@@ -693,8 +851,15 @@ static int grid_cubic_run(GridHandle* h, const double* d_fields, int T, int nf, 
     a.out_f32 = h->out_f32;
     const long long nblk = (h->g.ncell + GRID_THREADS - 1) / GRID_THREADS;
     SMRFB_CHECK(nblk < 2147483647LL, SMRFB_ERR_LIMIT, "too many cells for one launch");
-    if (nf == 1) grid_cubic_kernel<1><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
-    else grid_cubic_kernel<2><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    if (getenv("SMRFB_GRID_CUBIC_DIRECT")) {       // the kernel without staging, for comparison
+        if (nf == 1) grid_cubic_kernel<1><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+        else grid_cubic_kernel<2><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    } else {
+        // one cell per thread: two adjacent cells sharing their loads (CPT = 2) need 128 registers with two fields and were
+        // measured slower (11.4 / 16.0 ms against 11.0 / 15.4 ms per 256 steps on the C5 grid, mask / local detrend)
+        if (nf == 1) grid_cubic_staged_kernel<1, 1><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+        else grid_cubic_staged_kernel<2, 1><<<(unsigned)nblk, GRID_THREADS, 0, st>>>(a);
+    }
     count_launch();
     SMRFB_CUDA(cudaGetLastError());
     return SMRFB_OK;

@@ -167,6 +167,19 @@ def test_grid_local_staged_kernel_matches_direct_loads(sp, monkeypatch):
         for t in (0, 15, 16, 36):
             ref = orc.set_min_max(o.detrendedInterpolation(f[t].copy(), -1, "linear"), -40.0, 40.0)
             assert parity(staged[t], ref, step_scale(f[t])) <= TOL
+        # the Clough-Tocher kernel stages the same way (8 steps at a time): local detrend (two fields) and mask detrend (one)
+        f11 = f[:11]
+        cub = {}
+        for tag in ("staged", "direct"):
+            if tag == "direct":
+                monkeypatch.setenv("SMRFB_GRID_CUBIC_DIRECT", "1")
+            cub[tag] = (grid.distribute_block_local(f11, flag=-1, grid_method="cubic", vmin=-40.0, vmax=40.0),
+                        grid.distribute_block(f11, detrend=True, flag=-1, grid_method="cubic"))
+            monkeypatch.delenv("SMRFB_GRID_CUBIC_DIRECT", raising=False)
+        np.testing.assert_array_equal(cub["staged"][0], cub["direct"][0])
+        np.testing.assert_array_equal(cub["staged"][1], cub["direct"][1])
+        ref = orc.set_min_max(o.detrendedInterpolation(f11[10].copy(), -1, "cubic"), -40.0, 40.0)
+        assert parity(cub["staged"][0][10], ref, step_scale(f11[10])) <= TOL
 
 
 def _md(g):
