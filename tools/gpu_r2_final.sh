@@ -16,8 +16,10 @@ timeout 900 ncu --set full --import-source on --clock-control none -k regex:idw_
     python tools/idw_far_perf.py 1024 10000 200 720 > gpurun_out/r02_ncu_far.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:idw_far_kernel -s 2 -c 1 -f -o gpurun_out/r02_far_c5 \
     python tools/idw_far_perf.py 4000 4000 200 512 10 4000 > gpurun_out/r02_ncu_far_c5.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:grid_local_fold2_kernel -s 1 -c 1 -f -o gpurun_out/r02_grid_fold \
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:grid_local_fold_staged_kernel -s 1 -c 1 -f -o gpurun_out/r02_grid_fold \
     python tools/grid_perf.py 4000 4000 256 > gpurun_out/r02_ncu_grid_fold.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:idw_far_node_mma_kernel -s 2 -c 1 -f -o gpurun_out/r02_far_node \
+    python tools/idw_far_perf.py 1024 10000 200 720 > gpurun_out/r02_ncu_far_node.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:dk_distribute_mma_kernel -s 2 -c 1 -f -o gpurun_out/r02_dk_mma \
     python tools/dk_steady_perf.py > gpurun_out/r02_ncu_dk_mma.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:dk_sets_kernel -c 1 -f -o gpurun_out/r02_dk_sets \

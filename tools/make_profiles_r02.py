@@ -28,6 +28,7 @@ KEYS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64 pipe"),
+    ("sm__inst_executed_pipe_fp64_op_dmma.avg.pct_of_peak_sustained_active", "fp64 tensor pipe (DMMA)"),
     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 / shared wavefronts"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate"),
@@ -48,9 +49,11 @@ CAPTURES = [
     ("r02_far_c5.ncu-rep", "idw_far_kernel on the dense C5 network (4000 x 4000 cells of 10 m, the same 200 stations over 40 km: 12 x 12 nodes "
                            "from theta = 4, 4.8 near stations per patch, 512 steps) -- `python tools/idw_far_perf.py 4000 4000 200 512 10 4000`",
      {"kernel": "idw_far_kernel", "shape": "cells16000000_T512_S200"}),
-    ("r02_grid_fold.ncu-rep", "grid_local_fold2_kernel, GRID grid_local (folded form) on the C5 grid (4000 x 4000 cells, 4900 source points, "
-                              "256 steps) -- `python tools/grid_perf.py 4000 4000 256`",
-     {"kernel": "grid_local_fold2_kernel", "shape": "cells16000000_T256_P4900"}),
+    ("r02_grid_fold.ncu-rep", "grid_local_fold_staged_kernel, GRID grid_local (folded form, vertex values staged per CTA) on the C5 grid "
+                              "(4000 x 4000 cells, 4900 source points, 256 steps) -- `python tools/grid_perf.py 4000 4000 256`",
+     {"kernel": "grid_local_fold_staged_kernel", "shape": "cells16000000_T256_P4900"}),
+    ("r02_far_node.ncu-rep", "idw_far_node_mma_kernel, the node sums of one IDW field on a C4 slab (632 patches x 100 nodes x 200 stations x 1440 "
+                             "columns, DMMA) -- `python tools/idw_far_perf.py 1024 10000 200 720`", None),
     ("r02_dk_mma.ncu-rep", "dk_distribute_mma_kernel, DK steady state on a C4 row band (300 x 10000 cells, 720 steps) "
                            "-- `python tools/dk_steady_perf.py`",
      {"kernel": "dk_distribute_mma_kernel", "shape": "cells3000000_T720_S200"}),
