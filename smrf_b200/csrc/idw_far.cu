@@ -377,7 +377,10 @@ __device__ __forceinline__ void far_phase_a(const double* __restrict__ gsl, cons
 // Monotone map of a double's high word to unsigned: key(a) < key(b) implies a < b for non-NaN a, b; NaNs map beyond +-inf.
 __host__ __device__ __forceinline__ unsigned hi_key(int hi) { return (unsigned)hi ^ ((unsigned)(hi >> 31) | 0x80000000u); }
 
-template <int NN, typename OutT, bool CLAMP>
+// CLAMP: 0 none; otherwise the screen that proves a value strictly inside (vmin, vmax) from its high word alone:
+//   1 general (monotone key of the high word: 3 integer instructions per value), 2 vmin >= 0 (the high word itself is monotone
+//   there; a negative value or a NaN falls outside as an unsigned number), 3 vmin < 0 < vmax (|value| below the smaller bound)
+template <int NN, typename OutT, int CLAMP>
 __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
     constexpr int NNODE = NN * NN;
     constexpr int NH = NN / 2;
@@ -599,7 +602,11 @@ __global__ void __launch_bounds__(FAR_THREADS, 2) idw_far_kernel(FarArgs a) {
                 // NaNs included, the exact NaN-preserving clamp of utils.py:137-161
                 bool out = false;
 #pragma unroll
-                for (int j = 0; j < 4; j++) out |= hi_key(__double2hiint(val[j])) - a.klo >= a.kspan;
+                for (int j = 0; j < 4; j++) {
+                    const int hi = __double2hiint(val[j]);
+                    const unsigned key = CLAMP == 2 ? (unsigned)hi : CLAMP == 3 ? (unsigned)hi & 0x7fffffffu : hi_key(hi);
+                    out |= key - a.klo >= a.kspan;
+                }
                 if (__any_sync(0xffffffffu, out)) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) val[j] = clamp_nan_keep(val[j], a.vmin, a.vmax);
@@ -798,11 +805,15 @@ static int far_launch(cudaStream_t st, IdwFarPlan* plan, FarNodeArgs& na, FarArg
         idw_far_kernel<NN, OT, CL><<<grid, FAR_THREADS, smem, st>>>(fa);                                                 \
     } while (0)
     if (fa.out_f32) {
-        if (fa.clamp) FAR_LAUNCH(float, true);
-        else FAR_LAUNCH(float, false);
+        if (fa.clamp == 3) FAR_LAUNCH(float, 3);
+        else if (fa.clamp == 2) FAR_LAUNCH(float, 2);
+        else if (fa.clamp) FAR_LAUNCH(float, 1);
+        else FAR_LAUNCH(float, 0);
     } else {
-        if (fa.clamp) FAR_LAUNCH(double, true);
-        else FAR_LAUNCH(double, false);
+        if (fa.clamp == 3) FAR_LAUNCH(double, 3);
+        else if (fa.clamp == 2) FAR_LAUNCH(double, 2);
+        else if (fa.clamp) FAR_LAUNCH(double, 1);
+        else FAR_LAUNCH(double, 0);
     }
 #undef FAR_LAUNCH
     far_mark(plan, st);
@@ -894,9 +905,20 @@ int idw_far_run(cudaStream_t st, IdwFarPlan* plan, const Geom& g, const double* 
         long long blo, bhi;
         memcpy(&blo, &vmin, 8);
         memcpy(&bhi, &vmax, 8);
-        const unsigned klo = hi_key((int)(blo >> 32)), khi = hi_key((int)(bhi >> 32));
-        fa.klo = klo + 1;
-        fa.kspan = khi > klo + 1 ? khi - (klo + 1) : 0;
+        const int hlo = (int)(blo >> 32), hhi = (int)(bhi >> 32);
+        if (clamp && hlo >= 0 && vmax > vmin) {                // vmin >= +0: the high word orders the non-negative doubles
+            fa.clamp = 2;
+            fa.klo = (unsigned)hlo + 1;
+            fa.kspan = (unsigned)hhi > fa.klo ? (unsigned)hhi - fa.klo : 0;
+        } else if (clamp && vmin < 0.0 && vmax > 0.0) {        // |v| < min(-vmin, vmax), compared on the high words
+            fa.clamp = 3;
+            fa.klo = 0;
+            fa.kspan = (unsigned)std::min(hlo & 0x7fffffff, hhi);
+        } else {
+            const unsigned klo = hi_key(hlo), khi = hi_key(hhi);
+            fa.klo = klo + 1;
+            fa.kspan = khi > klo + 1 ? khi - (klo + 1) : 0;
+        }
     }
     SMRFB_PROPAGATE(nn == 10 ? far_launch<10>(st, plan, na, fa, npl, nbands, smem_max)
                              : far_launch<12>(st, plan, na, fa, npl, nbands, smem_max));
