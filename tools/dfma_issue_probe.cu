@@ -59,6 +59,46 @@ void run(int warps, double* out, int* iout) {
            cyc / (iters * 8.0 * wpp), K, LDS ? "LDS" : "IMAD");
 }
 
+
+// DFMAs with three distinct register operands (acc = y * z + acc with y, z, acc all in registers), as in the far-field kernel's
+// interpolation sums, against the two-register form above: does operand delivery slow the pipe down?
+template <int NCH>
+__global__ void probe3(double* out, int iters, double a) {
+    double x[NCH], y[NCH], z[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) x[i] = threadIdx.x * 1e-3 + i, y[i] = 1.0 - 1e-7 * (threadIdx.x + i), z[i] = a + 1e-9 * i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) x[i] = fma(y[i], z[(i + 1) % NCH], x[i]);
+#pragma unroll
+        for (int i = 0; i < NCH; i++) y[i] = fma(x[i], z[i], y[(i + 3) % NCH]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += x[i] + y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int NCH>
+void run3(int warps, double* out) {
+    const int iters = 20000;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    probe3<NCH><<<148, warps * 32>>>(out, 100, 1e-9);
+    cudaEventRecord(e0);
+    probe3<NCH><<<148, warps * 32>>>(out, iters, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    int clk = 0;
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    const double cyc = ms * 1e-3 * clk * 1e3;
+    printf("3-register DFMA, %2d chains, warps/SM=%2d: %.3f ms  %.2f clk per DFMA per sub-partition\n", NCH, warps, ms,
+           cyc / (iters * 2.0 * NCH * (warps / 4.0)));
+}
+
 int main() {
     double* out;
     int* iout;
@@ -71,6 +111,10 @@ int main() {
         run<3, false>(warps, out, iout);
         run<1, true>(warps, out, iout);
         run<2, true>(warps, out, iout);
+    }
+    for (int warps : {4, 16, 32}) {
+        run3<8>(warps, out);
+        run3<16>(warps, out);
     }
     return 0;
 }
