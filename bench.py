@@ -692,10 +692,9 @@ def roofline(wl, fields, objs, launch_ms, far, far_ms, steps, nslab, slab_cells,
                 "fp64_view": {"achieved_tflops": flops / (main_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                               "frac": flops / (main_ms * 1e-3) / 1e12 / fp64_peak,
                               "flop_per_output": flops / (slab_cells * Tb),
-                              "note": "what limits the kernel is instruction issue, not a pipe: ~89 fp64 and ~91 other warp instructions per four "
-                                      "outputs; a DFMA holds a sub-partition's fp64 pipe for 2 clk and the others do not hide under it at 16 warps "
-                                      "per SM (tools/dfma_issue_probe.cu, profiles/r02_dfma_issue_probe.txt; ncu's per-instruction samples give "
-                                      "DFMA 46 % of the time = exactly 2 clk each, the rest ~1.7 clk each); the fp64 peak is builder-measured "
+                              "note": "what limits the kernel: ~89 fp64 and ~91 other warp instructions per four outputs at 16 warps per SM and 128 "
+                                      "registers; the time follows the fp64 instruction count (DESIGN.md 4.1: tools/dfma_issue_probe.cu, "
+                                      "profiles/r02_dfma_issue_probe.txt, profiles/r02_far_variants.txt); the fp64 peak is builder-measured "
                                       "(DFMA issue loop, profiles/r01_peak_probe.json), "
                                       "MEASURED_PEAKS.json holds no fp64 figure"},
                 "why": "the reference's dense sum is 4 S = 800 flop per 8-byte output (100 flop/B, far right of the fp64 ridge at 5.2 "
