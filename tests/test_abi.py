@@ -45,6 +45,23 @@ def test_no_cpu_fallback_without_gpu(libpath):
     X, Y = np.meshgrid(np.arange(4.0), np.arange(3.0))
     with pytest.raises(_lib.SmrfbError):
         IDW(np.array([0.5, 2.5]), np.array([0.5, 1.5]), X, Y, mz=np.array([1.0, 2.0]), GridZ=np.ones((3, 4)))
+    # the consumers likewise: the device or nothing
+    from smrf_b200 import envphys_c
+    from smrf_b200.snow import Snow
+    with pytest.raises(_lib.SmrfbError):
+        Snow.phase_and_density(np.array([-3.0, 1.0]), np.array([1.0, 2.0]), "marks2017")
+    with pytest.raises(_lib.SmrfbError):
+        envphys_c.cdewpt(np.array([600.0, 900.0]), np.zeros(2), 0.01, 1)
+
+
+def test_snow_wrapper_argument_errors():
+    """snow.py:64-69: an unknown model is a ValueError before anything touches the device."""
+    from smrf_b200.snow import Snow
+    assert sorted(Snow.MODELS) == ["marks2017", "piecewise_susong1999", "susong1999"]        # snow.py:29-33
+    with pytest.raises(ValueError):
+        Snow.phase_and_density(np.zeros(2), np.zeros(2), "nope")
+    with pytest.raises(ValueError):
+        Snow.phase_and_density(np.zeros(3), np.zeros(2), "susong1999")
 
 
 def test_product_does_not_import_oracle():
