@@ -64,6 +64,26 @@ def test_snow_wrapper_argument_errors():
         Snow.phase_and_density(np.zeros(3), np.zeros(2), "susong1999")
 
 
+def test_plain_c_client_compiles_and_links(libpath, tmp_path):
+    """include/smrfb.h is plain C99 and examples/c_abi_demo.c -- what a cgo / JNI / Cython binding would wrap -- builds against the
+    library with gcc alone; without a GPU it stops at the first call with the library's error text (no fallback)."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "c_abi_demo")
+    hdr = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c",
+                          os.path.join(ROOT, "include", "smrfb.h")], capture_output=True, text=True)
+    assert hdr.returncode == 0 and not hdr.stderr.strip(), hdr.stderr
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", os.path.dirname(libpath), "-lsmrfb",
+                        "-Wl,-rpath," + os.path.dirname(libpath), "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "susong1999 at cell 0" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode != 0 and "smrfb_device_count" in run.stderr, run.stdout + run.stderr
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "smrf_b200")
     for dp, _, files in os.walk(pkg):
